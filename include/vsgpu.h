@@ -1,0 +1,132 @@
+/*
+ * libvsgpu — B200-native batched region-query engine for VariantStore indexes.
+ *
+ * C ABI boundary.  The reference (Kingsford-Group/variantstore) has no plugin/FFI layer: its
+ * query path is a set of C++ free functions over (VariantGraph*, Index*) called from the switch
+ * in query_main (src/commands.cc:150-193).  Each entry point below names the reference interface
+ * it replaces.  Plain pointers and sizes only; the caller owns every input array; result objects
+ * are owned by the library until the matching *_free call.  Every function returns 0 on success
+ * or a negative VSGPU_E* code; vsgpu_last_error() gives the message for the calling thread.
+ * Nothing here writes to stdout — the front-end prints the reference's count lines.
+ *
+ * There is no CPU fallback: every query entry point fails with VSGPU_ENODEVICE when no CUDA
+ * device is usable.
+ */
+#ifndef VSGPU_H_
+#define VSGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSGPU_OK 0
+#define VSGPU_EINVAL (-1)      /* bad argument (e.g. region start < 1: the reference aborts, index.h:151-154) */
+#define VSGPU_EIO (-2)         /* ser/ directory unreadable or malformed */
+#define VSGPU_ESHAPE (-3)      /* graph shape the flattened form cannot represent */
+#define VSGPU_ENODEVICE (-4)   /* no usable CUDA device / CUDA runtime error */
+#define VSGPU_ENOMEM (-5)
+
+#define VSGPU_NONE 0xFFFFFFFFu
+
+/* t4 hit code layout (vsgpu_result_hits) */
+#define VSGPU_HIT_START 0x80000000u   /* the walk started on this vertex: a substitution prints ref "" (query.h:650,706) */
+#define VSGPU_HIT_REJOIN 0x40000000u  /* the row is the backbone vertex the alt edge rejoins */
+#define VSGPU_HIT_ENTRY_MASK 0x3FFFFFFFu
+
+typedef struct vsgpu_index vsgpu_index;
+typedef struct vsgpu_result vsgpu_result;
+typedef struct vsgpu_batch vsgpu_batch;
+
+typedef struct vsgpu_info_t {
+	uint64_t ref_length;        /* VariantGraph::get_ref_length  variant_graph.h:1215 */
+	uint64_t seq_length;        /* VariantGraph::get_seq_length  variant_graph.h:1207 */
+	uint64_t num_vertices_cqf;  /* Graph::get_num_vertices = "#Vertices" printed by query_main (commands.cc:134-136) */
+	uint64_t num_vertices;      /* vertices in the protobuf blocks */
+	uint32_t num_samples;       /* including "ref" */
+	uint32_t num_classes;       /* sample-vector classes (0 in explicit-id mode) */
+	uint32_t class_mode;        /* 1 = bit-vector encoding, 0 = explicit sample ids */
+	uint32_t backbone_vertices; /* M */
+	uint32_t distinct_starts;   /* D = set bits of index.sdsl */
+	uint32_t branch_records;    /* R */
+	uint32_t walk_entries;      /* compact t4 entries */
+	uint32_t has_suspect_dups;
+	uint64_t device_bytes;      /* HBM held by the flattened index */
+	char chr[64];               /* VariantGraph::get_chr */
+} vsgpu_info_t;
+
+/* ---- lifecycle -------------------------------------------------------------------------------
+ * Replaces `Index idx(prefix); VariantGraph vg(prefix, mode);` (src/commands.cc:116-132,
+ * include/index.h:108-117, include/variant_graph.h:366-446, include/graph.h:149-172): loads the
+ * serialised directory once, flattens it and uploads it to `device`. */
+int vsgpu_open(const char* ser_prefix, int device, vsgpu_index** out);
+void vsgpu_close(vsgpu_index* idx);
+const char* vsgpu_last_error(void);
+int vsgpu_info(const vsgpu_index* idx, vsgpu_info_t* out);
+/* Launch kernels and copies on this CUDA stream (a cudaStream_t) instead of the library's own. */
+int vsgpu_set_stream(vsgpu_index* idx, void* cuda_stream);
+
+/* sampleid_map lookups (variant_graph.h:1230-1236, :1333-1338) */
+int vsgpu_sample_id(const vsgpu_index* idx, const char* name, uint32_t* id);
+const char* vsgpu_sample_name(const vsgpu_index* idx, uint32_t id);
+
+/* ---- t6: get_var_in_ref(vg, idx, pos_x, pos_y) — include/query.h:736-784 -----------------------
+ * For every region [x[i], y[i]) writes the slice [rec_lo[i], rec_hi[i]) of the branch-record table
+ * (records in the order the reference pushes them) and counts[i] = rows the reference returns
+ * ("Number of variants get_var_in_ref: N").  rec_lo / rec_hi may be NULL.  Host buffers. */
+int vsgpu_query_t6(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y,
+                   uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts);
+
+/* ---- t4: get_sample_var_in_ref(vg, idx, pos_x, pos_y, sample) — include/query.h:618-729 ---------
+ * Result = CSR: offsets[n+1] into hits[]; each hit is a walk-entry code (VSGPU_HIT_*), in the
+ * order the reference pushes the rows.  sample_ids are sampleid_map ids (1..num_samples-1). */
+int vsgpu_query_t4(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y,
+                   const uint32_t* sample_ids, vsgpu_result** out);
+uint64_t vsgpu_result_num_queries(const vsgpu_result* r);
+const uint64_t* vsgpu_result_offsets(const vsgpu_result* r);   /* n + 1 */
+const uint32_t* vsgpu_result_hits(const vsgpu_result* r);
+void vsgpu_result_free(vsgpu_result* r);
+
+/* ---- t7: samples_has_var(vg, idx, pos, ref, alt) — include/query.h:792-823 ----------------------
+ * rec[i] = branch record whose (ref, pos, alt) equals the query among the records found by one
+ * next_variant_in_ref(pos) call, or VSGPU_NONE ("There is no such variant!").  refs/alts are n
+ * NUL-terminated strings ("" for an empty ref/alt). */
+int vsgpu_query_t7(vsgpu_index* idx, uint64_t n, const uint64_t* pos, const char* const* refs,
+                   const char* const* alts, uint32_t* rec);
+
+/* ---- materialisation (host side) ---------------------------------------------------------------
+ * Build the rows the reference's operators return (struct Variant, query.h:30-36) from record ids
+ * / hit codes.  Text form = what print_var writes (query.h:43-50): "pos\tref\talt\tname(gt) ...\n".
+ * The returned buffer is malloc'd; free it with vsgpu_free.  with_samples = 0 leaves the carrier
+ * list empty (rows end "\t\n"). */
+int vsgpu_rows_t6(const vsgpu_index* idx, uint32_t rec_lo, uint32_t rec_hi, int with_samples, char** text, uint64_t* nrows);
+int vsgpu_rows_t4(const vsgpu_index* idx, const uint32_t* hits, uint64_t nhits, int with_samples, char** text);
+/* "name gt" pairs concatenated as samples_has_var writes them (query.h:807-816) */
+int vsgpu_rows_t7(const vsgpu_index* idx, uint32_t rec, char** text, uint64_t* ncarriers);
+void vsgpu_free(void* p);
+/* FNV-1a 64 digests of the row text per query (multi-threaded); used by the parity tests. */
+int vsgpu_digest_t6(const vsgpu_index* idx, uint64_t n, const uint32_t* rec_lo, const uint32_t* rec_hi, int with_samples, uint64_t* digests);
+int vsgpu_digest_t4(const vsgpu_index* idx, uint64_t n, const uint64_t* offsets, const uint32_t* hits, int with_samples, uint64_t* digests);
+int vsgpu_digest_t7(const vsgpu_index* idx, uint64_t n, const uint32_t* rec, uint64_t* ncarriers, uint64_t* digests);
+
+/* ---- device-resident batches (bench harness; replaces the timing loop of src/bm_query.cc:74-135)
+ * A batch keeps its regions and results in HBM so a run times the kernels alone.
+ * type = 4, 6 or 7.  For type 7 pass refs/alts; for type 4 pass sample_ids. */
+int vsgpu_batch_create(vsgpu_index* idx, int type, uint64_t n, const uint64_t* x, const uint64_t* y,
+                       const uint32_t* sample_ids, const char* const* refs, const char* const* alts,
+                       vsgpu_batch** out);
+/* Enqueue one pass of the hot path over the batch on the index's stream (no host sync). */
+int vsgpu_batch_run(vsgpu_batch* b);
+/* Synchronise, then copy results out.  Any pointer may be NULL.  t6: rec_lo/rec_hi/counts;
+ * t4: counts (per query) and *out (CSR); t7: rec_lo receives the record ids. */
+int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts, vsgpu_result** out);
+/* Algorithmic bytes of the last run (SURVEY.md §8d formulas) and the number of kernels it launched. */
+int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* kernel_launches);
+void vsgpu_batch_free(vsgpu_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSGPU_H_ */

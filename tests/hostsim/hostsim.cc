@@ -1,0 +1,139 @@
+// TEST-ONLY host simulator of libvsgpu's kernels.
+//
+// Exports the same C symbols as include/vsgpu.h (the query subset), but runs the per-region logic
+// of variantstore_b200/csrc/device_logic.cuh compiled for the host, over the same flattened tables.
+// Purpose: let the `-m "not gpu"` suite check loader + flattener + walk rules + materialiser against
+// the oracle on a machine without a GPU.  It is never linked into, loaded by, or shipped with
+// libvsgpu.so — the product has no CPU path.
+#include "../../include/vsgpu.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+
+#include "../../variantstore_b200/csrc/device_logic.cuh"
+#include "../../variantstore_b200/csrc/host_index.h"
+
+using namespace vsgpu;
+
+struct vsgpu_result { std::vector<uint64_t> offsets; std::vector<uint32_t> hits; };
+struct vsgpu_index : HostIndex {
+	DevIndex dev;
+	std::vector<std::vector<uint32_t>> lv;
+	std::vector<uint2> t7;
+};
+
+namespace {
+thread_local std::string g_err;
+int set_err(int code, const std::string& m) { g_err = m; return code; }
+char* dup_text(const std::string& s) { char* p = (char*)malloc(s.size() + 1); memcpy(p, s.data(), s.size()); p[s.size()] = 0; return p; }
+struct VecSink { std::vector<uint32_t>* v; void emit(uint32_t c) { v->push_back(c); } };
+}
+
+extern "C" {
+const char* vsgpu_last_error(void) { return g_err.c_str(); }
+void vsgpu_free(void* p) { free(p); }
+
+int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
+	*out = nullptr;
+	std::unique_ptr<vsgpu_index> ix(new vsgpu_index);
+	int stage = 0;
+	try { build_host_index(prefix, *ix, &stage); build_levels(ix->flat, ix->lv); }
+	catch (const std::exception& e) { return set_err(stage == 0 ? VSGPU_EIO : VSGPU_ESHAPE, e.what()); }
+	FlatIndex& f = ix->flat; DevIndex& d = ix->dev;
+	memset(&d, 0, sizeof d);
+	d.D = f.D; d.M = f.M; d.R = f.R; d.num_cent = (uint32_t)f.cent.size(); d.words_per_set = f.words_per_set;
+	d.num_samples = f.num_samples; d.class_mode = f.class_mode; d.index_bits = f.index_bits; d.last_end = ix->last_end;
+	d.nlvl = (uint32_t)ix->lv.size();
+	for (size_t i = 0; i < ix->lv.size(); i++) { d.lvl[i] = ix->lv[i].data(); d.lvl_n[i] = (uint32_t)ix->lv[i].size(); }
+	ix->t7.resize(f.D);
+	for (uint32_t i = 0; i < f.D; i++) ix->t7[i] = make_uint2(f.t7_lo[i], f.t7_hi[i]);
+	d.dlev = (const uint4*)f.dlev.data(); d.dinfo = f.dinfo.data(); d.t7rng = ix->t7.data(); d.cent = (const uint4*)f.cent.data();
+	d.bb_set = f.bb_set.data(); d.vstart = f.vstart.data(); d.bitmap = f.bitmap.data(); d.list_begin = f.list_begin.data();
+	d.list_ids = f.list_ids.data(); d.rec_pos = f.rec_pos.data(); d.rec_hash = f.rec_hash.data(); d.rec_flags = f.rec_flags.data();
+	*out = ix.release();
+	return VSGPU_OK;
+}
+void vsgpu_close(vsgpu_index* ix) { delete ix; }
+
+int vsgpu_info(const vsgpu_index* ix, vsgpu_info_t* o) {
+	memset(o, 0, sizeof *o);
+	o->ref_length = ix->ser.ref_length; o->seq_length = ix->ser.seq.size(); o->num_vertices_cqf = ix->ser.cqf_distinct;
+	o->num_vertices = ix->ser.num_vertices; o->num_samples = ix->ser.num_samples;
+	o->num_classes = ix->flat.class_mode ? ix->flat.num_sets - 1 : 0; o->class_mode = ix->flat.class_mode;
+	o->backbone_vertices = ix->flat.M; o->distinct_starts = ix->flat.D; o->branch_records = ix->flat.R;
+	o->walk_entries = (uint32_t)ix->flat.cent.size(); o->has_suspect_dups = ix->flat.has_suspect_dups;
+	strncpy(o->chr, ix->ser.chr.c_str(), sizeof o->chr - 1);
+	return VSGPU_OK;
+}
+int vsgpu_sample_id(const vsgpu_index* ix, const char* name, uint32_t* id) {
+	auto it = ix->name2id.find(name);
+	if (it == ix->name2id.end()) return set_err(VSGPU_EINVAL, std::string("Sample not found: ") + name);
+	*id = it->second; return VSGPU_OK;
+}
+const char* vsgpu_sample_name(const vsgpu_index* ix, uint32_t id) { return id < ix->ser.num_samples ? ix->ser.sample_names[id].c_str() : nullptr; }
+
+int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts) {
+	const uint32_t* top = ix->dev.lvl[ix->dev.nlvl - 1];
+	std::vector<uint32_t> tmp;
+	for (uint64_t i = 0; i < n; i++) {
+		bool bad = false;
+		uint2 r = logic::t6_bounds(ix->dev, top, x[i], y[i], &bad);
+		if (bad) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+		if (lo) lo[i] = r.x;
+		if (hi) hi[i] = r.y;
+		if (counts) { if (t6_needs_literal(ix, y[i], r.x, r.y)) { t6_literal(ix, x[i], y[i], tmp); counts[i] = (uint32_t)tmp.size(); } else counts[i] = r.y - r.x; }
+	}
+	return VSGPU_OK;
+}
+
+int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_result** out) {
+	const uint32_t* top = ix->dev.lvl[ix->dev.nlvl - 1];
+	std::unique_ptr<vsgpu_result> r(new vsgpu_result);
+	r->offsets.assign(n + 1, 0);
+	VecSink sink{&r->hits};
+	for (uint64_t i = 0; i < n; i++) {
+		if (x[i] < 1 || s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+		logic::walk_region(ix->dev, top, x[i], y[i], s[i], sink);
+		r->offsets[i + 1] = r->hits.size();
+	}
+	*out = r.release();
+	return VSGPU_OK;
+}
+uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r->offsets.size() - 1; }
+const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r->offsets.data(); }
+const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r->hits.data(); }
+void vsgpu_result_free(vsgpu_result* r) { delete r; }
+
+int vsgpu_query_t7(vsgpu_index* ix, uint64_t n, const uint64_t* pos, const char* const* refs, const char* const* alts, uint32_t* rec) {
+	const uint32_t* top = ix->dev.lvl[ix->dev.nlvl - 1];
+	for (uint64_t i = 0; i < n; i++) {
+		bool bad = false;
+		uint32_t r = logic::t7_lookup(ix->dev, top, pos[i], hash_query(refs[i], alts[i]), &bad);
+		if (bad) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+		rec[i] = t7_confirm(ix, pos[i], refs[i], alts[i], r);
+	}
+	return VSGPU_OK;
+}
+
+int vsgpu_rows_t6(const vsgpu_index* ix, uint32_t lo, uint32_t hi, int ws, char** text, uint64_t* nrows) {
+	if (lo > hi || hi > ix->flat.R) return set_err(VSGPU_EINVAL, "bad record slice");
+	std::string s; uint64_t cnt = 0; rows_t6(ix, lo, hi, ws != 0, s, cnt);
+	if (nrows) *nrows = cnt;
+	*text = dup_text(s); return VSGPU_OK;
+}
+int vsgpu_rows_t4(const vsgpu_index* ix, const uint32_t* hits, uint64_t nhits, int ws, char** text) {
+	std::string s;
+	for (uint64_t i = 0; i < nhits; i++) t4_row(ix, hits[i], ws != 0, s);
+	*text = dup_text(s); return VSGPU_OK;
+}
+int vsgpu_rows_t7(const vsgpu_index* ix, uint32_t rec, char** text, uint64_t* nc) {
+	std::string s; uint64_t c = t7_carriers(ix, rec, &s, nullptr);
+	if (nc) *nc = c;
+	*text = dup_text(s); return VSGPU_OK;
+}
+int vsgpu_digest_t6(const vsgpu_index* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, int ws, uint64_t* d) { bool bad = false; digests_t6(ix, n, lo, hi, ws != 0, d, &bad); return bad ? VSGPU_EINVAL : VSGPU_OK; }
+int vsgpu_digest_t4(const vsgpu_index* ix, uint64_t n, const uint64_t* off, const uint32_t* hits, int ws, uint64_t* d) { digests_t4(ix, n, off, hits, ws != 0, d); return VSGPU_OK; }
+int vsgpu_digest_t7(const vsgpu_index* ix, uint64_t n, const uint32_t* rec, uint64_t* nc, uint64_t* d) { digests_t7(ix, n, rec, nc, d); return VSGPU_OK; }
+}  // extern "C"

@@ -1,0 +1,228 @@
+"""Host-side mirror of the reference's query operators (include/query.h) over libvsgpu.
+
+Names, argument meaning and error behaviour follow the reference:
+  get_var_in_ref(pos_x, pos_y)                 query.h:736-784   (t6)
+  get_sample_var_in_ref(pos_x, pos_y, sample)  query.h:618-729   (t4)
+  samples_has_var(pos, ref, alt)               query.h:792-823   (t7)
+plus batched forms that take whole arrays of regions — the reason this engine exists.
+Positions are 1-based, regions are [pos_x, pos_y).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+NONE = 0xFFFFFFFF
+
+
+class VsgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vsgpu error {code}: {msg}")
+        self.code = code
+
+
+@dataclass
+class Variant:                      # struct Variant, query.h:30-36
+    var_pos: int
+    ref: str
+    alt: str
+    samples: List[Tuple[str, str]] = field(default_factory=list)
+
+
+def load_library(path: Optional[str] = None, subset: bool = False):
+    return _lib.load(path, subset)
+
+
+def read_regions(region: str) -> List[Tuple[int, int]]:
+    """src/commands.cc:64-93 — comma list of beg[:end]; the result is sorted like the reference's."""
+    out = []
+    for tok in region.split(","):
+        if ":" in tok:
+            b, e = tok.split(":", 1)
+            out.append((int(b), int(e)))
+        else:
+            out.append((int(tok), 0))
+    out.sort()
+    return out
+
+
+def read_sequences(s: str) -> List[str]:
+    """src/commands.cc:96-111"""
+    return s.split(",")
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _parse_rows(text: str) -> List[Variant]:
+    rows = []
+    for line in text.split("\n"):
+        if not line:
+            continue
+        pos, ref, alt, samples = line.split("\t")
+        carriers = []
+        for tok in samples.split(" "):
+            if tok:
+                name, gt = tok[:-1].split("(")
+                carriers.append((name, gt))
+        rows.append(Variant(int(pos), ref, alt, carriers))
+    return rows
+
+
+class VariantStoreIndex:
+    """`Index idx(prefix); VariantGraph vg(prefix, mode)` of query_main (commands.cc:116-132) in one
+    object: loads ser/, flattens it and keeps it resident on one GPU."""
+
+    def __init__(self, prefix: str, device: int = 0, lib=None):
+        self._lib = lib or _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.vsgpu_open(prefix.encode(), device, C.byref(h))
+        if rc != 0:
+            raise VsgpuError(rc, self._lib.vsgpu_last_error().decode())
+        self._h = h
+        info = _lib.InfoT()
+        self._lib.vsgpu_info(self._h, C.byref(info))
+        self.info = info
+        self.chr = info.chr.decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vsgpu_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VsgpuError(rc, self._lib.vsgpu_last_error().decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.vsgpu_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # ---- sample ids
+    def sample_id(self, name: str) -> int:
+        v = C.c_uint32()
+        self._check(self._lib.vsgpu_sample_id(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def sample_name(self, sid: int) -> str:
+        return self._lib.vsgpu_sample_name(self._h, sid).decode()
+
+    # ---- batched operators
+    def batch_var_in_ref(self, x, y):
+        """t6 over arrays: returns (rec_lo, rec_hi, counts)."""
+        x, y = _u64(x), _u64(y)
+        n = len(x)
+        lo, hi, cnt = (np.zeros(n, np.uint32) for _ in range(3))
+        self._check(self._lib.vsgpu_query_t6(self._h, n, _ptr(x), _ptr(y), _ptr(lo), _ptr(hi), _ptr(cnt)))
+        return lo, hi, cnt
+
+    def batch_sample_var_in_ref(self, x, y, sample_ids):
+        """t4 over arrays: returns (offsets[n+1], hit codes)."""
+        x, y = _u64(x), _u64(y)
+        s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        n = len(x)
+        r = C.c_void_p()
+        self._check(self._lib.vsgpu_query_t4(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(r)))
+        try:
+            off = np.ctypeslib.as_array(self._lib.vsgpu_result_offsets(r), shape=(n + 1,)).copy()
+            total = int(off[-1])
+            hits = np.ctypeslib.as_array(self._lib.vsgpu_result_hits(r), shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+        finally:
+            self._lib.vsgpu_result_free(r)
+        return off, hits
+
+    def batch_samples_has_var(self, pos, refs: Sequence[str], alts: Sequence[str]):
+        """t7 over arrays: returns record ids (NONE where the reference says "There is no such variant!")."""
+        pos = _u64(pos)
+        n = len(pos)
+        ra = (C.c_char_p * n)(*[r.encode() for r in refs])
+        aa = (C.c_char_p * n)(*[a.encode() for a in alts])
+        rec = np.zeros(n, np.uint32)
+        self._check(self._lib.vsgpu_query_t7(self._h, n, _ptr(pos), ra, aa, _ptr(rec)))
+        return rec
+
+    # ---- digests / text (parity tests, -v output)
+    def digest_t6(self, lo, hi, with_samples=True):
+        d = np.zeros(len(lo), np.uint64)
+        self._check(self._lib.vsgpu_digest_t6(self._h, len(lo), _ptr(lo), _ptr(hi), int(with_samples), _ptr(d)))
+        return d
+
+    def digest_t4(self, offsets, hits, with_samples=True):
+        n = len(offsets) - 1
+        d = np.zeros(n, np.uint64)
+        hits = np.ascontiguousarray(hits, np.uint32)
+        self._check(self._lib.vsgpu_digest_t4(self._h, n, _ptr(offsets), _ptr(hits), int(with_samples), _ptr(d)))
+        return d
+
+    def digest_t7(self, rec):
+        n = len(rec)
+        d, c = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        self._check(self._lib.vsgpu_digest_t7(self._h, n, _ptr(rec), _ptr(c), _ptr(d)))
+        return c, d
+
+    def _take_text(self, p):
+        try:
+            return C.string_at(p).decode()
+        finally:
+            self._lib.vsgpu_free(p)
+
+    def rows_t6_text(self, lo, hi, with_samples=True):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.vsgpu_rows_t6(self._h, int(lo), int(hi), int(with_samples), C.byref(p), C.byref(n)))
+        return self._take_text(p)
+
+    def rows_t4_text(self, hits, with_samples=True):
+        hits = np.ascontiguousarray(hits, np.uint32)
+        p = C.c_void_p()
+        self._check(self._lib.vsgpu_rows_t4(self._h, _ptr(hits), len(hits), int(with_samples), C.byref(p)))
+        return self._take_text(p)
+
+    def rows_t7_text(self, rec):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.vsgpu_rows_t7(self._h, int(rec), C.byref(p), C.byref(n)))
+        return self._take_text(p)
+
+    # ---- single-region operators with the reference's signatures
+    def get_var_in_ref(self, pos_x: int, pos_y: int) -> List[Variant]:
+        lo, hi, cnt = self.batch_var_in_ref([pos_x], [pos_y])
+        if cnt[0] == hi[0] - lo[0]:
+            return _parse_rows(self.rows_t6_text(lo[0], hi[0]))
+        return _parse_rows(self.rows_t6_text(lo[0], hi[0]))[: int(cnt[0])]
+
+    def get_sample_var_in_ref(self, pos_x: int, pos_y: int, sample_id: str) -> List[Variant]:
+        off, hits = self.batch_sample_var_in_ref([pos_x], [pos_y], [self.sample_id(sample_id)])
+        return _parse_rows(self.rows_t4_text(hits))
+
+    def samples_has_var(self, pos: int, ref: str, alt: str) -> List[Tuple[str, str]]:
+        rec = self.batch_samples_has_var([pos], [ref], [alt])
+        if rec[0] == NONE:
+            return []                 # the reference logs "There is no such variant!" (query.h:820)
+        c = self._lib
+        ids = []
+        text = self.rows_t7_text(rec[0])
+        # "name gt" pairs are concatenated without a separator; gt is always 3 characters
+        i = 0
+        while i < len(text):
+            sp = text.index(" ", i)
+            ids.append((text[i:sp], text[sp + 1:sp + 4]))
+            i = sp + 4
+        return ids

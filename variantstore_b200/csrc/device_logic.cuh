@@ -1,0 +1,159 @@
+// libvsgpu — per-region logic of the query kernels, written once as __host__ __device__ inline
+// functions.  kernels.cu instantiates it inside the sm_100a kernels; tests/hostsim compiles the
+// same text for the host so the flattened tables and the walk rules can be checked against the
+// oracle on a machine without a GPU (test-only: libvsgpu.so never runs this code on the CPU).
+#pragma once
+#include "kernels.cuh"
+
+#if defined(__CUDACC__)
+#define VSGPU_HD __host__ __device__ __forceinline__
+#else
+#define VSGPU_HD inline
+#endif
+
+namespace vsgpu {
+namespace logic {
+
+template <class T> VSGPU_HD T ldg(const T* p) {
+#if defined(__CUDA_ARCH__)
+	return __ldg(p);
+#else
+	return *p;
+#endif
+}
+VSGPU_HD uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+constexpr uint32_t kEntAlt = 1u << 31, kEntTgtCarriers = 1u << 30, kEntMarker = 1u << 29, kEntTgtMask = (1u << 29) - 1;
+constexpr uint32_t kHitStart = 0x80000000u, kHitRejoin = 0x40000000u;
+constexpr uint32_t kNoneU32 = 0xFFFFFFFFu;
+
+VSGPU_HD uint32_t clamp_pos(uint64_t v) { return v > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)v; }
+
+// number of keys <= x in a sorted run of n <= 32 keys living in one 128-byte line
+VSGPU_HD uint32_t count_le_node(const uint32_t* __restrict__ p, uint32_t n, uint32_t x) {
+	uint32_t lo = 0, hi = n;
+#pragma unroll
+	for (int i = 0; i < 6; i++) {
+		if (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (ldg(p + mid) <= x) lo = mid + 1; else hi = mid; }
+	}
+	return lo;
+}
+
+// rank(x) = number of distinct backbone starts <= x  (rank_rrrb(pos) of index.h:128,142,158)
+VSGPU_HD uint32_t rank_le(const DevIndex& ix, const uint32_t* s_top, uint32_t x) {
+	uint32_t lo = 0, hi = ix.lvl_n[ix.nlvl - 1];
+	while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_top[mid] <= x) lo = mid + 1; else hi = mid; }
+	uint32_t c = lo;
+	for (int lev = (int)ix.nlvl - 2; lev >= 0; lev--) {
+		if (c == 0) return 0;
+		uint32_t base = (c - 1) * kFan;
+		uint32_t n = umin(kFan, ix.lvl_n[lev] - base);
+		c = base + count_le_node(ix.lvl[lev] + base, n, x);
+	}
+	return c;
+}
+
+VSGPU_HD bool member(const DevIndex& ix, uint32_t s, uint32_t set_id) {
+	if (ix.class_mode) return (ldg(ix.bitmap + (uint64_t)set_id * ix.words_per_set + (s >> 6)) >> (s & 63)) & 1;
+	for (uint64_t i = ldg(ix.list_begin + set_id), e = ldg(ix.list_begin + set_id + 1); i < e; i++)
+		if (ldg(ix.list_ids + i) == s) return true;
+	return false;
+}
+
+// ------------------------------------------------------------------ t6 slice bounds (query.h:736-784)
+VSGPU_HD uint2 t6_bounds(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, bool* bad) {
+	uint2 r = make_uint2(0, 0);
+	if (x64 < 1) { *bad = true; return r; }
+	if (x64 > ix.index_bits) return r;                                     // is_empty: pos_x > size -> empty
+	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
+	const uint32_t rk = rank_le(ix, s_top, x);
+	// gate (index.h:158-165): next distinct start s' must satisfy s' - 1 <= y
+	if (rk >= 1 && rk < ix.D && (uint64_t)ldg(ix.lvl[0] + rk) <= (uint64_t)y + 1) {
+		const uint32_t lo = ldg(&ix.dlev[rk - 1].y);
+		const uint32_t e = y ? rank_le(ix, s_top, y - 1) : 0;               // first start >= y
+		uint32_t hi;
+		if (e < ix.D) hi = ldg(&ix.dlev[e].z);                              // rec_begin[k(e) - 1]
+		else hi = ((uint64_t)ix.last_end >= y) ? ldg(&ix.dlev[ix.D].z) : ix.R;
+		r = make_uint2(lo, hi > lo ? hi : lo);
+	}
+	return r;
+}
+
+// ------------------------------------------------------------------ t7 lookup (query.h:792-823)
+VSGPU_HD uint32_t t7_lookup(const DevIndex& ix, const uint32_t* s_top, uint64_t p64, uint64_t h, bool* bad) {
+	if (p64 < 1) { *bad = true; return kNoneU32; }
+	const uint32_t p = clamp_pos(p64);
+	uint32_t rk = p64 >= ix.index_bits ? ix.D : rank_le(ix, s_top, p);      // Index::find (index.h:125-132)
+	if (rk < 1) rk = 1;
+	const uint2 rng = ldg(ix.t7rng + (rk - 1));
+	for (uint32_t r = rng.x; r < rng.y; r++)
+		if ((ldg(ix.rec_flags + r) & 1) && p64 == ldg(ix.rec_pos + r) && ldg(ix.rec_hash + r) == h) return r;
+	return kNoneU32;
+}
+
+// ------------------------------------------------------------------ t4 walk (one thread per region)
+struct CountSink {
+	uint32_t* dst; uint32_t n;
+	VSGPU_HD void emit(uint32_t code) { if (n < kScratchHits) dst[n] = code; n++; }
+};
+struct DirectSink {
+	uint32_t* dst; uint32_t n;
+	VSGPU_HD void emit(uint32_t code) { dst[n++] = code; }
+};
+
+template <class Sink>
+VSGPU_HD void walk_region(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	if (x64 > ix.index_bits) return;
+	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
+	const uint32_t rk = rank_le(ix, s_top, x);
+	if (rk < 1 || rk >= ix.D) return;
+	if ((uint64_t)ldg(ix.lvl[0] + rk) > (uint64_t)y + 1) return;                // is_empty gate
+	// ---- get_prev_vertex_with_sample (query.h:57-113)
+	uint64_t cur = (x64 >= ix.index_bits) ? ix.D - 1 : rk - 1;                   // ref_node_rank (index.h:135-148)
+	uint32_t c_found = kNoneU32;
+	for (;;) {
+		if (cur > ix.D) cur = 0;                                                   // reference: unsigned wrap + OOB read; defined here as vertex 0
+		if (cur <= 1) break;
+		const uint64_t info = ldg(ix.dinfo + (cur - 1));
+		const uint32_t cb = (uint32_t)info, ncar = (uint32_t)(info >> 32) & 0xFFFF, deg = (uint32_t)(info >> 48);
+		for (uint32_t c = cb; c < cb + ncar; c++) if (member(ix, s, ldg(&ix.cent[c].z))) c_found = c;   // last carrier wins
+		cur -= deg;                                                                // once per neighbour (:103)
+		if (c_found != kNoneU32) break;
+	}
+	// ---- forward walk (query.h:649-716)
+	const uint32_t e_y = y ? rank_le(ix, s_top, y - 1) : 0;
+	const uint32_t k_end = ldg(&ix.dlev[e_y].x);                                // first backbone vertex whose start >= y
+	uint32_t cur_k = 0, c = 0;
+	if (c_found != kNoneU32) {
+		const uint4 e = ldg(ix.cent + c_found);
+		if (e.w >= y) return;
+		if (e.w >= x) sink.emit(c_found | kHitStart);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask || tk >= k_end) return;
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(c_found | kHitRejoin);
+			cur_k = tk;
+		} else cur_k = e.y & kEntTgtMask;
+		c = c_found + 1;
+	} else {
+		if (1 >= y) return;
+	}
+	for (; c < ix.num_cent; c++) {
+		const uint4 e = ldg(ix.cent + c);
+		if (e.x < cur_k) continue;                                                 // hidden behind a taken detour / later sibling
+		if (e.x > cur_k && e.x >= k_end) break;                                    // the walk stopped before reaching P[e.x]
+		if (e.y & kEntMarker) { if (e.w >= y) break; continue; }
+		if (!member(ix, s, e.z)) continue;
+		if (e.w >= y) break;
+		if (e.w >= x) sink.emit(c);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask || tk >= k_end) break;
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(c | kHitRejoin);
+			cur_k = tk;
+		} else cur_k = e.y & kEntTgtMask;
+	}
+}
+
+}  // namespace logic
+}  // namespace vsgpu

@@ -1,0 +1,63 @@
+// libvsgpu host side — the loaded + flattened index as the host sees it, and the materialisation
+// of result rows (struct Variant of include/query.h:30-36 as print_var text, query.h:43-50) from
+// record ids / walk-entry hit codes.  No CUDA in here.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "flatten.h"
+#include "ser_reader.h"
+
+namespace vsgpu {
+
+struct HostIndex {
+	SerData ser;
+	FlatIndex flat;
+	uint32_t last_end = 0;                                  // start + length of the last backbone vertex
+	std::unordered_map<std::string, uint32_t> name2id;
+};
+
+// load_ser + flatten + derived fields; throws std::runtime_error
+void build_host_index(const std::string& prefix, HostIndex& h, int* stage = nullptr);
+// sampled search hierarchy over dstart: lv[0] = dstart, lv[i+1][j] = lv[i][32 j], until <= kTopMax keys
+void build_levels(const FlatIndex& f, std::vector<std::vector<uint32_t>>& lv);
+
+void append_seq(const HostIndex* ix, uint32_t v, std::string& out);
+void append_carriers(const HostIndex* ix, uint32_t v, std::string& out);
+void t6_row(const HostIndex* ix, uint32_t r, bool with_samples, std::string& out);
+void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& out);
+bool push_rule(const HostIndex* ix, const std::vector<uint32_t>& vars, uint32_t r);
+uint32_t host_rank(const FlatIndex& f, uint64_t pos);
+void t6_literal(const HostIndex* ix, uint64_t x, uint64_t y, std::vector<uint32_t>& vars);
+bool t6_needs_literal(const HostIndex* ix, uint64_t y, uint32_t lo, uint32_t hi);
+uint64_t hash_query(const char* ref, const char* alt);
+uint32_t t7_confirm(const HostIndex* ix, uint64_t pos, const char* ref, const char* alt, uint32_t r);
+uint64_t t7_carriers(const HostIndex* ix, uint32_t rec, std::string* text, uint64_t* digest);
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t n);
+constexpr uint64_t kFnvInit = 14695981039346656037ULL;
+
+// rows / digests shared by the C ABI and the test-only host simulator
+void rows_t6(const HostIndex* ix, uint32_t lo, uint32_t hi, bool with_samples, std::string& text, uint64_t& nrows);
+void digests_t6(const HostIndex* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, bool with_samples, uint64_t* digests, bool* bad);
+void digests_t4(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, bool with_samples, uint64_t* digests);
+void digests_t7(const HostIndex* ix, uint64_t n, const uint32_t* rec, uint64_t* ncarriers, uint64_t* digests);
+
+template <class F> void parallel_for(uint64_t n, F&& fn);
+
+}  // namespace vsgpu
+
+#include <algorithm>
+#include <thread>
+namespace vsgpu {
+template <class F>
+void parallel_for(uint64_t n, F&& fn) {
+	unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)((n + 4095) / 4096)));
+	if (nt <= 1) { fn((uint64_t)0, n); return; }
+	std::vector<std::thread> th;
+	uint64_t chunk = (n + nt - 1) / nt;
+	for (unsigned t = 0; t < nt; t++) { uint64_t a = t * chunk, b = std::min<uint64_t>(n, a + chunk); if (a < b) th.emplace_back([=, &fn]() { fn(a, b); }); }
+	for (auto& t : th) t.join();
+}
+}  // namespace vsgpu

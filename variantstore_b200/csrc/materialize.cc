@@ -1,0 +1,257 @@
+// libvsgpu host side — see host_index.h.
+#include "host_index.h"
+
+#include <atomic>
+#include <cstring>
+#include <stdexcept>
+
+#include "../../include/vsgpu.h"
+#include "kernels.cuh"
+
+namespace vsgpu {
+
+void build_levels(const FlatIndex& f, std::vector<std::vector<uint32_t>>& lv) {
+	lv.clear(); lv.push_back(f.dstart);
+	while (lv.back().size() > kTopMax) {
+		const auto& b = lv.back(); std::vector<uint32_t> s((b.size() + kFan - 1) / kFan);
+		for (size_t j = 0; j < s.size(); j++) s[j] = b[j * kFan];
+		lv.push_back(std::move(s));
+		if (lv.size() > (size_t)kMaxLevels) throw std::runtime_error("vsgpu: index too large for the search hierarchy");
+	}
+}
+
+void build_host_index(const std::string& prefix, HostIndex& h, int* stage) {
+	if (stage) *stage = 0;
+	load_ser(prefix, h.ser);
+	if (stage) *stage = 1;
+	flatten(h.ser, h.flat);
+	for (uint32_t i = 0; i < h.ser.num_samples; i++) h.name2id[h.ser.sample_names[i]] = i;
+	uint64_t le = (uint64_t)h.flat.vstart[h.flat.M - 1] + h.flat.vlen[h.flat.M - 1];
+	h.last_end = le > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)le;
+	// host copies nothing needs again
+	std::vector<uint32_t>().swap(h.ser.s_index); std::vector<uint64_t>().swap(h.ser.sample_vector);
+	if (stage) *stage = 2;
+}
+
+// ------------------------------------------------------------------ row materialisation
+static const char kBase[8] = {'A', 'C', 'T', 'G', 'N', 5, 5, 5};   // map_int, src/util.cc:32-41
+
+void append_seq(const HostIndex* ix, uint32_t v, std::string& out) {   // VariantGraph::get_sequence, variant_graph.h:1261-1268
+	if (v == kNone) return;
+	const uint8_t* p = &ix->ser.seq[ix->ser.v_offset[v]];
+	for (uint32_t i = 0, n = ix->ser.v_length[v]; i < n; i++) out += kBase[p[i] & 7];
+}
+
+// get_samples (query.h:268-285): every non-ref carrier of vertex v as name(phasing), s_info order
+template <class F>
+void for_each_carrier(const HostIndex* ix, uint32_t v, F&& fn) {
+	const SerData& s = ix->ser; const FlatIndex& f = ix->flat;
+	const uint64_t b = s.v_sinfo_begin[v], e = s.v_sinfo_begin[v + 1];
+	if (s.class_mode) {
+		const uint64_t* row = &f.bitmap[(uint64_t)s.v_class[v] * f.words_per_set];
+		uint64_t i = b;
+		for (uint32_t w = 0; w < f.words_per_set && i < e; w++) {
+			uint64_t bits = row[w];
+			while (bits && i < e) {
+				uint32_t id = w * 64 + (uint32_t)__builtin_ctzll(bits); bits &= bits - 1;
+				if (id != 0) fn(id, s.s_flags[i]);
+				i++;
+			}
+		}
+	} else {
+		for (uint64_t i = b; i < e; i++) if (s.s_sample_id[i] != 0) fn(s.s_sample_id[i], s.s_flags[i]);
+	}
+}
+void append_carriers(const HostIndex* ix, uint32_t v, std::string& out) {
+	for_each_carrier(ix, v, [&](uint32_t id, uint8_t fl) {
+		out += ix->ser.sample_names[id]; out += '(';
+		out += (fl & 2) ? '1' : '0'; out += (fl & 1) ? '|' : '/'; out += (fl & 4) ? '1' : '0';   // get_sample_phasing, variant_graph.h:882-900
+		out += ") ";
+	});
+}
+
+void t6_row(const HostIndex* ix, uint32_t r, bool with_samples, std::string& out) {
+	const FlatIndex& f = ix->flat;
+	out += std::to_string(f.rec_pos[r]); out += '\t';
+	append_seq(ix, f.rec_refv[r], out); out += '\t';
+	append_seq(ix, f.rec_altv[r], out); out += '\t';
+	if (with_samples && !(f.rec_flags[r] & 4)) append_carriers(ix, f.rec_vertex[r], out);
+	out += '\n';
+}
+
+bool rec_same_pos_alt(const HostIndex* ix, uint32_t a, uint32_t b) {
+	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
+	if (f.rec_pos[a] != f.rec_pos[b]) return false;
+	uint32_t va = f.rec_altv[a], vb = f.rec_altv[b];
+	uint32_t la = va == kNone ? 0 : s.v_length[va], lb = vb == kNone ? 0 : s.v_length[vb];
+	if (la != lb) return false;
+	return la == 0 || memcmp(&s.seq[s.v_offset[va]], &s.seq[s.v_offset[vb]], la) == 0;
+}
+
+// the "only add var if not seen before" rule of next_variant_in_ref (query.h:397-414)
+bool push_rule(const HostIndex* ix, const std::vector<uint32_t>& vars, uint32_t r) {
+	const FlatIndex& f = ix->flat;
+	if (vars.empty()) return true;
+	if (rec_same_pos_alt(ix, vars.back(), r)) return false;
+	if (vars.size() > 1 && f.rec_pos[vars.back()] == f.rec_pos[r]) {
+		for (size_t q = vars.size(); q-- > 0;) {
+			if (f.rec_pos[vars[q]] < f.rec_pos[r]) break;
+			if (rec_same_pos_alt(ix, vars[q], r)) return false;
+		}
+	}
+	return true;
+}
+
+uint32_t host_rank(const FlatIndex& f, uint64_t pos) { return (uint32_t)(std::upper_bound(f.dstart.begin(), f.dstart.end(), pos > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)pos) - f.dstart.begin()); }
+
+// Literal get_var_in_ref loop (query.h:758-771) over the flattened tables.  Only used for regions
+// whose record slice contains suspect duplicates or that run past the end of the contig, where the
+// reference's re-find / dedup interplay is not a plain slice.
+void t6_literal(const HostIndex* ix, uint64_t x, uint64_t y, std::vector<uint32_t>& vars) {
+	const FlatIndex& f = ix->flat;
+	vars.clear();
+	uint64_t cur = x; uint64_t guard = 0;
+	while (cur < y && guard++ < (uint64_t)f.M + 8) {
+		bool found = false;
+		uint32_t rk = cur >= f.index_bits ? f.D : host_rank(f, cur);
+		if (rk < 1) rk = 1;
+		uint32_t k = f.dlev[rk - 1].k;
+		for (; k < f.M; k++) {
+			if ((uint64_t)f.vstart[k] + f.vlen[k] >= y) break;
+			for (uint32_t r = f.rec_begin[k]; r < f.rec_begin[k + 1]; r++) if (push_rule(ix, vars, r)) { vars.push_back(r); found = true; }
+			if (found) break;
+		}
+		if (!found) break;
+		cur = k + 1 < f.M ? f.vstart[k + 1] : 1;   // *next_it is vertex 0 (index 1) once the ref path is exhausted
+		if (cur >= y) break;
+	}
+}
+
+bool t6_needs_literal(const HostIndex* ix, uint64_t y, uint32_t lo, uint32_t hi) {
+	const FlatIndex& f = ix->flat;
+	if (hi > lo && f.has_suspect_dups && f.rec_dup_prefix[hi] - f.rec_dup_prefix[lo] > 0) return true;
+	if (y > ix->last_end && hi > lo && f.rec_begin[f.M] > f.rec_begin[f.M - 1]) return true;
+	return false;
+}
+
+// t4 row from a hit code: emission rules of get_sample_var_in_ref (query.h:677-710)
+void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& out) {
+	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
+	const uint32_t c = code & VSGPU_HIT_ENTRY_MASK;
+	const CEntry& e = f.cent[c];
+	uint32_t u, ref_pos, cur_ref_v; bool cur_ref_empty = false, u_is_bb; uint32_t u_k = kNone;
+	if (code & VSGPU_HIT_REJOIN) {
+		u_k = e.tgt & kEntTgtMask; u = f.bb_vertex[u_k]; u_is_bb = true;
+		ref_pos = f.vstart[u_k]; cur_ref_v = u;                         // state left by the alt vertex: ref_pos = index(N), cur_ref = seq(N)
+	} else {
+		u = f.cent_vertex[c]; ref_pos = e.arrival; cur_ref_v = f.bb_nref[e.src];
+		u_is_bb = !(e.tgt & kEntAlt);
+		if (u_is_bb) u_k = e.tgt & kEntTgtMask;
+		if (code & VSGPU_HIT_START) cur_ref_empty = true;
+	}
+	// next_ref_pos at u (query.h:660-674)
+	uint64_t next_ref_pos;
+	if (u_is_bb) next_ref_pos = f.bb_nrp[u_k];
+	else {
+		uint32_t tk = e.tgt & kEntTgtMask;
+		next_ref_pos = tk == kEntTgtNone ? (uint64_t)ref_pos + s.v_length[u] : f.vstart[tk];
+	}
+	std::string ref, alt; uint64_t pos;
+	if (ref_pos == next_ref_pos) { pos = (uint64_t)ref_pos - 1; append_seq(ix, u, alt); }                 // insertion
+	else if (u_is_bb) {                                                                                   // deletion: cur_ref = seq(find(ref_pos - 1))
+		uint64_t p = ref_pos > 1 ? ref_pos - 1 : 1;
+		uint32_t rk = p >= f.index_bits ? f.D : host_rank(f, p);
+		if (rk < 1) rk = 1;
+		uint32_t wk = f.dlev[rk - 1].k;
+		append_seq(ix, f.bb_vertex[wk], ref); pos = f.vstart[wk];
+	} else { pos = ref_pos; if (!cur_ref_empty) append_seq(ix, cur_ref_v, ref); append_seq(ix, u, alt); } // substitution
+	out += std::to_string(pos); out += '\t'; out += ref; out += '\t'; out += alt; out += '\t';
+	if (with_samples) append_carriers(ix, u, out);
+	out += '\n';
+}
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+	const unsigned char* p = (const unsigned char*)data;
+	for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ULL; }
+	return h;
+}
+
+uint64_t hash_query(const char* ref, const char* alt) { return hash_ref_alt(ref, strlen(ref), alt, strlen(alt)); }
+
+// t7 post-check on the host: a device hit is a 64-bit hash match; confirm the strings (a colliding
+// hash would otherwise be a false positive) and, if they differ, finish the compare on the strings.
+uint32_t t7_confirm(const HostIndex* ix, uint64_t pos, const char* ref, const char* alt, uint32_t r) {
+	if (r == VSGPU_NONE) return r;
+	const FlatIndex& f = ix->flat;
+	std::string a, b;
+	append_seq(ix, f.rec_refv[r], a); append_seq(ix, f.rec_altv[r], b);
+	if (a == ref && b == alt) return r;
+	uint32_t k = f.rec_k[r];
+	for (uint32_t q = f.rec_begin[k]; q < f.rec_begin[k + 1]; q++) {
+		if (!(f.rec_flags[q] & 1) || f.rec_pos[q] != pos) continue;
+		a.clear(); b.clear(); append_seq(ix, f.rec_refv[q], a); append_seq(ix, f.rec_altv[q], b);
+		if (a == ref && b == alt) return q;
+	}
+	return VSGPU_NONE;
+}
+
+
+uint64_t t7_carriers(const HostIndex* ix, uint32_t rec, std::string* text, uint64_t* digest) {
+	uint64_t h = kFnvInit, cnt = 0;
+	if (rec != kNone && rec < ix->flat.R && !(ix->flat.rec_flags[rec] & 4))
+		for_each_carrier(ix, ix->flat.rec_vertex[rec], [&](uint32_t id, uint8_t fl) {
+			const std::string& nm = ix->ser.sample_names[id];
+			char gt[3] = {(fl & 2) ? '1' : '0', (fl & 1) ? '|' : '/', (fl & 4) ? '1' : '0'};
+			if (text) { *text += nm; *text += ' '; text->append(gt, 3); }
+			h = fnv1a(h, nm.data(), nm.size()); h = fnv1a(h, " ", 1); h = fnv1a(h, gt, 3); cnt++;
+		});
+	if (digest) *digest = h;
+	return cnt;
+}
+
+void rows_t6(const HostIndex* ix, uint32_t lo, uint32_t hi, bool with_samples, std::string& s, uint64_t& cnt) {
+	cnt = 0;
+	std::vector<uint32_t> vars;
+	if (ix->flat.has_suspect_dups && ix->flat.rec_dup_prefix[hi] - ix->flat.rec_dup_prefix[lo] > 0) {
+		for (uint32_t r = lo; r < hi; r++) if (push_rule(ix, vars, r)) vars.push_back(r);
+		for (uint32_t r : vars) { t6_row(ix, r, with_samples, s); cnt++; }
+	} else for (uint32_t r = lo; r < hi; r++) { t6_row(ix, r, with_samples, s); cnt++; }
+}
+
+void digests_t6(const HostIndex* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, bool with_samples, uint64_t* digests, bool* bad_out) {
+	std::atomic<bool> bad{false};
+	parallel_for(n, [&](uint64_t a, uint64_t b) {
+		std::string row; std::vector<uint32_t> vars;
+		for (uint64_t i = a; i < b; i++) {
+			uint64_t h = kFnvInit;
+			if (lo[i] > hi[i] || hi[i] > ix->flat.R) { bad = true; continue; }
+			bool dd = ix->flat.has_suspect_dups && ix->flat.rec_dup_prefix[hi[i]] - ix->flat.rec_dup_prefix[lo[i]] > 0;
+			vars.clear();
+			for (uint32_t r = lo[i]; r < hi[i]; r++) {
+				if (dd) { if (!push_rule(ix, vars, r)) continue; vars.push_back(r); }
+				row.clear(); t6_row(ix, r, with_samples, row); h = fnv1a(h, row.data(), row.size());
+			}
+			digests[i] = h;
+		}
+	});
+	if (bad_out) *bad_out = bad;
+}
+
+void digests_t4(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, bool with_samples, uint64_t* digests) {
+	parallel_for(n, [&](uint64_t a, uint64_t b) {
+		std::string row;
+		for (uint64_t i = a; i < b; i++) {
+			uint64_t h = kFnvInit;
+			for (uint64_t j = offsets[i]; j < offsets[i + 1]; j++) { row.clear(); t4_row(ix, hits[j], with_samples, row); h = fnv1a(h, row.data(), row.size()); }
+			digests[i] = h;
+		}
+	});
+}
+
+void digests_t7(const HostIndex* ix, uint64_t n, const uint32_t* rec, uint64_t* ncarriers, uint64_t* digests) {
+	parallel_for(n, [&](uint64_t a, uint64_t b) {
+		for (uint64_t i = a; i < b; i++) { uint64_t d; uint64_t c = t7_carriers(ix, rec[i], nullptr, &d); if (digests) digests[i] = d; if (ncarriers) ncarriers[i] = c; }
+	});
+}
+
+}  // namespace vsgpu

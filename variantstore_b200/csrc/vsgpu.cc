@@ -1,0 +1,461 @@
+// libvsgpu — C ABI (include/vsgpu.h): index lifecycle, batched query entry points, host-side
+// materialisation of result rows.  The query path has no CPU implementation: without a CUDA
+// device every query entry point fails with VSGPU_ENODEVICE.
+#include "../../include/vsgpu.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "host_index.h"
+#include "kernels.cuh"
+
+using namespace vsgpu;
+
+namespace {
+thread_local std::string g_err;
+int set_err(int code, const std::string& m) { g_err = m; return code; }
+
+struct DevBuf {
+	void* p = nullptr; size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T* as() const { return (T*)p; }
+};
+}  // namespace
+
+struct vsgpu_result {
+	std::vector<uint64_t> offsets;
+	std::vector<uint32_t> hits;
+};
+
+struct vsgpu_index : vsgpu::HostIndex {
+	DevIndex dev;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	std::vector<void*> allocs;
+	uint64_t device_bytes = 0;
+	uint32_t* d_status = nullptr;
+	std::mutex mu;
+	DevBuf bx, by, bs, bout, bcounts, bscratch, boffsets, bhits, bstate, bhash, brec;
+	~vsgpu_index() {
+		cudaSetDevice(device);
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &bcounts, &bscratch, &boffsets, &bhits, &bstate, &bhash, &brec}) b->release();
+		for (void* p : allocs) cudaFree(p);
+		if (d_status) cudaFree(d_status);
+		if (own_stream && stream) cudaStreamDestroy(stream);
+	}
+};
+
+struct vsgpu_batch {
+	vsgpu_index* idx = nullptr;
+	int type = 0; uint64_t n = 0;
+	DevBuf x, y, s, hash, out, counts, scratch, offsets, hits, state, rec;
+	uint64_t hits_cap = 0;
+	uint32_t launches = 0;
+	uint64_t algo_bytes = 0; bool algo_valid = false;
+	std::vector<uint64_t> hx, hy;   // host copies kept for the byte accounting
+	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); for (DevBuf* b : {&x, &y, &s, &hash, &out, &counts, &scratch, &offsets, &hits, &state, &rec}) b->release(); }
+};
+
+namespace {
+
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e__) + " at " #call); } while (0)
+
+template <class T>
+const T* upload(vsgpu_index* ix, const std::vector<T>& v) {
+	size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+	void* p = nullptr;
+	CU(cudaMalloc(&p, bytes));
+	ix->allocs.push_back(p); ix->device_bytes += bytes;
+	if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	return (const T*)p;
+}
+
+void upload_index(vsgpu_index* ix) {
+	FlatIndex& f = ix->flat; DevIndex& d = ix->dev;
+	memset(&d, 0, sizeof d);
+	d.D = f.D; d.M = f.M; d.R = f.R; d.num_cent = (uint32_t)f.cent.size(); d.words_per_set = f.words_per_set;
+	d.num_samples = f.num_samples; d.class_mode = f.class_mode ? 1 : 0; d.index_bits = f.index_bits;
+	d.last_end = ix->last_end;
+	std::vector<std::vector<uint32_t>> lv;
+	build_levels(f, lv);
+	d.nlvl = (uint32_t)lv.size();
+	for (size_t i = 0; i < lv.size(); i++) { d.lvl[i] = upload(ix, lv[i]); d.lvl_n[i] = (uint32_t)lv[i].size(); }
+	static_assert(sizeof(DLevel) == sizeof(uint4) && sizeof(CEntry) == sizeof(uint4), "AoS rows are 16 bytes");
+	d.dlev = (const uint4*)upload(ix, f.dlev);
+	d.dinfo = upload(ix, f.dinfo);
+	std::vector<uint2> t7(f.D);
+	for (uint32_t i = 0; i < f.D; i++) t7[i] = make_uint2(f.t7_lo[i], f.t7_hi[i]);
+	d.t7rng = upload(ix, t7);
+	d.cent = (const uint4*)upload(ix, f.cent);
+	d.bb_set = upload(ix, f.bb_set);
+	d.vstart = upload(ix, f.vstart);
+	d.bitmap = upload(ix, f.bitmap);
+	d.list_begin = upload(ix, f.list_begin);
+	d.list_ids = upload(ix, f.list_ids);
+	d.rec_pos = upload(ix, f.rec_pos);
+	d.rec_hash = upload(ix, f.rec_hash);
+	d.rec_flags = upload(ix, f.rec_flags);
+	CU(cudaMalloc((void**)&ix->d_status, 4));
+	CU(cudaMemset(ix->d_status, 0, 4));
+}
+
+char* dup_text(const std::string& s) { char* p = (char*)malloc(s.size() + 1); if (!p) return nullptr; memcpy(p, s.data(), s.size()); p[s.size()] = 0; return p; }
+
+int check_device(vsgpu_index* ix) {
+	cudaError_t e = cudaSetDevice(ix->device);
+	if (e != cudaSuccess) return set_err(VSGPU_ENODEVICE, std::string("CUDA: ") + cudaGetErrorString(e));
+	return VSGPU_OK;
+}
+
+uint32_t read_status(vsgpu_index* ix) {
+	uint32_t st = 0;
+	cudaMemcpyAsync(&st, ix->d_status, 4, cudaMemcpyDeviceToHost, ix->stream);
+	cudaStreamSynchronize(ix->stream);
+	if (st) { cudaMemsetAsync(ix->d_status, 0, 4, ix->stream); }
+	return st;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vsgpu_last_error(void) { return g_err.c_str(); }
+void vsgpu_free(void* p) { free(p); }
+
+int vsgpu_open(const char* ser_prefix, int device, vsgpu_index** out) {
+	if (!ser_prefix || !out) return set_err(VSGPU_EINVAL, "vsgpu_open: null argument");
+	*out = nullptr;
+	std::unique_ptr<vsgpu_index> ix(new vsgpu_index);
+	ix->device = device;
+	int stage = 0;
+	try { build_host_index(ser_prefix, *ix, &stage); } catch (const std::exception& e) { return set_err(stage == 0 ? VSGPU_EIO : VSGPU_ESHAPE, e.what()); }
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { cudaGetLastError(); return set_err(VSGPU_ENODEVICE, "vsgpu_open: no usable CUDA device (libvsgpu has no CPU path)"); }
+	try {
+		CU(cudaSetDevice(device));
+		CU(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)); ix->own_stream = true;
+		upload_index(ix.get());
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	*out = ix.release();
+	return VSGPU_OK;
+}
+
+void vsgpu_close(vsgpu_index* idx) { delete idx; }
+
+int vsgpu_info(const vsgpu_index* ix, vsgpu_info_t* o) {
+	if (!ix || !o) return set_err(VSGPU_EINVAL, "vsgpu_info: null argument");
+	memset(o, 0, sizeof *o);
+	o->ref_length = ix->ser.ref_length; o->seq_length = ix->ser.seq.size(); o->num_vertices_cqf = ix->ser.cqf_distinct;
+	o->num_vertices = ix->ser.num_vertices; o->num_samples = ix->ser.num_samples;
+	o->num_classes = ix->flat.class_mode ? ix->flat.num_sets - 1 : 0; o->class_mode = ix->flat.class_mode;
+	o->backbone_vertices = ix->flat.M; o->distinct_starts = ix->flat.D; o->branch_records = ix->flat.R;
+	o->walk_entries = (uint32_t)ix->flat.cent.size(); o->has_suspect_dups = ix->flat.has_suspect_dups; o->device_bytes = ix->device_bytes;
+	strncpy(o->chr, ix->ser.chr.c_str(), sizeof o->chr - 1);
+	return VSGPU_OK;
+}
+
+int vsgpu_set_stream(vsgpu_index* ix, void* s) {
+	if (!ix) return set_err(VSGPU_EINVAL, "vsgpu_set_stream: null index");
+	std::lock_guard<std::mutex> g(ix->mu);
+	if (ix->own_stream && ix->stream) { cudaSetDevice(ix->device); cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
+	ix->stream = (cudaStream_t)s; ix->own_stream = false;
+	return VSGPU_OK;
+}
+
+int vsgpu_sample_id(const vsgpu_index* ix, const char* name, uint32_t* id) {
+	if (!ix || !name || !id) return set_err(VSGPU_EINVAL, "vsgpu_sample_id: null argument");
+	auto it = ix->name2id.find(name);
+	if (it == ix->name2id.end()) return set_err(VSGPU_EINVAL, std::string("Sample not found: ") + name);
+	*id = it->second; return VSGPU_OK;
+}
+const char* vsgpu_sample_name(const vsgpu_index* ix, uint32_t id) { return (ix && id < ix->ser.num_samples) ? ix->ser.sample_names[id].c_str() : nullptr; }
+
+// ------------------------------------------------------------------ t6
+int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts) {
+	if (!ix || (n && (!x || !y))) return set_err(VSGPU_EINVAL, "vsgpu_query_t6: null argument");
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	try {
+		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bout.ensure(n * 8));
+		CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
+		CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream));
+		CU(launch_t6(ix->dev, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bout.as<uint2>(), ix->d_status, ix->stream));
+		std::vector<uint2> out(n);
+		CU(cudaMemcpyAsync(out.data(), ix->bout.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
+		uint32_t st = read_status(ix);
+		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");   // index.h:151-154 aborts
+		std::vector<uint32_t> tmp;
+		for (uint64_t i = 0; i < n; i++) {
+			if (rec_lo) rec_lo[i] = out[i].x;
+			if (rec_hi) rec_hi[i] = out[i].y;
+			if (counts) {
+				if (t6_needs_literal(ix, y[i], out[i].x, out[i].y)) { t6_literal(ix, x[i], y[i], tmp); counts[i] = (uint32_t)tmp.size(); }
+				else counts[i] = out[i].y - out[i].x;
+			}
+		}
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+
+// ------------------------------------------------------------------ t4
+namespace {
+void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& counts, DevBuf& scratch,
+            DevBuf& offsets, DevBuf& state, DevBuf& hits, uint64_t& hits_cap, uint32_t* launches) {
+	CU(counts.ensure(n * 4)); CU(scratch.ensure(n * 4 * kScratchHits)); CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(scan_state_words(n) * 8));
+	CU(cudaMemsetAsync(state.p, 0, scan_state_words(n) * 8, ix->stream));
+	CU(launch_t4_walk(ix->dev, n, dx, dy, ds, counts.as<uint32_t>(), scratch.as<uint32_t>(), ix->d_status, ix->stream));
+	CU(launch_scan(n, counts.as<uint32_t>(), offsets.as<uint64_t>(), state.as<uint64_t>(), ix->stream));
+	if (launches) *launches = 2;
+	if (hits_cap == 0) {   // first run of this shape: size the output from the scanned total
+		uint64_t total = 0;
+		CU(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
+		CU(cudaStreamSynchronize(ix->stream));
+		hits_cap = std::max<uint64_t>(total, 1);
+		CU(hits.ensure(hits_cap * 4));
+	}
+	CU(launch_t4_gather(ix->dev, n, dx, dy, ds, counts.as<uint32_t>(), scratch.as<uint32_t>(), offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, ix->d_status, ix->stream));
+	if (launches) *launches = 3;
+}
+}  // namespace
+
+int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out) {
+	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t4: null argument");
+	*out = nullptr;
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	try {
+		std::unique_ptr<vsgpu_result> r(new vsgpu_result);
+		r->offsets.assign(n + 1, 0);
+		if (n) {
+			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
+			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream));
+			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream));
+			uint64_t cap = 0;
+			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcounts, ix->bscratch, ix->boffsets, ix->bstate, ix->bhits, cap, nullptr);
+			CU(cudaMemcpyAsync(r->offsets.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
+			r->hits.resize(cap);
+			CU(cudaMemcpyAsync(r->hits.data(), ix->bhits.p, cap * 4, cudaMemcpyDeviceToHost, ix->stream));
+			uint32_t st = read_status(ix);
+			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
+			r->hits.resize(r->offsets[n]);
+		}
+		*out = r.release();
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r ? r->offsets.size() - 1 : 0; }
+const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r ? r->offsets.data() : nullptr; }
+const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r ? r->hits.data() : nullptr; }
+void vsgpu_result_free(vsgpu_result* r) { delete r; }
+
+// ------------------------------------------------------------------ t7
+int vsgpu_query_t7(vsgpu_index* ix, uint64_t n, const uint64_t* pos, const char* const* refs, const char* const* alts, uint32_t* rec) {
+	if (!ix || (n && (!pos || !refs || !alts || !rec))) return set_err(VSGPU_EINVAL, "vsgpu_query_t7: null argument");
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	try {
+		std::vector<uint64_t> qh(n);
+		parallel_for(n, [&](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; i++) qh[i] = hash_query(refs[i], alts[i]); });
+		CU(ix->bx.ensure(n * 8)); CU(ix->bhash.ensure(n * 8)); CU(ix->brec.ensure(n * 4));
+		CU(cudaMemcpyAsync(ix->bx.p, pos, n * 8, cudaMemcpyHostToDevice, ix->stream));
+		CU(cudaMemcpyAsync(ix->bhash.p, qh.data(), n * 8, cudaMemcpyHostToDevice, ix->stream));
+		CU(launch_t7(ix->dev, n, ix->bx.as<uint64_t>(), ix->bhash.as<uint64_t>(), ix->brec.as<uint32_t>(), ix->d_status, ix->stream));
+		CU(cudaMemcpyAsync(rec, ix->brec.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+		uint32_t st = read_status(ix);
+		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+		parallel_for(n, [&](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; i++) rec[i] = t7_confirm(ix, pos[i], refs[i], alts[i], rec[i]); });
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+
+// ------------------------------------------------------------------ materialisation
+int vsgpu_rows_t6(const vsgpu_index* ix, uint32_t lo, uint32_t hi, int with_samples, char** text, uint64_t* nrows) {
+	if (!ix || !text || lo > hi || hi > ix->flat.R) return set_err(VSGPU_EINVAL, "vsgpu_rows_t6: bad record slice");
+	std::string s; uint64_t cnt = 0;
+	rows_t6(ix, lo, hi, with_samples != 0, s, cnt);
+	if (nrows) *nrows = cnt;
+	*text = dup_text(s);
+	return *text ? VSGPU_OK : set_err(VSGPU_ENOMEM, "out of memory");
+}
+
+int vsgpu_rows_t4(const vsgpu_index* ix, const uint32_t* hits, uint64_t nhits, int with_samples, char** text) {
+	if (!ix || !text || (nhits && !hits)) return set_err(VSGPU_EINVAL, "vsgpu_rows_t4: null argument");
+	std::string s;
+	for (uint64_t i = 0; i < nhits; i++) {
+		if ((hits[i] & VSGPU_HIT_ENTRY_MASK) >= ix->flat.cent.size()) return set_err(VSGPU_EINVAL, "vsgpu_rows_t4: hit code out of range");
+		t4_row(ix, hits[i], with_samples != 0, s);
+	}
+	*text = dup_text(s);
+	return *text ? VSGPU_OK : set_err(VSGPU_ENOMEM, "out of memory");
+}
+
+int vsgpu_rows_t7(const vsgpu_index* ix, uint32_t rec, char** text, uint64_t* ncarriers) {
+	if (!ix || !text) return set_err(VSGPU_EINVAL, "vsgpu_rows_t7: null argument");
+	if (rec != VSGPU_NONE && rec >= ix->flat.R) return set_err(VSGPU_EINVAL, "vsgpu_rows_t7: record id out of range");
+	std::string s;
+	uint64_t cnt = t7_carriers(ix, rec, &s, nullptr);
+	if (ncarriers) *ncarriers = cnt;
+	*text = dup_text(s);
+	return *text ? VSGPU_OK : set_err(VSGPU_ENOMEM, "out of memory");
+}
+
+int vsgpu_digest_t6(const vsgpu_index* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, int with_samples, uint64_t* digests) {
+	if (!ix || (n && (!lo || !hi || !digests))) return set_err(VSGPU_EINVAL, "vsgpu_digest_t6: null argument");
+	bool bad = false;
+	digests_t6(ix, n, lo, hi, with_samples != 0, digests, &bad);
+	return bad ? set_err(VSGPU_EINVAL, "vsgpu_digest_t6: bad record slice") : VSGPU_OK;
+}
+
+int vsgpu_digest_t4(const vsgpu_index* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, int with_samples, uint64_t* digests) {
+	if (!ix || (n && (!offsets || !digests))) return set_err(VSGPU_EINVAL, "vsgpu_digest_t4: null argument");
+	digests_t4(ix, n, offsets, hits, with_samples != 0, digests);
+	return VSGPU_OK;
+}
+
+int vsgpu_digest_t7(const vsgpu_index* ix, uint64_t n, const uint32_t* rec, uint64_t* ncarriers, uint64_t* digests) {
+	if (!ix || (n && !rec)) return set_err(VSGPU_EINVAL, "vsgpu_digest_t7: null argument");
+	digests_t7(ix, n, rec, ncarriers, digests);
+	return VSGPU_OK;
+}
+
+// ------------------------------------------------------------------ device-resident batches
+int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids,
+                       const char* const* refs, const char* const* alts, vsgpu_batch** out) {
+	if (!ix || !out || !x || n == 0) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: null argument");
+	if (type != 4 && type != 6 && type != 7) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: type must be 4, 6 or 7");
+	if ((type != 7 && !y) || (type == 4 && !sample_ids) || (type == 7 && (!refs || !alts))) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: missing input array");
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	try {
+		std::unique_ptr<vsgpu_batch> b(new vsgpu_batch);
+		b->idx = ix; b->type = type; b->n = n;
+		b->hx.assign(x, x + n); if (y) b->hy.assign(y, y + n);
+		CU(b->x.ensure(n * 8));
+		CU(cudaMemcpyAsync(b->x.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
+		if (type != 7) { CU(b->y.ensure(n * 8)); CU(cudaMemcpyAsync(b->y.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream)); }
+		if (type == 6) CU(b->out.ensure(n * 8));
+		if (type == 4) { CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 8)); }
+		if (type == 7) {
+			std::vector<uint64_t> qh(n);
+			for (uint64_t i = 0; i < n; i++) qh[i] = hash_query(refs[i], alts[i]);
+			CU(b->hash.ensure(n * 8)); CU(b->rec.ensure(n * 4));
+			CU(cudaMemcpyAsync(b->hash.p, qh.data(), n * 8, cudaMemcpyHostToDevice, ix->stream));
+			CU(cudaStreamSynchronize(ix->stream));
+		}
+		CU(cudaStreamSynchronize(ix->stream));
+		*out = b.release();
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+
+int vsgpu_batch_run(vsgpu_batch* b) {
+	if (!b) return set_err(VSGPU_EINVAL, "vsgpu_batch_run: null batch");
+	vsgpu_index* ix = b->idx;
+	if (int rc = check_device(ix)) return rc;
+	try {
+		if (b->type == 6) { CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), ix->d_status, ix->stream)); b->launches = 1; }
+		else if (b->type == 7) { CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), ix->d_status, ix->stream)); b->launches = 1; }
+		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->counts, b->scratch, b->offsets, b->state, b->hits, b->hits_cap, &b->launches);
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+
+int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts, vsgpu_result** out) {
+	if (!b) return set_err(VSGPU_EINVAL, "vsgpu_batch_fetch: null batch");
+	vsgpu_index* ix = b->idx;
+	if (int rc = check_device(ix)) return rc;
+	try {
+		const uint64_t n = b->n;
+		if (b->type == 6) {
+			std::vector<uint2> o(n);
+			CU(cudaMemcpyAsync(o.data(), b->out.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
+			uint32_t st = read_status(ix);
+			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+			std::vector<uint32_t> tmp;
+			for (uint64_t i = 0; i < n; i++) {
+				if (rec_lo) rec_lo[i] = o[i].x;
+				if (rec_hi) rec_hi[i] = o[i].y;
+				if (counts) {
+					if (t6_needs_literal(ix, b->hy[i], o[i].x, o[i].y)) { t6_literal(ix, b->hx[i], b->hy[i], tmp); counts[i] = (uint32_t)tmp.size(); }
+					else counts[i] = o[i].y - o[i].x;
+				}
+			}
+		} else if (b->type == 7) {
+			if (rec_lo) CU(cudaMemcpyAsync(rec_lo, b->rec.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			uint32_t st = read_status(ix);
+			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+		} else {
+			if (counts) CU(cudaMemcpyAsync(counts, b->counts.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			std::unique_ptr<vsgpu_result> r;
+			if (out) {
+				r.reset(new vsgpu_result); r->offsets.resize(n + 1); r->hits.resize(b->hits_cap);
+				CU(cudaMemcpyAsync(r->offsets.data(), b->offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
+				CU(cudaMemcpyAsync(r->hits.data(), b->hits.p, b->hits_cap * 4, cudaMemcpyDeviceToHost, ix->stream));
+			}
+			uint32_t st = read_status(ix);
+			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
+			if (out) { r->hits.resize(r->offsets[n]); *out = r.release(); }
+		}
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+
+// Algorithmic bytes per SURVEY.md §8d:  t6 288 B/region;  t4 292 + 20 v + 4 h (v = branch records
+// of the region's slice, h = hits);  t7 148 + 16 r (r = records compared).
+int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* kernel_launches) {
+	if (!b) return set_err(VSGPU_EINVAL, "vsgpu_batch_stats: null batch");
+	vsgpu_index* ix = b->idx;
+	if (kernel_launches) *kernel_launches = b->launches;
+	if (!algorithmic_bytes) return VSGPU_OK;
+	if (!b->algo_valid) {
+		if (int rc = check_device(ix)) return rc;
+		try {
+			const uint64_t n = b->n; uint64_t bytes = 0;
+			if (b->type == 6) bytes = 288 * n;
+			else if (b->type == 7) {
+				const FlatIndex& f = ix->flat;
+				for (uint64_t i = 0; i < n; i++) {
+					uint32_t rk = b->hx[i] >= f.index_bits ? f.D : host_rank(f, b->hx[i]); if (rk < 1) rk = 1;
+					bytes += 148 + 16ull * (f.t7_hi[rk - 1] - f.t7_lo[rk - 1]);
+				}
+			} else {
+				CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), ix->d_status, ix->stream));
+				std::vector<uint2> o(n); uint64_t total = 0;
+				CU(cudaMemcpyAsync(o.data(), b->out.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
+				CU(cudaMemcpyAsync(&total, b->offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
+				CU(cudaStreamSynchronize(ix->stream));
+				uint64_t v = 0; for (auto& r : o) v += r.y - r.x;
+				bytes = 292 * n + 20 * v + 4 * total;
+			}
+			b->algo_bytes = bytes; b->algo_valid = true;
+		} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	}
+	*algorithmic_bytes = b->algo_bytes;
+	return VSGPU_OK;
+}
+
+void vsgpu_batch_free(vsgpu_batch* b) { delete b; }
+
+}  // extern "C"
