@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — region queries/s (types 4/6) of the batched region path on B200.
+
+A step = one pass of the hot path over one batch of synthetic input: t6 (get_var_in_ref) over all
+regions, then t4 (get_sample_var_in_ref) over the same regions with one random sample each.
+Workload at N=1 = BASELINE.json configs[1]: a chr22-shaped synthetic index (~1.1 M records x 2,504
+samples) and 1 M random 1 kb regions (sorted, as the reference's read_regions does).  With N > 1
+every rank owns its own contig shard of that shape and its own regions (weak scaling, no collective
+on the data path — the reference shards by contig too, eval_data_records/evaluation.txt:34).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            this engine (libvsgpu, CUDA)
+  python bench.py --impl reference ...                       the reference's CPU path (oracle port,
+                                                             all host cores, bounded sample per step)
+"""
+import argparse
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+POS_LO, REF_LEN = 16_050_000, 51_304_566          # scripts/bm_vs_query.sh:13, scripts/run_query.sh:6
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def get_oracle():
+    import vs_testlib as T            # the oracle binding lives with the tests (test infrastructure)
+    return T
+
+
+def ensure_index(args, rank):
+    """Synthetic ser/ for this rank's contig shard, built once per box with the oracle's construct
+    restatement (construction is out of scope for the engine and the reference binary cannot be
+    built here) and cached under --cache-dir for the other arm / later runs."""
+    key = hashlib.sha1(f"v3|{args.records}|{args.samples}|{args.fmax}|{rank}".encode()).hexdigest()[:12]
+    prefix = os.path.join(args.cache_dir, f"shard_{key}", "ser")
+    done = os.path.join(prefix, ".done")
+    if not os.path.exists(done):
+        T = get_oracle()
+        os.makedirs(os.path.dirname(prefix), exist_ok=True)
+        t0 = time.time()
+        scale = args.records / 1_103_547
+        ref_len = max(200_000, int(REF_LEN * scale)) if scale < 1 else REF_LEN
+        pos_lo = int(POS_LO * min(1.0, scale)) if scale < 1 else POS_LO
+        o = T.Oracle.synth(prefix, chr_name=str(22 - rank if rank < 22 else rank), ref_length=ref_len, pos_lo=max(2, pos_lo),
+                           pos_hi=ref_len - 60_000 if ref_len > 200_000 else ref_len - 1000, n_records=args.records,
+                           n_samples=args.samples, fmax=args.fmax, seed=2022 + rank, cqf_log2=25, fix_idx=False, gzip_level=1)
+        info = getattr(o, 'construct_info', None) or o.info()
+        o.close()
+        with open(done, "w") as f:
+            json.dump({"ref_length": ref_len, "pos_lo": pos_lo, "oracle_info": info}, f)
+        log(f"[rank {rank}] built synthetic index in {time.time() - t0:.1f}s: {info}")
+    meta = json.load(open(done))
+    return prefix, meta
+
+
+def make_regions(args, meta, rank):
+    rng = np.random.default_rng(1 + 1000 * rank)
+    lo = max(1, meta["pos_lo"])
+    hi = meta["ref_length"] - args.width
+    x = np.sort(rng.integers(lo, hi, args.regions)).astype(np.uint64)      # read_regions sorts (commands.cc:91)
+    y = x + np.uint64(args.width)
+    s = np.random.default_rng(2 + 1000 * rank).integers(1, args.samples + 1, args.regions).astype(np.uint32)
+    return x, y, s
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_sample(args, prefix, meta, nthreads, n_sample, steps=1, warmup=0):
+    """Times the oracle (CPU port of the reference's operators) on a bounded sample of the workload."""
+    T = get_oracle()
+    t0 = time.time()
+    o = T.Oracle.open(prefix)
+    load_s = time.time() - t0
+    x, y, s = make_regions(args, meta, 0)
+    pick = np.random.default_rng(7).choice(len(x), min(n_sample, len(x)), replace=False)
+    pick.sort()
+    xs, ys, ss = x[pick], y[pick], s[pick]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.time()
+        o.timed_counts(6, xs, ys, nthreads=nthreads)
+        o.timed_counts(4, xs, ys, ss, nthreads=nthreads)
+        dt = time.time() - t0
+        if it >= warmup:
+            times.append(dt)
+    o.close()
+    return 2 * len(xs), times, load_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    prefix, meta = ensure_index(args, 0)
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample
+    nq, times, load_s = cpu_sample(args, prefix, meta, cores, n_sample, steps=args.steps, warmup=args.warmup)
+    ms = 1000 * float(np.mean(times))
+    val = nq / (ms / 1000)
+    line = {
+        "impl": "reference", "metric": "region queries/s (types 4/6)", "value": val, "unit": "regions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, meta),
+        "cpu_baseline": {"value": val, "unit": "regions/s", "cores": cores, "kind": "port",
+                         "sample": f"{nq // 2} of the {args.regions} regions per type per step (t6 + t4), oracle port of include/query.h, {cores} worker threads over disjoint chunks; index load {load_s:.1f}s not timed"},
+        "e2e": {"value": val, "unit": "regions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, meta):
+    return {"workload": f"chr22-shaped synthetic index ({args.records} records x {args.samples} samples, ref_length {meta['ref_length']}), "
+                        f"{args.regions} random {args.width} bp regions per GPU sorted by start; one step = t6 + t4 over all regions",
+            "regions_per_gpu": args.regions, "region_width": args.width, "records": args.records, "samples": args.samples,
+            "sharding": "one contig shard per GPU, regions routed by the host, no collective on the data path",
+            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+
+def run_vsgpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        log("bench.py: no CUDA device — libvsgpu has no CPU path")
+        return 2
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from variantstore_b200 import Batch, VariantStoreIndex
+
+    prefix, meta = ensure_index(args, rank)
+    t0 = time.time()
+    idx = VariantStoreIndex(prefix, device=local)
+    open_s = time.time() - t0
+    idx.set_stream(torch.cuda.current_stream().cuda_stream)
+    x, y, s = make_regions(args, meta, rank)
+    n = len(x)
+    b6, b4 = Batch(idx, 6, x, y), Batch(idx, 4, x, y, sample_ids=s)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        b6.run()
+        b4.run()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    algo6, launches6 = b6.stats()
+    algo4, launches4 = b4.stats()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    step_ms, k6_ms, k4_ms = [], [], []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        k6_ms.append(b6.timings_ms())
+        k4_ms.append(b4.timings_ms())
+    barrier()
+    sampler.stop_flag = True
+    total_ms = float(np.sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = 2 * n * world / (ms_per_step / 1000)
+
+    # ---- end to end through the C ABI with host buffers (pinned inputs), H2D + kernels + D2H each step
+    px = torch.from_numpy(x.astype(np.int64)).pin_memory()
+    py = torch.from_numpy(y.astype(np.int64)).pin_memory()
+    ps = torch.from_numpy(s.astype(np.int32)).pin_memory()
+    lib, h = idx._lib, idx._h
+    lo, hi, cnt = (np.zeros(n, np.uint32) for _ in range(3))
+    vp = C.c_void_p
+
+    def e2e_step():
+        rc = lib.vsgpu_query_t6(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(lo.ctypes.data), vp(hi.ctypes.data), vp(cnt.ctypes.data))
+        assert rc == 0, lib.vsgpu_last_error()
+        r = vp()
+        rc = lib.vsgpu_query_t4(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(ps.data_ptr()), C.byref(r))
+        assert rc == 0, lib.vsgpu_last_error()
+        total = int(lib.vsgpu_result_offsets(r)[n])
+        lib.vsgpu_result_free(r)
+        return total
+
+    for _ in range(2):
+        hits_total = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        hits_total = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = 2 * n * world / e2e_s
+    h2d = n * 16 + n * 20
+    d2h = n * 8 + (n + 1) * 8 + hits_total * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    walk_ms = float(np.mean([k[0] for k in k4_ms]))
+    t6_ms = float(np.mean([k[0] for k in k6_ms]))
+    achieved = algo4 / (walk_ms / 1000) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_t4_walk_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "region queries/s (types 4/6)", "value": value, "unit": "regions/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic", "config": workload_config(args, meta),
+        "by_kernel": {"t6_regions_per_s": n / (t6_ms / 1000), "t4_regions_per_s": n / (float(np.mean([sum(k) for k in k4_ms])) / 1000),
+                      "k_t6_ms": t6_ms, "k_t4_walk_ms": walk_ms, "k_scan_ms": float(np.mean([k[1] for k in k4_ms])),
+                      "k_t4_gather_ms": float(np.mean([k[2] for k in k4_ms])), "t6_algorithmic_GBps": algo6 / (t6_ms / 1000) / 1e9,
+                      "t4_hits_per_region": hits_total / n, "index_open_s": open_s, "device_bytes": int(idx.info.device_bytes)},
+        "roofline": {"bound": "hbm", "kernel": "k_t4_walk", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo4},
+        "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": (launches6 + launches4) * args.steps,
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            nq, times, load_s = cpu_sample(args, prefix, meta, 1, args.cpu_sample_single)
+            line["cpu_baseline"] = {"value": nq / times[0], "unit": "regions/s", "cores": 1, "kind": "port",
+                                    "sample": f"{nq // 2} of the {n} regions per type (t6 + t4), single thread like the reference's query loop; oracle port of include/query.h; index load {load_s:.1f}s not timed"}
+        except Exception as ex:           # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "regions/s", "cores": 1, "kind": "port", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vsgpu", choices=["vsgpu", "reference"])
+    ap.add_argument("--regions", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1000)
+    ap.add_argument("--records", type=int, default=1_103_547)
+    ap.add_argument("--samples", type=int, default=2504)
+    ap.add_argument("--fmax", type=int, default=1100)
+    ap.add_argument("--cpu-sample", type=int, default=20_000, help="regions per type per step of the reference arm")
+    ap.add_argument("--cpu-sample-single", type=int, default=2_000, help="regions per type of the single-thread cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cache-dir", default=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"))
+    args = ap.parse_args()
+    import __graft_entry__
+    if not os.path.exists(os.path.join(ROOT, "variantstore_b200", "libvsgpu.so")) or not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        __graft_entry__.build()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_vsgpu(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,9 @@ int vsgpu_batch_run(vsgpu_batch* b);
 int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts, vsgpu_result** out);
 /* Algorithmic bytes of the last run (SURVEY.md §8d formulas) and the number of kernels it launched. */
 int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* kernel_launches);
+/* Device time (ms) of each kernel of the last run, from CUDA events on the launch stream
+ * (t6/t7: 1 kernel; t4: walk, scan, gather).  Synchronises. */
+int vsgpu_batch_timings(vsgpu_batch* b, float* ms, uint32_t cap, uint32_t* n);
 void vsgpu_batch_free(vsgpu_batch* b);
 
 #ifdef __cplusplus

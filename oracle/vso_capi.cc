@@ -10,6 +10,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <sys/stat.h>
+#include <thread>
 
 using namespace vso;
 
@@ -182,6 +183,42 @@ int vso_batch_t7(void* hp, uint64_t n, const uint64_t* pos, const char* const* r
 	} catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// Multi-threaded timing arms for bench.py (`--impl reference`, cpu_baseline): the reference query
+// path is single-threaded; "all host cores" = independent workers over disjoint region chunks, which
+// is how its evaluation ran contigs side by side (eval_data_records/evaluation.txt:34).
+int vso_batch_t6_mt(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, uint64_t* counts, int nthreads) {
+	Handle* h = (Handle*)hp;
+	if (nthreads < 1) nthreads = 1;
+	std::vector<std::thread> th; std::vector<int> rc(nthreads, 0);
+	for (int t = 0; t < nthreads; t++) th.emplace_back([&, t]() {
+		try {
+			QueryLog log;
+			for (uint64_t i = t; i < n; i += nthreads) { log.out.clear(); counts[i] = get_var_in_ref(h->vg.get(), h->idx.get(), x[i], y[i], false, "", &log).size(); }
+		} catch (const std::exception&) { rc[t] = -1; }
+	});
+	for (auto& t : th) t.join();
+	for (int r : rc) if (r) return r;
+	return 0;
+}
+int vso_batch_t4_mt(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, uint64_t* counts, int nthreads) {
+	Handle* h = (Handle*)hp;
+	if (nthreads < 1) nthreads = 1;
+	std::vector<std::thread> th; std::vector<int> rc(nthreads, 0);
+	for (int t = 0; t < nthreads; t++) th.emplace_back([&, t]() {
+		try {
+			QueryLog log;
+			for (uint64_t i = t; i < n; i += nthreads) {
+				log.out.clear();
+				std::string name = h->vg->get_sample_name(sample_ids[i]);
+				counts[i] = get_sample_var_in_ref(h->vg.get(), h->idx.get(), x[i], y[i], name, false, "", &log).size();
+			}
+		} catch (const std::exception&) { rc[t] = -1; }
+	});
+	for (auto& t : th) t.join();
+	for (int r : rc) if (r) return r;
+	return 0;
+}
+
 // Every distinct record next_variant_in_ref can report, in backbone order: used by tests to build
 // t7 lookups that hit.  Returns a malloc'd text "pos\tref\talt\n"... (one row per record).
 char* vso_all_variants_text(void* hp) {
@@ -203,7 +240,7 @@ char* vso_all_variants_text(void* hp) {
 // overlap != 0 lets a record start inside the previous record's REF span.
 void* vso_synth(const char* prefix, const char* chr, uint64_t ref_length, uint64_t pos_lo, uint64_t pos_hi,
                 uint64_t n_records, uint32_t n_samples, uint32_t fmax, double frac_multi, double frac_indel,
-                int mode, int overlap, uint64_t seed, int cqf_log2, int fix_idx, int gzip_level) {
+                int mode, int overlap, uint64_t seed, int cqf_log2, int fix_idx, int gzip_level, double reuse_prob) {
 	try {
 		Rng rng(seed);
 		std::string ref(ref_length, 'A');
@@ -252,6 +289,15 @@ void* vso_synth(const char* prefix, const char* chr, uint64_t ref_length, uint64
 			}
 		};
 		std::vector<SampleStruct> carriers;
+		// linkage stand-in: with probability reuse_prob an allele repeats the carrier set of one of the
+		// last 64 alleles, so that ~half of the alleles share a sample class as in 1000 Genomes
+		// (eval_data_records/logs/vs_v1.log: 1 106 184 alleles -> 490 775 classes on chr22)
+		std::vector<std::vector<SampleStruct>> recent; size_t recent_next = 0;
+		auto next_carriers = [&]() {
+			if (!recent.empty() && rng.unit() < reuse_prob) { carriers = recent[rng.below(recent.size())]; return; }
+			draw_carriers(carriers);
+			if (recent.size() < 64) recent.push_back(carriers); else { recent[recent_next] = carriers; recent_next = (recent_next + 1) % 64; }
+		};
 		uint64_t prev_end = 0;   // last reference base covered by the previous record's REF
 		for (size_t i = 0; i < pos.size(); i++) {
 			uint64_t p = pos[i];
@@ -276,7 +322,7 @@ void* vso_synth(const char* prefix, const char* chr, uint64_t ref_length, uint64
 				if (rng.unit() < frac_multi) { char b2; do { b2 = other_base(ref[p - 1]); } while (b2 == a); alts.push_back(std::string(1, b2)); }
 			}
 			h->vg->count_record();
-			for (auto& a : alts) { draw_carriers(carriers); h->vg->add_allele(r, a, p, carriers); }
+			for (auto& a : alts) { next_carriers(); h->vg->add_allele(r, a, p, carriers); }
 			prev_end = p + r.size() - 1;
 		}
 		h->vg->finish_construct();

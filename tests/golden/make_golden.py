@@ -1,0 +1,34 @@
+"""Regenerates tests/golden/: run here (where /root/reference exists).
+
+x_ser/, xsmall_ser/ = `ser/` directories the oracle's construct writes for the reference's own
+fixtures data/x.fa + data/x.vcf.gz and data/x.small.fa + data/x.small.vcf (CQF table 2^12 / 2^10
+slots instead of the reference's 2^25 so the files stay small).  expected.json = the oracle's
+answers on them; the first entries are pinned by the reference's README (README.md:58-60, :93-95).
+"""
+import json
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import vs_testlib as T  # noqa: E402
+from vs_testlib import Oracle  # noqa: E402
+
+out = {}
+for name, fa, vcf, log2 in [("x", "x.fa", "x.vcf.gz", 12), ("xsmall", "x.small.fa", "x.small.vcf", 10)]:
+    prefix = os.path.join(HERE, name + "_ser")
+    shutil.rmtree(prefix, ignore_errors=True)
+    o = Oracle.construct(os.path.join(T.REF_DATA, fa), os.path.join(T.REF_DATA, vcf), prefix, cqf_log2=log2)
+    ref_len = o.info()["ref_length"]
+    ex = {"construct_info": o.construct_info, "t6": {}, "t4": {}, "t7": {}}
+    regions = [(10, 105), (14, 105), (9, 105), (1, ref_len + 1), (100, 104), (466, 470), (972, 1000), (660, 700), (1, 80), (25, 27), (500, 400)]
+    for x, y in regions:
+        ex["t6"][f"{x}:{y}"] = o.t6_text(x, y)
+        ex["t4"][f"{x}:{y}"] = o.t4_text(x, y, "1")[0]
+    for p, r, a in o.all_variants() + [(58, "G", "GT"), (11, "C", "T")]:
+        ex["t7"][f"{p}|{r}|{a}"] = o.t7_text(p, r, a)
+    out[name] = ex
+    o.close()
+json.dump(out, open(os.path.join(HERE, "expected.json"), "w"), indent=1, sort_keys=True)
+print("golden fixtures written")

@@ -1,0 +1,109 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI of libvsgpu, against the oracle
+on the same seeded inputs — bit-exact (integer / byte / index work)."""
+import os
+
+import numpy as np
+import pytest
+
+import vs_testlib as T
+from vs_testlib import Oracle
+
+pytestmark = pytest.mark.gpu
+NONE = 0xFFFFFFFF
+
+
+def _t7_check(o, e, limit=None):
+    av = o.all_variants()
+    if limit:
+        av = av[:limit]
+    pos = [p for p, _, _ in av] + [p + 1 for p, _, _ in av[:64]]
+    refs = [r for _, r, _ in av] + [r for _, r, _ in av[:64]]
+    alts = [a for _, _, a in av] + [a for _, _, a in av[:64]]
+    f7, c7, d7 = o.batch_t7(pos, refs, alts)
+    rec = e.batch_samples_has_var(pos, refs, alts)
+    ec, ed = e.digest_t7(rec)
+    assert np.array_equal(rec != NONE, f7 == 1)
+    hit = f7 == 1
+    assert np.array_equal(c7[hit], ec[hit]) and np.array_equal(d7[hit], ed[hit])
+    return int(hit.sum()), len(pos)
+
+
+@pytest.mark.parametrize("overlap,sparse", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fuzz_parity_cuda(tmp_path, seed, overlap, sparse):
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), seed, overlap=overlap, sparse=sparse)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"), force_enc=0 if sparse else -1)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        assert e.info.class_mode == (0 if sparse else 1)
+        x, y, s = T.random_regions(seed + 100, 400, 4000, n_samples=len(names))
+        bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+        assert not bad6 and not bad4
+        hits, total = _t7_check(o, e)
+        assert 0 < hits < total
+
+
+def test_golden_fixture_cuda():
+    """README.md:93-95 of the reference: query -t 6 -r 10:105 on data/x.* -> 8 variants."""
+    prefix = os.path.join(T.GOLDEN, "x_ser")
+    with T.open_engine(prefix, "cuda") as e:
+        assert e.info.num_vertices_cqf == 212 and e.info.seq_length == 1074 and e.info.num_classes == 2
+        lo, hi, cnt = e.batch_var_in_ref([10, 14, 9, 1, 100, 466, 972], [105, 105, 105, 1001, 104, 470, 1000])
+        assert list(cnt) == [8, 6, 8, 75, 1, 1, 1]
+        rows = e.get_var_in_ref(10, 105)
+        assert [(v.var_pos, v.ref, v.alt) for v in rows] == [(10, "C", "T"), (14, "G", "A"), (34, "T", "A"), (39, "T", "A"),
+                                                             (52, "T", "G"), (58, "", "T"), (100, "T", "C"), (103, "T", "C")]
+        assert [v.samples for v in rows][:2] == [[("1", "1|1")], [("1", "1|0")]]
+        assert len(e.get_sample_var_in_ref(14, 105, "1")) == 7
+        assert e.samples_has_var(10, "C", "T") == [("1", "1|1")]
+        assert e.samples_has_var(58, "", "T") == [("1", "0|1")]
+        assert e.samples_has_var(14, "G", "A") == []
+
+
+def test_synthetic_1000g_shape_cuda(tmp_path):
+    """A scaled chr22-shaped index (classes, 300 samples): batch API == host-buffer API == oracle."""
+    from variantstore_b200 import Batch
+    o = Oracle.synth(str(tmp_path / "ser"), ref_length=2_000_000, n_records=60_000, n_samples=300, fmax=120, seed=5, cqf_log2=20)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        rng = np.random.default_rng(3)
+        n = 20_000
+        x = np.sort(rng.integers(1, 2_000_000, n)).astype(np.uint64)
+        y = x + rng.choice([100, 1000, 10_000, 100_000], n).astype(np.uint64)
+        s = rng.integers(1, 301, n).astype(np.uint32)
+        # oracle on a subsample (it walks vertex by vertex), engine on everything
+        sub = rng.choice(n, 1500, replace=False)
+        bad6, bad4, _ = T.compare_all(o, e, x[sub], y[sub], s[sub])
+        assert not bad6 and not bad4
+        lo, hi, cnt = e.batch_var_in_ref(x, y)
+        off, hits = e.batch_sample_var_in_ref(x, y, s)
+        b6, b4 = Batch(e, 6, x, y), Batch(e, 4, x, y, sample_ids=s)
+        for _ in range(2):
+            b6.run()
+            b4.run()
+        lo2, hi2, cnt2 = b6.fetch()
+        off2, hits2, cnt4 = b4.fetch()
+        assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2) and np.array_equal(cnt, cnt2)
+        assert np.array_equal(off, off2) and np.array_equal(hits, hits2) and np.array_equal(np.diff(off), cnt4)
+        assert len(b4.timings_ms()) == 3 and b4.stats()[1] == 3 and b6.stats()[0] == 288 * n
+        # size-independent properties: slices are monotone in x for sorted regions of equal width,
+        # a t4 answer never has more rows than twice the t6 slice (+ the start / rejoin rows)
+        same_w = y - x == 1000
+        assert np.all(np.diff(lo[same_w].astype(np.int64)) >= 0)
+        assert np.all(np.diff(off).astype(np.int64) <= 2 * (hi.astype(np.int64) - lo) + 2)
+        hits7, total7 = _t7_check(o, e, limit=3000)
+        assert hits7 > 0
+
+
+def test_error_paths_cuda(tmp_path):
+    from variantstore_b200 import VsgpuError
+    prefix = os.path.join(T.GOLDEN, "x_ser")
+    with T.open_engine(prefix, "cuda") as e:
+        with pytest.raises(VsgpuError):
+            e.batch_var_in_ref([0], [10])           # the reference aborts on pos < 1 (index.h:151-154)
+        with pytest.raises(VsgpuError):
+            e.sample_id("nobody")
+        lo, hi, cnt = e.batch_var_in_ref([2000, 1], [3000, 1])   # beyond the contig / empty region
+        assert list(cnt) == [0, 0]
+        off, hits = e.batch_sample_var_in_ref(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+        assert len(off) == 1 and len(hits) == 0
+    with pytest.raises(VsgpuError):
+        T.open_engine(str(tmp_path / "missing"), "cuda")

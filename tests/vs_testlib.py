@@ -73,10 +73,12 @@ class Oracle:
             L.vso_sample_name.argtypes = [vp, C.c_uint32]
             L.vso_batch_t6.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t4.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.c_int]
+            L.vso_batch_t6_mt.argtypes = [vp, u64, vp, vp, vp, C.c_int]
+            L.vso_batch_t4_mt.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t7.argtypes = [vp, u64, vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), vp, vp, vp]
             L.vso_synth.restype = vp
             L.vso_synth.argtypes = [C.c_char_p, C.c_char_p, u64, u64, u64, u64, C.c_uint32, C.c_uint32, C.c_double, C.c_double,
-                                    C.c_int, C.c_int, u64, C.c_int, C.c_int, C.c_int]
+                                    C.c_int, C.c_int, u64, C.c_int, C.c_int, C.c_int, C.c_double]
             L.vso_rrr_roundtrip.argtypes = [vp, u64, C.c_char_p]
             L.vso_encode_vertices.restype = vp
             L.vso_encode_vertices.argtypes = [u64, vp, vp, vp, vp, vp, vp, C.POINTER(u64)]
@@ -110,10 +112,11 @@ class Oracle:
 
     @classmethod
     def synth(cls, prefix, chr_name="22", ref_length=200000, pos_lo=1000, pos_hi=None, n_records=5000, n_samples=64,
-              fmax=40, frac_multi=0.0025, frac_indel=0.035, mode=0, overlap=0, seed=1, cqf_log2=18, fix_idx=False, gzip_level=1):
+              fmax=40, frac_multi=0.0025, frac_indel=0.035, mode=0, overlap=0, seed=1, cqf_log2=18, fix_idx=False, gzip_level=1,
+              reuse_prob=0.55):
         pos_hi = pos_hi or ref_length - 1000
         o = cls(cls.lib().vso_synth(prefix.encode(), chr_name.encode(), ref_length, pos_lo, pos_hi, n_records, n_samples, fmax,
-                                    frac_multi, frac_indel, mode, overlap, seed, cqf_log2, int(fix_idx), gzip_level))
+                                    frac_multi, frac_indel, mode, overlap, seed, cqf_log2, int(fix_idx), gzip_level, reuse_prob))
         ci = o.info()
         o.close()
         r = cls.open(prefix)
@@ -179,6 +182,19 @@ class Oracle:
         if rc != 0:
             raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
         return cnt, dig, ub
+
+    def timed_counts(self, qtype, x, y, sample_ids=None, nthreads=1):
+        """Counts only, optionally over several worker threads (bench timing arms)."""
+        x, y = np.ascontiguousarray(x, np.uint64), np.ascontiguousarray(y, np.uint64)
+        cnt = np.zeros(len(x), np.uint64)
+        if qtype == 6:
+            rc = self.lib().vso_batch_t6_mt(self.h, len(x), x.ctypes.data, y.ctypes.data, cnt.ctypes.data, nthreads)
+        else:
+            s = np.ascontiguousarray(sample_ids, np.uint32)
+            rc = self.lib().vso_batch_t4_mt(self.h, len(x), x.ctypes.data, y.ctypes.data, s.ctypes.data, cnt.ctypes.data, nthreads)
+        if rc != 0:
+            raise RuntimeError("oracle batch failed")
+        return cnt
 
     def batch_t7(self, pos, refs, alts):
         pos = np.ascontiguousarray(pos, np.uint64)

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "vsgpu_batch_run": (C.c_int, [vp]),
     "vsgpu_batch_fetch": (C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
     "vsgpu_batch_stats": (C.c_int, [vp, u64p, u32p]),
+    "vsgpu_batch_timings": (C.c_int, [vp, vp, C.c_uint32, u32p]),
     "vsgpu_batch_free": (None, [vp]),
 }
 # subset a test-only host simulator has to provide

@@ -226,3 +226,67 @@ class VariantStoreIndex:
             ids.append((text[i:sp], text[sp + 1:sp + 4]))
             i = sp + 4
         return ids
+
+
+class Batch:
+    """Device-resident batch of regions (vsgpu_batch_*): the bench harness that replaces the timing
+    loop of src/bm_query.cc:74-135.  Inputs and results stay in HBM; run() only enqueues kernels."""
+
+    def __init__(self, index: VariantStoreIndex, qtype: int, x, y=None, sample_ids=None, refs=None, alts=None):
+        self._ix, self._lib, self.type = index, index._lib, qtype
+        x = _u64(x)
+        self.n = len(x)
+        y = _u64(y) if y is not None else None
+        s = np.ascontiguousarray(sample_ids, np.uint32) if sample_ids is not None else None
+        ra = (C.c_char_p * self.n)(*[r.encode() for r in refs]) if refs is not None else None
+        aa = (C.c_char_p * self.n)(*[a.encode() for a in alts]) if alts is not None else None
+        h = C.c_void_p()
+        index._check(self._lib.vsgpu_batch_create(index._h, qtype, self.n, _ptr(x), _ptr(y) if y is not None else None,
+                                                  _ptr(s) if s is not None else None, ra, aa, C.byref(h)))
+        self._h = h
+
+    def run(self):
+        self._ix._check(self._lib.vsgpu_batch_run(self._h))
+
+    def timings_ms(self):
+        ms = (C.c_float * 4)()
+        n = C.c_uint32()
+        self._ix._check(self._lib.vsgpu_batch_timings(self._h, ms, 4, C.byref(n)))
+        return [ms[i] for i in range(n.value)]
+
+    def stats(self):
+        b, k = C.c_uint64(), C.c_uint32()
+        self._ix._check(self._lib.vsgpu_batch_stats(self._h, C.byref(b), C.byref(k)))
+        return b.value, k.value
+
+    def fetch(self):
+        n = self.n
+        if self.type == 6:
+            lo, hi, cnt = (np.zeros(n, np.uint32) for _ in range(3))
+            self._ix._check(self._lib.vsgpu_batch_fetch(self._h, _ptr(lo), _ptr(hi), _ptr(cnt), None))
+            return lo, hi, cnt
+        if self.type == 7:
+            rec = np.zeros(n, np.uint32)
+            self._ix._check(self._lib.vsgpu_batch_fetch(self._h, _ptr(rec), None, None, None))
+            return rec
+        cnt = np.zeros(n, np.uint32)
+        r = C.c_void_p()
+        self._ix._check(self._lib.vsgpu_batch_fetch(self._h, None, None, _ptr(cnt), C.byref(r)))
+        try:
+            off = np.ctypeslib.as_array(self._lib.vsgpu_result_offsets(r), shape=(n + 1,)).copy()
+            total = int(off[-1])
+            hits = np.ctypeslib.as_array(self._lib.vsgpu_result_hits(r), shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+        finally:
+            self._lib.vsgpu_result_free(r)
+        return off, hits, cnt
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vsgpu_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,107 @@
+// vsgpu_query — front-end with the reference's `variantstore query` flags
+// (src/variantstore.cc:101-134, src/commands.cc:113-215):
+//   -p <ser prefix> -t <4|6|7> -r <beg[:end][,...]> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]
+// -m is accepted and ignored (both modes give identical results; only the reference's paging differs).
+// Unlike query_main's per-region loop the whole region list goes to the GPU as one batch; the lines
+// printed per region are the reference's.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/vsgpu.h"
+
+static std::vector<std::tuple<uint64_t, uint64_t>> read_regions(std::string region) {   // commands.cc:64-93
+	std::vector<std::tuple<uint64_t, uint64_t>> regions;
+	auto pos = region.find(',');
+	while (true) {
+		std::string token = region.substr(0, pos);
+		auto pos2 = token.find(':');
+		uint64_t beg = 0, end = 0;
+		if (pos2 == std::string::npos) beg = std::stoi(token);
+		else { end = std::stoi(token.substr(pos2 + 1)); beg = std::stoi(token.substr(0, pos2)); }
+		regions.push_back(std::make_tuple(beg, end));
+		if (pos == std::string::npos) break;
+		region = region.substr(pos + 1);
+		pos = region.find(',');
+	}
+	std::sort(regions.begin(), regions.end());
+	return regions;
+}
+static std::vector<std::string> read_sequences(std::string s) {   // commands.cc:96-111
+	std::vector<std::string> seqs;
+	auto pos = s.find(',');
+	while (true) { seqs.push_back(s.substr(0, pos)); if (pos == std::string::npos) break; s = s.substr(pos + 1); pos = s.find(','); }
+	return seqs;
+}
+static const char* opt(int argc, char** argv, const char* f, const char* d) { for (int i = 1; i + 1 < argc; i++) if (!strcmp(argv[i], f)) return argv[i + 1]; return d; }
+static bool flag(int argc, char** argv, const char* f) { for (int i = 1; i < argc; i++) if (!strcmp(argv[i], f)) return true; return false; }
+static void write_rows(const std::string& outfile, const char* text, bool header) {
+	std::ofstream out; out.open(outfile);                 // truncating rewrite per call, as the reference does
+	if (header) out << "Pos\tRef\tAlt\tSamples\n";
+	out << text; out.close();
+}
+
+int main(int argc, char** argv) {
+	int a0 = (argc > 1 && !strcmp(argv[1], "query")) ? 2 : 1;
+	argc -= a0 - 1; argv += a0 - 1;
+	const char* prefix = opt(argc, argv, "-p", nullptr); const char* tstr = opt(argc, argv, "-t", nullptr); const char* rstr = opt(argc, argv, "-r", nullptr);
+	if (!prefix || !tstr || !rstr) { fprintf(stderr, "usage: vsgpu_query [query] -p <prefix> -t <4|6|7> -r <regions> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]\n"); return 1; }
+	const int type = atoi(tstr);
+	const std::string outfile = opt(argc, argv, "-o", ""), sample = opt(argc, argv, "-s", "");
+	const bool verbose = flag(argc, argv, "-v");
+	vsgpu_index* idx = nullptr;
+	if (vsgpu_open(prefix, atoi(opt(argc, argv, "--device", "0")), &idx) != 0) { fprintf(stderr, "%s\n", vsgpu_last_error()); return 2; }
+	vsgpu_info_t info; vsgpu_info(idx, &info);
+	printf("Chromosome: %s #Vertices: %lu #Edges: 0 Seq length: %lu\n", info.chr, (unsigned long)info.num_vertices_cqf, (unsigned long)info.seq_length);
+	auto regions = read_regions(rstr);
+	const uint64_t n = regions.size();
+	std::vector<uint64_t> x(n), y(n);
+	for (uint64_t i = 0; i < n; i++) { x[i] = std::get<0>(regions[i]); y[i] = std::get<1>(regions[i]); }
+	auto t0 = std::chrono::steady_clock::now();
+	int rc = 0;
+	if (type == 6) {
+		std::vector<uint32_t> lo(n), hi(n), cnt(n);
+		rc = vsgpu_query_t6(idx, n, x.data(), y.data(), lo.data(), hi.data(), cnt.data());
+		for (uint64_t i = 0; i < n && rc == 0; i++) {
+			// the reference prints the t4 label when its is_empty gate fires (query.h:746)
+			printf("Number of variants %s: %u\n", cnt[i] == 0 && lo[i] == 0 && hi[i] == 0 ? "get_sample_var_in_ref" : "get_var_in_ref", cnt[i]);
+			if (verbose) { char* text = nullptr; uint64_t nr; if (vsgpu_rows_t6(idx, lo[i], hi[i], 1, &text, &nr) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
+		}
+	} else if (type == 4) {
+		uint32_t sid = 0;
+		if (vsgpu_sample_id(idx, sample.c_str(), &sid) != 0) { fprintf(stderr, "%s\n", vsgpu_last_error()); return 2; }
+		std::vector<uint32_t> s(n, sid);
+		vsgpu_result* res = nullptr;
+		rc = vsgpu_query_t4(idx, n, x.data(), y.data(), s.data(), &res);
+		if (rc == 0) {
+			const uint64_t* off = vsgpu_result_offsets(res); const uint32_t* hits = vsgpu_result_hits(res);
+			for (uint64_t i = 0; i < n; i++) {
+				printf("Number of variants get_sample_var_in_ref: %lu\n", (unsigned long)(off[i + 1] - off[i]));
+				if (verbose) { char* text = nullptr; if (vsgpu_rows_t4(idx, hits + off[i], off[i + 1] - off[i], 1, &text) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
+			}
+			vsgpu_result_free(res);
+		}
+	} else if (type == 7) {
+		auto alts = read_sequences(opt(argc, argv, "-a", "")), refs = read_sequences(opt(argc, argv, "-b", ""));
+		if (alts.size() < n || refs.size() < n) { fprintf(stderr, "-a/-b need one entry per position\n"); return 1; }
+		std::vector<const char*> rp(n), ap(n);
+		for (uint64_t i = 0; i < n; i++) { rp[i] = refs[i].c_str(); ap[i] = alts[i].c_str(); }
+		std::vector<uint32_t> rec(n);
+		rc = vsgpu_query_t7(idx, n, x.data(), rp.data(), ap.data(), rec.data());
+		for (uint64_t i = 0; i < n && rc == 0; i++) {
+			if (rec[i] == VSGPU_NONE) { fprintf(stderr, "There is no such variant!\n"); continue; }
+			if (verbose) { char* text = nullptr; uint64_t nc; if (vsgpu_rows_t7(idx, rec[i], &text, &nc) == 0) { std::string t = std::string(text) + "\n"; write_rows(outfile, t.c_str(), false); vsgpu_free(text); } }
+		}
+	} else { fprintf(stderr, "Unsupported query type\n"); rc = 1; }
+	if (rc != 0) { fprintf(stderr, "%s\n", vsgpu_last_error()); vsgpu_close(idx); return 2; }
+	double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	std::cout << "Query" << n << ": " << (type == 6 ? "(query_var_in_ref) " : "") << "Total Time Elapsed: " << std::to_string(dt) << "seconds" << std::endl;
+	vsgpu_close(idx);
+	return 0;
+}

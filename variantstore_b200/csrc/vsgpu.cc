@@ -72,7 +72,8 @@ struct vsgpu_batch {
 	uint32_t launches = 0;
 	uint64_t algo_bytes = 0; bool algo_valid = false;
 	std::vector<uint64_t> hx, hy;   // host copies kept for the byte accounting
-	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); for (DevBuf* b : {&x, &y, &s, &hash, &out, &counts, &scratch, &offsets, &hits, &state, &rec}) b->release(); }
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &counts, &scratch, &offsets, &hits, &state, &rec}) b->release(); }
 };
 
 namespace {
@@ -219,11 +220,14 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 // ------------------------------------------------------------------ t4
 namespace {
 void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& counts, DevBuf& scratch,
-            DevBuf& offsets, DevBuf& state, DevBuf& hits, uint64_t& hits_cap, uint32_t* launches) {
+            DevBuf& offsets, DevBuf& state, DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr) {
 	CU(counts.ensure(n * 4)); CU(scratch.ensure(n * 4 * kScratchHits)); CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(scan_state_words(n) * 8));
 	CU(cudaMemsetAsync(state.p, 0, scan_state_words(n) * 8, ix->stream));
+	if (ev) CU(cudaEventRecord(ev[0], ix->stream));
 	CU(launch_t4_walk(ix->dev, n, dx, dy, ds, counts.as<uint32_t>(), scratch.as<uint32_t>(), ix->d_status, ix->stream));
+	if (ev) CU(cudaEventRecord(ev[1], ix->stream));
 	CU(launch_scan(n, counts.as<uint32_t>(), offsets.as<uint64_t>(), state.as<uint64_t>(), ix->stream));
+	if (ev) CU(cudaEventRecord(ev[2], ix->stream));
 	if (launches) *launches = 2;
 	if (hits_cap == 0) {   // first run of this shape: size the output from the scanned total
 		uint64_t total = 0;
@@ -233,6 +237,7 @@ void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy,
 		CU(hits.ensure(hits_cap * 4));
 	}
 	CU(launch_t4_gather(ix->dev, n, dx, dy, ds, counts.as<uint32_t>(), scratch.as<uint32_t>(), offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, ix->d_status, ix->stream));
+	if (ev) CU(cudaEventRecord(ev[3], ix->stream));
 	if (launches) *launches = 3;
 }
 }  // namespace
@@ -374,9 +379,10 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 	vsgpu_index* ix = b->idx;
 	if (int rc = check_device(ix)) return rc;
 	try {
-		if (b->type == 6) { CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), ix->d_status, ix->stream)); b->launches = 1; }
-		else if (b->type == 7) { CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), ix->d_status, ix->stream)); b->launches = 1; }
-		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->counts, b->scratch, b->offsets, b->state, b->hits, b->hits_cap, &b->launches);
+		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
+		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), ix->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), ix->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->counts, b->scratch, b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
@@ -453,6 +459,19 @@ int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* ker
 		} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	}
 	*algorithmic_bytes = b->algo_bytes;
+	return VSGPU_OK;
+}
+
+// Device time of each kernel of the last vsgpu_batch_run, from CUDA events recorded on the launch
+// stream (t6/t7: 1 kernel; t4: walk, scan, gather).  Synchronises on the last event.
+int vsgpu_batch_timings(vsgpu_batch* b, float* ms, uint32_t cap, uint32_t* n) {
+	if (!b || !ms || !n) return set_err(VSGPU_EINVAL, "vsgpu_batch_timings: null argument");
+	if (b->launches == 0 || !b->ev[0]) return set_err(VSGPU_EINVAL, "vsgpu_batch_timings: batch has not run");
+	if (int rc = check_device(b->idx)) return rc;
+	uint32_t k = b->launches;
+	if (cudaEventSynchronize(b->ev[k]) != cudaSuccess) return set_err(VSGPU_ENODEVICE, "CUDA: event synchronize failed");
+	*n = 0;
+	for (uint32_t i = 0; i < k && i < cap; i++) { if (cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]) != cudaSuccess) return set_err(VSGPU_ENODEVICE, "CUDA: event elapsed failed"); (*n)++; }
 	return VSGPU_OK;
 }
 
