@@ -22,6 +22,7 @@ struct vsgpu_index : HostIndex {
 	DevIndex dev;
 	std::vector<std::vector<uint32_t>> lv;
 	std::vector<uint2> t7;
+	std::vector<uint32_t> hitmap;
 };
 
 namespace {
@@ -52,6 +53,21 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 	d.dlev = (const uint4*)f.dlev.data(); d.dinfo = f.dinfo.data(); d.t7rng = ix->t7.data(); d.cent = (const uint4*)f.cent.data();
 	d.bb_set = f.bb_set.data(); d.vstart = f.vstart.data(); d.bitmap = f.bitmap.data(); d.list_begin = f.list_begin.data();
 	d.list_ids = f.list_ids.data(); d.rec_pos = f.rec_pos.data(); d.rec_hash = f.rec_hash.data(); d.rec_flags = f.rec_flags.data();
+	d.marker_bits = f.marker_bits.data(); d.cent_begin_k = f.cent_begin.data(); d.row_words = f.row_words; d.hitmap = nullptr;
+	if (!getenv("VSGPU_DISABLE_HITMAP")) {   // host copy of k_build_hitmap
+		ix->hitmap.assign((size_t)f.num_samples * f.row_words, 0);
+		for (size_t c = 0; c < f.cent.size(); c++) {
+			const CEntry& e = f.cent[c];
+			if (e.tgt & kEntMarker) continue;
+			if (f.class_mode) {
+				for (uint32_t w = 0; w < f.words_per_set; w++) {
+					uint64_t bits = f.bitmap[(uint64_t)e.set_id * f.words_per_set + w];
+					while (bits) { uint32_t s = w * 64 + (uint32_t)__builtin_ctzll(bits); bits &= bits - 1; if (s) ix->hitmap[(size_t)s * f.row_words + (c >> 5)] |= 1u << (c & 31); }
+				}
+			} else for (uint64_t i = f.list_begin[e.set_id]; i < f.list_begin[e.set_id + 1]; i++) ix->hitmap[(size_t)f.list_ids[i] * f.row_words + (c >> 5)] |= 1u << (c & 31);
+		}
+		d.hitmap = ix->hitmap.data();
+	}
 	*out = ix.release();
 	return VSGPU_OK;
 }
@@ -95,7 +111,7 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	VecSink sink{&r->hits};
 	for (uint64_t i = 0; i < n; i++) {
 		if (x[i] < 1 || s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
-		logic::walk_region(ix->dev, top, x[i], y[i], s[i], sink);
+		logic::walk_any(ix->dev, top, x[i], y[i], s[i], sink);
 		r->offsets[i + 1] = r->hits.size();
 	}
 	*out = r.release();

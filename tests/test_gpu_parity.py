@@ -28,9 +28,20 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
+@pytest.fixture(params=["hitmap", "class-bitmaps"])
+def walk_path(request, monkeypatch):
+    """Both t4 kernels paths: the sample-major hit map (default) and the per-entry class-bitmap test
+    used when the map does not fit the memory budget."""
+    if request.param == "class-bitmaps":
+        monkeypatch.setenv("VSGPU_DISABLE_HITMAP", "1")
+    else:
+        monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("overlap,sparse", [(False, False), (True, False), (False, True), (True, True)])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_fuzz_parity_cuda(tmp_path, seed, overlap, sparse):
+def test_fuzz_parity_cuda(tmp_path, seed, overlap, sparse, walk_path):
     fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), seed, overlap=overlap, sparse=sparse)
     o = Oracle.construct(fa, vcf, str(tmp_path / "ser"), force_enc=0 if sparse else -1)
     with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
@@ -59,7 +70,7 @@ def test_golden_fixture_cuda():
         assert e.samples_has_var(14, "G", "A") == []
 
 
-def test_synthetic_1000g_shape_cuda(tmp_path):
+def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
     """A scaled chr22-shaped index (classes, 300 samples): batch API == host-buffer API == oracle."""
     from variantstore_b200 import Batch
     o = Oracle.synth(str(tmp_path / "ser"), ref_length=2_000_000, n_records=60_000, n_samples=300, fmax=120, seed=5, cqf_log2=20)

@@ -1,0 +1,106 @@
+"""CPU-side parity: loader + flattener + the kernels' per-region logic (compiled for the host, test
+only) + materialiser against the oracle, on the fuzz shapes of SURVEY.md §4."""
+import os
+
+import numpy as np
+import pytest
+
+import vs_testlib as T
+from vs_testlib import Oracle
+
+NONE = 0xFFFFFFFF
+
+
+def t7_parity(o, e):
+    av = o.all_variants()
+    pos = [p for p, _, _ in av] + [p + 1 for p, _, _ in av[:40]] + [max(1, p - 1) for p, _, _ in av[:40]]
+    refs = [r for _, r, _ in av] + [r for _, r, _ in av[:80]]
+    alts = [a for _, _, a in av] + [a for _, _, a in av[:80]]
+    f7, c7, d7 = o.batch_t7(pos, refs, alts)
+    rec = e.batch_samples_has_var(pos, refs, alts)
+    ec, ed = e.digest_t7(rec)
+    assert np.array_equal(rec != NONE, f7 == 1)
+    hit = f7 == 1
+    assert np.array_equal(c7[hit], ec[hit]) and np.array_equal(d7[hit], ed[hit])
+    return int(hit.sum())
+
+
+@pytest.fixture(params=["hitmap", "class-bitmaps"])
+def walk_path(request, monkeypatch):
+    if request.param == "class-bitmaps":
+        monkeypatch.setenv("VSGPU_DISABLE_HITMAP", "1")
+    else:
+        monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("overlap,sparse", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_parity(tmp_path, seed, overlap, sparse, walk_path):
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), seed, overlap=overlap, sparse=sparse)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"), force_enc=0 if sparse else -1)
+    e = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    assert e.info.class_mode == (0 if sparse else 1)
+    assert e.info.num_vertices_cqf == o.info()["cqf_vertices"] and e.info.num_vertices == o.info()["vertices"]
+    x, y, s = T.random_regions(seed + 100, 300, 4000, n_samples=len(names))
+    bad6, bad4, ub = T.compare_all(o, e, x, y, s)
+    assert not bad6 and not bad4
+    assert t7_parity(o, e) > 0
+
+
+def test_many_samples_auto_sparse_detection(tmp_path):
+    """40 samples with rare carriers: density <= 5 % in the first 99 records -> explicit sample ids
+    (variant_graph.h:568-617), chosen by the construct restatement itself."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 21, n_samples=40, sparse=True)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    e = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    x, y, s = T.random_regions(4, 300, 4000, n_samples=len(names))
+    bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+    assert not bad6 and not bad4
+
+
+def test_edges_of_the_contig(tmp_path):
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 7)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    e = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    x = np.array([1, 1, 2, 3990, 3999, 4000, 4000, 4001, 5000, 1, 100, 100], np.uint64)
+    y = np.array([2, 4001, 3, 4000, 4001, 4001, 9000, 4100, 6000, 100000, 100, 50], np.uint64)
+    s = np.array([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12], np.uint32)
+    bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+    assert not bad6 and not bad4
+
+
+def test_synthetic_generator_parity(tmp_path):
+    """The bench's data path: programmatic synthetic construct (no VCF text), both modes."""
+    for mode, kw in ((0, dict(n_samples=200, fmax=80)), (1, dict(n_samples=3000))):
+        o = Oracle.synth(str(tmp_path / f"ser{mode}"), ref_length=300_000, n_records=12_000, mode=mode, seed=3 + mode, **kw)
+        e = T.open_engine(str(tmp_path / f"ser{mode}"), "hostsim")
+        assert e.info.class_mode == (1 if mode == 0 else 0)
+        rng = np.random.default_rng(8)
+        x = rng.integers(1, 300_000, 1200).astype(np.uint64)
+        y = x + rng.choice([1, 50, 1000, 20_000], 1200).astype(np.uint64)
+        s = rng.integers(1, kw["n_samples"] + 1, 1200).astype(np.uint32)
+        bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+        assert not bad6 and not bad4
+        assert t7_parity(o, e) > 0
+
+
+def test_duplicate_records_take_the_literal_path(tmp_path):
+    """A VCF that repeats a record: the reference's dedup (query.h:397-414) makes the t6 answer depend
+    on where the region starts; the engine detects such slices and re-counts them literally."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 2, n_records=60)
+    lines = open(vcf).read().split("\n")
+    body = [l for l in lines if l and not l.startswith("#")]
+    snps = [l for l in body if len(l.split("\t")[3]) == 1 and len(l.split("\t")[4]) == 1]
+    out = []
+    for l in lines:
+        out.append(l)
+        if l in snps[:8]:
+            out.append(l)                                   # exact duplicate record
+    open(vcf, "w").write("\n".join(out))
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    e = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    assert e.info.has_suspect_dups == 1
+    x, y, s = T.random_regions(3, 400, 1200, widths=(1, 2, 5, 20, 100, 1000), n_samples=len(names))
+    bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+    assert not bad6 and not bad4

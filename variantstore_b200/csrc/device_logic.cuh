@@ -155,5 +155,116 @@ VSGPU_HD void walk_region(const DevIndex& ix, const uint32_t* s_top, uint64_t x6
 	}
 }
 
+// ------------------------------------------------------------------ t4 walk over the sample-major hit map
+// hitmap row s, bit c = "sample s is a carrier of the target of walk entry c".  One 32-bit load
+// answers the membership question for 32 consecutive entries, so the scan only touches the entries
+// the sample actually carries (plus the rare markers).  Same rules, same order, same output as
+// walk_region above; used whenever the map fits the memory budget.
+VSGPU_HD uint32_t ctz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__ffs((int)v) - 1;
+#else
+	return (uint32_t)__builtin_ctz(v);
+#endif
+}
+VSGPU_HD uint32_t clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__clz((int)v);
+#else
+	return (uint32_t)__builtin_clz(v);
+#endif
+}
+// bits [pos, pos+len) of a row, len <= 32
+VSGPU_HD uint32_t row_bits(const uint32_t* row, uint32_t pos, uint32_t len) {
+	const uint32_t w = pos >> 5, off = pos & 31;
+	uint64_t v = ldg(row + w);
+	if (off + len > 32) v |= (uint64_t)ldg(row + w + 1) << 32;
+	return (uint32_t)(v >> off) & (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1));
+}
+
+template <class Sink>
+VSGPU_HD void walk_region_fast(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	if (x64 > ix.index_bits) return;
+	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
+	const uint32_t rk = rank_le(ix, s_top, x);
+	if (rk < 1 || rk >= ix.D) return;
+	if ((uint64_t)ldg(ix.lvl[0] + rk) > (uint64_t)y + 1) return;                // is_empty gate
+	const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
+	// ---- get_prev_vertex_with_sample (query.h:57-113)
+	uint64_t cur = (x64 >= ix.index_bits) ? ix.D - 1 : rk - 1;
+	uint32_t c_found = kNoneU32;
+	for (;;) {
+		if (cur > ix.D) cur = 0;
+		if (cur <= 1) break;
+		const uint64_t info = ldg(ix.dinfo + (cur - 1));
+		const uint32_t cb = (uint32_t)info, ncar = (uint32_t)(info >> 32) & 0xFFFF, deg = (uint32_t)(info >> 48);
+		for (uint32_t hi = cb + ncar; hi > cb;) {                                 // last carrier wins: scan from the top
+			const uint32_t len = hi - cb > 32 ? 32 : hi - cb;
+			const uint32_t bits = row_bits(row, hi - len, len);
+			if (bits) { c_found = hi - len + (31 - clz32(bits)); break; }
+			hi -= len;
+		}
+		cur -= deg;
+		if (c_found != kNoneU32) break;
+	}
+	// ---- forward walk (query.h:649-716)
+	const uint32_t e_y = y ? rank_le(ix, s_top, y - 1) : 0;
+	const uint4 dl = ldg(ix.dlev + e_y);
+	const uint32_t k_end = dl.x;                                                // first backbone vertex whose start >= y
+	uint32_t limit = dl.w;                                                      // entries >= limit have src >= k_end
+	uint32_t cur_k = 0, c = 0;
+	if (c_found != kNoneU32) {
+		const uint4 e = ldg(ix.cent + c_found);
+		if (e.w >= y) return;
+		if (e.w >= x) sink.emit(c_found | kHitStart);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask || tk >= k_end) return;
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(c_found | kHitRejoin);
+			cur_k = tk;
+		} else {
+			cur_k = e.y & kEntTgtMask;
+			if (cur_k >= k_end) { const uint32_t nl = ldg(ix.cent_begin_k + cur_k + 1); if (nl > limit) limit = nl; }   // its own entries still count
+		}
+		c = c_found + 1;
+	} else {
+		if (1 >= y) return;
+	}
+	if (c >= limit) return;
+	uint32_t w = c >> 5;
+	uint32_t m = (ldg(row + w) | ldg(ix.marker_bits + w)) & (0xFFFFFFFFu << (c & 31));
+	for (;;) {
+		while (m == 0) {
+			w++;
+			if ((w << 5) >= limit) return;
+			m = ldg(row + w) | ldg(ix.marker_bits + w);
+		}
+		const uint32_t ci = (w << 5) + ctz32(m);
+		m &= m - 1;
+		if (ci >= limit) return;
+		const uint4 e = ldg(ix.cent + ci);
+		if (e.x < cur_k) continue;                                                 // hidden behind a taken detour / later sibling
+		if (e.x > cur_k && e.x >= k_end) return;                                   // the walk stopped before reaching P[e.x]
+		if (e.y & kEntMarker) { if (e.w >= y) return; continue; }
+		if (e.w >= y) return;
+		if (e.w >= x) sink.emit(ci);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask || tk >= k_end) return;
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(ci | kHitRejoin);
+			cur_k = tk;
+		} else {
+			cur_k = e.y & kEntTgtMask;
+			if (cur_k >= k_end) { const uint32_t nl = ldg(ix.cent_begin_k + cur_k + 1); if (nl > limit) limit = nl; }
+		}
+	}
+}
+
+template <class Sink>
+VSGPU_HD void walk_any(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	if (ix.hitmap) walk_region_fast(ix, s_top, x64, y64, s, sink);
+	else walk_region(ix, s_top, x64, y64, s, sink);
+}
+
 }  // namespace logic
 }  // namespace vsgpu

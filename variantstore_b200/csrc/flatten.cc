@@ -217,6 +217,10 @@ void flatten(const SerData& d, FlatIndex& f) {
 		}
 	}
 	f.rec_begin[M] = f.R = (uint32_t)f.rec_k.size(); f.cent_begin[M] = (uint32_t)f.cent.size();
+	if (f.cent.size() >= (1u << 30)) fail("too many walk entries for one shard");
+	f.row_words = (uint32_t)(((f.cent.size() + 32) / 32 + 31) / 32 * 32);   // one spare word past the end
+	f.marker_bits.assign(f.row_words, 0);
+	for (size_t c = 0; c < f.cent.size(); c++) if (f.cent[c].tgt & kEntMarker) f.marker_bits[c >> 5] |= 1u << (c & 31);
 
 	// suspect duplicates for t6: an earlier record with the same (pos, alt) inside the preceding run
 	// of records whose pos is >= this one's.  Ranges containing a suspect are re-counted on the host

@@ -63,6 +63,8 @@ struct FlatIndex {
 	// compact t4 entries
 	std::vector<CEntry> cent;
 	std::vector<uint32_t> cent_vertex;    // target vertex id (kNone for markers)
+	uint32_t row_words = 0;               // hit-map row length in 32-bit words (multiple of 32)
+	std::vector<uint32_t> marker_bits;    // row_words: bit c = walk entry c is a marker
 
 	// t6/t7 branch records, (backbone index, out-order) order
 	std::vector<uint32_t> rec_k, rec_vertex, rec_pos, rec_refv, rec_altv;   // *_v: vertex whose sequence is the string, kNone = ""

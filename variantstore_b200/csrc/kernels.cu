@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) k_t4_walk(const DevIndex ix, uint64_t n, 
 		const uint64_t x = xs[i];
 		const uint32_t s = sample[i];
 		if (x < 1 || s == 0 || s >= ix.num_samples) atomicOr(status, kStatusBadRegion);
-		else walk_region(ix, s_top, x, ys[i], s, sink);
+		else walk_any(ix, s_top, x, ys[i], s, sink);
 		counts[i] = sink.n;
 	}
 }
@@ -75,7 +75,32 @@ __global__ void __launch_bounds__(256) k_t4_gather(const DevIndex ix, uint64_t n
 		const uint32_t cnt = counts[i];
 		const uint64_t off = offsets[i];
 		if (cnt <= kScratchHits) { for (uint32_t j = 0; j < cnt; j++) hits[off + j] = scratch[i * kScratchHits + j]; }
-		else { DirectSink sink{hits + off, 0}; walk_region(ix, s_top, xs[i], ys[i], sample[i], sink); }
+		else { DirectSink sink{hits + off, 0}; walk_any(ix, s_top, xs[i], ys[i], sample[i], sink); }
+	}
+}
+
+// ------------------------------------------------------------------ hit map build (once, at vsgpu_open)
+// one warp per walk entry: lanes sweep the words of the entry's carrier set and scatter its bits
+// into the sample rows.
+__global__ void __launch_bounds__(256) k_build_hitmap(const DevIndex ix, uint32_t* __restrict__ hitmap) {
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t c = warp; c < ix.num_cent; c += nwarps) {
+		const uint4 e = __ldg(ix.cent + c);
+		if (e.y & kEntMarker) continue;
+		const uint32_t bit = 1u << (c & 31); const uint64_t col = c >> 5;
+		if (ix.class_mode) {
+			for (uint32_t w = lane; w < ix.words_per_set; w += 32) {
+				uint64_t bits = __ldg(ix.bitmap + (uint64_t)e.z * ix.words_per_set + w);
+				while (bits) {
+					const uint32_t s = w * 64 + (uint32_t)__ffsll((long long)bits) - 1; bits &= bits - 1;
+					if (s != 0) atomicOr(hitmap + (uint64_t)s * ix.row_words + col, bit);
+				}
+			}
+		} else {
+			for (uint64_t i = __ldg(ix.list_begin + e.z) + lane, end = __ldg(ix.list_begin + e.z + 1); i < end; i += 32)
+				atomicOr(hitmap + (uint64_t)__ldg(ix.list_ids + i) * ix.row_words + col, bit);
+		}
 	}
 }
 
@@ -138,6 +163,11 @@ inline uint32_t grid_for(uint64_t n, uint32_t block, int ctas_per_sm) {
 
 }  // namespace
 
+cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream) {
+	if (ix.num_cent == 0) return cudaSuccess;
+	k_build_hitmap<<<grid_for((uint64_t)ix.num_cent * 32, 256, 8), 256, 0, stream>>>(ix, hitmap);
+	return cudaGetLastError();
+}
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint2* out, uint32_t* status, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	k_t6<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, x, y, out, status);

@@ -28,7 +28,15 @@ struct DevIndex {
 	const uint32_t* rec_pos;              // R
 	const uint64_t* rec_hash;             // R
 	const uint8_t* rec_flags;             // R
+	// sample-major hit map over the walk entries (nullptr: not built, kernels use the class bitmaps)
+	const uint32_t* hitmap;               // num_samples rows x row_words
+	uint32_t row_words;                   // 32-bit words per row, multiple of 32 (128-byte rows)
+	const uint32_t* marker_bits;          // row_words words: bit c = walk entry c is a marker
+	const uint32_t* cent_begin_k;         // M + 1: first walk entry with src >= k
 };
+
+// fills `hitmap` (zeroed, num_samples x row_words) from the walk entries and their carrier sets
+cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream);
 
 // All launchers enqueue on `stream` and return the CUDA error of the launch.
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint2* out, uint32_t* status, cudaStream_t stream);

@@ -115,8 +115,29 @@ void upload_index(vsgpu_index* ix) {
 	d.rec_pos = upload(ix, f.rec_pos);
 	d.rec_hash = upload(ix, f.rec_hash);
 	d.rec_flags = upload(ix, f.rec_flags);
+	d.marker_bits = upload(ix, f.marker_bits);
+	d.cent_begin_k = upload(ix, f.cent_begin);
+	d.row_words = f.row_words;
+	d.hitmap = nullptr;
 	CU(cudaMalloc((void**)&ix->d_status, 4));
 	CU(cudaMemset(ix->d_status, 0, 4));
+	// Sample-major hit map: num_samples rows of row_words words.  Built on the device; skipped (the
+	// kernels then test class bitmaps per entry) when it would not fit the budget:
+	// VSGPU_HITMAP_MAX_GB (default 64) and at most half of the free device memory.
+	const uint64_t hm_bytes = (uint64_t)f.num_samples * f.row_words * 4;
+	double max_gb = 64.0;
+	if (const char* e = getenv("VSGPU_HITMAP_MAX_GB")) max_gb = atof(e);
+	size_t free_b = 0, total_b = 0;
+	CU(cudaMemGetInfo(&free_b, &total_b));
+	if (!getenv("VSGPU_DISABLE_HITMAP") && hm_bytes <= (uint64_t)(max_gb * (1ull << 30)) && hm_bytes <= free_b / 2) {
+		uint32_t* hm = nullptr;
+		CU(cudaMalloc((void**)&hm, std::max<uint64_t>(hm_bytes, 16)));
+		ix->allocs.push_back(hm); ix->device_bytes += hm_bytes;
+		CU(cudaMemsetAsync(hm, 0, hm_bytes, ix->stream));
+		CU(launch_build_hitmap(d, hm, ix->stream));
+		CU(cudaStreamSynchronize(ix->stream));
+		d.hitmap = hm;
+	}
 }
 
 char* dup_text(const std::string& s) { char* p = (char*)malloc(s.size() + 1); if (!p) return nullptr; memcpy(p, s.data(), s.size()); p[s.size()] = 0; return p; }
