@@ -53,7 +53,7 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 	d.dlev = (const uint4*)f.dlev.data(); d.dinfo = f.dinfo.data(); d.t7rng = ix->t7.data(); d.cent = (const uint4*)f.cent.data();
 	d.bb_set = f.bb_set.data(); d.vstart = f.vstart.data(); d.bitmap = f.bitmap.data(); d.list_begin = f.list_begin.data();
 	d.list_ids = f.list_ids.data(); d.rec_pos = f.rec_pos.data(); d.rec_hash = f.rec_hash.data(); d.rec_flags = f.rec_flags.data();
-	d.marker_bits = f.marker_bits.data(); d.cent_begin_k = f.cent_begin.data(); d.row_words = f.row_words; d.hitmap = nullptr;
+	d.marker_bits = f.marker_bits.data(); d.cent_begin_k = f.cent_begin.data(); d.dtin = f.dtin.data(); d.cent_anc = (const uint2*)f.cent_anc.data(); d.row_words = f.row_words; d.hitmap = nullptr;
 	if (!getenv("VSGPU_DISABLE_HITMAP")) {   // host copy of k_build_hitmap
 		ix->hitmap.assign((size_t)f.num_samples * f.row_words, 0);
 		for (size_t c = 0; c < f.cent.size(); c++) {

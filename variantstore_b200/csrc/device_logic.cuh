@@ -191,21 +191,29 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, const uint32_t* s_top, uint64
 	if ((uint64_t)ldg(ix.lvl[0] + rk) > (uint64_t)y + 1) return;                // is_empty gate
 	const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
 	// ---- get_prev_vertex_with_sample (query.h:57-113)
-	uint64_t cur = (x64 >= ix.index_bits) ? ix.D - 1 : rk - 1;
+	// The reference steps back through node_list by out-degree until a neighbour carries the sample.
+	// Those steps are the ancestors of the start state in the back-walk forest, so instead of
+	// stepping: take the sample's carried entries below the start, highest first (one row word covers
+	// 32 entries), and stop at the first whose source is examined by an ancestor state.
+	const uint64_t cur = (x64 >= ix.index_bits) ? ix.D - 1 : rk - 1;            // ref_node_rank (index.h:135-148)
 	uint32_t c_found = kNoneU32;
-	for (;;) {
-		if (cur > ix.D) cur = 0;
-		if (cur <= 1) break;
+	if (cur >= 2) {
 		const uint64_t info = ldg(ix.dinfo + (cur - 1));
-		const uint32_t cb = (uint32_t)info, ncar = (uint32_t)(info >> 32) & 0xFFFF, deg = (uint32_t)(info >> 48);
-		for (uint32_t hi = cb + ncar; hi > cb;) {                                 // last carrier wins: scan from the top
-			const uint32_t len = hi - cb > 32 ? 32 : hi - cb;
-			const uint32_t bits = row_bits(row, hi - len, len);
-			if (bits) { c_found = hi - len + (31 - clz32(bits)); break; }
-			hi -= len;
+		const uint32_t pos = (uint32_t)info + ((uint32_t)(info >> 32) & 0xFFFF);    // entries below pos are candidates
+		if (pos > 0) {
+			const uint32_t t = ldg(ix.dtin + cur);
+			uint32_t w = (pos - 1) >> 5;
+			uint32_t m = ldg(row + w) & (0xFFFFFFFFu >> (31 - ((pos - 1) & 31)));
+			for (;;) {
+				while (m == 0 && w > 0) { w--; m = ldg(row + w); }
+				if (m == 0) break;
+				const uint32_t b = 31 - clz32(m);
+				m &= ~(1u << b);
+				const uint32_t p = (w << 5) + b;
+				const uint2 a = ldg(ix.cent_anc + p);
+				if (a.x <= t && t <= a.y) { c_found = p; break; }                      // last carrier of the nearest examined vertex
+			}
 		}
-		cur -= deg;
-		if (c_found != kNoneU32) break;
 	}
 	// ---- forward walk (query.h:649-716)
 	const uint32_t e_y = y ? rank_le(ix, s_top, y - 1) : 0;

@@ -253,6 +253,27 @@ void flatten(const SerData& d, FlatIndex& f) {
 		if (kb < M) { f.t7_lo[i] = f.rec_begin[kb]; f.t7_hi[i] = f.rec_begin[kb + 1]; }
 	}
 	f.dlev[D] = DLevel{M, f.R, M ? f.rec_begin[M - 1] : 0, (uint32_t)f.cent.size()};
+
+	// ------------------------------------------------------------ back-walk forest
+	// State c (= cur_ref_node_idx) examines node_list[c-1] and moves to c - outdeg; states 0 and 1 end
+	// the walk at vertex 0.  parent < child, so subtree sizes and pre-order times need no recursion.
+	{
+		std::vector<uint32_t> parent(D + 1, 0), sz(D + 1, 1), slot(D + 1, 0);
+		for (uint32_t c = 2; c <= D; c++) { uint32_t deg = outdeg[f.dlev[c - 1].k]; parent[c] = c >= deg ? c - deg : 0; if (parent[c] >= c) parent[c] = c - 1; }
+		for (uint32_t c = D; c >= 2; c--) sz[parent[c]] += sz[c];
+		f.dtin.assign(D + 1, 0);
+		f.dtin[0] = 0; slot[0] = 1;
+		if (D >= 1) { f.dtin[1] = sz[0]; slot[1] = f.dtin[1] + 1; }
+		for (uint32_t c = 2; c <= D; c++) { f.dtin[c] = slot[parent[c]]; slot[parent[c]] += sz[c]; slot[c] = f.dtin[c] + 1; }
+		f.cent_anc.assign(2 * f.cent.size(), 0);
+		std::vector<uint32_t> k2c(M, 0);
+		for (uint32_t i = 1; i < D; i++) k2c[f.dlev[i].k] = i + 1;        // node_list[i] is examined by state i + 1 (>= 2)
+		for (size_t e = 0; e < f.cent.size(); e++) {
+			uint32_t c = (f.cent[e].tgt & kEntMarker) ? 0 : k2c[f.cent[e].src];
+			if (c >= 2) { f.cent_anc[2 * e] = f.dtin[c]; f.cent_anc[2 * e + 1] = f.dtin[c] + sz[c] - 1; }
+			else { f.cent_anc[2 * e] = 1; f.cent_anc[2 * e + 1] = 0; }
+		}
+	}
 }
 
 }  // namespace vsgpu

@@ -65,6 +65,10 @@ struct FlatIndex {
 	std::vector<uint32_t> cent_vertex;    // target vertex id (kNone for markers)
 	uint32_t row_words = 0;               // hit-map row length in 32-bit words (multiple of 32)
 	std::vector<uint32_t> marker_bits;    // row_words: bit c = walk entry c is a marker
+	// get_prev_vertex_with_sample steps back through node_list by out-degree (query.h:103); as a forest
+	// parent(c) = c - outdeg(node_list[c-1]) that walk visits exactly the ancestors of its start.
+	std::vector<uint32_t> dtin;           // D + 1: Euler-tour entry time of back-walk state c
+	std::vector<uint32_t> cent_anc;       // 2 per walk entry: [tin, last] of the state that examines its source vertex (1,0: never examined)
 
 	// t6/t7 branch records, (backbone index, out-order) order
 	std::vector<uint32_t> rec_k, rec_vertex, rec_pos, rec_refv, rec_altv;   // *_v: vertex whose sequence is the string, kNone = ""

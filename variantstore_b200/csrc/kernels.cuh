@@ -33,6 +33,8 @@ struct DevIndex {
 	uint32_t row_words;                   // 32-bit words per row, multiple of 32 (128-byte rows)
 	const uint32_t* marker_bits;          // row_words words: bit c = walk entry c is a marker
 	const uint32_t* cent_begin_k;         // M + 1: first walk entry with src >= k
+	const uint32_t* dtin;                 // D + 1: pre-order time of back-walk state c in the back-walk forest
+	const uint2* cent_anc;                // per walk entry: pre-order interval of the state examining its source
 };
 
 // fills `hitmap` (zeroed, num_samples x row_words) from the walk entries and their carrier sets

@@ -117,6 +117,8 @@ void upload_index(vsgpu_index* ix) {
 	d.rec_flags = upload(ix, f.rec_flags);
 	d.marker_bits = upload(ix, f.marker_bits);
 	d.cent_begin_k = upload(ix, f.cent_begin);
+	d.dtin = upload(ix, f.dtin);
+	d.cent_anc = (const uint2*)upload(ix, f.cent_anc);
 	d.row_words = f.row_words;
 	d.hitmap = nullptr;
 	CU(cudaMalloc((void**)&ix->d_status, 4));
