@@ -20,7 +20,7 @@ using namespace vsgpu;
 struct vsgpu_result { std::vector<uint64_t> offsets; std::vector<uint32_t> hits; };
 struct vsgpu_index : HostIndex {
 	DevIndex dev;
-	std::vector<std::vector<uint32_t>> lv;
+	std::vector<uint32_t> bucket;
 	std::vector<uint2> t7;
 	std::vector<uint32_t> hitmap;
 };
@@ -40,14 +40,14 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 	*out = nullptr;
 	std::unique_ptr<vsgpu_index> ix(new vsgpu_index);
 	int stage = 0;
-	try { build_host_index(prefix, *ix, &stage); build_levels(ix->flat, ix->lv); }
+	try { build_host_index(prefix, *ix, &stage); }
 	catch (const std::exception& e) { return set_err(stage == 0 ? VSGPU_EIO : VSGPU_ESHAPE, e.what()); }
 	FlatIndex& f = ix->flat; DevIndex& d = ix->dev;
 	memset(&d, 0, sizeof d);
 	d.D = f.D; d.M = f.M; d.R = f.R; d.num_cent = (uint32_t)f.cent.size(); d.words_per_set = f.words_per_set;
 	d.num_samples = f.num_samples; d.class_mode = f.class_mode; d.index_bits = f.index_bits; d.last_end = ix->last_end;
-	d.nlvl = (uint32_t)ix->lv.size();
-	for (size_t i = 0; i < ix->lv.size(); i++) { d.lvl[i] = ix->lv[i].data(); d.lvl_n[i] = (uint32_t)ix->lv[i].size(); }
+	build_buckets(f, ix->bucket, d.bucket_shift);
+	d.nbuckets = (uint32_t)ix->bucket.size() - 1; d.bucket = ix->bucket.data(); d.dstart = f.dstart.data();
 	ix->t7.resize(f.D);
 	for (uint32_t i = 0; i < f.D; i++) ix->t7[i] = make_uint2(f.t7_lo[i], f.t7_hi[i]);
 	d.dlev = (const uint4*)f.dlev.data(); d.dinfo = f.dinfo.data(); d.t7rng = ix->t7.data(); d.cent = (const uint4*)f.cent.data();
@@ -91,11 +91,10 @@ int vsgpu_sample_id(const vsgpu_index* ix, const char* name, uint32_t* id) {
 const char* vsgpu_sample_name(const vsgpu_index* ix, uint32_t id) { return id < ix->ser.num_samples ? ix->ser.sample_names[id].c_str() : nullptr; }
 
 int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts) {
-	const uint32_t* top = ix->dev.lvl[ix->dev.nlvl - 1];
 	std::vector<uint32_t> tmp;
 	for (uint64_t i = 0; i < n; i++) {
 		bool bad = false;
-		uint2 r = logic::t6_bounds(ix->dev, top, x[i], y[i], &bad);
+		uint2 r = logic::t6_bounds(ix->dev, x[i], y[i], &bad);
 		if (bad) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
 		if (lo) lo[i] = r.x;
 		if (hi) hi[i] = r.y;
@@ -105,13 +104,12 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 }
 
 int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_result** out) {
-	const uint32_t* top = ix->dev.lvl[ix->dev.nlvl - 1];
 	std::unique_ptr<vsgpu_result> r(new vsgpu_result);
 	r->offsets.assign(n + 1, 0);
 	VecSink sink{&r->hits};
 	for (uint64_t i = 0; i < n; i++) {
 		if (x[i] < 1 || s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
-		logic::walk_any(ix->dev, top, x[i], y[i], s[i], sink);
+		logic::walk_any(ix->dev, x[i], y[i], s[i], sink);
 		r->offsets[i + 1] = r->hits.size();
 	}
 	*out = r.release();
@@ -123,10 +121,9 @@ const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r->hits.data()
 void vsgpu_result_free(vsgpu_result* r) { delete r; }
 
 int vsgpu_query_t7(vsgpu_index* ix, uint64_t n, const uint64_t* pos, const char* const* refs, const char* const* alts, uint32_t* rec) {
-	const uint32_t* top = ix->dev.lvl[ix->dev.nlvl - 1];
 	for (uint64_t i = 0; i < n; i++) {
 		bool bad = false;
-		uint32_t r = logic::t7_lookup(ix->dev, top, pos[i], hash_query(refs[i], alts[i]), &bad);
+		uint32_t r = logic::t7_lookup(ix->dev, pos[i], hash_query(refs[i], alts[i]), &bad);
 		if (bad) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
 		rec[i] = t7_confirm(ix, pos[i], refs[i], alts[i], r);
 	}

@@ -29,28 +29,16 @@ constexpr uint32_t kNoneU32 = 0xFFFFFFFFu;
 
 VSGPU_HD uint32_t clamp_pos(uint64_t v) { return v > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)v; }
 
-// number of keys <= x in a sorted run of n <= 32 keys living in one 128-byte line
-VSGPU_HD uint32_t count_le_node(const uint32_t* __restrict__ p, uint32_t n, uint32_t x) {
-	uint32_t lo = 0, hi = n;
-#pragma unroll
-	for (int i = 0; i < 6; i++) {
-		if (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (ldg(p + mid) <= x) lo = mid + 1; else hi = mid; }
-	}
+// rank(x) = number of distinct backbone starts <= x  (rank_rrrb(pos) of index.h:128,142,158).
+// A direct-mapped bucket table over positions gives the slice of `dstart` that can hold the answer
+// (about kBucketTarget keys, one or two 128-byte lines); a short binary search finishes it.
+VSGPU_HD uint32_t rank_le(const DevIndex& ix, uint32_t x) {
+	uint32_t b = x >> ix.bucket_shift;
+	if (b >= ix.nbuckets) b = ix.nbuckets - 1;
+	const uint2 r = make_uint2(ldg(ix.bucket + b), ldg(ix.bucket + b + 1));
+	uint32_t lo = r.x, hi = b + 1 == ix.nbuckets ? ix.D : r.y;
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ldg(ix.dstart + mid) <= x) lo = mid + 1; else hi = mid; }
 	return lo;
-}
-
-// rank(x) = number of distinct backbone starts <= x  (rank_rrrb(pos) of index.h:128,142,158)
-VSGPU_HD uint32_t rank_le(const DevIndex& ix, const uint32_t* s_top, uint32_t x) {
-	uint32_t lo = 0, hi = ix.lvl_n[ix.nlvl - 1];
-	while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (s_top[mid] <= x) lo = mid + 1; else hi = mid; }
-	uint32_t c = lo;
-	for (int lev = (int)ix.nlvl - 2; lev >= 0; lev--) {
-		if (c == 0) return 0;
-		uint32_t base = (c - 1) * kFan;
-		uint32_t n = umin(kFan, ix.lvl_n[lev] - base);
-		c = base + count_le_node(ix.lvl[lev] + base, n, x);
-	}
-	return c;
 }
 
 VSGPU_HD bool member(const DevIndex& ix, uint32_t s, uint32_t set_id) {
@@ -61,16 +49,16 @@ VSGPU_HD bool member(const DevIndex& ix, uint32_t s, uint32_t set_id) {
 }
 
 // ------------------------------------------------------------------ t6 slice bounds (query.h:736-784)
-VSGPU_HD uint2 t6_bounds(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, bool* bad) {
+VSGPU_HD uint2 t6_bounds(const DevIndex& ix, uint64_t x64, uint64_t y64, bool* bad) {
 	uint2 r = make_uint2(0, 0);
 	if (x64 < 1) { *bad = true; return r; }
 	if (x64 > ix.index_bits) return r;                                     // is_empty: pos_x > size -> empty
 	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
-	const uint32_t rk = rank_le(ix, s_top, x);
+	const uint32_t rk = rank_le(ix, x);
 	// gate (index.h:158-165): next distinct start s' must satisfy s' - 1 <= y
-	if (rk >= 1 && rk < ix.D && (uint64_t)ldg(ix.lvl[0] + rk) <= (uint64_t)y + 1) {
+	if (rk >= 1 && rk < ix.D && (uint64_t)ldg(ix.dstart + rk) <= (uint64_t)y + 1) {
 		const uint32_t lo = ldg(&ix.dlev[rk - 1].y);
-		const uint32_t e = y ? rank_le(ix, s_top, y - 1) : 0;               // first start >= y
+		const uint32_t e = y ? rank_le(ix, y - 1) : 0;               // first start >= y
 		uint32_t hi;
 		if (e < ix.D) hi = ldg(&ix.dlev[e].z);                              // rec_begin[k(e) - 1]
 		else hi = ((uint64_t)ix.last_end >= y) ? ldg(&ix.dlev[ix.D].z) : ix.R;
@@ -80,10 +68,10 @@ VSGPU_HD uint2 t6_bounds(const DevIndex& ix, const uint32_t* s_top, uint64_t x64
 }
 
 // ------------------------------------------------------------------ t7 lookup (query.h:792-823)
-VSGPU_HD uint32_t t7_lookup(const DevIndex& ix, const uint32_t* s_top, uint64_t p64, uint64_t h, bool* bad) {
+VSGPU_HD uint32_t t7_lookup(const DevIndex& ix, uint64_t p64, uint64_t h, bool* bad) {
 	if (p64 < 1) { *bad = true; return kNoneU32; }
 	const uint32_t p = clamp_pos(p64);
-	uint32_t rk = p64 >= ix.index_bits ? ix.D : rank_le(ix, s_top, p);      // Index::find (index.h:125-132)
+	uint32_t rk = p64 >= ix.index_bits ? ix.D : rank_le(ix, p);      // Index::find (index.h:125-132)
 	if (rk < 1) rk = 1;
 	const uint2 rng = ldg(ix.t7rng + (rk - 1));
 	for (uint32_t r = rng.x; r < rng.y; r++)
@@ -102,12 +90,12 @@ struct DirectSink {
 };
 
 template <class Sink>
-VSGPU_HD void walk_region(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+VSGPU_HD void walk_region(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
 	if (x64 > ix.index_bits) return;
 	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
-	const uint32_t rk = rank_le(ix, s_top, x);
+	const uint32_t rk = rank_le(ix, x);
 	if (rk < 1 || rk >= ix.D) return;
-	if ((uint64_t)ldg(ix.lvl[0] + rk) > (uint64_t)y + 1) return;                // is_empty gate
+	if ((uint64_t)ldg(ix.dstart + rk) > (uint64_t)y + 1) return;                // is_empty gate
 	// ---- get_prev_vertex_with_sample (query.h:57-113)
 	uint64_t cur = (x64 >= ix.index_bits) ? ix.D - 1 : rk - 1;                   // ref_node_rank (index.h:135-148)
 	uint32_t c_found = kNoneU32;
@@ -121,7 +109,7 @@ VSGPU_HD void walk_region(const DevIndex& ix, const uint32_t* s_top, uint64_t x6
 		if (c_found != kNoneU32) break;
 	}
 	// ---- forward walk (query.h:649-716)
-	const uint32_t e_y = y ? rank_le(ix, s_top, y - 1) : 0;
+	const uint32_t e_y = y ? rank_le(ix, y - 1) : 0;
 	const uint32_t k_end = ldg(&ix.dlev[e_y].x);                                // first backbone vertex whose start >= y
 	uint32_t cur_k = 0, c = 0;
 	if (c_found != kNoneU32) {
@@ -183,12 +171,12 @@ VSGPU_HD uint32_t row_bits(const uint32_t* row, uint32_t pos, uint32_t len) {
 }
 
 template <class Sink>
-VSGPU_HD void walk_region_fast(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
 	if (x64 > ix.index_bits) return;
 	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
-	const uint32_t rk = rank_le(ix, s_top, x);
+	const uint32_t rk = rank_le(ix, x);
 	if (rk < 1 || rk >= ix.D) return;
-	if ((uint64_t)ldg(ix.lvl[0] + rk) > (uint64_t)y + 1) return;                // is_empty gate
+	if ((uint64_t)ldg(ix.dstart + rk) > (uint64_t)y + 1) return;                // is_empty gate
 	const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
 	// ---- get_prev_vertex_with_sample (query.h:57-113)
 	// The reference steps back through node_list by out-degree until a neighbour carries the sample.
@@ -216,7 +204,7 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, const uint32_t* s_top, uint64
 		}
 	}
 	// ---- forward walk (query.h:649-716)
-	const uint32_t e_y = y ? rank_le(ix, s_top, y - 1) : 0;
+	const uint32_t e_y = y ? rank_le(ix, y - 1) : 0;
 	const uint4 dl = ldg(ix.dlev + e_y);
 	const uint32_t k_end = dl.x;                                                // first backbone vertex whose start >= y
 	uint32_t limit = dl.w;                                                      // entries >= limit have src >= k_end
@@ -269,9 +257,9 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, const uint32_t* s_top, uint64
 }
 
 template <class Sink>
-VSGPU_HD void walk_any(const DevIndex& ix, const uint32_t* s_top, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
-	if (ix.hitmap) walk_region_fast(ix, s_top, x64, y64, s, sink);
-	else walk_region(ix, s_top, x64, y64, s, sink);
+VSGPU_HD void walk_any(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	if (ix.hitmap) walk_region_fast(ix, x64, y64, s, sink);
+	else walk_region(ix, x64, y64, s, sink);
 }
 
 }  // namespace logic

@@ -20,8 +20,8 @@ struct HostIndex {
 
 // load_ser + flatten + derived fields; throws std::runtime_error
 void build_host_index(const std::string& prefix, HostIndex& h, int* stage = nullptr);
-// sampled search hierarchy over dstart: lv[0] = dstart, lv[i+1][j] = lv[i][32 j], until <= kTopMax keys
-void build_levels(const FlatIndex& f, std::vector<std::vector<uint32_t>>& lv);
+// direct-mapped rank buckets over positions: bucket[b] = number of distinct starts < (b << shift)
+void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& shift);
 
 void append_seq(const HostIndex* ix, uint32_t v, std::string& out);
 void append_carriers(const HostIndex* ix, uint32_t v, std::string& out);

@@ -5,17 +5,16 @@
 
 namespace vsgpu {
 
-constexpr int kMaxLevels = 6;
-constexpr uint32_t kFan = 32;           // keys per search node = one 128-byte line
-constexpr uint32_t kTopMax = 4096;      // top search level staged in shared memory (16 KB)
 constexpr uint32_t kScratchHits = 8;    // t4 hits kept inline per region before the overflow path
+constexpr uint32_t kBucketTarget = 12;  // average number of distinct starts per rank bucket
 
 struct DevIndex {
-	uint32_t D, M, R, num_cent, words_per_set, num_samples, class_mode, nlvl;
+	uint32_t D, M, R, num_cent, words_per_set, num_samples, class_mode;
 	uint64_t index_bits;
 	uint32_t last_end;                    // vstart[M-1] + vlen[M-1]
-	const uint32_t* lvl[kMaxLevels];      // lvl[0] = dstart, lvl[i+1][j] = lvl[i][32 j]
-	uint32_t lvl_n[kMaxLevels];
+	const uint32_t* dstart;               // D distinct backbone starts, ascending
+	const uint32_t* bucket;               // nbuckets + 1: bucket[b] = number of starts < (b << bucket_shift)
+	uint32_t nbuckets, bucket_shift;
 	const uint4* dlev;                    // D + 1: {k, rec_lo, rec_hi_prev, cent_begin}
 	const uint64_t* dinfo;                // D
 	const uint2* t7rng;                   // D
@@ -43,17 +42,13 @@ cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream
 // All launchers enqueue on `stream` and return the CUDA error of the launch.
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint2* out, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const uint64_t* qhash, uint32_t* rec, uint32_t* status, cudaStream_t stream);
-// t4 phase 1: walk every region; counts[i] = hits, scratch[i*kScratchHits ..] = first hits
-cudaError_t launch_t4_walk(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                           uint32_t* counts, uint32_t* scratch, uint32_t* status, cudaStream_t stream);
-// exclusive scan of counts -> offsets[n+1] (single pass, decoupled look-back). `tile_state` needs
-// scan_state_words(n) zeroed 64-bit words.
-uint64_t scan_state_words(uint64_t n);
-cudaError_t launch_scan(uint64_t n, const uint32_t* counts, uint64_t* offsets, uint64_t* tile_state, cudaStream_t stream);
-// t4 phase 2: ordered compaction into hits[] (capacity `cap`; *overflow set when offsets[n] > cap)
-cudaError_t launch_t4_gather(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                             const uint32_t* counts, const uint32_t* scratch, const uint64_t* offsets, uint32_t* hits,
-                             uint64_t cap, uint32_t* status, cudaStream_t stream);
+// t4: one launch — walk, CTA scan, decoupled look-back, ordered write of the hits.
+// offsets[n+1] (exclusive, offsets[n] = total); hits has room for `cap` codes, kStatusOverflow is
+// raised (and nothing past cap written) when the total exceeds it.  `tile_state` needs
+// t4_state_words(n) zeroed 64-bit words before every launch.
+uint64_t t4_state_words(uint64_t n);
+cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
+                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, cudaStream_t stream);
 
 // status word bits
 constexpr uint32_t kStatusBadRegion = 1;   // some region had x < 1

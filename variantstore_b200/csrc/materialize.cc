@@ -10,13 +10,18 @@
 
 namespace vsgpu {
 
-void build_levels(const FlatIndex& f, std::vector<std::vector<uint32_t>>& lv) {
-	lv.clear(); lv.push_back(f.dstart);
-	while (lv.back().size() > kTopMax) {
-		const auto& b = lv.back(); std::vector<uint32_t> s((b.size() + kFan - 1) / kFan);
-		for (size_t j = 0; j < s.size(); j++) s[j] = b[j * kFan];
-		lv.push_back(std::move(s));
-		if (lv.size() > (size_t)kMaxLevels) throw std::runtime_error("vsgpu: index too large for the search hierarchy");
+void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& shift) {
+	const uint64_t span = std::max<uint64_t>(f.dstart.empty() ? 1 : f.dstart.back(), 1);
+	shift = 0;
+	while (shift < 31 && (span >> (shift + 1)) * kBucketTarget >= f.D) shift++;    // ~kBucketTarget starts per bucket
+	while ((span >> shift) + 2 > (1u << 28)) shift++;
+	const uint32_t nb = (uint32_t)(span >> shift) + 1;
+	bucket.assign(nb + 1, 0);
+	size_t j = 0;
+	for (uint32_t b = 0; b <= nb; b++) {
+		const uint64_t lim = (uint64_t)b << shift;
+		while (j < f.dstart.size() && f.dstart[j] < lim) j++;
+		bucket[b] = (uint32_t)j;
 	}
 }
 

@@ -96,10 +96,11 @@ void upload_index(vsgpu_index* ix) {
 	d.D = f.D; d.M = f.M; d.R = f.R; d.num_cent = (uint32_t)f.cent.size(); d.words_per_set = f.words_per_set;
 	d.num_samples = f.num_samples; d.class_mode = f.class_mode ? 1 : 0; d.index_bits = f.index_bits;
 	d.last_end = ix->last_end;
-	std::vector<std::vector<uint32_t>> lv;
-	build_levels(f, lv);
-	d.nlvl = (uint32_t)lv.size();
-	for (size_t i = 0; i < lv.size(); i++) { d.lvl[i] = upload(ix, lv[i]); d.lvl_n[i] = (uint32_t)lv[i].size(); }
+	std::vector<uint32_t> bucket;
+	build_buckets(f, bucket, d.bucket_shift);
+	d.nbuckets = (uint32_t)bucket.size() - 1;
+	d.dstart = upload(ix, f.dstart);
+	d.bucket = upload(ix, bucket);
 	static_assert(sizeof(DLevel) == sizeof(uint4) && sizeof(CEntry) == sizeof(uint4), "AoS rows are 16 bytes");
 	d.dlev = (const uint4*)upload(ix, f.dlev);
 	d.dinfo = upload(ix, f.dinfo);
@@ -242,26 +243,35 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 
 // ------------------------------------------------------------------ t4
 namespace {
-void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& counts, DevBuf& scratch,
-            DevBuf& offsets, DevBuf& state, DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr) {
-	CU(counts.ensure(n * 4)); CU(scratch.ensure(n * 4 * kScratchHits)); CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(scan_state_words(n) * 8));
-	CU(cudaMemsetAsync(state.p, 0, scan_state_words(n) * 8, ix->stream));
+// One pass of t4 over device-resident inputs.  The hit buffer is sized from a guess (4 codes per
+// region) and, if the kernel reports an overflow, re-sized from the total it computed and the pass
+// repeated — results are deterministic, so a batch pays that at most once.
+void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
+            DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr) {
+	CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(t4_state_words(n) * 8));
+	if (hits_cap == 0) { hits_cap = std::max<uint64_t>(4 * n, 1024); CU(hits.ensure(hits_cap * 4)); }
+	CU(cudaMemsetAsync(state.p, 0, t4_state_words(n) * 8, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[0], ix->stream));
-	CU(launch_t4_walk(ix->dev, n, dx, dy, ds, counts.as<uint32_t>(), scratch.as<uint32_t>(), ix->d_status, ix->stream));
+	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), ix->d_status, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[1], ix->stream));
-	CU(launch_scan(n, counts.as<uint32_t>(), offsets.as<uint64_t>(), state.as<uint64_t>(), ix->stream));
-	if (ev) CU(cudaEventRecord(ev[2], ix->stream));
-	if (launches) *launches = 2;
-	if (hits_cap == 0) {   // first run of this shape: size the output from the scanned total
+	if (launches) *launches = 1;
+}
+
+// Synchronise and resolve a possible overflow of the hit buffer by re-running with the exact size.
+// Returns the status bits left after that.
+uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
+                   DevBuf& hits, uint64_t& hits_cap) {
+	uint32_t st = read_status(ix);
+	if (st & kStatusOverflow) {
 		uint64_t total = 0;
 		CU(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
 		CU(cudaStreamSynchronize(ix->stream));
-		hits_cap = std::max<uint64_t>(total, 1);
+		hits_cap = total + total / 16 + 1024;
 		CU(hits.ensure(hits_cap * 4));
+		run_t4(ix, n, dx, dy, ds, offsets, state, hits, hits_cap, nullptr);
+		st = (st & ~kStatusOverflow) | read_status(ix);
 	}
-	CU(launch_t4_gather(ix->dev, n, dx, dy, ds, counts.as<uint32_t>(), scratch.as<uint32_t>(), offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, ix->d_status, ix->stream));
-	if (ev) CU(cudaEventRecord(ev[3], ix->stream));
-	if (launches) *launches = 3;
+	return st;
 }
 }  // namespace
 
@@ -278,14 +288,16 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
 			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream));
 			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream));
-			uint64_t cap = 0;
-			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcounts, ix->bscratch, ix->boffsets, ix->bstate, ix->bhits, cap, nullptr);
-			CU(cudaMemcpyAsync(r->offsets.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
-			r->hits.resize(cap);
-			CU(cudaMemcpyAsync(r->hits.data(), ix->bhits.p, cap * 4, cudaMemcpyDeviceToHost, ix->stream));
-			uint32_t st = read_status(ix);
+			uint64_t cap = ix->bhits.cap / 4;
+			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr);
+			uint32_t st = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
+			CU(cudaMemcpyAsync(r->offsets.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
+			CU(cudaStreamSynchronize(ix->stream));
+			r->hits.resize(r->offsets[n]);
+			if (r->offsets[n]) CU(cudaMemcpyAsync(r->hits.data(), ix->bhits.p, r->offsets[n] * 4, cudaMemcpyDeviceToHost, ix->stream));
+			CU(cudaStreamSynchronize(ix->stream));
 			r->hits.resize(r->offsets[n]);
 		}
 		*out = r.release();
@@ -405,7 +417,7 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
 		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), ix->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), ix->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
-		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->counts, b->scratch, b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev);
+		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
@@ -435,17 +447,20 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 			uint32_t st = read_status(ix);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
 		} else {
-			if (counts) CU(cudaMemcpyAsync(counts, b->counts.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
-			std::unique_ptr<vsgpu_result> r;
-			if (out) {
-				r.reset(new vsgpu_result); r->offsets.resize(n + 1); r->hits.resize(b->hits_cap);
-				CU(cudaMemcpyAsync(r->offsets.data(), b->offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
-				CU(cudaMemcpyAsync(r->hits.data(), b->hits.p, b->hits_cap * 4, cudaMemcpyDeviceToHost, ix->stream));
-			}
-			uint32_t st = read_status(ix);
+			uint32_t st = finish_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
-			if (out) { r->hits.resize(r->offsets[n]); *out = r.release(); }
+			std::unique_ptr<vsgpu_result> r(new vsgpu_result);
+			r->offsets.resize(n + 1);
+			CU(cudaMemcpyAsync(r->offsets.data(), b->offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
+			CU(cudaStreamSynchronize(ix->stream));
+			if (counts) for (uint64_t i = 0; i < n; i++) counts[i] = (uint32_t)(r->offsets[i + 1] - r->offsets[i]);
+			if (out) {
+				r->hits.resize(r->offsets[n]);
+				if (r->offsets[n]) CU(cudaMemcpyAsync(r->hits.data(), b->hits.p, r->offsets[n] * 4, cudaMemcpyDeviceToHost, ix->stream));
+				CU(cudaStreamSynchronize(ix->stream));
+				*out = r.release();
+			}
 		}
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
