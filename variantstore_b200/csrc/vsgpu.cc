@@ -73,7 +73,8 @@ struct vsgpu_batch {
 	uint64_t algo_bytes = 0; bool algo_valid = false;
 	std::vector<uint64_t> hx, hy;   // host copies kept for the byte accounting
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &counts, &scratch, &offsets, &hits, &state, &rec}) b->release(); }
+	uint32_t* d_status = nullptr;    // per batch: several batches may be in flight on one index
+	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &counts, &scratch, &offsets, &hits, &state, &rec}) b->release(); }
 };
 
 namespace {
@@ -151,11 +152,12 @@ int check_device(vsgpu_index* ix) {
 	return VSGPU_OK;
 }
 
-uint32_t read_status(vsgpu_index* ix) {
+uint32_t read_status(vsgpu_index* ix, uint32_t* d_status = nullptr) {
+	if (!d_status) d_status = ix->d_status;
 	uint32_t st = 0;
-	cudaMemcpyAsync(&st, ix->d_status, 4, cudaMemcpyDeviceToHost, ix->stream);
+	cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, ix->stream);
 	cudaStreamSynchronize(ix->stream);
-	if (st) { cudaMemsetAsync(ix->d_status, 0, 4, ix->stream); }
+	if (st) { cudaMemsetAsync(d_status, 0, 4, ix->stream); }
 	return st;
 }
 
@@ -247,31 +249,32 @@ namespace {
 // region) and, if the kernel reports an overflow, re-sized from the total it computed and the pass
 // repeated — results are deterministic, so a batch pays that at most once.
 void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
-            DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr) {
+            DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr, uint32_t* d_status = nullptr) {
+	if (!d_status) d_status = ix->d_status;
 	CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(t4_state_words(n) * 8));
 	if (hits_cap == 0) { hits_cap = std::max<uint64_t>(4 * n, 1024); CU(hits.ensure(hits_cap * 4)); }
 	CU(cudaMemsetAsync(state.p, 0, t4_state_words(n) * 8, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[0], ix->stream));
-	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), ix->d_status, ix->stream));
+	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[1], ix->stream));
 	if (launches) *launches = 1;
 }
 
-// Synchronise and resolve a possible overflow of the hit buffer by re-running with the exact size.
+// Synchronise and resolve an overflow of the hit buffer by re-running with the exact size.  The
+// decision is taken from the total the kernel computed, not from the (shared) status word.
 // Returns the status bits left after that.
 uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
-                   DevBuf& hits, uint64_t& hits_cap) {
-	uint32_t st = read_status(ix);
-	if (st & kStatusOverflow) {
-		uint64_t total = 0;
-		CU(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
-		CU(cudaStreamSynchronize(ix->stream));
+                   DevBuf& hits, uint64_t& hits_cap, uint32_t* d_status) {
+	uint64_t total = 0;
+	CU(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
+	uint32_t st = read_status(ix, d_status);
+	if (total > hits_cap) {
 		hits_cap = total + total / 16 + 1024;
 		CU(hits.ensure(hits_cap * 4));
-		run_t4(ix, n, dx, dy, ds, offsets, state, hits, hits_cap, nullptr);
-		st = (st & ~kStatusOverflow) | read_status(ix);
+		run_t4(ix, n, dx, dy, ds, offsets, state, hits, hits_cap, nullptr, nullptr, d_status);
+		st = (st | read_status(ix, d_status));
 	}
-	return st;
+	return st & ~kStatusOverflow;
 }
 }  // namespace
 
@@ -290,7 +293,7 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream));
 			uint64_t cap = ix->bhits.cap / 4;
 			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr);
-			uint32_t st = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap);
+			uint32_t st = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
 			CU(cudaMemcpyAsync(r->offsets.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
@@ -390,6 +393,7 @@ int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x,
 	try {
 		std::unique_ptr<vsgpu_batch> b(new vsgpu_batch);
 		b->idx = ix; b->type = type; b->n = n;
+		CU(cudaMalloc((void**)&b->d_status, 4)); CU(cudaMemset(b->d_status, 0, 4));
 		b->hx.assign(x, x + n); if (y) b->hy.assign(y, y + n);
 		CU(b->x.ensure(n * 8));
 		CU(cudaMemcpyAsync(b->x.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
@@ -415,9 +419,9 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 	if (int rc = check_device(ix)) return rc;
 	try {
 		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
-		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), ix->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
-		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), ix->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
-		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev);
+		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
@@ -431,7 +435,7 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 		if (b->type == 6) {
 			std::vector<uint2> o(n);
 			CU(cudaMemcpyAsync(o.data(), b->out.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
-			uint32_t st = read_status(ix);
+			uint32_t st = read_status(ix, b->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
 			std::vector<uint32_t> tmp;
 			for (uint64_t i = 0; i < n; i++) {
@@ -444,10 +448,10 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 			}
 		} else if (b->type == 7) {
 			if (rec_lo) CU(cudaMemcpyAsync(rec_lo, b->rec.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
-			uint32_t st = read_status(ix);
+			uint32_t st = read_status(ix, b->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
 		} else {
-			uint32_t st = finish_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap);
+			uint32_t st = finish_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, b->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
 			std::unique_ptr<vsgpu_result> r(new vsgpu_result);
