@@ -236,11 +236,11 @@ def run_vsgpu(args):
     py = torch.from_numpy(y.astype(np.int64)).pin_memory()
     ps = torch.from_numpy(s.astype(np.int32)).pin_memory()
     lib, h = idx._lib, idx._h
-    lo, hi, cnt = (np.zeros(n, np.uint32) for _ in range(3))
+    plo, phi, pcnt = (torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(3))      # page-locked result arrays
     vp = C.c_void_p
 
     def e2e_step():
-        rc = lib.vsgpu_query_t6(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(lo.ctypes.data), vp(hi.ctypes.data), vp(cnt.ctypes.data))
+        rc = lib.vsgpu_query_t6(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(plo.data_ptr()), vp(phi.data_ptr()), vp(pcnt.data_ptr()))
         assert rc == 0, lib.vsgpu_last_error()
         r = vp()
         rc = lib.vsgpu_query_t4(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(ps.data_ptr()), C.byref(r))
@@ -264,7 +264,7 @@ def run_vsgpu(args):
         e2e_s = float(t.item())
     e2e_val = 2 * n * world / e2e_s
     h2d = n * 16 + n * 20
-    d2h = n * 8 + (n + 1) * 8 + hits_total * 4
+    d2h = n * 8 + (n + 1) * 8 + hits_total * 4          # t6 lo+hi; t4 offsets + hit codes
 
     if rank != 0:
         if dist is not None:

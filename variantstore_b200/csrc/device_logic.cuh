@@ -41,6 +41,25 @@ VSGPU_HD uint32_t rank_le(const DevIndex& ix, uint32_t x) {
 	return lo;
 }
 
+// Two independent ranks at once: both bucket lookups are issued together and the two binary
+// searches advance in lock step, so every step has two loads in flight instead of one.
+VSGPU_HD void rank_le2(const DevIndex& ix, uint32_t xa, uint32_t xb, uint32_t& ra, uint32_t& rb) {
+	uint32_t ba = xa >> ix.bucket_shift, bb = xb >> ix.bucket_shift;
+	if (ba >= ix.nbuckets) ba = ix.nbuckets - 1;
+	if (bb >= ix.nbuckets) bb = ix.nbuckets - 1;
+	uint32_t lo1 = ldg(ix.bucket + ba), hi1 = ldg(ix.bucket + ba + 1), lo2 = ldg(ix.bucket + bb), hi2 = ldg(ix.bucket + bb + 1);
+	if (ba + 1 == ix.nbuckets) hi1 = ix.D;
+	if (bb + 1 == ix.nbuckets) hi2 = ix.D;
+	while (lo1 < hi1 || lo2 < hi2) {
+		const uint32_t m1 = (lo1 + hi1) >> 1, m2 = (lo2 + hi2) >> 1;
+		const bool a1 = lo1 < hi1, a2 = lo2 < hi2;
+		const uint32_t k1 = a1 ? ldg(ix.dstart + m1) : 0, k2 = a2 ? ldg(ix.dstart + m2) : 0;
+		if (a1) { if (k1 <= xa) lo1 = m1 + 1; else hi1 = m1; }
+		if (a2) { if (k2 <= xb) lo2 = m2 + 1; else hi2 = m2; }
+	}
+	ra = lo1; rb = lo2;
+}
+
 VSGPU_HD bool member(const DevIndex& ix, uint32_t s, uint32_t set_id) {
 	if (ix.class_mode) return (ldg(ix.bitmap + (uint64_t)set_id * ix.words_per_set + (s >> 6)) >> (s & 63)) & 1;
 	for (uint64_t i = ldg(ix.list_begin + set_id), e = ldg(ix.list_begin + set_id + 1); i < e; i++)
@@ -54,11 +73,12 @@ VSGPU_HD uint2 t6_bounds(const DevIndex& ix, uint64_t x64, uint64_t y64, bool* b
 	if (x64 < 1) { *bad = true; return r; }
 	if (x64 > ix.index_bits) return r;                                     // is_empty: pos_x > size -> empty
 	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
-	const uint32_t rk = rank_le(ix, x);
+	uint32_t rk, e;                                                        // rank(x); first start >= y
+	rank_le2(ix, x, y ? y - 1 : 0, rk, e);
+	if (!y) e = 0;
 	// gate (index.h:158-165): next distinct start s' must satisfy s' - 1 <= y
 	if (rk >= 1 && rk < ix.D && (uint64_t)ldg(ix.dstart + rk) <= (uint64_t)y + 1) {
 		const uint32_t lo = ldg(&ix.dlev[rk - 1].y);
-		const uint32_t e = y ? rank_le(ix, y - 1) : 0;               // first start >= y
 		uint32_t hi;
 		if (e < ix.D) hi = ldg(&ix.dlev[e].z);                              // rec_begin[k(e) - 1]
 		else hi = ((uint64_t)ix.last_end >= y) ? ldg(&ix.dlev[ix.D].z) : ix.R;
@@ -174,22 +194,27 @@ template <class Sink>
 VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
 	if (x64 > ix.index_bits) return;
 	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
-	const uint32_t rk = rank_le(ix, x);
+	uint32_t rk, e_y;                                                           // rank(x); first start >= y
+	rank_le2(ix, x, y ? y - 1 : 0, rk, e_y);
+	if (!y) e_y = 0;
 	if (rk < 1 || rk >= ix.D) return;
-	if ((uint64_t)ldg(ix.dstart + rk) > (uint64_t)y + 1) return;                // is_empty gate
+	// everything the next steps need from the index, issued together
+	const uint32_t next_start = ldg(ix.dstart + rk);
+	const uint64_t info = ldg(ix.dinfo + (rk >= 2 ? rk - 2 : 0));
+	const uint32_t t = ldg(ix.dtin + (rk - 1));
+	const uint4 dl = ldg(ix.dlev + e_y);
+	if ((uint64_t)next_start > (uint64_t)y + 1) return;                         // is_empty gate
 	const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
 	// ---- get_prev_vertex_with_sample (query.h:57-113)
 	// The reference steps back through node_list by out-degree until a neighbour carries the sample.
 	// Those steps are the ancestors of the start state in the back-walk forest, so instead of
 	// stepping: take the sample's carried entries below the start, highest first (one row word covers
 	// 32 entries), and stop at the first whose source is examined by an ancestor state.
-	const uint64_t cur = (x64 >= ix.index_bits) ? ix.D - 1 : rk - 1;            // ref_node_rank (index.h:135-148)
+	const uint32_t cur = rk - 1;                                                // ref_node_rank (index.h:135-148); x < index_bits here since rk < D
 	uint32_t c_found = kNoneU32;
 	if (cur >= 2) {
-		const uint64_t info = ldg(ix.dinfo + (cur - 1));
 		const uint32_t pos = (uint32_t)info + ((uint32_t)(info >> 32) & 0xFFFF);    // entries below pos are candidates
 		if (pos > 0) {
-			const uint32_t t = ldg(ix.dtin + cur);
 			uint32_t w = (pos - 1) >> 5;
 			uint32_t m = ldg(row + w) & (0xFFFFFFFFu >> (31 - ((pos - 1) & 31)));
 			for (;;) {
@@ -204,8 +229,6 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, u
 		}
 	}
 	// ---- forward walk (query.h:649-716)
-	const uint32_t e_y = y ? rank_le(ix, y - 1) : 0;
-	const uint4 dl = ldg(ix.dlev + e_y);
 	const uint32_t k_end = dl.x;                                                // first backbone vertex whose start >= y
 	uint32_t limit = dl.w;                                                      // entries >= limit have src >= k_end
 	uint32_t cur_k = 0, c = 0;

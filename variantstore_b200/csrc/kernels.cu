@@ -22,10 +22,12 @@ using namespace logic;
 constexpr uint32_t kTile = 256;          // regions per CTA, one per thread
 
 __global__ void __launch_bounds__(256) k_t6(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
-                                            const uint64_t* __restrict__ ys, uint2* __restrict__ out, uint32_t* status) {
+                                            const uint64_t* __restrict__ ys, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi,
+                                            uint32_t* status) {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		bool bad = false;
-		out[i] = t6_bounds(ix, xs[i], ys[i], &bad);
+		const uint2 r = t6_bounds(ix, xs[i], ys[i], &bad);
+		lo[i] = r.x; hi[i] = r.y;
 		if (bad) atomicOr(status, kStatusBadRegion);
 	}
 }
@@ -166,9 +168,9 @@ cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream
 	k_build_hitmap<<<grid_for((uint64_t)ix.num_cent * 32, 256, 8), 256, 0, stream>>>(ix, hitmap);
 	return cudaGetLastError();
 }
-cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint2* out, uint32_t* status, cudaStream_t stream) {
+cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
-	k_t6<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, x, y, out, status);
+	k_t6<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, x, y, lo, hi, status);
 	return cudaGetLastError();
 }
 cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const uint64_t* qhash, uint32_t* rec, uint32_t* status, cudaStream_t stream) {

@@ -40,7 +40,8 @@ struct DevIndex {
 cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream);
 
 // All launchers enqueue on `stream` and return the CUDA error of the launch.
-cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint2* out, uint32_t* status, cudaStream_t stream);
+// t6 writes the record slice of every region as two arrays lo[n], hi[n]
+cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const uint64_t* qhash, uint32_t* rec, uint32_t* status, cudaStream_t stream);
 // t4: one launch — walk, CTA scan, decoupled look-back, ordered write of the hits.
 // offsets[n+1] (exclusive, offsets[n] = total); hits has room for `cap` codes, kStatusOverflow is

@@ -40,9 +40,13 @@ struct DevBuf {
 };
 }  // namespace
 
+// Host side of a t4 answer.  Both arrays live in page-locked memory taken from the owning index's
+// pool (device->host copies run at full PCIe rate and nothing is re-allocated per call).
 struct vsgpu_result {
-	std::vector<uint64_t> offsets;
-	std::vector<uint32_t> hits;
+	vsgpu_index* owner = nullptr;
+	uint64_t n = 0;
+	uint64_t* offsets = nullptr; size_t offsets_cap = 0;   // bytes
+	uint32_t* hits = nullptr; size_t hits_cap = 0;         // bytes
 };
 
 struct vsgpu_index : vsgpu::HostIndex {
@@ -54,10 +58,31 @@ struct vsgpu_index : vsgpu::HostIndex {
 	uint64_t device_bytes = 0;
 	uint32_t* d_status = nullptr;
 	std::mutex mu;
-	DevBuf bx, by, bs, bout, bcounts, bscratch, boffsets, bhits, bstate, bhash, brec;
+	DevBuf bx, by, bs, bout, boffsets, bhits, bstate, bhash, brec;
+	// page-locked host buffers: a free list for results + two staging areas for t6
+	std::mutex pool_mu;
+	std::vector<std::pair<void*, size_t>> pinned_free;
+	void* stage[2] = {nullptr, nullptr}; size_t stage_cap[2] = {0, 0};
+	void* pinned_acquire(size_t bytes, size_t* cap) {
+		std::lock_guard<std::mutex> g(pool_mu);
+		size_t best = SIZE_MAX;
+		for (size_t i = 0; i < pinned_free.size(); i++) if (pinned_free[i].second >= bytes && (best == SIZE_MAX || pinned_free[i].second < pinned_free[best].second)) best = i;
+		if (best != SIZE_MAX) { auto b = pinned_free[best]; pinned_free.erase(pinned_free.begin() + best); *cap = b.second; return b.first; }
+		size_t want = 4096; while (want < bytes) want <<= 1;
+		void* p = nullptr;
+		if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+		*cap = want; return p;
+	}
+	void pinned_release(void* p, size_t cap) { if (!p) return; std::lock_guard<std::mutex> g(pool_mu); pinned_free.emplace_back(p, cap); }
+	void* staging(int which, size_t bytes) {
+		if (stage_cap[which] < bytes) { if (stage[which]) cudaFreeHost(stage[which]); stage[which] = nullptr; stage_cap[which] = 0; size_t want = 4096; while (want < bytes) want <<= 1; if (cudaHostAlloc(&stage[which], want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } stage_cap[which] = want; }
+		return stage[which];
+	}
 	~vsgpu_index() {
 		cudaSetDevice(device);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &bcounts, &bscratch, &boffsets, &bhits, &bstate, &bhash, &brec}) b->release();
+		for (auto& b : pinned_free) cudaFreeHost(b.first);
+		for (void* p : stage) if (p) cudaFreeHost(p);
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec}) b->release();
 		for (void* p : allocs) cudaFree(p);
 		if (d_status) cudaFree(d_status);
 		if (own_stream && stream) cudaStreamDestroy(stream);
@@ -67,14 +92,14 @@ struct vsgpu_index : vsgpu::HostIndex {
 struct vsgpu_batch {
 	vsgpu_index* idx = nullptr;
 	int type = 0; uint64_t n = 0;
-	DevBuf x, y, s, hash, out, counts, scratch, offsets, hits, state, rec;
+	DevBuf x, y, s, hash, out, offsets, hits, state, rec;
 	uint64_t hits_cap = 0;
 	uint32_t launches = 0;
 	uint64_t algo_bytes = 0; bool algo_valid = false;
 	std::vector<uint64_t> hx, hy;   // host copies kept for the byte accounting
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint32_t* d_status = nullptr;    // per batch: several batches may be in flight on one index
-	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &counts, &scratch, &offsets, &hits, &state, &rec}) b->release(); }
+	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec}) b->release(); }
 };
 
 namespace {
@@ -217,28 +242,48 @@ int vsgpu_sample_id(const vsgpu_index* ix, const char* name, uint32_t* id) {
 const char* vsgpu_sample_name(const vsgpu_index* ix, uint32_t id) { return (ix && id < ix->ser.num_samples) ? ix->ser.sample_names[id].c_str() : nullptr; }
 
 // ------------------------------------------------------------------ t6
+namespace {
+// counts[i] = rows the reference returns for region i: the slice length, except where the slice
+// holds suspect duplicates or the region runs past the contig end (then the literal rule decides).
+void fill_counts(const vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* lo, const uint32_t* hi, uint32_t* counts) {
+	const FlatIndex& f = ix->flat;
+	const bool special = f.has_suspect_dups || f.rec_begin[f.M] > f.rec_begin[f.M - 1];
+	if (!special) { for (uint64_t i = 0; i < n; i++) counts[i] = hi[i] - lo[i]; return; }
+	std::vector<uint32_t> tmp;
+	for (uint64_t i = 0; i < n; i++) {
+		if (t6_needs_literal(ix, y[i], lo[i], hi[i])) { t6_literal(ix, x[i], y[i], tmp); counts[i] = (uint32_t)tmp.size(); }
+		else counts[i] = hi[i] - lo[i];
+	}
+}
+
+// device lo[] / hi[] -> caller arrays (directly: page-locked caller memory gets the full PCIe rate)
+// or, where the caller passed NULL but counts are wanted, into the index's page-locked staging.
+void fetch_t6(vsgpu_index* ix, uint64_t n, const uint32_t* d_lo, const uint32_t* d_hi, const uint64_t* x, const uint64_t* y,
+              uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts, uint32_t* d_status) {
+	uint32_t* lo = rec_lo; uint32_t* hi = rec_hi;
+	if (counts && !lo) { lo = (uint32_t*)ix->staging(0, n * 4); if (!lo) throw std::runtime_error("CUDA: cannot allocate page-locked staging"); }
+	if (counts && !hi) { hi = (uint32_t*)ix->staging(1, n * 4); if (!hi) throw std::runtime_error("CUDA: cannot allocate page-locked staging"); }
+	if (lo) CU(cudaMemcpyAsync(lo, d_lo, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+	if (hi) CU(cudaMemcpyAsync(hi, d_hi, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+	uint32_t st = read_status(ix, d_status);
+	if (st & kStatusBadRegion) throw std::invalid_argument("Can't find node corresponding to pos 0");   // index.h:151-154 aborts
+	if (counts) fill_counts(ix, n, x, y, lo, hi, counts);
+}
+}  // namespace
+
 int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts) {
 	if (!ix || (n && (!x || !y))) return set_err(VSGPU_EINVAL, "vsgpu_query_t6: null argument");
+	if (n == 0) return VSGPU_OK;
 	if (int rc = check_device(ix)) return rc;
 	std::lock_guard<std::mutex> g(ix->mu);
 	try {
 		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bout.ensure(n * 8));
 		CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
 		CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream));
-		CU(launch_t6(ix->dev, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bout.as<uint2>(), ix->d_status, ix->stream));
-		std::vector<uint2> out(n);
-		CU(cudaMemcpyAsync(out.data(), ix->bout.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
-		uint32_t st = read_status(ix);
-		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");   // index.h:151-154 aborts
-		std::vector<uint32_t> tmp;
-		for (uint64_t i = 0; i < n; i++) {
-			if (rec_lo) rec_lo[i] = out[i].x;
-			if (rec_hi) rec_hi[i] = out[i].y;
-			if (counts) {
-				if (t6_needs_literal(ix, y[i], out[i].x, out[i].y)) { t6_literal(ix, x[i], y[i], tmp); counts[i] = (uint32_t)tmp.size(); }
-				else counts[i] = out[i].y - out[i].x;
-			}
-		}
+		uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n;
+		CU(launch_t6(ix->dev, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), d_lo, d_hi, ix->d_status, ix->stream));
+		fetch_t6(ix, n, d_lo, d_hi, x, y, rec_lo, rec_hi, counts, ix->d_status);
+	} catch (const std::invalid_argument& e) { return set_err(VSGPU_EINVAL, e.what());
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
@@ -278,14 +323,35 @@ uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64
 }
 }  // namespace
 
+namespace {
+// copy a finished t4 answer (device offsets[n+1] + hits) into a pooled page-locked result
+vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const DevBuf& hits, bool want_hits) {
+	std::unique_ptr<vsgpu_result> r(new vsgpu_result);
+	r->owner = ix; r->n = n;
+	r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
+	if (!r->offsets) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+	r->offsets[0] = 0; r->offsets[n] = 0;
+	if (n) {
+		CU(cudaMemcpyAsync(r->offsets, offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
+		CU(cudaStreamSynchronize(ix->stream));
+	}
+	const uint64_t total = r->offsets[n];
+	if (want_hits && total) {
+		r->hits = (uint32_t*)ix->pinned_acquire(total * 4, &r->hits_cap);
+		if (!r->hits) { ix->pinned_release(r->offsets, r->offsets_cap); throw std::runtime_error("CUDA: cannot allocate page-locked result memory"); }
+		CU(cudaMemcpyAsync(r->hits, hits.p, total * 4, cudaMemcpyDeviceToHost, ix->stream));
+		CU(cudaStreamSynchronize(ix->stream));
+	}
+	return r.release();
+}
+}  // namespace
+
 int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out) {
 	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t4: null argument");
 	*out = nullptr;
 	if (int rc = check_device(ix)) return rc;
 	std::lock_guard<std::mutex> g(ix->mu);
 	try {
-		std::unique_ptr<vsgpu_result> r(new vsgpu_result);
-		r->offsets.assign(n + 1, 0);
 		if (n) {
 			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
 			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
@@ -295,22 +361,19 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr);
 			uint32_t st = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
-			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
-			CU(cudaMemcpyAsync(r->offsets.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
-			CU(cudaStreamSynchronize(ix->stream));
-			r->hits.resize(r->offsets[n]);
-			if (r->offsets[n]) CU(cudaMemcpyAsync(r->hits.data(), ix->bhits.p, r->offsets[n] * 4, cudaMemcpyDeviceToHost, ix->stream));
-			CU(cudaStreamSynchronize(ix->stream));
-			r->hits.resize(r->offsets[n]);
 		}
-		*out = r.release();
+		*out = fetch_t4(ix, n, ix->boffsets, ix->bhits, true);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
-uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r ? r->offsets.size() - 1 : 0; }
-const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r ? r->offsets.data() : nullptr; }
-const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r ? r->hits.data() : nullptr; }
-void vsgpu_result_free(vsgpu_result* r) { delete r; }
+uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r ? r->n : 0; }
+const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r ? r->offsets : nullptr; }
+const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r ? r->hits : nullptr; }
+void vsgpu_result_free(vsgpu_result* r) {
+	if (!r) return;
+	if (r->owner) { r->owner->pinned_release(r->offsets, r->offsets_cap); r->owner->pinned_release(r->hits, r->hits_cap); }
+	delete r;
+}
 
 // ------------------------------------------------------------------ t7
 int vsgpu_query_t7(vsgpu_index* ix, uint64_t n, const uint64_t* pos, const char* const* refs, const char* const* alts, uint32_t* rec) {
@@ -419,7 +482,7 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 	if (int rc = check_device(ix)) return rc;
 	try {
 		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
-		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + b->n, b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
@@ -433,19 +496,7 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 	try {
 		const uint64_t n = b->n;
 		if (b->type == 6) {
-			std::vector<uint2> o(n);
-			CU(cudaMemcpyAsync(o.data(), b->out.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
-			uint32_t st = read_status(ix, b->d_status);
-			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
-			std::vector<uint32_t> tmp;
-			for (uint64_t i = 0; i < n; i++) {
-				if (rec_lo) rec_lo[i] = o[i].x;
-				if (rec_hi) rec_hi[i] = o[i].y;
-				if (counts) {
-					if (t6_needs_literal(ix, b->hy[i], o[i].x, o[i].y)) { t6_literal(ix, b->hx[i], b->hy[i], tmp); counts[i] = (uint32_t)tmp.size(); }
-					else counts[i] = o[i].y - o[i].x;
-				}
-			}
+			fetch_t6(ix, n, b->out.as<uint32_t>(), b->out.as<uint32_t>() + n, b->hx.data(), b->hy.data(), rec_lo, rec_hi, counts, b->d_status);
 		} else if (b->type == 7) {
 			if (rec_lo) CU(cudaMemcpyAsync(rec_lo, b->rec.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
 			uint32_t st = read_status(ix, b->d_status);
@@ -453,19 +504,11 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 		} else {
 			uint32_t st = finish_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, b->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
-			if (st & kStatusOverflow) return set_err(VSGPU_ENOMEM, "t4 hit buffer overflow");
-			std::unique_ptr<vsgpu_result> r(new vsgpu_result);
-			r->offsets.resize(n + 1);
-			CU(cudaMemcpyAsync(r->offsets.data(), b->offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
-			CU(cudaStreamSynchronize(ix->stream));
+			vsgpu_result* r = fetch_t4(ix, n, b->offsets, b->hits, out != nullptr);
 			if (counts) for (uint64_t i = 0; i < n; i++) counts[i] = (uint32_t)(r->offsets[i + 1] - r->offsets[i]);
-			if (out) {
-				r->hits.resize(r->offsets[n]);
-				if (r->offsets[n]) CU(cudaMemcpyAsync(r->hits.data(), b->hits.p, r->offsets[n] * 4, cudaMemcpyDeviceToHost, ix->stream));
-				CU(cudaStreamSynchronize(ix->stream));
-				*out = r.release();
-			}
+			if (out) *out = r; else vsgpu_result_free(r);
 		}
+	} catch (const std::invalid_argument& e) { return set_err(VSGPU_EINVAL, e.what());
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
@@ -489,12 +532,12 @@ int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* ker
 					bytes += 148 + 16ull * (f.t7_hi[rk - 1] - f.t7_lo[rk - 1]);
 				}
 			} else {
-				CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint2>(), ix->d_status, ix->stream));
-				std::vector<uint2> o(n); uint64_t total = 0;
+				CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + n, b->d_status, ix->stream));
+				std::vector<uint32_t> o(2 * n); uint64_t total = 0;
 				CU(cudaMemcpyAsync(o.data(), b->out.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
 				CU(cudaMemcpyAsync(&total, b->offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
 				CU(cudaStreamSynchronize(ix->stream));
-				uint64_t v = 0; for (auto& r : o) v += r.y - r.x;
+				uint64_t v = 0; for (uint64_t i = 0; i < n; i++) v += o[n + i] - o[i];
 				bytes = 292 * n + 20 * v + 4 * total;
 			}
 			b->algo_bytes = bytes; b->algo_valid = true;
