@@ -13,13 +13,14 @@
 //   K6  k_build_hitmap: transposes (walk entry -> carrier set) into the sample-major hit map, once
 //       per vsgpu_open.
 // Integer-only; nothing here is a contraction, so no tensor-core path exists.
+#include <cstdlib>
+
 #include "device_logic.cuh"
 
 namespace vsgpu {
 namespace {
 using namespace logic;
 
-constexpr uint32_t kTile = 256;          // regions per CTA, one per thread
 
 __global__ void __launch_bounds__(256) k_t6(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                             const uint64_t* __restrict__ ys, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi,
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) k_t7(const DevIndex ix, uint64_t n, const
 #define kFlagIncl (2ull << 62)
 #define kValMask ((1ull << 62) - 1)
 
+template <uint32_t kTile>
 struct SmemSink {            // first kScratchHits codes of this thread, strided so lanes hit distinct banks
 	uint32_t* slot; uint32_t n;
 	__device__ __forceinline__ void emit(uint32_t code) { if (n < kScratchHits) slot[n * kTile] = code; n++; }
@@ -57,7 +59,9 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 	return v;
 }
 
-__global__ void __launch_bounds__(kTile) k_t4(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
+// kTile = regions per CTA, one per thread
+template <uint32_t kTile, uint32_t kMinCtas>
+__global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
                                               uint64_t* tile_state, uint32_t* status) {
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(kTile) k_t4(const DevIndex ix, uint64_t n, con
 	const uint64_t i = (uint64_t)tile * kTile + threadIdx.x;
 
 	// ---- phase 1: walk this thread's region
-	SmemSink sink{s_hits + threadIdx.x, 0};
+	SmemSink<kTile> sink{s_hits + threadIdx.x, 0};
 	uint64_t x = 0, y = 0; uint32_t s = 0;
 	if (i < n) {
 		x = xs[i]; y = ys[i]; s = sample[i];
@@ -178,11 +182,20 @@ cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const
 	k_t7<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, pos, qhash, rec, status);
 	return cudaGetLastError();
 }
-uint64_t t4_state_words(uint64_t n) { return 2 + (n + kTile - 1) / kTile; }
+static uint32_t t4_tile() {
+	static uint32_t tile = 0;
+	if (!tile) { const char* e = getenv("VSGPU_T4_TILE"); tile = e ? (uint32_t)atoi(e) : 256; if (tile != 64 && tile != 128 && tile != 256) tile = 256; }
+	return tile;
+}
+uint64_t t4_state_words(uint64_t n) { return 2 + (n + 63) / 64; }
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
-	k_t4<<<(uint32_t)((n + kTile - 1) / kTile), kTile, 0, stream>>>(ix, n, x, y, sample, offsets, hits, cap, tile_state, status);
+	const uint32_t tile = t4_tile();
+	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
+	if (tile == 64) k_t4<64, 16><<<grid, 64, 0, stream>>>(ix, n, x, y, sample, offsets, hits, cap, tile_state, status);
+	else if (tile == 128) k_t4<128, 10><<<grid, 128, 0, stream>>>(ix, n, x, y, sample, offsets, hits, cap, tile_state, status);
+	else k_t4<256, 5><<<grid, 256, 0, stream>>>(ix, n, x, y, sample, offsets, hits, cap, tile_state, status);
 	return cudaGetLastError();
 }
 
