@@ -1,0 +1,95 @@
+"""GPU parity on the other BASELINE.json configurations (scaled so the oracle finishes in seconds):
+[2] several contigs sharded over GPUs, [3] TCGA-like sparse cohort with t7 lookups (explicit sample
+ids), [4] region widths from 100 bp to 1 Mb (search-bound to scan-bound)."""
+import numpy as np
+import pytest
+
+import vs_testlib as T
+from vs_testlib import Oracle
+
+pytestmark = pytest.mark.gpu
+NONE = 0xFFFFFFFF
+
+
+def test_tcga_like_sparse_t7_cuda(tmp_path):
+    o = Oracle.synth(str(tmp_path / "ser"), chr_name="2", ref_length=3_000_000, n_records=150_000, n_samples=10_000, mode=1, seed=9, cqf_log2=21)
+    assert o.construct_info["use_bit_vector"] == 0
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        assert e.info.class_mode == 0 and e.info.num_samples == 10_001
+        av = o.all_variants()
+        rng = np.random.default_rng(1)
+        pick = rng.choice(len(av), 6000, replace=False)
+        pos = [av[i][0] for i in pick] + [av[i][0] + 1 for i in pick[:500]]
+        refs = [av[i][1] for i in pick] + [av[i][1] for i in pick[:500]]
+        alts = [av[i][2] for i in pick] + [av[i][2] for i in pick[:500]]
+        f7, c7, d7 = o.batch_t7(pos, refs, alts)
+        rec = e.batch_samples_has_var(pos, refs, alts)
+        ec, ed = e.digest_t7(rec)
+        assert np.array_equal(rec != NONE, f7 == 1)
+        hit = f7 == 1
+        assert 0 < hit.sum() < len(pos)                       # both outcomes are exercised
+        assert np.array_equal(c7[hit], ec[hit]) and np.array_equal(d7[hit], ed[hit])
+        # the same lookups through the device-resident batch
+        from variantstore_b200 import Batch
+        b7 = Batch(e, 7, pos, refs=refs, alts=alts)
+        b7.run()
+        assert np.array_equal(b7.fetch() != NONE, f7 == 1)
+        # t4 / t6 in explicit-id mode at this scale (rare carriers: long back-walks)
+        x = rng.integers(1, 3_000_000, 1500).astype(np.uint64)
+        y = x + rng.choice([100, 1000, 50_000], 1500).astype(np.uint64)
+        s = rng.integers(1, 10_001, 1500).astype(np.uint32)
+        bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+        assert not bad6 and not bad4
+
+
+def test_width_sweep_cuda(tmp_path):
+    o = Oracle.synth(str(tmp_path / "ser"), ref_length=3_000_000, n_records=90_000, n_samples=300, fmax=120, seed=12, cqf_log2=20)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        rng = np.random.default_rng(2)
+        for width, n in [(100, 400), (1000, 400), (10_000, 300), (100_000, 120), (1_000_000, 30)]:
+            x = rng.integers(1, 3_000_000 - width, n).astype(np.uint64)
+            y = x + np.uint64(width)
+            s = rng.integers(1, 301, n).astype(np.uint32)
+            bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+            assert not bad6 and not bad4, width
+        # whole contig and beyond
+        x = np.array([1, 1, 2_999_000], np.uint64)
+        y = np.array([3_000_001, 10_000_000, 3_100_000], np.uint64)
+        bad6, bad4, _ = T.compare_all(o, e, x, y, np.array([5, 17, 250], np.uint32))
+        assert not bad6 and not bad4
+
+
+def test_multi_contig_sharded_cuda(tmp_path):
+    """Config [2] in small: contigs as independent shards on one GPU, routed by the host."""
+    from variantstore_b200 import VariantStoreIndex
+    from variantstore_b200.sharding import ShardedIndex, assign_contigs, route
+    names = ["20", "21", "22"]
+    prefixes, oracles, sizes = {}, {}, {}
+    for i, c in enumerate(names):
+        oracles[c] = Oracle.synth(str(tmp_path / c), chr_name=c, ref_length=400_000 + 100_000 * i, n_records=9000 + 3000 * i,
+                                  n_samples=100, fmax=60, seed=30 + i, cqf_log2=18)
+        prefixes[c] = str(tmp_path / c)
+        sizes[c] = 9000 + 3000 * i
+    owner = assign_contigs(sizes, 2)
+    assert sorted(set(owner.values())) == [0, 1]
+    sh = ShardedIndex(prefixes, lambda p: VariantStoreIndex(p, device=0))
+    rng = np.random.default_rng(4)
+    n = 3000
+    contigs = [names[i] for i in rng.integers(0, 3, n)]
+    x = rng.integers(1, 400_000, n).astype(np.uint64)
+    y = x + rng.choice([10, 1000, 20_000], n).astype(np.uint64)
+    parts = route(contigs, owner, 2)
+    assert sum(len(p) for p in parts) == n
+    got6 = sh.var_in_ref(contigs, x, y)
+    samples = [f"S{int(i):03d}" for i in rng.integers(1, 101, n)]
+    got4, texts = sh.sample_var_in_ref(contigs, x, y, samples)
+    for c in names:
+        idx = np.nonzero(np.array(contigs) == c)[0]
+        assert np.array_equal(got6[idx].astype(np.uint64), oracles[c].batch_t6(x[idx], y[idx])[0])
+        sid = np.array([int(samples[i][1:]) for i in idx], np.uint32)
+        c4, _, _ = oracles[c].batch_t4(x[idx], y[idx], sid)
+        assert np.array_equal(got4[idx].astype(np.uint64), c4)
+        for i in idx[:40]:
+            want = "\n".join(oracles[c].t4_text(int(x[i]), int(y[i]), samples[i])[0].split("\n")[2:])
+            assert texts[i] == want
+    sh.close()

@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Secondary measurements on one B200 (not the bench line): BASELINE.json config [3] — batched t7
+lookups on a TCGA-like sparse cohort — and config [4] — the region-width sweep for t4/t6 on the
+chr22-shaped index.  Prints one JSON line per measurement; results are copied into profiles/."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def timed(batch, steps=10, warmup=3):
+    import torch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(warmup):
+        batch.run()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(steps):
+        flush.zero_()
+        batch.run()
+        ms.append(sum(batch.timings_ms()))
+    return float(np.mean(ms))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="tcga,width")
+    ap.add_argument("--tcga-records", type=int, default=3_000_000)
+    ap.add_argument("--tcga-samples", type=int, default=10_000)
+    ap.add_argument("--lookups", type=int, default=10_000_000)
+    args = ap.parse_args()
+    import torch
+    import vs_testlib as T
+    from variantstore_b200 import Batch, VariantStoreIndex
+    torch.cuda.set_device(0)
+    if "tcga" in args.what:
+        prefix = "/tmp/vsgpu_bench/tcga/ser"
+        t0 = time.time()
+        o = T.Oracle.synth(prefix, chr_name="2", ref_length=243_199_373, pos_lo=10_000, n_records=args.tcga_records,
+                           n_samples=args.tcga_samples, mode=1, seed=77, cqf_log2=25, gzip_level=1)
+        av = o.all_variants()
+        build_s = time.time() - t0
+        idx = VariantStoreIndex(prefix, device=0)
+        idx.set_stream(torch.cuda.current_stream().cuda_stream)
+        rng = np.random.default_rng(5)
+        # half of the lookups use a reported variant as is (insertions and alleles hanging off a dummy
+        # vertex are findable, isolated SNPs are not — reference behaviour), half are perturbed
+        pick = rng.integers(0, len(av), args.lookups)
+        pos = np.array([av[i][0] for i in pick], np.uint64)
+        pos[len(pos) // 2:] += 1
+        refs = [av[i][1] for i in pick]
+        alts = [av[i][2] for i in pick]
+        b7 = Batch(idx, 7, pos, refs=refs, alts=alts)
+        ms = timed(b7)
+        rec = b7.fetch()
+        algo, launches = b7.stats()
+        # parity on a sample
+        sub = rng.choice(len(pos), 3000, replace=False)
+        f7, _, _ = o.batch_t7(pos[sub], [refs[i] for i in sub], [alts[i] for i in sub])
+        ok = bool(np.array_equal(rec[sub] != 0xFFFFFFFF, f7 == 1))
+        print(json.dumps({"config": "tcga-like sparse t7", "records": args.tcga_records, "samples": args.tcga_samples, "lookups": len(pos),
+                          "k_t7_ms": ms, "lookups_per_s": len(pos) / (ms / 1000), "found_fraction": float((rec != 0xFFFFFFFF).mean()),
+                          "algorithmic_GBps": algo / (ms / 1000) / 1e9, "class_mode": int(idx.info.class_mode),
+                          "device_bytes": int(idx.info.device_bytes), "parity_sample_ok": ok, "build_s": build_s}), flush=True)
+        idx.close()
+        o.close()
+    if "width" in args.what:
+        import bench
+        class A: pass
+        a = A(); a.records, a.samples, a.fmax, a.cache_dir, a.regions, a.width = 1_103_547, 2504, 1100, "/tmp/vsgpu_bench", 1_000_000, 1000
+        prefix, meta = bench.ensure_index(a, 0)
+        idx = VariantStoreIndex(prefix, device=0)
+        idx.set_stream(torch.cuda.current_stream().cuda_stream)
+        rng = np.random.default_rng(6)
+        for width, n in [(100, 1_000_000), (1000, 1_000_000), (10_000, 1_000_000), (100_000, 200_000), (1_000_000, 50_000), (10_000_000, 10_000)]:
+            x = np.sort(rng.integers(meta["pos_lo"], meta["ref_length"] - min(width, 30_000_000), n)).astype(np.uint64)
+            y = x + np.uint64(width)
+            s = rng.integers(1, 2505, n).astype(np.uint32)
+            b6, b4 = Batch(idx, 6, x, y), Batch(idx, 4, x, y, sample_ids=s)
+            ms6, ms4 = timed(b6), timed(b4)
+            off, hits, cnt = b4.fetch()
+            lo, hi, c6 = b6.fetch()
+            algo4, _ = b4.stats()
+            print(json.dumps({"config": "width sweep", "width": width, "regions": n, "k_t6_ms": ms6, "k_t4_ms": ms4,
+                              "t6_regions_per_s": n / (ms6 / 1000), "t4_regions_per_s": n / (ms4 / 1000),
+                              "t6_rows_per_region": float(c6.mean()), "t4_rows_per_region": float(cnt.mean()),
+                              "t4_rows_per_s": float(cnt.sum()) / (ms4 / 1000), "t4_algorithmic_GBps": algo4 / (ms4 / 1000) / 1e9}), flush=True)
+            b6.close(); b4.close()
+        idx.close()
+
+
+if __name__ == "__main__":
+    main()
