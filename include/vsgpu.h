@@ -75,7 +75,9 @@ const char* vsgpu_sample_name(const vsgpu_index* idx, uint32_t id);
 /* ---- t6: get_var_in_ref(vg, idx, pos_x, pos_y) — include/query.h:736-784 -----------------------
  * For every region [x[i], y[i]) writes the slice [rec_lo[i], rec_hi[i]) of the branch-record table
  * (records in the order the reference pushes them) and counts[i] = rows the reference returns
- * ("Number of variants get_var_in_ref: N").  rec_lo / rec_hi may be NULL.  Host buffers. */
+ * ("Number of variants get_var_in_ref: N").  Where the reference's Index::is_empty gate fires
+ * (index.h:150-166; it then prints the t4 label, query.h:746) rec_lo = rec_hi = VSGPU_NONE and the
+ * count is 0.  rec_lo / rec_hi may be NULL.  Host buffers. */
 int vsgpu_query_t6(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y,
                    uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts);
 

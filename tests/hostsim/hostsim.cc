@@ -131,7 +131,7 @@ int vsgpu_query_t7(vsgpu_index* ix, uint64_t n, const uint64_t* pos, const char*
 }
 
 int vsgpu_rows_t6(const vsgpu_index* ix, uint32_t lo, uint32_t hi, int ws, char** text, uint64_t* nrows) {
-	if (lo > hi || hi > ix->flat.R) return set_err(VSGPU_EINVAL, "bad record slice");
+	if ((lo != VSGPU_NONE || hi != VSGPU_NONE) && (lo > hi || hi > ix->flat.R)) return set_err(VSGPU_EINVAL, "bad record slice");
 	std::string s; uint64_t cnt = 0; rows_t6(ix, lo, hi, ws != 0, s, cnt);
 	if (nrows) *nrows = cnt;
 	*text = dup_text(s); return VSGPU_OK;

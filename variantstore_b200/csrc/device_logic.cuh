@@ -69,7 +69,7 @@ VSGPU_HD bool member(const DevIndex& ix, uint32_t s, uint32_t set_id) {
 
 // ------------------------------------------------------------------ t6 slice bounds (query.h:736-784)
 VSGPU_HD uint2 t6_bounds(const DevIndex& ix, uint64_t x64, uint64_t y64, bool* bad) {
-	uint2 r = make_uint2(0, 0);
+	uint2 r = make_uint2(kNoneU32, kNoneU32);                                // is_empty gate fired: (NONE, NONE)
 	if (x64 < 1) { *bad = true; return r; }
 	if (x64 > ix.index_bits) return r;                                     // is_empty: pos_x > size -> empty
 	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);

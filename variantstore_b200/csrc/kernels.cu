@@ -47,10 +47,10 @@ __global__ void __launch_bounds__(256) k_t7(const DevIndex ix, uint64_t n, const
 #define kFlagIncl (2ull << 62)
 #define kValMask ((1ull << 62) - 1)
 
-template <uint32_t kTile>
-struct SmemSink {            // first kScratchHits codes of this thread, strided so lanes hit distinct banks
+template <uint32_t kTile, uint32_t kKeep>
+struct SmemSink {            // first kKeep codes of this thread, strided so lanes hit distinct banks
 	uint32_t* slot; uint32_t n;
-	__device__ __forceinline__ void emit(uint32_t code) { if (n < kScratchHits) slot[n * kTile] = code; n++; }
+	__device__ __forceinline__ void emit(uint32_t code) { if (n < kKeep) slot[n * kTile] = code; n++; }
 };
 
 __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
@@ -59,13 +59,14 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 	return v;
 }
 
-// kTile = regions per CTA, one per thread
-template <uint32_t kTile, uint32_t kMinCtas>
+// kTile = regions per CTA, one per thread; kKeep = hits per region staged in shared memory (a
+// region with more walks a second time, straight into its final place)
+template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
 __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
                                               uint64_t* tile_state, uint32_t* status) {
-	__shared__ uint32_t s_hits[kTile * kScratchHits];
+	__shared__ uint32_t s_hits[kTile * kKeep];
 	__shared__ uint64_t s_warp[kTile / 32];
 	__shared__ uint64_t s_base;
 	__shared__ uint32_t s_tile;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	const uint64_t i = (uint64_t)tile * kTile + threadIdx.x;
 
 	// ---- phase 1: walk this thread's region
-	SmemSink<kTile> sink{s_hits + threadIdx.x, 0};
+	SmemSink<kTile, kKeep> sink{s_hits + threadIdx.x, 0};
 	uint64_t x = 0, y = 0; uint32_t s = 0;
 	if (i < n) {
 		x = xs[i]; y = ys[i]; s = sample[i];
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 		offsets[i] = off;
 		if (i == n - 1) offsets[n] = off + cnt;
 		if (off + cnt > cap) atomicOr(status, kStatusOverflow);
-		else if (cnt <= kScratchHits) { for (uint32_t j = 0; j < cnt; j++) hits[off + j] = s_hits[j * kTile + threadIdx.x]; }
+		else if (cnt <= kKeep) { for (uint32_t j = 0; j < cnt; j++) hits[off + j] = s_hits[j * kTile + threadIdx.x]; }
 		else { DirectSink direct{hits + off, 0}; walk_any(ix, x, y, s, direct); }   // rare: wide region, walk again straight into place
 	}
 }
@@ -189,13 +190,22 @@ static uint32_t t4_tile() {
 }
 uint64_t t4_state_words(uint64_t n) { return 2 + (n + 63) / 64; }
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, cudaStream_t stream) {
+                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool many_hits,
+                      cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	const uint32_t tile = t4_tile();
 	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
-	if (tile == 64) k_t4<64, 16><<<grid, 64, 0, stream>>>(ix, n, x, y, sample, offsets, hits, cap, tile_state, status);
-	else if (tile == 128) k_t4<128, 10><<<grid, 128, 0, stream>>>(ix, n, x, y, sample, offsets, hits, cap, tile_state, status);
-	else k_t4<256, 5><<<grid, 256, 0, stream>>>(ix, n, x, y, sample, offsets, hits, cap, tile_state, status);
+#define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
+	if (many_hits) {            // wide regions: keep 32 hits per region on chip before falling back to a second walk
+		if (tile == 64) k_t4<64, 16, 32><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
+		else if (tile == 128) k_t4<128, 10, 32><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
+		else k_t4<256, 5, 32><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	} else {
+		if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
+		else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
+		else k_t4<256, 5, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	}
+#undef VSGPU_T4_ARGS
 	return cudaGetLastError();
 }
 

@@ -216,6 +216,7 @@ uint64_t t7_carriers(const HostIndex* ix, uint32_t rec, std::string* text, uint6
 
 void rows_t6(const HostIndex* ix, uint32_t lo, uint32_t hi, bool with_samples, std::string& s, uint64_t& cnt) {
 	cnt = 0;
+	if (lo == kNone && hi == kNone) return;        // the is_empty gate fired: no rows
 	std::vector<uint32_t> vars;
 	if (ix->flat.has_suspect_dups && ix->flat.rec_dup_prefix[hi] - ix->flat.rec_dup_prefix[lo] > 0) {
 		for (uint32_t r = lo; r < hi; r++) if (push_rule(ix, vars, r)) vars.push_back(r);
@@ -229,6 +230,7 @@ void digests_t6(const HostIndex* ix, uint64_t n, const uint32_t* lo, const uint3
 		std::string row; std::vector<uint32_t> vars;
 		for (uint64_t i = a; i < b; i++) {
 			uint64_t h = kFnvInit;
+			if (lo[i] == kNone && hi[i] == kNone) { digests[i] = h; continue; }
 			if (lo[i] > hi[i] || hi[i] > ix->flat.R) { bad = true; continue; }
 			bool dd = ix->flat.has_suspect_dups && ix->flat.rec_dup_prefix[hi[i]] - ix->flat.rec_dup_prefix[lo[i]] > 0;
 			vars.clear();

@@ -70,7 +70,7 @@ int main(int argc, char** argv) {
 		rc = vsgpu_query_t6(idx, n, x.data(), y.data(), lo.data(), hi.data(), cnt.data());
 		for (uint64_t i = 0; i < n && rc == 0; i++) {
 			// the reference prints the t4 label when its is_empty gate fires (query.h:746)
-			printf("Number of variants %s: %u\n", cnt[i] == 0 && lo[i] == 0 && hi[i] == 0 ? "get_sample_var_in_ref" : "get_var_in_ref", cnt[i]);
+			printf("Number of variants %s: %u\n", lo[i] == VSGPU_NONE ? "get_sample_var_in_ref" : "get_var_in_ref", cnt[i]);
 			if (verbose) { char* text = nullptr; uint64_t nr; if (vsgpu_rows_t6(idx, lo[i], hi[i], 1, &text, &nr) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
 		}
 	} else if (type == 4) {
