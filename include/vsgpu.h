@@ -91,6 +91,12 @@ const uint64_t* vsgpu_result_offsets(const vsgpu_result* r);   /* n + 1 */
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r);
 void vsgpu_result_free(vsgpu_result* r);
 
+/* ---- t1: closest_var(vg, idx, pos, vars) — include/query.h:441-483 (SURVEY.md §8f "next" row 1) -----
+ * rec_lo[i] = rec_hi[i] = VSGPU_NONE where the operator returns false (no variant on the contig);
+ * otherwise the rows are the records of [rec_lo, rec_hi) that a fresh next_variant_in_ref call keeps
+ * (vsgpu_rows_t1 / vsgpu_digest_t1 apply that), possibly none. */
+int vsgpu_query_t1(vsgpu_index* idx, uint64_t n, const uint64_t* pos, uint32_t* rec_lo, uint32_t* rec_hi);
+
 /* ---- t7: samples_has_var(vg, idx, pos, ref, alt) — include/query.h:792-823 ----------------------
  * rec[i] = branch record whose (ref, pos, alt) equals the query among the records found by one
  * next_variant_in_ref(pos) call, or VSGPU_NONE ("There is no such variant!").  refs/alts are n
@@ -104,12 +110,14 @@ int vsgpu_query_t7(vsgpu_index* idx, uint64_t n, const uint64_t* pos, const char
  * The returned buffer is malloc'd; free it with vsgpu_free.  with_samples = 0 leaves the carrier
  * list empty (rows end "\t\n"). */
 int vsgpu_rows_t6(const vsgpu_index* idx, uint32_t rec_lo, uint32_t rec_hi, int with_samples, char** text, uint64_t* nrows);
+int vsgpu_rows_t1(const vsgpu_index* idx, uint32_t rec_lo, uint32_t rec_hi, int with_samples, char** text, uint64_t* nrows);
 int vsgpu_rows_t4(const vsgpu_index* idx, const uint32_t* hits, uint64_t nhits, int with_samples, char** text);
 /* "name gt" pairs concatenated as samples_has_var writes them (query.h:807-816) */
 int vsgpu_rows_t7(const vsgpu_index* idx, uint32_t rec, char** text, uint64_t* ncarriers);
 void vsgpu_free(void* p);
 /* FNV-1a 64 digests of the row text per query (multi-threaded); used by the parity tests. */
 int vsgpu_digest_t6(const vsgpu_index* idx, uint64_t n, const uint32_t* rec_lo, const uint32_t* rec_hi, int with_samples, uint64_t* digests);
+int vsgpu_digest_t1(const vsgpu_index* idx, uint64_t n, const uint32_t* rec_lo, const uint32_t* rec_hi, int with_samples, uint64_t* counts, uint64_t* digests);
 int vsgpu_digest_t4(const vsgpu_index* idx, uint64_t n, const uint64_t* offsets, const uint32_t* hits, int with_samples, uint64_t* digests);
 int vsgpu_digest_t7(const vsgpu_index* idx, uint64_t n, const uint32_t* rec, uint64_t* ncarriers, uint64_t* digests);
 

@@ -183,6 +183,20 @@ int vso_batch_t7(void* hp, uint64_t n, const uint64_t* pos, const char* const* r
 	} catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// closest_var (query.h:441-483): found flag, row count, digest of the rows
+int vso_batch_t1(void* hp, uint64_t n, const uint64_t* pos, uint8_t* found, uint64_t* counts, uint64_t* digests, int with_samples) {
+	Handle* h = (Handle*)hp;
+	try {
+		for (uint64_t i = 0; i < n; i++) {
+			std::vector<Variant> vars;
+			found[i] = closest_var(h->vg.get(), h->idx.get(), pos[i], vars) ? 1 : 0;
+			counts[i] = vars.size();
+			if (digests) digests[i] = rows_digest(vars, with_samples != 0);
+		}
+		return 0;
+	} catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // Multi-threaded timing arms for bench.py (`--impl reference`, cpu_baseline): the reference query
 // path is single-threaded; "all host cores" = independent workers over disjoint region chunks, which
 // is how its evaluation ran contigs side by side (eval_data_records/evaluation.txt:34).

@@ -156,8 +156,9 @@ bool closest_var(const VariantGraph* vg, const Index* idx, const uint64_t pos, s
 		int cur_pos = (int)(pos - (next_var_pos - pos));
 		if (cur_pos > 0) {
 			next_variant_in_ref(vg, idx, cur_pos, prev_var, next_pos);
-			uint64_t prev_var_pos = prev_var[0].var_pos;
-			if (prev_var_pos != next_var_pos) vars = prev_var; else vars = next_var;
+			// the reference reads prev_var[0] even when that call found nothing (possible when the next
+			// variant's pos is below `pos`, so the mirrored position lies beyond it): defined as "keep next_var"
+			if (!prev_var.empty() && prev_var[0].var_pos != next_var_pos) vars = prev_var; else vars = next_var;
 		} else vars = next_var;
 	} else {
 		int cur_pos = (int)pos - 1;

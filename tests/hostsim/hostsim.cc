@@ -45,7 +45,7 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 	FlatIndex& f = ix->flat; DevIndex& d = ix->dev;
 	memset(&d, 0, sizeof d);
 	d.D = f.D; d.M = f.M; d.R = f.R; d.num_cent = (uint32_t)f.cent.size(); d.words_per_set = f.words_per_set;
-	d.num_samples = f.num_samples; d.class_mode = f.class_mode; d.index_bits = f.index_bits; d.last_end = ix->last_end;
+	d.num_samples = f.num_samples; d.class_mode = f.class_mode; d.index_bits = f.index_bits; d.last_end = ix->last_end; d.t1_fallback_pos = ix->t1_fallback_pos;
 	build_buckets(f, ix->bucket, d.bucket_shift);
 	d.nbuckets = (uint32_t)ix->bucket.size() - 1; d.bucket = ix->bucket.data(); d.dstart = f.dstart.data();
 	ix->t7.resize(f.D);
@@ -119,6 +119,22 @@ uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r->offsets.siz
 const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r->offsets.data(); }
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r->hits.data(); }
 void vsgpu_result_free(vsgpu_result* r) { delete r; }
+
+int vsgpu_query_t1(vsgpu_index* ix, uint64_t n, const uint64_t* pos, uint32_t* lo, uint32_t* hi) {
+	for (uint64_t i = 0; i < n; i++) {
+		bool bad = false;
+		uint2 r = logic::t1_lookup(ix->dev, pos[i], &bad);
+		if (bad) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+		lo[i] = r.x; hi[i] = r.y;
+	}
+	return VSGPU_OK;
+}
+int vsgpu_rows_t1(const vsgpu_index* ix, uint32_t lo, uint32_t hi, int ws, char** text, uint64_t* nrows) {
+	std::string s; uint64_t cnt = 0; rows_t1(ix, lo, hi, ws != 0, s, cnt);
+	if (nrows) *nrows = cnt;
+	*text = dup_text(s); return VSGPU_OK;
+}
+int vsgpu_digest_t1(const vsgpu_index* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, int ws, uint64_t* c, uint64_t* d) { digests_t1(ix, n, lo, hi, ws != 0, c, d); return VSGPU_OK; }
 
 int vsgpu_query_t7(vsgpu_index* ix, uint64_t n, const uint64_t* pos, const char* const* refs, const char* const* alts, uint32_t* rec) {
 	for (uint64_t i = 0; i < n; i++) {

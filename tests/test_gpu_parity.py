@@ -51,6 +51,8 @@ def test_fuzz_parity_cuda(tmp_path, seed, overlap, sparse, walk_path):
         assert not bad6 and not bad4
         hits, total = _t7_check(o, e)
         assert 0 < hits < total
+        pos = np.concatenate([np.arange(1, 300), np.random.default_rng(seed).integers(1, 4000, 500), [3999, 4000, 4001, 5000]]).astype(np.uint64)
+        assert not T.compare_t1(o, e, pos)
 
 
 def test_golden_fixture_cuda():
@@ -68,6 +70,8 @@ def test_golden_fixture_cuda():
         assert e.samples_has_var(10, "C", "T") == [("1", "1|1")]
         assert e.samples_has_var(58, "", "T") == [("1", "0|1")]
         assert e.samples_has_var(14, "G", "A") == []
+        found, rows = e.closest_var(20)
+        assert found and [(v.var_pos, v.ref, v.alt) for v in rows] == [(34, "T", "A")]
 
 
 def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):

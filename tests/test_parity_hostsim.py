@@ -46,6 +46,9 @@ def test_fuzz_parity(tmp_path, seed, overlap, sparse, walk_path):
     bad6, bad4, ub = T.compare_all(o, e, x, y, s)
     assert not bad6 and not bad4
     assert t7_parity(o, e) > 0
+    # closest_var (t1): every position of the contig's head, a random spread, and past the end
+    pos = np.concatenate([np.arange(1, 400), np.random.default_rng(seed).integers(1, 4000, 600), [3999, 4000, 4001, 5000]]).astype(np.uint64)
+    assert not T.compare_t1(o, e, pos)
 
 
 def test_many_samples_auto_sparse_detection(tmp_path):

@@ -73,6 +73,7 @@ class Oracle:
             L.vso_sample_name.argtypes = [vp, C.c_uint32]
             L.vso_batch_t6.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t4.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.c_int]
+            L.vso_batch_t1.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t6_mt.argtypes = [vp, u64, vp, vp, vp, C.c_int]
             L.vso_batch_t4_mt.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t7.argtypes = [vp, u64, vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), vp, vp, vp]
@@ -183,6 +184,15 @@ class Oracle:
             raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
         return cnt, dig, ub
 
+    def batch_t1(self, pos, with_samples=True):
+        pos = np.ascontiguousarray(pos, np.uint64)
+        n = len(pos)
+        found, cnt, dig = np.zeros(n, np.uint8), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        rc = self.lib().vso_batch_t1(self.h, n, pos.ctypes.data, found.ctypes.data, cnt.ctypes.data, dig.ctypes.data, int(with_samples))
+        if rc != 0:
+            raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
+        return found, cnt, dig
+
     def timed_counts(self, qtype, x, y, sample_ids=None, nthreads=1):
         """Counts only, optionally over several worker threads (bench timing arms)."""
         x, y = np.ascontiguousarray(x, np.uint64), np.ascontiguousarray(y, np.uint64)
@@ -277,6 +287,16 @@ def open_engine(prefix, backend):
     if backend == "hostsim":
         return VariantStoreIndex(prefix, lib=load_library(HOSTSIM_SO, subset=True))
     return VariantStoreIndex(prefix, device=0)
+
+
+def compare_t1(oracle, eng, pos, with_samples=True):
+    """closest_var on both sides; returns mismatching indices."""
+    f, c, d = oracle.batch_t1(pos, with_samples)
+    lo, hi = eng.batch_closest_var(pos)
+    ec, ed = eng.digest_t1(lo, hi, with_samples)
+    efound = lo != 0xFFFFFFFF
+    bad = (efound != (f == 1)) | ((f == 1) & ((c != ec) | (d != ed)))
+    return [int(i) for i in np.nonzero(bad)[0]]
 
 
 def compare_all(oracle, eng, x, y, s, with_samples=True, skip_ub=True):

@@ -42,6 +42,7 @@ def main():
     torch.cuda.set_device(0)
     if "tcga" in args.what:
         prefix = "/tmp/vsgpu_bench/tcga/ser"
+        os.makedirs(os.path.dirname(prefix), exist_ok=True)
         t0 = time.time()
         o = T.Oracle.synth(prefix, chr_name="2", ref_length=243_199_373, pos_lo=10_000, n_records=args.tcga_records,
                            n_samples=args.tcga_samples, mode=1, seed=77, cqf_log2=25, gzip_level=1)

@@ -34,6 +34,9 @@ PROTOTYPES = {
     "vsgpu_result_offsets": (u64p, [vp]),
     "vsgpu_result_hits": (u32p, [vp]),
     "vsgpu_result_free": (None, [vp]),
+    "vsgpu_query_t1": (C.c_int, [vp, C.c_uint64, vp, vp, vp]),
+    "vsgpu_rows_t1": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp), u64p]),
+    "vsgpu_digest_t1": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, vp, vp]),
     "vsgpu_query_t7": (C.c_int, [vp, C.c_uint64, vp, cpp, cpp, vp]),
     "vsgpu_rows_t6": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp), u64p]),
     "vsgpu_rows_t4": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.POINTER(vp)]),

@@ -150,6 +150,29 @@ class VariantStoreIndex:
             self._lib.vsgpu_result_free(r)
         return off, hits
 
+    def batch_closest_var(self, pos):
+        """t1 over an array of positions: (rec_lo, rec_hi); both NONE where the operator returns false."""
+        pos = _u64(pos)
+        n = len(pos)
+        lo, hi = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        self._check(self._lib.vsgpu_query_t1(self._h, n, _ptr(pos), _ptr(lo), _ptr(hi)))
+        return lo, hi
+
+    def digest_t1(self, lo, hi, with_samples=True):
+        n = len(lo)
+        c, d = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        self._check(self._lib.vsgpu_digest_t1(self._h, n, _ptr(lo), _ptr(hi), int(with_samples), _ptr(c), _ptr(d)))
+        return c, d
+
+    def closest_var(self, pos: int):
+        """closest_var(vg, idx, pos, vars) of query.h:441-483: (found, rows)."""
+        lo, hi = self.batch_closest_var([pos])
+        if lo[0] == NONE:
+            return False, []
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.vsgpu_rows_t1(self._h, int(lo[0]), int(hi[0]), 1, C.byref(p), C.byref(n)))
+        return True, _parse_rows(self._take_text(p))
+
     def batch_samples_has_var(self, pos, refs: Sequence[str], alts: Sequence[str]):
         """t7 over arrays: returns record ids (NONE where the reference says "There is no such variant!")."""
         pos = _u64(pos)

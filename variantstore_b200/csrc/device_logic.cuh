@@ -99,6 +99,35 @@ VSGPU_HD uint32_t t7_lookup(const DevIndex& ix, uint64_t p64, uint64_t h, bool* 
 	return kNoneU32;
 }
 
+// ------------------------------------------------------------------ t1 closest_var (query.h:441-483)
+// Records of the first backbone vertex at/after `pos` that has any (one next_variant_in_ref call).
+VSGPU_HD uint2 first_branchy(const DevIndex& ix, uint64_t p64) {
+	uint32_t rk = p64 >= ix.index_bits ? ix.D : rank_le(ix, clamp_pos(p64));
+	if (rk < 1) rk = 1;
+	return ldg(ix.t7rng + (rk - 1));
+}
+// (NONE, NONE): the operator returns false; lo == hi: true with no rows; else the record range whose
+// kept records (rec_flags bit 0) are the rows.
+VSGPU_HD uint2 t1_lookup(const DevIndex& ix, uint64_t p64, bool* bad) {
+	if (p64 < 1) { *bad = true; return make_uint2(kNoneU32, kNoneU32); }
+	const uint2 a = first_branchy(ix, p64);
+	if (a.x < a.y) {
+		const uint64_t p1 = ldg(ix.rec_pos + a.x);                            // next_var[0].var_pos
+		const int cur = (int)(uint32_t)(p64 - (p1 - p64));                    // int cur_pos = pos-(next_var_pos-pos)  (:451)
+		if (cur > 0) {
+			const uint2 b = first_branchy(ix, (uint64_t)cur);
+			if (b.x < b.y && ldg(ix.rec_pos + b.x) != p1) return b;             // an earlier variant sits inside the mirrored window
+		}
+		return a;
+	}
+	// nothing at or after pos: step back until a call finds something (:464-470)
+	if (p64 < 2) return make_uint2(0, 0);
+	if (ix.t1_fallback_pos == 0) return make_uint2(kNoneU32, kNoneU32);      // no variant anywhere: returns false at cur_pos == 1
+	uint64_t cur = p64 - 1;
+	if (cur > ix.t1_fallback_pos) cur = ix.t1_fallback_pos;                  // largest position whose call succeeds
+	return first_branchy(ix, cur);
+}
+
 // ------------------------------------------------------------------ t4 walk (one thread per region)
 struct CountSink {
 	uint32_t* dst; uint32_t n;

@@ -15,6 +15,7 @@ struct HostIndex {
 	SerData ser;
 	FlatIndex flat;
 	uint32_t last_end = 0;                                  // start + length of the last backbone vertex
+	uint32_t t1_fallback_pos = 0;                           // see DevIndex::t1_fallback_pos
 	std::unordered_map<std::string, uint32_t> name2id;
 };
 
@@ -39,6 +40,9 @@ uint64_t fnv1a(uint64_t h, const void* data, size_t n);
 constexpr uint64_t kFnvInit = 14695981039346656037ULL;
 
 // rows / digests shared by the C ABI and the test-only host simulator
+// rows of a closest_var answer: the records of [lo, hi) a fresh next_variant_in_ref call keeps
+void rows_t1(const HostIndex* ix, uint32_t lo, uint32_t hi, bool with_samples, std::string& text, uint64_t& nrows);
+void digests_t1(const HostIndex* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, bool with_samples, uint64_t* counts, uint64_t* digests);
 void rows_t6(const HostIndex* ix, uint32_t lo, uint32_t hi, bool with_samples, std::string& text, uint64_t& nrows);
 void digests_t6(const HostIndex* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, bool with_samples, uint64_t* digests, bool* bad);
 void digests_t4(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, bool with_samples, uint64_t* digests);

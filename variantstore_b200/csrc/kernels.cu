@@ -42,6 +42,16 @@ __global__ void __launch_bounds__(256) k_t7(const DevIndex ix, uint64_t n, const
 	}
 }
 
+__global__ void __launch_bounds__(256) k_t1(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ pos,
+                                            uint32_t* __restrict__ lo, uint32_t* __restrict__ hi, uint32_t* status) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		bool bad = false;
+		const uint2 r = t1_lookup(ix, pos[i], &bad);
+		lo[i] = r.x; hi[i] = r.y;
+		if (bad) atomicOr(status, kStatusBadRegion);
+	}
+}
+
 // ------------------------------------------------------------------ t4: walk + ordered compaction
 #define kFlagAgg (1ull << 62)
 #define kFlagIncl (2ull << 62)
@@ -176,6 +186,11 @@ cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	k_t6<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, x, y, lo, hi, status);
+	return cudaGetLastError();
+}
+cudaError_t launch_t1(const DevIndex& ix, uint64_t n, const uint64_t* pos, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	k_t1<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, pos, lo, hi, status);
 	return cudaGetLastError();
 }
 cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const uint64_t* qhash, uint32_t* rec, uint32_t* status, cudaStream_t stream) {

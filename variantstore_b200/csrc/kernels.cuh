@@ -15,6 +15,7 @@ struct DevIndex {
 	const uint32_t* dstart;               // D distinct backbone starts, ascending
 	const uint32_t* bucket;               // nbuckets + 1: bucket[b] = number of starts < (b << bucket_shift)
 	uint32_t nbuckets, bucket_shift;
+	uint32_t t1_fallback_pos;             // largest position from which next_variant_in_ref still finds a variant (0: no variants)
 	const uint4* dlev;                    // D + 1: {k, rec_lo, rec_hi_prev, cent_begin}
 	const uint64_t* dinfo;                // D
 	const uint2* t7rng;                   // D
@@ -42,6 +43,7 @@ cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream
 // All launchers enqueue on `stream` and return the CUDA error of the launch.
 // t6 writes the record slice of every region as two arrays lo[n], hi[n]
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream);
+cudaError_t launch_t1(const DevIndex& ix, uint64_t n, const uint64_t* pos, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const uint64_t* qhash, uint32_t* rec, uint32_t* status, cudaStream_t stream);
 // t4: one launch — walk, CTA scan, decoupled look-back, ordered write of the hits.
 // offsets[n+1] (exclusive, offsets[n] = total); hits has room for `cap` codes, kStatusOverflow is

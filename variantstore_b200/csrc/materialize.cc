@@ -33,6 +33,11 @@ void build_host_index(const std::string& prefix, HostIndex& h, int* stage) {
 	for (uint32_t i = 0; i < h.ser.num_samples; i++) h.name2id[h.ser.sample_names[i]] = i;
 	uint64_t le = (uint64_t)h.flat.vstart[h.flat.M - 1] + h.flat.vlen[h.flat.M - 1];
 	h.last_end = le > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)le;
+	{   // largest d whose first-branchy range is non-empty; the position just before the next start
+		const FlatIndex& f = h.flat;
+		h.t1_fallback_pos = 0;
+		for (uint32_t d = f.D; d-- > 0;) if (f.t7_hi[d] > f.t7_lo[d]) { h.t1_fallback_pos = d + 1 < f.D ? f.dstart[d + 1] - 1 : 0xFFFFFFFEu; break; }
+	}
 	// host copies nothing needs again
 	std::vector<uint32_t>().swap(h.ser.s_index); std::vector<uint64_t>().swap(h.ser.sample_vector);
 	if (stage) *stage = 2;
@@ -212,6 +217,25 @@ uint64_t t7_carriers(const HostIndex* ix, uint32_t rec, std::string* text, uint6
 		});
 	if (digest) *digest = h;
 	return cnt;
+}
+
+void rows_t1(const HostIndex* ix, uint32_t lo, uint32_t hi, bool with_samples, std::string& s, uint64_t& cnt) {
+	cnt = 0;
+	if (lo == kNone || hi > ix->flat.R) return;
+	for (uint32_t r = lo; r < hi; r++) if (ix->flat.rec_flags[r] & 1) { t6_row(ix, r, with_samples, s); cnt++; }
+}
+
+void digests_t1(const HostIndex* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, bool with_samples, uint64_t* counts, uint64_t* digests) {
+	parallel_for(n, [&](uint64_t a, uint64_t b) {
+		std::string row;
+		for (uint64_t i = a; i < b; i++) {
+			uint64_t h = kFnvInit, c = 0;
+			if (lo[i] != kNone && hi[i] <= ix->flat.R)
+				for (uint32_t r = lo[i]; r < hi[i]; r++) if (ix->flat.rec_flags[r] & 1) { row.clear(); t6_row(ix, r, with_samples, row); h = fnv1a(h, row.data(), row.size()); c++; }
+			if (digests) digests[i] = h;
+			if (counts) counts[i] = c;
+		}
+	});
 }
 
 void rows_t6(const HostIndex* ix, uint32_t lo, uint32_t hi, bool with_samples, std::string& s, uint64_t& cnt) {

@@ -124,6 +124,7 @@ void upload_index(vsgpu_index* ix) {
 	d.D = f.D; d.M = f.M; d.R = f.R; d.num_cent = (uint32_t)f.cent.size(); d.words_per_set = f.words_per_set;
 	d.num_samples = f.num_samples; d.class_mode = f.class_mode ? 1 : 0; d.index_bits = f.index_bits;
 	d.last_end = ix->last_end;
+	d.t1_fallback_pos = ix->t1_fallback_pos;
 	std::vector<uint32_t> bucket;
 	build_buckets(f, bucket, d.bucket_shift);
 	d.nbuckets = (uint32_t)bucket.size() - 1;
@@ -397,6 +398,25 @@ void vsgpu_result_free(vsgpu_result* r) {
 	delete r;
 }
 
+// ------------------------------------------------------------------ t1
+int vsgpu_query_t1(vsgpu_index* ix, uint64_t n, const uint64_t* pos, uint32_t* rec_lo, uint32_t* rec_hi) {
+	if (!ix || (n && (!pos || !rec_lo || !rec_hi))) return set_err(VSGPU_EINVAL, "vsgpu_query_t1: null argument");
+	if (n == 0) return VSGPU_OK;
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	try {
+		CU(ix->bx.ensure(n * 8)); CU(ix->bout.ensure(n * 8));
+		CU(cudaMemcpyAsync(ix->bx.p, pos, n * 8, cudaMemcpyHostToDevice, ix->stream));
+		uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n;
+		CU(launch_t1(ix->dev, n, ix->bx.as<uint64_t>(), d_lo, d_hi, ix->d_status, ix->stream));
+		CU(cudaMemcpyAsync(rec_lo, d_lo, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+		CU(cudaMemcpyAsync(rec_hi, d_hi, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+		uint32_t st = read_status(ix);
+		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+
 // ------------------------------------------------------------------ t7
 int vsgpu_query_t7(vsgpu_index* ix, uint64_t n, const uint64_t* pos, const char* const* refs, const char* const* alts, uint32_t* rec) {
 	if (!ix || (n && (!pos || !refs || !alts || !rec))) return set_err(VSGPU_EINVAL, "vsgpu_query_t7: null argument");
@@ -425,6 +445,21 @@ int vsgpu_rows_t6(const vsgpu_index* ix, uint32_t lo, uint32_t hi, int with_samp
 	if (nrows) *nrows = cnt;
 	*text = dup_text(s);
 	return *text ? VSGPU_OK : set_err(VSGPU_ENOMEM, "out of memory");
+}
+
+int vsgpu_rows_t1(const vsgpu_index* ix, uint32_t lo, uint32_t hi, int with_samples, char** text, uint64_t* nrows) {
+	if (!ix || !text || (lo != VSGPU_NONE && (lo > hi || hi > ix->flat.R))) return set_err(VSGPU_EINVAL, "vsgpu_rows_t1: bad record range");
+	std::string s; uint64_t cnt = 0;
+	rows_t1(ix, lo, hi, with_samples != 0, s, cnt);
+	if (nrows) *nrows = cnt;
+	*text = dup_text(s);
+	return *text ? VSGPU_OK : set_err(VSGPU_ENOMEM, "out of memory");
+}
+
+int vsgpu_digest_t1(const vsgpu_index* ix, uint64_t n, const uint32_t* lo, const uint32_t* hi, int with_samples, uint64_t* counts, uint64_t* digests) {
+	if (!ix || (n && (!lo || !hi))) return set_err(VSGPU_EINVAL, "vsgpu_digest_t1: null argument");
+	digests_t1(ix, n, lo, hi, with_samples != 0, counts, digests);
+	return VSGPU_OK;
 }
 
 int vsgpu_rows_t4(const vsgpu_index* ix, const uint32_t* hits, uint64_t nhits, int with_samples, char** text) {
