@@ -205,21 +205,19 @@ static uint32_t t4_tile() {
 }
 uint64_t t4_state_words(uint64_t n) { return 2 + (n + 63) / 64; }
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool many_hits,
-                      cudaStream_t stream) {
+                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	const uint32_t tile = t4_tile();
 	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
+	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
+	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 5; }
 #define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
-	if (many_hits) {            // wide regions: keep 32 hits per region on chip before falling back to a second walk
-		if (tile == 64) k_t4<64, 16, 32><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
-		else if (tile == 128) k_t4<128, 10, 32><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
-		else k_t4<256, 5, 32><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
-	} else {
-		if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
-		else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
-		else k_t4<256, 5, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
-	}
+	if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (min_ctas == 6) k_t4<256, 6, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (min_ctas == 8) k_t4<256, 8, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (min_ctas == 4) k_t4<256, 4, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else k_t4<256, 5, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
 #undef VSGPU_T4_ARGS
 	return cudaGetLastError();
 }
