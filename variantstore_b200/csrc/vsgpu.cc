@@ -309,7 +309,7 @@ void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy,
             DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr, uint32_t* d_status = nullptr, bool many_hits = false) {
 	if (!d_status) d_status = ix->d_status;
 	CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(t4_state_words(n) * 8));
-	if (hits_cap == 0) { hits_cap = std::max<uint64_t>((many_hits ? 32 : 4) * n, 1024);   // only sizes the first guess of the hit buffer CU(hits.ensure(hits_cap * 4)); }
+	if (hits_cap == 0) { hits_cap = std::max<uint64_t>((many_hits ? 32 : 4) * n, 1024); CU(hits.ensure(hits_cap * 4)); }   // many_hits only sizes the first guess
 	CU(cudaMemsetAsync(state.p, 0, t4_state_words(n) * 8, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[0], ix->stream));
 	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, ix->stream));
