@@ -219,28 +219,6 @@ VSGPU_HD uint32_t row_bits(const uint32_t* row, uint32_t pos, uint32_t len) {
 	return (uint32_t)(v >> off) & (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1));
 }
 
-// One step of the forward walk on a carried entry (or marker) `ci`.  Returns true when the walk ends.
-struct FwdState { uint32_t cur_k, limit, k_end, x, y; };
-template <class Sink>
-VSGPU_HD bool fwd_step(const DevIndex& ix, FwdState& st, uint32_t s, uint32_t ci, const uint4& e, Sink& sink) {
-	if (ci >= st.limit) return true;
-	if (e.x < st.cur_k) return false;                                          // hidden behind a taken detour / later sibling
-	if (e.x > st.cur_k && e.x >= st.k_end) return true;                        // the walk stopped before reaching P[e.x]
-	if (e.y & kEntMarker) return e.w >= st.y;
-	if (e.w >= st.y) return true;
-	if (e.w >= st.x) sink.emit(ci);
-	if (e.y & kEntAlt) {
-		const uint32_t tk = e.y & kEntTgtMask;
-		if (tk == kEntTgtMask || tk >= st.k_end) return true;
-		if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= st.x) sink.emit(ci | kHitRejoin);
-		st.cur_k = tk;
-	} else {
-		st.cur_k = e.y & kEntTgtMask;
-		if (st.cur_k >= st.k_end) { const uint32_t nl = ldg(ix.cent_begin_k + st.cur_k + 1); if (nl > st.limit) st.limit = nl; }   // its own entries still count
-	}
-	return false;
-}
-
 template <class Sink>
 VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
 	if (x64 > ix.index_bits) return;
@@ -260,8 +238,7 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, u
 	// The reference steps back through node_list by out-degree until a neighbour carries the sample.
 	// Those steps are the ancestors of the start state in the back-walk forest, so instead of
 	// stepping: take the sample's carried entries below the start, highest first (one row word covers
-	// 32 entries), and stop at the first whose source is examined by an ancestor state.  Loads are
-	// issued in pairs (two row words / two candidates) to shorten the dependent chain.
+	// 32 entries), and stop at the first whose source is examined by an ancestor state.
 	const uint32_t cur = rk - 1;                                                // ref_node_rank (index.h:135-148); x < index_bits here since rk < D
 	uint32_t c_found = kNoneU32;
 	if (cur >= 2) {
@@ -270,60 +247,64 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, u
 			uint32_t w = (pos - 1) >> 5;
 			uint32_t m = ldg(row + w) & (0xFFFFFFFFu >> (31 - ((pos - 1) & 31)));
 			for (;;) {
-				if (m == 0) {
-					if (w == 0) break;
-					const uint32_t w1 = w - 1, w2 = w1 ? w1 - 1 : 0;
-					const uint32_t m1 = ldg(row + w1), m2 = ldg(row + w2);
-					if (m1 || w1 == 0) { w = w1; m = m1; } else { w = w2; m = m2; }
-					continue;
-				}
-				const uint32_t b1 = 31 - clz32(m);
-				const uint32_t rest = m & ~(1u << b1);
-				const uint32_t b2 = rest ? 31 - clz32(rest) : b1;
-				const uint2 a1 = ldg(ix.cent_anc + ((w << 5) + b1)), a2 = ldg(ix.cent_anc + ((w << 5) + b2));
-				if (a1.x <= t && t <= a1.y) { c_found = (w << 5) + b1; break; }        // last carrier of the nearest examined vertex
-				if (rest && a2.x <= t && t <= a2.y) { c_found = (w << 5) + b2; break; }
-				m = rest ? rest & ~(1u << b2) : 0;
+				while (m == 0 && w > 0) { w--; m = ldg(row + w); }
+				if (m == 0) break;
+				const uint32_t b = 31 - clz32(m);
+				m &= ~(1u << b);
+				const uint32_t p = (w << 5) + b;
+				const uint2 a = ldg(ix.cent_anc + p);
+				if (a.x <= t && t <= a.y) { c_found = p; break; }                      // last carrier of the nearest examined vertex
 			}
 		}
 	}
 	// ---- forward walk (query.h:649-716)
-	FwdState st{0, dl.w, dl.x, x, y};                                           // limit: entries >= it have src >= k_end
-	uint32_t c = 0;
+	const uint32_t k_end = dl.x;                                                // first backbone vertex whose start >= y
+	uint32_t limit = dl.w;                                                      // entries >= limit have src >= k_end
+	uint32_t cur_k = 0, c = 0;
 	if (c_found != kNoneU32) {
 		const uint4 e = ldg(ix.cent + c_found);
 		if (e.w >= y) return;
 		if (e.w >= x) sink.emit(c_found | kHitStart);
 		if (e.y & kEntAlt) {
 			const uint32_t tk = e.y & kEntTgtMask;
-			if (tk == kEntTgtMask || tk >= st.k_end) return;
+			if (tk == kEntTgtMask || tk >= k_end) return;
 			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(c_found | kHitRejoin);
-			st.cur_k = tk;
+			cur_k = tk;
 		} else {
-			st.cur_k = e.y & kEntTgtMask;
-			if (st.cur_k >= st.k_end) { const uint32_t nl = ldg(ix.cent_begin_k + st.cur_k + 1); if (nl > st.limit) st.limit = nl; }
+			cur_k = e.y & kEntTgtMask;
+			if (cur_k >= k_end) { const uint32_t nl = ldg(ix.cent_begin_k + cur_k + 1); if (nl > limit) limit = nl; }   // its own entries still count
 		}
 		c = c_found + 1;
 	} else {
 		if (1 >= y) return;
 	}
-	if (c >= st.limit) return;
+	if (c >= limit) return;
 	uint32_t w = c >> 5;
 	uint32_t m = (ldg(row + w) | ldg(ix.marker_bits + w)) & (0xFFFFFFFFu << (c & 31));
 	for (;;) {
 		while (m == 0) {
 			w++;
-			if ((w << 5) >= st.limit) return;
+			if ((w << 5) >= limit) return;
 			m = ldg(row + w) | ldg(ix.marker_bits + w);
 		}
-		// up to three carried entries of this word at once: their loads are independent
-		const uint32_t c0 = (w << 5) + ctz32(m); m &= m - 1;
-		const uint32_t c1 = m ? (w << 5) + ctz32(m) : c0; const bool h1 = m != 0; m &= m - 1;
-		const uint32_t c2 = m ? (w << 5) + ctz32(m) : c0; const bool h2 = m != 0; m &= m - 1;
-		const uint4 e0 = ldg(ix.cent + c0), e1 = ldg(ix.cent + c1), e2 = ldg(ix.cent + c2);
-		if (fwd_step(ix, st, s, c0, e0, sink)) return;
-		if (h1 && fwd_step(ix, st, s, c1, e1, sink)) return;
-		if (h2 && fwd_step(ix, st, s, c2, e2, sink)) return;
+		const uint32_t ci = (w << 5) + ctz32(m);
+		m &= m - 1;
+		if (ci >= limit) return;
+		const uint4 e = ldg(ix.cent + ci);
+		if (e.x < cur_k) continue;                                                 // hidden behind a taken detour / later sibling
+		if (e.x > cur_k && e.x >= k_end) return;                                   // the walk stopped before reaching P[e.x]
+		if (e.y & kEntMarker) { if (e.w >= y) return; continue; }
+		if (e.w >= y) return;
+		if (e.w >= x) sink.emit(ci);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask || tk >= k_end) return;
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(ci | kHitRejoin);
+			cur_k = tk;
+		} else {
+			cur_k = e.y & kEntTgtMask;
+			if (cur_k >= k_end) { const uint32_t nl = ldg(ix.cent_begin_k + cur_k + 1); if (nl > limit) limit = nl; }
+		}
 	}
 }
 
