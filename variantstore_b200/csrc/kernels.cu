@@ -210,7 +210,7 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 	const uint32_t tile = t4_tile();
 	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
 	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
-	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 5; }
+	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 6; }
 #define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
 	if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
 	else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
