@@ -1,0 +1,73 @@
+"""Malformed `ser/` directories must come back as VSGPU_EIO / VSGPU_ESHAPE errors, never as a crash
+or a silently wrong index (loader + flattener run identically under the CUDA library and the
+test-only host build)."""
+import os
+import shutil
+
+import pytest
+
+import vs_testlib as T
+
+
+def open_hostsim(prefix):
+    from variantstore_b200 import VariantStoreIndex, load_library
+    return VariantStoreIndex(prefix, lib=load_library(T.HOSTSIM_SO, subset=True))
+
+
+@pytest.fixture()
+def ser_copy(tmp_path):
+    dst = str(tmp_path / "ser")
+    shutil.copytree(os.path.join(T.GOLDEN, "x_ser"), dst)
+    return dst
+
+
+@pytest.mark.parametrize("victim", ["index.sdsl", "ref_node_id.sdsl", "adj_list.cqf", "aux_vertex_list.sdsl", "seq_buffer.sdsl",
+                                    "sample_vector.sdsl", "vertex_list_0.proto", "sampleid_map.lst"])
+def test_missing_file(ser_copy, victim):
+    from variantstore_b200 import VsgpuError
+    os.remove(os.path.join(ser_copy, victim))
+    with pytest.raises(VsgpuError) as ei:
+        open_hostsim(ser_copy)
+    assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("victim", ["index.sdsl", "adj_list.cqf", "vertex_list_0.proto", "seq_buffer.sdsl", "sample_vector.sdsl"])
+def test_truncated_file(ser_copy, victim):
+    from variantstore_b200 import VsgpuError
+    p = os.path.join(ser_copy, victim)
+    data = open(p, "rb").read()
+    open(p, "wb").write(data[: len(data) // 2])
+    with pytest.raises(VsgpuError) as ei:
+        open_hostsim(ser_copy)
+    assert ei.value.code in (-2, -3)
+
+
+def test_bad_cqf_magic(ser_copy):
+    from variantstore_b200 import VsgpuError
+    p = os.path.join(ser_copy, "adj_list.cqf")
+    data = bytearray(open(p, "rb").read())
+    data[0] ^= 0xFF
+    open(p, "wb").write(bytes(data))
+    with pytest.raises(VsgpuError) as ei:
+        open_hostsim(ser_copy)
+    assert ei.value.code == -2 and "magic" in str(ei.value)
+
+
+def test_index_of_another_graph_is_rejected(tmp_path, ser_copy):
+    """index.sdsl / ref_node_id.sdsl that do not describe this graph's ref path -> VSGPU_ESHAPE."""
+    from variantstore_b200 import VsgpuError
+    other = os.path.join(T.GOLDEN, "xsmall_ser")
+    for f in ("index.sdsl", "ref_node_id.sdsl"):
+        shutil.copy(os.path.join(other, f), os.path.join(ser_copy, f))
+    with pytest.raises(VsgpuError) as ei:
+        open_hostsim(ser_copy)
+    assert ei.value.code == -3
+
+
+def test_sample_count_mismatch(ser_copy):
+    from variantstore_b200 import VsgpuError
+    p = os.path.join(ser_copy, "sampleid_map.lst")
+    lines = open(p).read().split("\n")
+    open(p, "w").write("\n".join(lines[:2] + lines[3:]))       # drop one "<name> <id>" row
+    with pytest.raises(VsgpuError):
+        open_hostsim(ser_copy)
