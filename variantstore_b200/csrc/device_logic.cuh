@@ -219,20 +219,47 @@ VSGPU_HD uint32_t row_bits(const uint32_t* row, uint32_t pos, uint32_t len) {
 	return (uint32_t)(v >> off) & (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1));
 }
 
+// State of the forward walk: scan cursor `c` over the walk entries, the backbone index the walk
+// has reached (`cur_k`: entries with a smaller source are hidden), the scan bound `limit`.
+struct FwdState { const uint32_t* row; uint32_t c, cur_k, limit, k_end, x, y; };
+
+// One step of the forward walk on a carried entry (or marker) `ci`.  Returns true when the walk ends.
 template <class Sink>
-VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
-	if (x64 > ix.index_bits) return;
+VSGPU_HD bool fwd_step(const DevIndex& ix, FwdState& st, uint32_t s, uint32_t ci, const uint4& e, Sink& sink) {
+	if (ci >= st.limit) return true;
+	if (e.x < st.cur_k) return false;                                          // hidden behind a taken detour / later sibling
+	if (e.x > st.cur_k && e.x >= st.k_end) return true;                        // the walk stopped before reaching P[e.x]
+	if (e.y & kEntMarker) return e.w >= st.y;
+	if (e.w >= st.y) return true;
+	if (e.w >= st.x) sink.emit(ci);
+	if (e.y & kEntAlt) {
+		const uint32_t tk = e.y & kEntTgtMask;
+		if (tk == kEntTgtMask || tk >= st.k_end) return true;
+		if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= st.x) sink.emit(ci | kHitRejoin);
+		st.cur_k = tk;
+	} else {
+		st.cur_k = e.y & kEntTgtMask;
+		if (st.cur_k >= st.k_end) { const uint32_t nl = ldg(ix.cent_begin_k + st.cur_k + 1); if (nl > st.limit) st.limit = nl; }   // its own entries still count
+	}
+	return false;
+}
+
+// Ranks, gate, back-walk and the vertex the walk starts on.  Returns true when a forward scan from
+// st.c remains to be done.
+template <class Sink>
+VSGPU_HD bool fast_setup(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink, FwdState& st) {
+	if (x64 > ix.index_bits) return false;
 	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
 	uint32_t rk, e_y;                                                           // rank(x); first start >= y
 	rank_le2(ix, x, y ? y - 1 : 0, rk, e_y);
 	if (!y) e_y = 0;
-	if (rk < 1 || rk >= ix.D) return;
+	if (rk < 1 || rk >= ix.D) return false;
 	// everything the next steps need from the index, issued together
 	const uint32_t next_start = ldg(ix.dstart + rk);
 	const uint64_t info = ldg(ix.dinfo + (rk >= 2 ? rk - 2 : 0));
 	const uint32_t t = ldg(ix.dtin + (rk - 1));
 	const uint4 dl = ldg(ix.dlev + e_y);
-	if ((uint64_t)next_start > (uint64_t)y + 1) return;                         // is_empty gate
+	if ((uint64_t)next_start > (uint64_t)y + 1) return false;                   // is_empty gate
 	const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
 	// ---- get_prev_vertex_with_sample (query.h:57-113)
 	// The reference steps back through node_list by out-degree until a neighbour carries the sample.
@@ -257,55 +284,51 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, u
 			}
 		}
 	}
-	// ---- forward walk (query.h:649-716)
-	const uint32_t k_end = dl.x;                                                // first backbone vertex whose start >= y
-	uint32_t limit = dl.w;                                                      // entries >= limit have src >= k_end
-	uint32_t cur_k = 0, c = 0;
+	// ---- the vertex the walk starts on (query.h:649-654)
+	st.row = row; st.c = 0; st.cur_k = 0; st.limit = dl.w; st.k_end = dl.x; st.x = x; st.y = y;   // entries >= limit have src >= k_end
 	if (c_found != kNoneU32) {
 		const uint4 e = ldg(ix.cent + c_found);
-		if (e.w >= y) return;
+		if (e.w >= y) return false;
 		if (e.w >= x) sink.emit(c_found | kHitStart);
 		if (e.y & kEntAlt) {
 			const uint32_t tk = e.y & kEntTgtMask;
-			if (tk == kEntTgtMask || tk >= k_end) return;
+			if (tk == kEntTgtMask || tk >= st.k_end) return false;
 			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(c_found | kHitRejoin);
-			cur_k = tk;
+			st.cur_k = tk;
 		} else {
-			cur_k = e.y & kEntTgtMask;
-			if (cur_k >= k_end) { const uint32_t nl = ldg(ix.cent_begin_k + cur_k + 1); if (nl > limit) limit = nl; }   // its own entries still count
+			st.cur_k = e.y & kEntTgtMask;
+			if (st.cur_k >= st.k_end) { const uint32_t nl = ldg(ix.cent_begin_k + st.cur_k + 1); if (nl > st.limit) st.limit = nl; }   // its own entries still count
 		}
-		c = c_found + 1;
+		st.c = c_found + 1;
 	} else {
-		if (1 >= y) return;
+		if (1 >= y) return false;
 	}
-	if (c >= limit) return;
-	uint32_t w = c >> 5;
-	uint32_t m = (ldg(row + w) | ldg(ix.marker_bits + w)) & (0xFFFFFFFFu << (c & 31));
+	return st.c < st.limit;
+}
+
+// ---- forward walk (query.h:649-716), one thread
+template <class Sink>
+VSGPU_HD void fast_forward(const DevIndex& ix, FwdState& st, uint32_t s, Sink& sink) {
+	uint32_t w = st.c >> 5;
+	uint32_t m = (ldg(st.row + w) | ldg(ix.marker_bits + w)) & (0xFFFFFFFFu << (st.c & 31));
 	for (;;) {
 		while (m == 0) {
 			w++;
-			if ((w << 5) >= limit) return;
-			m = ldg(row + w) | ldg(ix.marker_bits + w);
+			if ((w << 5) >= st.limit) return;
+			m = ldg(st.row + w) | ldg(ix.marker_bits + w);
 		}
 		const uint32_t ci = (w << 5) + ctz32(m);
 		m &= m - 1;
-		if (ci >= limit) return;
+		if (ci >= st.limit) return;
 		const uint4 e = ldg(ix.cent + ci);
-		if (e.x < cur_k) continue;                                                 // hidden behind a taken detour / later sibling
-		if (e.x > cur_k && e.x >= k_end) return;                                   // the walk stopped before reaching P[e.x]
-		if (e.y & kEntMarker) { if (e.w >= y) return; continue; }
-		if (e.w >= y) return;
-		if (e.w >= x) sink.emit(ci);
-		if (e.y & kEntAlt) {
-			const uint32_t tk = e.y & kEntTgtMask;
-			if (tk == kEntTgtMask || tk >= k_end) return;
-			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(ci | kHitRejoin);
-			cur_k = tk;
-		} else {
-			cur_k = e.y & kEntTgtMask;
-			if (cur_k >= k_end) { const uint32_t nl = ldg(ix.cent_begin_k + cur_k + 1); if (nl > limit) limit = nl; }
-		}
+		if (fwd_step(ix, st, s, ci, e, sink)) return;
 	}
+}
+
+template <class Sink>
+VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	FwdState st;
+	if (fast_setup(ix, x64, y64, s, sink, st)) fast_forward(ix, st, s, sink);
 }
 
 template <class Sink>
