@@ -42,7 +42,12 @@ def test_tcga_like_sparse_t7_cuda(tmp_path):
         assert not bad6 and not bad4
 
 
-def test_width_sweep_cuda(tmp_path):
+@pytest.mark.parametrize("wide_entries", [None, "64"])
+def test_width_sweep_cuda(tmp_path, monkeypatch, wide_entries):
+    if wide_entries:
+        monkeypatch.setenv("VSGPU_WIDE_ENTRIES", wide_entries)     # push more regions onto the warp-cooperative path
+    else:
+        monkeypatch.delenv("VSGPU_WIDE_ENTRIES", raising=False)
     o = Oracle.synth(str(tmp_path / "ser"), ref_length=3_000_000, n_records=90_000, n_samples=300, fmax=120, seed=12, cqf_log2=20)
     with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
         rng = np.random.default_rng(2)

@@ -28,14 +28,17 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps"])
+@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative"])
 def walk_path(request, monkeypatch):
-    """Both t4 kernels paths: the sample-major hit map (default) and the per-entry class-bitmap test
-    used when the map does not fit the memory budget."""
+    """The t4 kernel paths: the sample-major hit map with one thread per region (default), the
+    per-entry class-bitmap test used when the map does not fit the memory budget, and the
+    warp-cooperative scan for wide regions (forced onto every region longer than 8 walk entries)."""
+    monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
+    monkeypatch.delenv("VSGPU_WIDE_ENTRIES", raising=False)
     if request.param == "class-bitmaps":
         monkeypatch.setenv("VSGPU_DISABLE_HITMAP", "1")
-    else:
-        monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
+    elif request.param == "warp-cooperative":
+        monkeypatch.setenv("VSGPU_WIDE_ENTRIES", "8")
     return request.param
 
 

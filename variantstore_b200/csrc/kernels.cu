@@ -69,13 +69,111 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 	return v;
 }
 
+// ------------------------------------------------------------------ wide regions: one warp per region
+// A region whose scan range is long keeps one thread busy for thousands of dependent loads while the
+// rest of its warp idles.  Here the whole warp takes such a region: 32 row words per load, the
+// carried entries of the window fetched 32 at a time, and the chain rules resolved in parallel —
+// every lane decides "hidden?" from an exclusive max-scan of the detour targets before it, checked
+// for self-consistency (a hidden entry must not have contributed), falling back to a lane-by-lane
+// pass for the batch when that check or a rare entry kind (rejoin carrier, walk past the bound) says so.
+// Output order is kept with ballot/popc ranks.  Same answers as fast_forward.
+struct CoopSink {            // all lanes call emit with identical arguments; lane 0 writes
+	uint32_t* slot; uint32_t stride, keep; uint32_t* direct; uint32_t n; bool writer;
+	__device__ __forceinline__ void put(uint32_t pos, uint32_t code) { if (direct) direct[pos] = code; else if (pos < keep) slot[pos * stride] = code; }
+	__device__ __forceinline__ void emit(uint32_t code) { if (writer) put(n, code); n++; }
+};
+
+__device__ __forceinline__ uint32_t warp_excl_max(uint32_t v, uint32_t lane) {   // exclusive prefix max, identity 0
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= (uint32_t)d) inc = max(inc, t); }
+	const uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+	return lane ? ex : 0;
+}
+
+__device__ __noinline__ uint32_t coop_forward(const DevIndex& ix, FwdState st, uint32_t s, CoopSink sink) {
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1;
+	while (st.c < st.limit) {
+		const uint32_t limit0 = st.limit;
+		const uint32_t w0 = st.c >> 5, w = w0 + lane;
+		uint32_t m = ((uint64_t)w << 5) < limit0 ? (__ldg(st.row + w) | __ldg(ix.marker_bits + w)) : 0;
+		if (lane == 0) m &= 0xFFFFFFFFu << (st.c & 31);
+		const uint32_t cnt = __popc(m);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+		const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - cnt;
+		bool restart = false;
+		for (uint32_t base = 0; base < total && !restart; base += 32) {
+			// lane j takes hit number base + j of the window: owner word = number of lanes whose inclusive count <= h
+			const uint32_t h = base + lane;
+			const bool valid = h < total;
+			uint32_t o = 0;
+#pragma unroll
+			for (int step = 16; step > 0; step >>= 1) { const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (o + step - 1) & 31); if (v <= h) o += step; }
+			o &= 31;
+			const uint32_t m_o = __shfl_sync(0xFFFFFFFFu, m, o), excl_o = __shfl_sync(0xFFFFFFFFu, excl, o);
+			const uint32_t ci = valid ? ((w0 + o) << 5) + __fns(m_o, 0, (int)(h - excl_o) + 1) : 0;
+			const uint4 e = valid ? __ldg(ix.cent + ci) : make_uint4(0, 0, 0, 0);
+			const uint32_t nb = min(32u, total - base);
+			// ---- per-lane facts
+			const bool marker = (e.y & kEntMarker) != 0, isalt = (e.y & kEntAlt) != 0;
+			const uint32_t tk = e.y & kEntTgtMask;
+			const uint32_t jump = (valid && !marker) ? tk : 0;             // where the walk continues if this entry is taken
+			const bool beyond = valid && ci >= st.limit;
+			// ---- hidden? fixed point of  hidden_j = src_j < max(cur_k, max over earlier non-hidden jumps)
+			uint32_t M = max(st.cur_k, warp_excl_max(jump == kEntTgtMask ? 0 : jump, lane));
+			bool hidden = valid && e.x < M;
+			bool ok = false;
+			for (int it = 0; it < 3 && !ok; it++) {
+				const uint32_t M2 = max(st.cur_k, warp_excl_max((hidden || jump == kEntTgtMask) ? 0 : jump, lane));
+				const bool hidden2 = valid && e.x < M2;
+				ok = !__any_sync(0xFFFFFFFFu, hidden2 != hidden);
+				hidden = hidden2; M = M2;
+			}
+			const bool stop_before = valid && (beyond || (!hidden && ((e.x > M && e.x >= st.k_end) || e.w >= st.y)));
+			const bool live = valid && !hidden && !marker && !stop_before;
+			const bool stop_after = live && isalt && (tk == kEntTgtMask || tk >= st.k_end);
+			const bool rare = live && ((isalt && (e.y & kEntTgtCarriers)) || (!isalt && tk >= st.k_end));
+			const uint32_t stop_mask = __ballot_sync(0xFFFFFFFFu, stop_before || stop_after);
+			const uint32_t first_stop = stop_mask ? (uint32_t)__ffs((int)stop_mask) - 1 : 32;
+			const uint32_t upto = first_stop < 32 ? (2u << first_stop) - 1 : 0xFFFFFFFFu;   // lanes 0..first_stop
+			const uint32_t rare_mask = __ballot_sync(0xFFFFFFFFu, rare) & upto;
+			if (!ok || rare_mask) {
+				// lane-by-lane pass over this batch with the single-thread rules (all lanes in lock step)
+				for (uint32_t j = 0; j < nb; j++) {
+					const uint32_t cj = __shfl_sync(0xFFFFFFFFu, ci, j);
+					const uint4 ej = make_uint4(__shfl_sync(0xFFFFFFFFu, e.x, j), __shfl_sync(0xFFFFFFFFu, e.y, j), __shfl_sync(0xFFFFFFFFu, e.z, j), __shfl_sync(0xFFFFFFFFu, e.w, j));
+					if (fwd_step(ix, st, s, cj, ej, sink)) return sink.n;
+				}
+				if (st.limit != limit0) { st.c = __shfl_sync(0xFFFFFFFFu, ci, nb - 1) + 1; restart = true; }   // the bound moved: reload the window
+				continue;
+			}
+			// ---- emit in order
+			const bool emit = live && e.w >= st.x && lane <= first_stop && !(lane == first_stop && stop_before);
+			const uint32_t emit_mask = __ballot_sync(0xFFFFFFFFu, emit);
+			if (emit) sink.put(sink.n + __popc(emit_mask & lt), ci);
+			sink.n += __popc(emit_mask);
+			if (first_stop < 32) return sink.n;
+			// ---- new walk position: the largest taken jump
+			const uint32_t Mend = max(M, (hidden || jump == kEntTgtMask) ? 0 : jump);
+			st.cur_k = max(st.cur_k, __shfl_sync(0xFFFFFFFFu, Mend, nb - 1));
+		}
+		if (!restart) st.c = (w0 + 32) << 5;
+	}
+	return sink.n;
+}
+
+// kCoop: compile the warp-cooperative path for wide regions in (the host picks it per batch; the lean
+// instantiation keeps the register budget of the common 1 kb case).
 // kTile = regions per CTA, one per thread; kKeep = hits per region staged in shared memory (a
 // region with more walks a second time, straight into its final place)
-template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
+template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep, bool kCoop>
 __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                              uint64_t* tile_state, uint32_t* status) {
+                                              uint64_t* tile_state, uint32_t* status, uint32_t wide_entries) {
 	__shared__ uint32_t s_hits[kTile * kKeep];
 	__shared__ uint64_t s_warp[kTile / 32];
 	__shared__ uint64_t s_base;
@@ -89,10 +187,26 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	// ---- phase 1: walk this thread's region
 	SmemSink<kTile, kKeep> sink{s_hits + threadIdx.x, 0};
 	uint64_t x = 0, y = 0; uint32_t s = 0;
+	FwdState st; st.c = st.limit = 0;
+	bool wide = false;
 	if (i < n) {
 		x = xs[i]; y = ys[i]; s = sample[i];
-		if (x < 1 || s == 0 || s >= ix.num_samples) atomicOr(status, kStatusBadRegion);
-		else walk_any(ix, x, y, s, sink);
+		if (x < 1 || s == 0 || s >= ix.num_samples) { atomicOr(status, kStatusBadRegion); s = 0; }
+		else if (!ix.hitmap) walk_region(ix, x, y, s, sink);
+		else if (fast_setup(ix, x, y, s, sink, st)) {
+			wide = kCoop && st.limit - st.c > wide_entries;
+			if (!wide) fast_forward(ix, st, s, sink);
+		}
+	}
+	if (kCoop) for (uint32_t wm = __ballot_sync(0xFFFFFFFFu, wide); wm; wm &= wm - 1) {       // the warp takes its wide regions one by one
+		const int L = __ffs((int)wm) - 1;
+		FwdState sl;
+		sl.row = (const uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)st.row, L);
+		sl.c = __shfl_sync(0xFFFFFFFFu, st.c, L); sl.cur_k = __shfl_sync(0xFFFFFFFFu, st.cur_k, L); sl.limit = __shfl_sync(0xFFFFFFFFu, st.limit, L);
+		sl.k_end = __shfl_sync(0xFFFFFFFFu, st.k_end, L); sl.x = __shfl_sync(0xFFFFFFFFu, st.x, L); sl.y = __shfl_sync(0xFFFFFFFFu, st.y, L);
+		CoopSink cs{s_hits + (threadIdx.x - lane + L), kTile, kKeep, nullptr, __shfl_sync(0xFFFFFFFFu, sink.n, L), lane == 0};
+		const uint32_t nl = coop_forward(ix, sl, __shfl_sync(0xFFFFFFFFu, s, L), cs);
+		if ((int)lane == L) sink.n = nl;
 	}
 	const uint32_t cnt = sink.n;
 
@@ -132,13 +246,32 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	__syncthreads();
 
 	// ---- phase 4: ordered write
+	const uint64_t off = s_base + wpre + (incl - cnt);
+	bool again = false;                    // more hits than the staging holds: walk again, straight into place
 	if (i < n) {
-		const uint64_t off = s_base + wpre + (incl - cnt);
 		offsets[i] = off;
 		if (i == n - 1) offsets[n] = off + cnt;
 		if (off + cnt > cap) atomicOr(status, kStatusOverflow);
 		else if (cnt <= kKeep) { for (uint32_t j = 0; j < cnt; j++) hits[off + j] = s_hits[j * kTile + threadIdx.x]; }
-		else { DirectSink direct{hits + off, 0}; walk_any(ix, x, y, s, direct); }   // rare: wide region, walk again straight into place
+		else again = true;
+	}
+	DirectSink direct{hits + off, 0};
+	wide = false;
+	if (again) {
+		if (!ix.hitmap) walk_region(ix, x, y, s, direct);
+		else if (fast_setup(ix, x, y, s, direct, st)) {
+			wide = kCoop && st.limit - st.c > wide_entries;
+			if (!wide) fast_forward(ix, st, s, direct);
+		}
+	}
+	if (kCoop) for (uint32_t wm = __ballot_sync(0xFFFFFFFFu, wide); wm; wm &= wm - 1) {
+		const int L = __ffs((int)wm) - 1;
+		FwdState sl;
+		sl.row = (const uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)st.row, L);
+		sl.c = __shfl_sync(0xFFFFFFFFu, st.c, L); sl.cur_k = __shfl_sync(0xFFFFFFFFu, st.cur_k, L); sl.limit = __shfl_sync(0xFFFFFFFFu, st.limit, L);
+		sl.k_end = __shfl_sync(0xFFFFFFFFu, st.k_end, L); sl.x = __shfl_sync(0xFFFFFFFFu, st.x, L); sl.y = __shfl_sync(0xFFFFFFFFu, st.y, L);
+		CoopSink cs{nullptr, 0, 0, (uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)direct.dst, L), __shfl_sync(0xFFFFFFFFu, direct.n, L), lane == 0};
+		coop_forward(ix, sl, __shfl_sync(0xFFFFFFFFu, s, L), cs);
 	}
 }
 
@@ -204,20 +337,27 @@ static uint32_t t4_tile() {
 	return tile;
 }
 uint64_t t4_state_words(uint64_t n) { return 2 + (n + 63) / 64; }
+uint32_t t4_wide_entries() {              // scan ranges longer than this many walk entries are taken by a whole warp
+	const char* e = getenv("VSGPU_WIDE_ENTRIES");          // test / tuning knob, read per launch
+	const uint32_t v = e ? (uint32_t)atoi(e) : 2048;
+	return v ? v : 1;
+}
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, cudaStream_t stream) {
+                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
+                      cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	const uint32_t tile = t4_tile();
 	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
 	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
 	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 6; }
-#define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
-	if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (min_ctas == 6) k_t4<256, 6, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (min_ctas == 8) k_t4<256, 8, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (min_ctas == 4) k_t4<256, 4, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
-	else k_t4<256, 5, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	uint32_t wide_entries = t4_wide_entries();
+#define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status, wide_entries
+	if (wide_regions && ix.hitmap) k_t4<256, 4, kScratchHits, true><<<(uint32_t)((n + 255) / 256), 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (tile == 64) k_t4<64, 16, kScratchHits, false><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (tile == 128) k_t4<128, 10, kScratchHits, false><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (min_ctas == 8) k_t4<256, 8, kScratchHits, false><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (min_ctas == 5) k_t4<256, 5, kScratchHits, false><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else k_t4<256, 6, kScratchHits, false><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
 #undef VSGPU_T4_ARGS
 	return cudaGetLastError();
 }

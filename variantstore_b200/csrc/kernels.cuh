@@ -51,7 +51,9 @@ cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const
 // t4_state_words(n) zeroed 64-bit words before every launch.
 uint64_t t4_state_words(uint64_t n);
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, cudaStream_t stream);
+                      uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
+                      cudaStream_t stream);
+uint32_t t4_wide_entries();
 
 // status word bits
 constexpr uint32_t kStatusBadRegion = 1;   // some region had x < 1

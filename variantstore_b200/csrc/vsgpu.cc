@@ -57,6 +57,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 	std::vector<void*> allocs;
 	uint64_t device_bytes = 0;
 	double hits_per_base = 0;         // walk-entry carriers per base for an average sample
+	double entries_per_base = 0;      // walk entries per covered base
 	uint32_t* d_status = nullptr;
 	std::mutex mu;
 	DevBuf bx, by, bs, bout, boffsets, bhits, bstate, bhash, brec;
@@ -153,6 +154,7 @@ void upload_index(vsgpu_index* ix) {
 		for (const auto& e : f.cent) if (!(e.tgt & kEntMarker)) carriers += set_size[e.set_id];
 		const long double span = std::max<long double>(1, (long double)f.dstart.back() - f.dstart[std::min<size_t>(1, f.dstart.size() - 1)] + 1);
 		ix->hits_per_base = (double)(carriers / (std::max<uint32_t>(f.num_samples, 2) - 1) / span);
+		ix->entries_per_base = (double)f.cent.size() / (double)span;
 	}
 	d.marker_bits = upload(ix, f.marker_bits);
 	d.cent_begin_k = upload(ix, f.cent_begin);
@@ -312,7 +314,7 @@ void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy,
 	if (hits_cap == 0) { hits_cap = std::max<uint64_t>((many_hits ? 32 : 4) * n, 1024); CU(hits.ensure(hits_cap * 4)); }   // many_hits only sizes the first guess
 	CU(cudaMemsetAsync(state.p, 0, t4_state_words(n) * 8, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[0], ix->stream));
-	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, ix->stream));
+	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, many_hits, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[1], ix->stream));
 	if (launches) *launches = 1;
 }
@@ -343,7 +345,12 @@ bool expect_many_hits(const vsgpu_index* ix, uint64_t n, const uint64_t* x, cons
 	const uint64_t step = std::max<uint64_t>(1, n / 1024);
 	long double w = 0; uint64_t m = 0;
 	for (uint64_t i = 0; i < n; i += step, m++) w += y[i] > x[i] ? (long double)std::min<uint64_t>(y[i] - x[i], ix->flat.ref_length) : 0;
-	return (double)(w / m) * ix->hits_per_base > 5.0;
+	(void)w;
+	// the widest sampled region, in walk entries: beyond the kernel's threshold the batch is launched
+	// with the warp-cooperative path compiled in
+	uint64_t wmax = 0;
+	for (uint64_t i = 0; i < n; i += step) if (y[i] > x[i]) wmax = std::max<uint64_t>(wmax, std::min<uint64_t>(y[i] - x[i], ix->flat.ref_length));
+	return (double)wmax * ix->entries_per_base > (double)t4_wide_entries();
 }
 
 // copy a finished t4 answer (device offsets[n+1] + hits) into a pooled page-locked result
