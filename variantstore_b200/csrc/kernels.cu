@@ -165,15 +165,13 @@ __device__ __noinline__ uint32_t coop_forward(const DevIndex& ix, FwdState st, u
 	return sink.n;
 }
 
-// kCoop: compile the warp-cooperative path for wide regions in (the host picks it per batch; the lean
-// instantiation keeps the register budget of the common 1 kb case).
 // kTile = regions per CTA, one per thread; kKeep = hits per region staged in shared memory (a
 // region with more walks a second time, straight into its final place)
-template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep, bool kCoop>
+template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
 __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                              uint64_t* tile_state, uint32_t* status, uint32_t wide_entries) {
+                                              uint64_t* tile_state, uint32_t* status) {
 	__shared__ uint32_t s_hits[kTile * kKeep];
 	__shared__ uint64_t s_warp[kTile / 32];
 	__shared__ uint64_t s_base;
@@ -187,26 +185,10 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	// ---- phase 1: walk this thread's region
 	SmemSink<kTile, kKeep> sink{s_hits + threadIdx.x, 0};
 	uint64_t x = 0, y = 0; uint32_t s = 0;
-	FwdState st; st.c = st.limit = 0;
-	bool wide = false;
 	if (i < n) {
 		x = xs[i]; y = ys[i]; s = sample[i];
-		if (x < 1 || s == 0 || s >= ix.num_samples) { atomicOr(status, kStatusBadRegion); s = 0; }
-		else if (!ix.hitmap) walk_region(ix, x, y, s, sink);
-		else if (fast_setup(ix, x, y, s, sink, st)) {
-			wide = kCoop && st.limit - st.c > wide_entries;
-			if (!wide) fast_forward(ix, st, s, sink);
-		}
-	}
-	if (kCoop) for (uint32_t wm = __ballot_sync(0xFFFFFFFFu, wide); wm; wm &= wm - 1) {       // the warp takes its wide regions one by one
-		const int L = __ffs((int)wm) - 1;
-		FwdState sl;
-		sl.row = (const uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)st.row, L);
-		sl.c = __shfl_sync(0xFFFFFFFFu, st.c, L); sl.cur_k = __shfl_sync(0xFFFFFFFFu, st.cur_k, L); sl.limit = __shfl_sync(0xFFFFFFFFu, st.limit, L);
-		sl.k_end = __shfl_sync(0xFFFFFFFFu, st.k_end, L); sl.x = __shfl_sync(0xFFFFFFFFu, st.x, L); sl.y = __shfl_sync(0xFFFFFFFFu, st.y, L);
-		CoopSink cs{s_hits + (threadIdx.x - lane + L), kTile, kKeep, nullptr, __shfl_sync(0xFFFFFFFFu, sink.n, L), lane == 0};
-		const uint32_t nl = coop_forward(ix, sl, __shfl_sync(0xFFFFFFFFu, s, L), cs);
-		if ((int)lane == L) sink.n = nl;
+		if (x < 1 || s == 0 || s >= ix.num_samples) atomicOr(status, kStatusBadRegion);
+		else walk_any(ix, x, y, s, sink);
 	}
 	const uint32_t cnt = sink.n;
 
@@ -246,32 +228,84 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	__syncthreads();
 
 	// ---- phase 4: ordered write
-	const uint64_t off = s_base + wpre + (incl - cnt);
-	bool again = false;                    // more hits than the staging holds: walk again, straight into place
 	if (i < n) {
+		const uint64_t off = s_base + wpre + (incl - cnt);
 		offsets[i] = off;
 		if (i == n - 1) offsets[n] = off + cnt;
 		if (off + cnt > cap) atomicOr(status, kStatusOverflow);
 		else if (cnt <= kKeep) { for (uint32_t j = 0; j < cnt; j++) hits[off + j] = s_hits[j * kTile + threadIdx.x]; }
-		else again = true;
+		else { DirectSink direct{hits + off, 0}; walk_any(ix, x, y, s, direct); }   // more hits than the staging holds: walk again, straight into place
 	}
-	DirectSink direct{hits + off, 0};
-	wide = false;
-	if (again) {
-		if (!ix.hitmap) walk_region(ix, x, y, s, direct);
-		else if (fast_setup(ix, x, y, s, direct, st)) {
-			wide = kCoop && st.limit - st.c > wide_entries;
-			if (!wide) fast_forward(ix, st, s, direct);
+}
+
+// ------------------------------------------------------------------ t4, one warp per region
+// For batches of few, wide regions (the scan-bound end of the width sweep): eight regions per CTA,
+// every warp runs the setup in lock step and then the cooperative scan above; up to kKeepW hits per
+// region are staged in shared memory and copied out coalesced once the look-back has the offset.
+template <uint32_t kKeepW>
+__global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
+                                                const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
+                                                uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
+                                                uint64_t* tile_state, uint32_t* status) {
+	constexpr uint32_t kWarps = 8;
+	__shared__ uint32_t s_hits[kWarps * kKeepW];
+	__shared__ uint32_t s_cnt[kWarps];
+	__shared__ uint64_t s_base;
+	__shared__ uint32_t s_tile;
+	if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);
+	__syncthreads();
+	const uint32_t tile = s_tile, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	volatile uint64_t* state = tile_state + 1;
+	const uint64_t i = (uint64_t)tile * kWarps + warp;
+	uint64_t x = 0, y = 0; uint32_t s = 0, cnt = 0;
+	bool valid = false;
+	if (i < n) {
+		x = xs[i]; y = ys[i]; s = sample[i];
+		if (x < 1 || s == 0 || s >= ix.num_samples) { if (lane == 0) atomicOr(status, kStatusBadRegion); }
+		else {
+			valid = true;
+			CoopSink sink{s_hits + warp * kKeepW, 1, kKeepW, nullptr, 0, lane == 0};
+			FwdState st;
+			if (!ix.hitmap) walk_region(ix, x, y, s, sink);
+			else if (fast_setup(ix, x, y, s, sink, st)) sink.n = coop_forward(ix, st, s, sink);
+			cnt = sink.n;
 		}
 	}
-	if (kCoop) for (uint32_t wm = __ballot_sync(0xFFFFFFFFu, wide); wm; wm &= wm - 1) {
-		const int L = __ffs((int)wm) - 1;
-		FwdState sl;
-		sl.row = (const uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)st.row, L);
-		sl.c = __shfl_sync(0xFFFFFFFFu, st.c, L); sl.cur_k = __shfl_sync(0xFFFFFFFFu, st.cur_k, L); sl.limit = __shfl_sync(0xFFFFFFFFu, st.limit, L);
-		sl.k_end = __shfl_sync(0xFFFFFFFFu, st.k_end, L); sl.x = __shfl_sync(0xFFFFFFFFu, st.x, L); sl.y = __shfl_sync(0xFFFFFFFFu, st.y, L);
-		CoopSink cs{nullptr, 0, 0, (uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)direct.dst, L), __shfl_sync(0xFFFFFFFFu, direct.n, L), lane == 0};
-		coop_forward(ix, sl, __shfl_sync(0xFFFFFFFFu, s, L), cs);
+	if (lane == 0) s_cnt[warp] = cnt;
+	__syncthreads();
+	uint64_t wpre = 0, agg = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < kWarps; w++) { if (w < warp) wpre += s_cnt[w]; agg += s_cnt[w]; }
+	if (warp == 0) {
+		uint64_t excl = 0;
+		if (tile == 0) { if (lane == 0) state[0] = kFlagIncl | agg; }
+		else {
+			if (lane == 0) state[tile] = kFlagAgg | agg;
+			for (int64_t idx = (int64_t)tile - 1;; idx -= 32) {
+				const int64_t j = idx - lane;
+				uint64_t stt = j >= 0 ? state[j] : kFlagIncl;
+				while (__any_sync(0xFFFFFFFFu, (stt >> 62) == 0)) { if ((stt >> 62) == 0) stt = state[j]; }
+				const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (stt >> 62) == 2);
+				const uint64_t v = stt & kValMask;
+				if (incl_mask) { const uint32_t first = (uint32_t)__ffs((int)incl_mask) - 1; excl += warp_sum(lane <= first ? v : 0); break; }
+				excl += warp_sum(v);
+			}
+			if (lane == 0) state[tile] = kFlagIncl | (excl + agg);
+		}
+		if (lane == 0) s_base = excl;
+	}
+	__syncthreads();
+	if (i < n) {
+		const uint64_t off = s_base + wpre;
+		if (lane == 0) { offsets[i] = off; if (i == n - 1) offsets[n] = off + cnt; }
+		if (off + cnt > cap) { if (lane == 0) atomicOr(status, kStatusOverflow); }
+		else if (cnt <= kKeepW) { for (uint32_t j = lane; j < cnt; j += 32) hits[off + j] = s_hits[warp * kKeepW + j]; }
+		else if (valid) {
+			CoopSink direct{nullptr, 0, 0, hits + off, 0, lane == 0};
+			FwdState st;
+			if (!ix.hitmap) walk_region(ix, x, y, s, direct);
+			else if (fast_setup(ix, x, y, s, direct, st)) coop_forward(ix, st, s, direct);
+		}
 	}
 }
 
@@ -336,12 +370,12 @@ static uint32_t t4_tile() {
 	if (!tile) { const char* e = getenv("VSGPU_T4_TILE"); tile = e ? (uint32_t)atoi(e) : 256; if (tile != 64 && tile != 128 && tile != 256) tile = 256; }
 	return tile;
 }
-uint64_t t4_state_words(uint64_t n) { return 2 + (n + 63) / 64; }
 uint32_t t4_wide_entries() {              // scan ranges longer than this many walk entries are taken by a whole warp
 	const char* e = getenv("VSGPU_WIDE_ENTRIES");          // test / tuning knob, read per launch
 	const uint32_t v = e ? (uint32_t)atoi(e) : 2048;
 	return v ? v : 1;
 }
+uint64_t t4_state_words(uint64_t n) { return 2 + (n + 7) / 8; }
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
                       cudaStream_t stream) {
@@ -350,14 +384,13 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
 	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
 	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 6; }
-	uint32_t wide_entries = t4_wide_entries();
-#define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status, wide_entries
-	if (wide_regions && ix.hitmap) k_t4<256, 4, kScratchHits, true><<<(uint32_t)((n + 255) / 256), 256, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (tile == 64) k_t4<64, 16, kScratchHits, false><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (tile == 128) k_t4<128, 10, kScratchHits, false><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (min_ctas == 8) k_t4<256, 8, kScratchHits, false><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
-	else if (min_ctas == 5) k_t4<256, 5, kScratchHits, false><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
-	else k_t4<256, 6, kScratchHits, false><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+#define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
+	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each
+	else if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (min_ctas == 8) k_t4<256, 8, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else if (min_ctas == 5) k_t4<256, 5, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	else k_t4<256, 6, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
 #undef VSGPU_T4_ARGS
 	return cudaGetLastError();
 }

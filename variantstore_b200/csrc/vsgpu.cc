@@ -350,7 +350,11 @@ bool expect_many_hits(const vsgpu_index* ix, uint64_t n, const uint64_t* x, cons
 	// with the warp-cooperative path compiled in
 	uint64_t wmax = 0;
 	for (uint64_t i = 0; i < n; i += step) if (y[i] > x[i]) wmax = std::max<uint64_t>(wmax, std::min<uint64_t>(y[i] - x[i], ix->flat.ref_length));
-	return (double)wmax * ix->entries_per_base > (double)t4_wide_entries();
+	// ... and only when a warp per region still fills the GPU sensibly (a thread per region is the
+	// better mapping for large batches, measured in profiles/README.md)
+	uint64_t max_regions = 150000;
+	if (const char* e = getenv("VSGPU_WIDE_MAX_REGIONS")) max_regions = strtoull(e, nullptr, 10);
+	return n <= max_regions && (double)wmax * ix->entries_per_base > (double)t4_wide_entries();
 }
 
 // copy a finished t4 answer (device offsets[n+1] + hits) into a pooled page-locked result
