@@ -101,7 +101,7 @@ struct vsgpu_batch {
 	std::vector<uint64_t> hx, hy;   // host copies kept for the byte accounting
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint32_t* d_status = nullptr;    // per batch: several batches may be in flight on one index
-	bool many_hits = false;
+	bool wide_regions = false;
 	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec}) b->release(); }
 };
 
@@ -308,13 +308,13 @@ namespace {
 // region) and, if the kernel reports an overflow, re-sized from the total it computed and the pass
 // repeated — results are deterministic, so a batch pays that at most once.
 void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
-            DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr, uint32_t* d_status = nullptr, bool many_hits = false) {
+            DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr, uint32_t* d_status = nullptr, bool wide_regions = false) {
 	if (!d_status) d_status = ix->d_status;
 	CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(t4_state_words(n) * 8));
-	if (hits_cap == 0) { hits_cap = std::max<uint64_t>((many_hits ? 32 : 4) * n, 1024); CU(hits.ensure(hits_cap * 4)); }   // many_hits only sizes the first guess
+	if (hits_cap == 0) { hits_cap = std::max<uint64_t>((wide_regions ? 64 : 4) * n, 1024); CU(hits.ensure(hits_cap * 4)); }
 	CU(cudaMemsetAsync(state.p, 0, t4_state_words(n) * 8, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[0], ix->stream));
-	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, many_hits, ix->stream));
+	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, wide_regions, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[1], ix->stream));
 	if (launches) *launches = 1;
 }
@@ -323,14 +323,14 @@ void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy,
 // decision is taken from the total the kernel computed, not from the (shared) status word.
 // Returns the status bits left after that.
 uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
-                   DevBuf& hits, uint64_t& hits_cap, uint32_t* d_status, bool many_hits = false) {
+                   DevBuf& hits, uint64_t& hits_cap, uint32_t* d_status, bool wide_regions = false) {
 	uint64_t total = 0;
 	CU(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
 	uint32_t st = read_status(ix, d_status);
 	if (total > hits_cap) {
 		hits_cap = total + total / 16 + 1024;
 		CU(hits.ensure(hits_cap * 4));
-		run_t4(ix, n, dx, dy, ds, offsets, state, hits, hits_cap, nullptr, nullptr, d_status, many_hits);
+		run_t4(ix, n, dx, dy, ds, offsets, state, hits, hits_cap, nullptr, nullptr, d_status, wide_regions);
 		st = (st | read_status(ix, d_status));
 	}
 	return st & ~kStatusOverflow;
@@ -338,14 +338,11 @@ uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64
 }  // namespace
 
 namespace {
-// Expected hits per region from a sample of the region widths and the index's carrier density
-// (hits per base for an average sample); above ~5 the kernel keeps 32 hits per region on chip.
-bool expect_many_hits(const vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y) {
+// Does this batch look like "few, wide regions" (the scan-bound end of the width sweep)?  Decided from
+// a sample of the region widths and the index's walk-entry density; such batches get a warp per region.
+bool expect_wide_regions(const vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y) {
 	if (n == 0) return false;
 	const uint64_t step = std::max<uint64_t>(1, n / 1024);
-	long double w = 0; uint64_t m = 0;
-	for (uint64_t i = 0; i < n; i += step, m++) w += y[i] > x[i] ? (long double)std::min<uint64_t>(y[i] - x[i], ix->flat.ref_length) : 0;
-	(void)w;
 	// the widest sampled region, in walk entries: beyond the kernel's threshold the batch is launched
 	// with the warp-cooperative path compiled in
 	uint64_t wmax = 0;
@@ -391,9 +388,9 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream));
 			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream));
 			uint64_t cap = ix->bhits.cap / 4;
-			const bool many = expect_many_hits(ix, n, x, y);
-			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, nullptr, many);
-			uint32_t st = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, many);
+			const bool wide = expect_wide_regions(ix, n, x, y);
+			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, nullptr, wide);
+			uint32_t st = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, wide);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 		}
 		*out = fetch_t4(ix, n, ix->boffsets, ix->bhits, true);
@@ -530,7 +527,7 @@ int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x,
 		CU(cudaMemcpyAsync(b->x.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
 		if (type != 7) { CU(b->y.ensure(n * 8)); CU(cudaMemcpyAsync(b->y.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream)); }
 		if (type == 6) CU(b->out.ensure(n * 8));
-		if (type == 4) { b->many_hits = expect_many_hits(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 8)); }
+		if (type == 4) { b->wide_regions = expect_wide_regions(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 8)); }
 		if (type == 7) {
 			std::vector<uint64_t> qh(n);
 			for (uint64_t i = 0; i < n; i++) qh[i] = hash_query(refs[i], alts[i]);
@@ -552,7 +549,7 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
 		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + b->n, b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
-		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status, b->many_hits);
+		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status, b->wide_regions);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
@@ -570,7 +567,7 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 			uint32_t st = read_status(ix, b->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
 		} else {
-			uint32_t st = finish_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, b->d_status, b->many_hits);
+			uint32_t st = finish_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, b->d_status, b->wide_regions);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 			vsgpu_result* r = fetch_t4(ix, n, b->offsets, b->hits, out != nullptr);
 			if (counts) for (uint64_t i = 0; i < n; i++) counts[i] = (uint32_t)(r->offsets[i + 1] - r->offsets[i]);
