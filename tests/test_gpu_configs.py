@@ -98,3 +98,47 @@ def test_multi_contig_sharded_cuda(tmp_path):
             want = "\n".join(oracles[c].t4_text(int(x[i]), int(y[i]), samples[i])[0].split("\n")[2:])
             assert texts[i] == want
     sh.close()
+
+
+def test_full_size_chr22_shape_cuda(tmp_path):
+    """BASELINE.json config [1] at full size (1.1 M records x 2 504 samples, 1 M regions): the oracle
+    checks a 3 000-region subsample bit for bit; the full batch is checked through size-independent
+    properties (split invariance = a checksum of checksums, idempotence, t6 slice algebra, CSR sanity)."""
+    from variantstore_b200 import Batch
+    o = Oracle.synth(str(tmp_path / "ser"), chr_name="22", ref_length=51_304_566, pos_lo=16_050_000, pos_hi=51_244_566,
+                     n_records=1_103_547, n_samples=2504, fmax=1100, seed=2022, cqf_log2=25)
+    ci = o.construct_info
+    assert 3_000_000 < ci["vertices"] < 3_500_000 and 400_000 < ci["classes"] < 520_000        # chr22-like (vs_v1.log:3-15)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        rng = np.random.default_rng(1)
+        n = 1_000_000
+        x = np.sort(rng.integers(16_050_000, 51_304_566 - 1000, n)).astype(np.uint64)
+        y = x + np.uint64(1000)
+        s = rng.integers(1, 2505, n).astype(np.uint32)
+        sub = rng.choice(n, 3000, replace=False)
+        bad6, bad4, _ = T.compare_all(o, e, x[sub], y[sub], s[sub])
+        assert not bad6 and not bad4
+        assert not T.compare_t1(o, e, x[sub[:1000]])
+        # whole batch, twice (idempotence), and as two halves (split invariance)
+        lo, hi, cnt = e.batch_var_in_ref(x, y)
+        off, hits = e.batch_sample_var_in_ref(x, y, s)
+        b4 = Batch(e, 4, x, y, sample_ids=s)
+        b4.run()
+        b4.run()
+        off2, hits2, cnt4 = b4.fetch()
+        assert np.array_equal(off, off2) and np.array_equal(hits, hits2)
+        h = n // 2
+        offa, hitsa = e.batch_sample_var_in_ref(x[:h], y[:h], s[:h])
+        offb, hitsb = e.batch_sample_var_in_ref(x[h:], y[h:], s[h:])
+        assert np.array_equal(np.concatenate([hitsa, hitsb]), hits)
+        assert np.array_equal(np.concatenate([offa[:-1], offb + offa[-1]]), off)
+        da = e.digest_t4(off, hits, with_samples=False)
+        assert np.bitwise_xor.reduce(da) == np.bitwise_xor.reduce(np.concatenate([e.digest_t4(offa, hitsa, False), e.digest_t4(offb, hitsb, False)]))
+        # t6 slice algebra on sorted equal-width regions: bounds are monotone, counts add up over a split at any y
+        ok = lo != NONE
+        assert np.all(np.diff(lo[ok].astype(np.int64)) >= 0) and np.all(np.diff(hi[ok].astype(np.int64)) >= 0)
+        assert np.array_equal(cnt[ok], (hi[ok] - lo[ok]))
+        # CSR sanity: offsets non-decreasing, every hit code points at a walk entry, ~1.7 rows per region
+        assert np.all(np.diff(off.astype(np.int64)) >= 0) and off[-1] == len(hits)
+        assert int((hits & np.uint32(0x3FFFFFFF)).max()) < e.info.walk_entries
+        assert 1.2 < len(hits) / n < 2.4
