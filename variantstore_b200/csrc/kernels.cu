@@ -238,6 +238,89 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	}
 }
 
+// ------------------------------------------------------------------ t4, persistent + pipelined
+// Same work as k_t4, but each CTA stays resident and takes tile after tile: the look-back and the
+// ordered write of tile k are done after the walk of tile k+1, by which time the predecessors of
+// tile k have published their counts — the wait that cost k_t4 a third of its warp time is hidden
+// behind useful work.  Two staging buffers alternate.
+template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
+__global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
+                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
+                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
+                                               uint64_t* tile_state, uint32_t* status) {
+	__shared__ uint32_t s_hits[2][kTile * kKeep];
+	__shared__ uint32_t s_warp[kTile / 32];
+	__shared__ uint64_t s_base;
+	__shared__ uint32_t s_tile;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t ntiles = (uint32_t)((n + kTile - 1) / kTile);
+	volatile uint64_t* state = tile_state + 1;
+	// what this thread still owes for the previous tile
+	uint32_t p_tile = 0xFFFFFFFFu, p_cnt = 0, p_pre = 0; uint64_t p_agg = 0;
+	uint32_t buf = 0;
+	for (;;) {
+		if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);   // tiles start in ticket order
+		__syncthreads();
+		const uint32_t tile = s_tile;
+		const bool has = tile < ntiles;
+		uint32_t cnt = 0, pre = 0; uint64_t agg = 0;
+		if (has) {
+			// ---- walk this thread's region of the new tile
+			const uint64_t i = (uint64_t)tile * kTile + threadIdx.x;
+			SmemSink<kTile, kKeep> sink{s_hits[buf] + threadIdx.x, 0};
+			if (i < n) {
+				const uint64_t x = xs[i]; const uint32_t s = sample[i];
+				if (x < 1 || s == 0 || s >= ix.num_samples) atomicOr(status, kStatusBadRegion);
+				else walk_any(ix, x, ys[i], s, sink);
+			}
+			cnt = sink.n;
+			uint32_t incl = cnt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+			if (lane == 31) s_warp[warp] = incl;
+			__syncthreads();
+			uint32_t wpre = 0;
+#pragma unroll
+			for (uint32_t w = 0; w < kTile / 32; w++) { if (w < warp) wpre += s_warp[w]; agg += s_warp[w]; }
+			pre = wpre + incl - cnt;
+			if (threadIdx.x == 0) state[tile] = (tile == 0 ? kFlagIncl : kFlagAgg) | agg;      // publish the count now; the prefix later
+		}
+		// ---- finish the previous tile: look-back, then the ordered write
+		if (p_tile != 0xFFFFFFFFu) {
+			if (warp == 0) {
+				uint64_t excl = 0;
+				if (p_tile != 0) {
+					for (int64_t idx = (int64_t)p_tile - 1;; idx -= 32) {
+						const int64_t j = idx - lane;
+						uint64_t st = j >= 0 ? state[j] : kFlagIncl;
+						while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0)) { if ((st >> 62) == 0) st = state[j]; }
+						const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
+						const uint64_t v = st & kValMask;
+						if (incl_mask) { const uint32_t first = (uint32_t)__ffs((int)incl_mask) - 1; excl += warp_sum(lane <= first ? v : 0); break; }
+						excl += warp_sum(v);
+					}
+					if (lane == 0) state[p_tile] = kFlagIncl | (excl + p_agg);
+				}
+				if (lane == 0) s_base = excl;
+			}
+			__syncthreads();
+			const uint64_t i = (uint64_t)p_tile * kTile + threadIdx.x;
+			if (i < n) {
+				const uint64_t off = s_base + p_pre;
+				offsets[i] = off;
+				if (i == n - 1) offsets[n] = off + p_cnt;
+				if (off + p_cnt > cap) atomicOr(status, kStatusOverflow);
+				else if (p_cnt <= kKeep) { const uint32_t* src = s_hits[buf ^ 1] + threadIdx.x; for (uint32_t j = 0; j < p_cnt; j++) hits[off + j] = src[j * kTile]; }
+				else { DirectSink direct{hits + off, 0}; walk_any(ix, xs[i], ys[i], sample[i], direct); }   // more hits than the staging holds: walk again, straight into place
+			}
+		}
+		if (!has) break;
+		p_tile = tile; p_cnt = cnt; p_pre = pre; p_agg = agg;
+		buf ^= 1;
+		__syncthreads();        // s_tile / s_warp / s_base are reused by the next round
+	}
+}
+
 // ------------------------------------------------------------------ t4, one warp per region
 // For batches of few, wide regions (the scan-bound end of the width sweep): eight regions per CTA,
 // every warp runs the setup in lock step and then the cooperative scan above; up to kKeepW hits per
@@ -385,7 +468,16 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
 	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 6; }
 #define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
+	static int pipe = -1;                          // 1: persistent pipelined kernel (default), 0: one CTA per tile
+	if (pipe < 0) { const char* e = getenv("VSGPU_T4_PIPE"); pipe = e ? atoi(e) : 1; }
 	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each
+	else if (pipe) {
+		const uint32_t tiles = (uint32_t)((n + 255) / 256);
+		const uint32_t pg = min(tiles, grid_for((uint64_t)tiles * 256, 256, min_ctas == 8 ? 8 : (min_ctas == 5 ? 5 : 6)));
+		if (min_ctas == 8) k_t4p<256, 8, kScratchHits><<<pg, 256, 0, stream>>>(VSGPU_T4_ARGS);
+		else if (min_ctas == 5) k_t4p<256, 5, kScratchHits><<<pg, 256, 0, stream>>>(VSGPU_T4_ARGS);
+		else k_t4p<256, 6, kScratchHits><<<pg, 256, 0, stream>>>(VSGPU_T4_ARGS);
+	}
 	else if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
 	else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);
 	else if (min_ctas == 8) k_t4<256, 8, kScratchHits><<<grid, 256, 0, stream>>>(VSGPU_T4_ARGS);
