@@ -28,13 +28,17 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative"])
+@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile"])
 def walk_path(request, monkeypatch):
     """The t4 kernel paths: the sample-major hit map with one thread per region (default), the
     per-entry class-bitmap test used when the map does not fit the memory budget, and the
-    warp-cooperative scan for wide regions (forced onto every region longer than 8 walk entries)."""
+    warp-cooperative scan for wide regions (forced onto every region longer than 8 walk entries);
+    plus the non-persistent variant of the per-thread kernel."""
     monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
     monkeypatch.delenv("VSGPU_WIDE_ENTRIES", raising=False)
+    monkeypatch.delenv("VSGPU_T4_PIPE", raising=False)
+    if request.param == "cta-per-tile":
+        monkeypatch.setenv("VSGPU_T4_PIPE", "0")        # k_t4 instead of the persistent pipelined k_t4p
     if request.param == "class-bitmaps":
         monkeypatch.setenv("VSGPU_DISABLE_HITMAP", "1")
     elif request.param == "warp-cooperative":

@@ -468,8 +468,8 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
 	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 6; }
 #define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
-	static int pipe = -1;                          // 1: persistent pipelined kernel (default), 0: one CTA per tile
-	if (pipe < 0) { const char* e = getenv("VSGPU_T4_PIPE"); pipe = e ? atoi(e) : 1; }
+	const char* pe = getenv("VSGPU_T4_PIPE");      // 1: persistent pipelined kernel (default), 0: one CTA per tile
+	const int pipe = pe ? atoi(pe) : 1;
 	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each
 	else if (pipe) {
 		const uint32_t tiles = (uint32_t)((n + 255) / 256);
