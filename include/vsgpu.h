@@ -55,6 +55,8 @@ typedef struct vsgpu_info_t {
 	uint32_t has_suspect_dups;
 	uint64_t device_bytes;      /* HBM held by the flattened index */
 	char chr[64];               /* VariantGraph::get_chr */
+	uint32_t walk_markers;      /* walk entries that are out-of-step arrival markers (deletion target listed last) */
+	uint32_t rejoin_carriers;   /* alt entries whose rejoin vertex carries samples itself (rows with VSGPU_HIT_REJOIN) */
 } vsgpu_info_t;
 
 /* ---- lifecycle -------------------------------------------------------------------------------

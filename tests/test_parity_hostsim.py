@@ -51,6 +51,26 @@ def test_fuzz_parity(tmp_path, seed, overlap, sparse, walk_path):
     assert not T.compare_t1(o, e, pos)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_exhaustive_windows_reach_the_rare_walk_entries(tmp_path, seed, walk_path):
+    """Every sample x a sliding window over the whole contig on overlapping-deletion graphs, so the
+    out-of-step arrival markers and the rejoin vertices that carry samples themselves (the two rare
+    kinds of walk entry) are hit, not just present."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 50 + seed, overlap=True, n_records=320)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    e = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    starts = np.arange(1, 4001, 3, dtype=np.uint64)
+    x = np.tile(np.concatenate([starts, starts]), len(names))
+    y = x + np.tile(np.concatenate([np.full(len(starts), 40), np.full(len(starts), 400)]).astype(np.uint64), len(names))
+    s = np.repeat(np.arange(1, len(names) + 1, dtype=np.uint32), 2 * len(starts))
+    bad6, bad4, ub = T.compare_all(o, e, x, y, s)
+    assert not bad6 and not bad4
+    off, hits = e.batch_sample_var_in_ref(x, y, s)
+    assert e.info.walk_markers > 0
+    if e.info.rejoin_carriers:
+        assert int(((hits & 0x40000000) != 0).sum()) > 0
+
+
 def test_many_samples_auto_sparse_detection(tmp_path):
     """40 samples with rare carriers: density <= 5 % in the first 99 records -> explicit sample ids
     (variant_graph.h:568-617), chosen by the construct restatement itself."""
