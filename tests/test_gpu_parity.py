@@ -28,12 +28,16 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile"])
+@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "chunked-calls"])
 def walk_path(request, monkeypatch):
     """The t4 kernel paths: the sample-major hit map with one thread per region (default), the
     per-entry class-bitmap test used when the map does not fit the memory budget, and the
     warp-cooperative scan for wide regions (forced onto every region longer than 8 walk entries);
-    plus the non-persistent variant of the per-thread kernel."""
+    plus the non-persistent variant of the per-thread kernel, and host-buffer calls cut into chunks
+    of 256 regions (copies of one chunk overlapping the kernels of the next; offsets chained)."""
+    monkeypatch.delenv("VSGPU_CHUNK_REGIONS", raising=False)
+    if request.param == "chunked-calls":
+        monkeypatch.setenv("VSGPU_CHUNK_REGIONS", "128")
     monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
     monkeypatch.delenv("VSGPU_WIDE_ENTRIES", raising=False)
     monkeypatch.delenv("VSGPU_T4_PIPE", raising=False)
@@ -113,6 +117,64 @@ def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
         assert np.all(np.diff(off).astype(np.int64) <= 2 * (hi.astype(np.int64) - lo) + 2)
         hits7, total7 = _t7_check(o, e, limit=3000)
         assert hits7 > 0
+
+
+def test_chunked_calls_keep_order_and_survive_overflow_cuda(tmp_path, monkeypatch):
+    """Host-buffer calls are cut into chunks whose copies overlap the kernels.  The chunks chain their
+    offsets on the device; a hit buffer guessed too small (wide regions: far more than 4 rows each)
+    makes the call fall back to one exact pass.  Same answer either way, and equal to the oracle."""
+    o = Oracle.synth(str(tmp_path / "ser"), ref_length=1_500_000, n_records=50_000, n_samples=200, fmax=90, seed=11, cqf_log2=20)
+    rng = np.random.default_rng(12)
+    n = 6_000
+    x = np.sort(rng.integers(1, 1_400_000, n)).astype(np.uint64)
+    y = x + rng.choice([500, 20_000, 60_000], n).astype(np.uint64)
+    s = rng.integers(1, 201, n).astype(np.uint32)
+    answers = []
+    for chunk in ("0", "256", "1000"):
+        monkeypatch.setenv("VSGPU_CHUNK_REGIONS", chunk)
+        with T.open_engine(str(tmp_path / "ser"), "cuda") as e:          # fresh handle: the first call guesses the hit capacity
+            off, hits = e.batch_sample_var_in_ref(x, y, s)
+            assert off[-1] > 4 * n                                        # the guess (4 per region) was too small
+            off2, hits2 = e.batch_sample_var_in_ref(x, y, s)              # second call: capacity known, chunks stream
+            assert np.array_equal(off, off2) and np.array_equal(hits, hits2)
+            lo, hi, cnt = e.batch_var_in_ref(x, y)
+            answers.append((off, hits, lo, hi, cnt))
+            if chunk == "256":
+                sub = rng.choice(n, 600, replace=False)
+                bad6, bad4, _ = T.compare_all(o, e, x[sub], y[sub], s[sub])
+                assert not bad6 and not bad4
+    for a in answers[1:]:
+        assert all(np.array_equal(p, q) for p, q in zip(answers[0], a))
+
+
+def test_duplicate_records_and_contig_tail_cuda(tmp_path, monkeypatch):
+    """t6 counts come from the kernel; slices holding a repeated VCF record, or regions running past
+    the contig end over tail records, are flagged on the device and re-counted with the literal
+    dedup rule (query.h:397-414) — also when the call is chunked."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 2, n_records=60)
+    lines = open(vcf).read().split("\n")
+    body = [l for l in lines if l and not l.startswith("#")]
+    snps = [l for l in body if len(l.split("\t")[3]) == 1 and len(l.split("\t")[4]) == 1]
+    out = []
+    for l in lines:
+        out.append(l)
+        if l in snps[:8]:
+            out.append(l)
+    open(vcf, "w").write("\n".join(out))
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    for chunk in ("0", "128"):
+        monkeypatch.setenv("VSGPU_CHUNK_REGIONS", chunk)
+        with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+            assert e.info.has_suspect_dups == 1
+            x, y, s = T.random_regions(3, 900, 1200, widths=(1, 2, 5, 20, 100, 1000, 5000), n_samples=len(names))
+            bad6, bad4, _ = T.compare_all(o, e, x, y, s)
+            assert not bad6 and not bad4
+            from variantstore_b200 import Batch
+            b6 = Batch(e, 6, x, y)
+            b6.run(); b6.run()
+            lo, hi, cnt = e.batch_var_in_ref(x, y)
+            lo2, hi2, cnt2 = b6.fetch()
+            assert np.array_equal(cnt, cnt2) and np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
 
 
 def test_error_paths_cuda(tmp_path):

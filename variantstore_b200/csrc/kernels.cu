@@ -22,13 +22,23 @@ namespace {
 using namespace logic;
 
 
+// counts[i] = rows the reference returns when that is the slice length; regions whose slice needs the
+// literal dedup rule (a suspect duplicate inside, or a region running past the contig end over tail
+// records — DESIGN.md section 7) are appended to `flagged` (count in status[1]) for the host to re-count.
 __global__ void __launch_bounds__(256) k_t6(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                             const uint64_t* __restrict__ ys, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi,
-                                            uint32_t* status) {
+                                            uint32_t* __restrict__ counts, uint32_t* __restrict__ flagged, uint32_t flag_base, uint32_t* status) {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		bool bad = false;
-		const uint2 r = t6_bounds(ix, xs[i], ys[i], &bad);
+		const uint64_t y = ys[i];
+		const uint2 r = t6_bounds(ix, xs[i], y, &bad);
 		lo[i] = r.x; hi[i] = r.y;
+		const uint32_t c = r.x == kNoneU32 ? 0 : r.y - r.x;
+		if (counts) counts[i] = c;
+		if (flagged && c) {
+			const bool literal = (ix.rec_dup_prefix && __ldg(ix.rec_dup_prefix + r.y) != __ldg(ix.rec_dup_prefix + r.x)) || (ix.tail_records && y > ix.last_end);
+			if (literal) flagged[atomicAdd(status + 1, 1u)] = flag_base + (uint32_t)i;
+		}
 		if (bad) atomicOr(status, kStatusBadRegion);
 	}
 }
@@ -62,6 +72,10 @@ struct SmemSink {            // first kKeep codes of this thread, strided so lan
 	uint32_t* slot; uint32_t n;
 	__device__ __forceinline__ void emit(uint32_t code) { if (n < kKeep) slot[n * kTile] = code; n++; }
 };
+
+// A batch may be launched as several chunks of regions (so that transfers overlap the kernels); the
+// offsets of chunk c continue from the total of chunk c-1, which that launch left in *base_ptr.
+__device__ __forceinline__ uint64_t chunk_base(const uint64_t* base_ptr) { return base_ptr ? *(const volatile uint64_t*)base_ptr : 0; }
 
 __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 #pragma unroll
@@ -171,7 +185,7 @@ template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
 __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                              uint64_t* tile_state, uint32_t* status) {
+                                              uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr) {
 	__shared__ uint32_t s_hits[kTile * kKeep];
 	__shared__ uint64_t s_warp[kTile / 32];
 	__shared__ uint64_t s_base;
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	// ---- phase 3: decoupled look-back (warp 0), 32 predecessor tiles per step
 	if (warp == 0) {
 		uint64_t excl = 0;
-		if (tile == 0) { if (lane == 0) state[0] = kFlagIncl | agg; }
+		if (tile == 0) { excl = chunk_base(base_ptr); if (lane == 0) state[0] = kFlagIncl | (excl + agg); }
 		else {
 			if (lane == 0) state[tile] = kFlagAgg | agg;
 			for (int64_t idx = (int64_t)tile - 1;; idx -= 32) {
@@ -247,7 +261,7 @@ template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
 __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                                const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                                uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                               uint64_t* tile_state, uint32_t* status) {
+                                               uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr) {
 	__shared__ uint32_t s_hits[2][kTile * kKeep];
 	__shared__ uint32_t s_warp[kTile / 32];
 	__shared__ uint64_t s_base;
@@ -283,13 +297,14 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 #pragma unroll
 			for (uint32_t w = 0; w < kTile / 32; w++) { if (w < warp) wpre += s_warp[w]; agg += s_warp[w]; }
 			pre = wpre + incl - cnt;
-			if (threadIdx.x == 0) state[tile] = (tile == 0 ? kFlagIncl : kFlagAgg) | agg;      // publish the count now; the prefix later
+			if (threadIdx.x == 0) state[tile] = tile == 0 ? (kFlagIncl | (chunk_base(base_ptr) + agg)) : (kFlagAgg | agg);      // publish the count now; the prefix later
 		}
 		// ---- finish the previous tile: look-back, then the ordered write
 		if (p_tile != 0xFFFFFFFFu) {
 			if (warp == 0) {
 				uint64_t excl = 0;
-				if (p_tile != 0) {
+				if (p_tile == 0) excl = chunk_base(base_ptr);
+				else {
 					for (int64_t idx = (int64_t)p_tile - 1;; idx -= 32) {
 						const int64_t j = idx - lane;
 						uint64_t st = j >= 0 ? state[j] : kFlagIncl;
@@ -329,7 +344,7 @@ template <uint32_t kKeepW>
 __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                                 const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                                 uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                                uint64_t* tile_state, uint32_t* status) {
+                                                uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr) {
 	constexpr uint32_t kWarps = 8;
 	__shared__ uint32_t s_hits[kWarps * kKeepW];
 	__shared__ uint32_t s_cnt[kWarps];
@@ -361,7 +376,7 @@ __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, c
 	for (uint32_t w = 0; w < kWarps; w++) { if (w < warp) wpre += s_cnt[w]; agg += s_cnt[w]; }
 	if (warp == 0) {
 		uint64_t excl = 0;
-		if (tile == 0) { if (lane == 0) state[0] = kFlagIncl | agg; }
+		if (tile == 0) { excl = chunk_base(base_ptr); if (lane == 0) state[0] = kFlagIncl | (excl + agg); }
 		else {
 			if (lane == 0) state[tile] = kFlagAgg | agg;
 			for (int64_t idx = (int64_t)tile - 1;; idx -= 32) {
@@ -433,9 +448,10 @@ cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream
 	k_build_hitmap<<<grid_for((uint64_t)ix.num_cent * 32, 256, 8), 256, 0, stream>>>(ix, hitmap);
 	return cudaGetLastError();
 }
-cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream) {
+cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts,
+                      uint32_t* flagged, uint32_t flag_base, uint32_t* status, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
-	k_t6<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, x, y, lo, hi, status);
+	k_t6<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, x, y, lo, hi, counts, flagged, flag_base, status);
 	return cudaGetLastError();
 }
 cudaError_t launch_t1(const DevIndex& ix, uint64_t n, const uint64_t* pos, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream) {
@@ -461,13 +477,13 @@ uint32_t t4_wide_entries() {              // scan ranges longer than this many w
 uint64_t t4_state_words(uint64_t n) { return 2 + (n + 7) / 8; }
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const uint64_t* base_ptr) {
 	if (n == 0) return cudaSuccess;
 	const uint32_t tile = t4_tile();
 	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
 	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
 	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 6; }
-#define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status
+#define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status, base_ptr
 	const char* pe = getenv("VSGPU_T4_PIPE");      // 1: persistent pipelined kernel (default), 0: one CTA per tile
 	const int pipe = pe ? atoi(pe) : 1;
 	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each

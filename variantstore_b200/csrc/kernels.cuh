@@ -28,6 +28,8 @@ struct DevIndex {
 	const uint32_t* rec_pos;              // R
 	const uint64_t* rec_hash;             // R
 	const uint8_t* rec_flags;             // R
+	const uint32_t* rec_dup_prefix;       // R + 1 prefix count of suspect duplicate records; nullptr when the index has none
+	uint32_t tail_records;                // 1: the last backbone vertex has branch records (regions past the contig end need the literal rule)
 	// sample-major hit map over the walk entries (nullptr: not built, kernels use the class bitmaps)
 	const uint32_t* hitmap;               // num_samples rows x row_words
 	uint32_t row_words;                   // 32-bit words per row, multiple of 32 (128-byte rows)
@@ -41,18 +43,22 @@ struct DevIndex {
 cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream);
 
 // All launchers enqueue on `stream` and return the CUDA error of the launch.
-// t6 writes the record slice of every region as two arrays lo[n], hi[n]
-cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream);
+// `status` is two words: [0] status bits, [1] number of entries appended to a t6 `flagged` list.
+// t6 writes the record slice of every region as two arrays lo[n], hi[n]; optionally counts[n] (slice
+// lengths) and, into flagged[], flag_base + i for every region whose count needs the literal rule.
+cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts,
+                      uint32_t* flagged, uint32_t flag_base, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_t1(const DevIndex& ix, uint64_t n, const uint64_t* pos, uint32_t* lo, uint32_t* hi, uint32_t* status, cudaStream_t stream);
 cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const uint64_t* qhash, uint32_t* rec, uint32_t* status, cudaStream_t stream);
 // t4: one launch — walk, CTA scan, decoupled look-back, ordered write of the hits.
 // offsets[n+1] (exclusive, offsets[n] = total); hits has room for `cap` codes, kStatusOverflow is
 // raised (and nothing past cap written) when the total exceeds it.  `tile_state` needs
-// t4_state_words(n) zeroed 64-bit words before every launch.
+// t4_state_words(n) zeroed 64-bit words before every launch.  `base_ptr` (nullable) holds the offset
+// the launch starts from: a batch cut into chunks passes the previous chunk's offsets[n] slot.
 uint64_t t4_state_words(uint64_t n);
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const uint64_t* base_ptr = nullptr);
 uint32_t t4_wide_entries();
 
 // status word bits

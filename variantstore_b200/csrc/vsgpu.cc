@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -23,6 +25,19 @@ using namespace vsgpu;
 namespace {
 thread_local std::string g_err;
 int set_err(int code, const std::string& m) { g_err = m; return code; }
+
+// VSGPU_TRACE=1: wall-clock phases of a query call on stderr (diagnostics for the end-to-end numbers).
+struct Trace {
+	const char* name; bool on; std::vector<std::pair<const char*, std::chrono::steady_clock::time_point>> t;
+	explicit Trace(const char* n) : name(n), on(getenv("VSGPU_TRACE") != nullptr) { mark("start"); }
+	void mark(const char* label) { if (on) t.emplace_back(label, std::chrono::steady_clock::now()); }
+	~Trace() {
+		if (!on || t.size() < 2) return;
+		fprintf(stderr, "[vsgpu trace] %s:", name);
+		for (size_t i = 1; i < t.size(); i++) fprintf(stderr, " %s %.1fus", t[i].first, std::chrono::duration<double, std::micro>(t[i].second - t[i - 1].second).count());
+		fprintf(stderr, " | total %.1fus\n", std::chrono::duration<double, std::micro>(t.back().second - t.front().second).count());
+	}
+};
 
 struct DevBuf {
 	void* p = nullptr; size_t cap = 0;
@@ -58,9 +73,15 @@ struct vsgpu_index : vsgpu::HostIndex {
 	uint64_t device_bytes = 0;
 	double hits_per_base = 0;         // walk-entry carriers per base for an average sample
 	double entries_per_base = 0;      // walk entries per covered base
-	uint32_t* d_status = nullptr;
+	uint32_t* d_status = nullptr;     // two words: status bits, length of the t6 flagged list
 	std::mutex mu;
-	DevBuf bx, by, bs, bout, boffsets, bhits, bstate, bhash, brec;
+	DevBuf bx, by, bs, bout, boffsets, bhits, bstate, bhash, brec, bflag;
+	// A large call is cut into chunks of regions so that the input copies (s_in), the kernels (stream)
+	// and the result copies (s_out) of different chunks overlap; PCIe is full duplex.
+	static constexpr int kMaxChunks = 16;
+	cudaStream_t s_in = nullptr, s_out = nullptr;
+	cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_out[kMaxChunks] = {};
+	uint64_t* pin_small = nullptr;    // page-locked: kMaxChunks running totals + the two status words
 	// page-locked host buffers: a free list for results + two staging areas for t6
 	std::mutex pool_mu;
 	std::vector<std::pair<void*, size_t>> pinned_free;
@@ -84,7 +105,11 @@ struct vsgpu_index : vsgpu::HostIndex {
 		cudaSetDevice(device);
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec}) b->release();
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag}) b->release();
+		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
+		if (s_in) cudaStreamDestroy(s_in);
+		if (s_out) cudaStreamDestroy(s_out);
+		if (pin_small) cudaFreeHost(pin_small);
 		for (void* p : allocs) cudaFree(p);
 		if (d_status) cudaFree(d_status);
 		if (own_stream && stream) cudaStreamDestroy(stream);
@@ -94,7 +119,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 struct vsgpu_batch {
 	vsgpu_index* idx = nullptr;
 	int type = 0; uint64_t n = 0;
-	DevBuf x, y, s, hash, out, offsets, hits, state, rec;
+	DevBuf x, y, s, hash, out, offsets, hits, state, rec, flag;
 	uint64_t hits_cap = 0;
 	uint32_t launches = 0;
 	uint64_t algo_bytes = 0; bool algo_valid = false;
@@ -102,7 +127,7 @@ struct vsgpu_batch {
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint32_t* d_status = nullptr;    // per batch: several batches may be in flight on one index
 	bool wide_regions = false;
-	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec}) b->release(); }
+	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec, &flag}) b->release(); }
 };
 
 namespace {
@@ -146,6 +171,8 @@ void upload_index(vsgpu_index* ix) {
 	d.rec_pos = upload(ix, f.rec_pos);
 	d.rec_hash = upload(ix, f.rec_hash);
 	d.rec_flags = upload(ix, f.rec_flags);
+	d.rec_dup_prefix = f.has_suspect_dups ? upload(ix, f.rec_dup_prefix) : nullptr;
+	d.tail_records = f.rec_begin[f.M] > f.rec_begin[f.M - 1] ? 1 : 0;
 	{   // carrier density: sum of carrier-set sizes over the walk entries / (samples x covered bases)
 		long double carriers = 0;
 		std::vector<uint32_t> set_size(f.num_sets, 0);
@@ -162,8 +189,12 @@ void upload_index(vsgpu_index* ix) {
 	d.cent_anc = (const uint2*)upload(ix, f.cent_anc);
 	d.row_words = f.row_words;
 	d.hitmap = nullptr;
-	CU(cudaMalloc((void**)&ix->d_status, 4));
-	CU(cudaMemset(ix->d_status, 0, 4));
+	CU(cudaMalloc((void**)&ix->d_status, 8));
+	CU(cudaMemset(ix->d_status, 0, 8));
+	CU(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&ix->s_out, cudaStreamNonBlocking));
+	for (int i = 0; i < vsgpu_index::kMaxChunks; i++) for (cudaEvent_t* e : {&ix->ev_in[i], &ix->ev_k[i], &ix->ev_out[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+	CU(cudaHostAlloc((void**)&ix->pin_small, (vsgpu_index::kMaxChunks + 1) * 8, cudaHostAllocDefault));
 	// Sample-major hit map: num_samples rows of row_words words.  Built on the device; skipped (the
 	// kernels then test class bitmaps per entry) when it would not fit the budget:
 	// VSGPU_HITMAP_MAX_GB (default 64) and at most half of the free device memory.
@@ -191,13 +222,26 @@ int check_device(vsgpu_index* ix) {
 	return VSGPU_OK;
 }
 
-uint32_t read_status(vsgpu_index* ix, uint32_t* d_status = nullptr) {
+// Reads (and clears, when set) the two status words on `stream` (default: the index's), synchronising it.
+uint32_t read_status(vsgpu_index* ix, uint32_t* d_status = nullptr, uint32_t* nflagged = nullptr, cudaStream_t stream = nullptr) {
 	if (!d_status) d_status = ix->d_status;
-	uint32_t st = 0;
-	cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, ix->stream);
-	cudaStreamSynchronize(ix->stream);
-	if (st) { cudaMemsetAsync(d_status, 0, 4, ix->stream); }
-	return st;
+	if (!stream) stream = ix->stream;
+	uint32_t st[2] = {0, 0};
+	cudaMemcpyAsync(st, d_status, 8, cudaMemcpyDeviceToHost, stream);
+	cudaStreamSynchronize(stream);
+	if (st[0] | st[1]) { cudaMemsetAsync(d_status, 0, 8, stream); cudaStreamSynchronize(stream); }
+	if (nflagged) *nflagged = st[1];
+	return st[0];
+}
+
+// regions per chunk of a large call (VSGPU_CHUNK_REGIONS; 0 = never cut) and the resulting plan
+int plan_chunks(uint64_t n, uint64_t* per_chunk) {
+	uint64_t cr = 262144;
+	if (const char* e = getenv("VSGPU_CHUNK_REGIONS")) cr = strtoull(e, nullptr, 10);
+	int c = 1;
+	if (cr && n > cr + cr / 2) c = (int)std::min<uint64_t>(vsgpu_index::kMaxChunks, (n + cr - 1) / cr);
+	*per_chunk = (((n + c - 1) / c) + 255) / 256 * 256;          // whole tiles per chunk
+	return (int)((n + *per_chunk - 1) / *per_chunk);
 }
 
 }  // namespace
@@ -260,29 +304,20 @@ const char* vsgpu_sample_name(const vsgpu_index* ix, uint32_t id) { return (ix &
 namespace {
 // counts[i] = rows the reference returns for region i: the slice length, except where the slice
 // holds suspect duplicates or the region runs past the contig end (then the literal rule decides).
-void fill_counts(const vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* lo, const uint32_t* hi, uint32_t* counts) {
-	const FlatIndex& f = ix->flat;
-	const bool special = f.has_suspect_dups || f.rec_begin[f.M] > f.rec_begin[f.M - 1];
-	if (!special) { for (uint64_t i = 0; i < n; i++) counts[i] = hi[i] - lo[i]; return; }
-	std::vector<uint32_t> tmp;
-	for (uint64_t i = 0; i < n; i++) {
-		if (t6_needs_literal(ix, y[i], lo[i], hi[i])) { t6_literal(ix, x[i], y[i], tmp); counts[i] = (uint32_t)tmp.size(); }
-		else counts[i] = hi[i] - lo[i];
-	}
-}
+// The kernel writes the slice lengths and lists the exceptions; the host re-counts only those.
+bool t6_special(const vsgpu_index* ix) { return ix->flat.has_suspect_dups || ix->dev.tail_records; }
 
-// device lo[] / hi[] -> caller arrays (directly: page-locked caller memory gets the full PCIe rate)
-// or, where the caller passed NULL but counts are wanted, into the index's page-locked staging.
-void fetch_t6(vsgpu_index* ix, uint64_t n, const uint32_t* d_lo, const uint32_t* d_hi, const uint64_t* x, const uint64_t* y,
-              uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts, uint32_t* d_status) {
-	uint32_t* lo = rec_lo; uint32_t* hi = rec_hi;
-	if (counts && !lo) { lo = (uint32_t*)ix->staging(0, n * 4); if (!lo) throw std::runtime_error("CUDA: cannot allocate page-locked staging"); }
-	if (counts && !hi) { hi = (uint32_t*)ix->staging(1, n * 4); if (!hi) throw std::runtime_error("CUDA: cannot allocate page-locked staging"); }
-	if (lo) CU(cudaMemcpyAsync(lo, d_lo, n * 4, cudaMemcpyDeviceToHost, ix->stream));
-	if (hi) CU(cudaMemcpyAsync(hi, d_hi, n * 4, cudaMemcpyDeviceToHost, ix->stream));
-	uint32_t st = read_status(ix, d_status);
+// Reads the status words on `stream` (synchronising it), raises on a bad region and re-counts the
+// regions the kernel flagged.
+void settle_t6(vsgpu_index* ix, const uint64_t* x, const uint64_t* y, uint32_t* counts, const uint32_t* d_flag, uint32_t* d_status, cudaStream_t stream) {
+	uint32_t nflag = 0;
+	const uint32_t st = read_status(ix, d_status, &nflag, stream);
 	if (st & kStatusBadRegion) throw std::invalid_argument("Can't find node corresponding to pos 0");   // index.h:151-154 aborts
-	if (counts) fill_counts(ix, n, x, y, lo, hi, counts);
+	if (!nflag || !counts || !d_flag) return;
+	std::vector<uint32_t> flagged(nflag), tmp;
+	CU(cudaMemcpyAsync(flagged.data(), d_flag, (size_t)nflag * 4, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	for (uint32_t i : flagged) { t6_literal(ix, x[i], y[i], tmp); counts[i] = (uint32_t)tmp.size(); }
 }
 }  // namespace
 
@@ -291,15 +326,38 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	if (n == 0) return VSGPU_OK;
 	if (int rc = check_device(ix)) return rc;
 	std::lock_guard<std::mutex> g(ix->mu);
+	Trace tr("t6");
 	try {
-		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bout.ensure(n * 8));
-		CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
-		CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream));
-		uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n;
-		CU(launch_t6(ix->dev, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), d_lo, d_hi, ix->d_status, ix->stream));
-		fetch_t6(ix, n, d_lo, d_hi, x, y, rec_lo, rec_hi, counts, ix->d_status);
-	} catch (const std::invalid_argument& e) { return set_err(VSGPU_EINVAL, e.what());
-	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+		const bool flag = counts && t6_special(ix);
+		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bout.ensure(n * 12));
+		if (flag) CU(ix->bflag.ensure(n * 4));
+		uint64_t* dx = ix->bx.as<uint64_t>(); uint64_t* dy = ix->by.as<uint64_t>();
+		uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n; uint32_t* d_cnt = d_hi + n;
+		uint64_t per = 0;
+		const int chunks = plan_chunks(n, &per);
+		// inputs on s_in, kernels on the index's stream, results on s_out: chunk c's results travel
+		// while chunk c+1's inputs arrive
+		for (int c = 0; c < chunks; c++) {
+			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
+			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
+			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
+			CU(cudaEventRecord(ix->ev_in[c], ix->s_in));
+		}
+		for (int c = 0; c < chunks; c++) {
+			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
+			CU(cudaStreamWaitEvent(ix->stream, ix->ev_in[c], 0));
+			CU(launch_t6(ix->dev, m, dx + a, dy + a, d_lo + a, d_hi + a, counts ? d_cnt + a : nullptr, flag ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a, ix->d_status, ix->stream));
+			CU(cudaEventRecord(ix->ev_k[c], ix->stream));
+			CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
+			if (rec_lo) CU(cudaMemcpyAsync(rec_lo + a, d_lo + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
+			if (rec_hi) CU(cudaMemcpyAsync(rec_hi + a, d_hi + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
+			if (counts) CU(cudaMemcpyAsync(counts + a, d_cnt + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
+		}
+		tr.mark("enqueue");
+		settle_t6(ix, x, y, counts, flag ? ix->bflag.as<uint32_t>() : nullptr, ix->d_status, ix->s_out);
+		tr.mark("h2d+kernel+d2h");
+	} catch (const std::invalid_argument& e) { cudaStreamSynchronize(ix->s_out); return set_err(VSGPU_EINVAL, e.what());
+	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
 
@@ -324,9 +382,9 @@ void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy,
 // decision is taken from the total the kernel computed, not from the (shared) status word.
 // Returns the status bits left after that.
 uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
-                   DevBuf& hits, uint64_t& hits_cap, uint32_t* d_status, bool wide_regions = false) {
-	uint64_t total = 0;
-	CU(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
+                   DevBuf& hits, uint64_t& hits_cap, uint32_t* d_status, bool wide_regions = false, uint64_t known_total = 0) {
+	uint64_t total = known_total;
+	if (!known_total) CU(cudaMemcpyAsync(&total, offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
 	uint32_t st = read_status(ix, d_status);
 	if (total > hits_cap) {
 		hits_cap = total + total / 16 + 1024;
@@ -356,7 +414,7 @@ bool expect_wide_regions(const vsgpu_index* ix, uint64_t n, const uint64_t* x, c
 }
 
 // copy a finished t4 answer (device offsets[n+1] + hits) into a pooled page-locked result
-vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const DevBuf& hits, bool want_hits) {
+vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const DevBuf& hits, bool want_hits, Trace* tr = nullptr) {
 	std::unique_ptr<vsgpu_result> r(new vsgpu_result);
 	r->owner = ix; r->n = n;
 	r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
@@ -365,6 +423,7 @@ vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const
 	if (n) {
 		CU(cudaMemcpyAsync(r->offsets, offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
 		CU(cudaStreamSynchronize(ix->stream));
+		if (tr) tr->mark("d2h offsets");
 	}
 	const uint64_t total = r->offsets[n];
 	if (want_hits && total) {
@@ -372,6 +431,7 @@ vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const
 		if (!r->hits) { ix->pinned_release(r->offsets, r->offsets_cap); throw std::runtime_error("CUDA: cannot allocate page-locked result memory"); }
 		CU(cudaMemcpyAsync(r->hits, hits.p, total * 4, cudaMemcpyDeviceToHost, ix->stream));
 		CU(cudaStreamSynchronize(ix->stream));
+		if (tr) tr->mark("d2h hits");
 	}
 	return r.release();
 }
@@ -382,20 +442,70 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	*out = nullptr;
 	if (int rc = check_device(ix)) return rc;
 	std::lock_guard<std::mutex> g(ix->mu);
+	Trace tr("t4");
+	std::unique_ptr<vsgpu_result, void (*)(vsgpu_result*)> r(nullptr, vsgpu_result_free);
 	try {
-		if (n) {
-			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
-			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
-			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream));
-			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream));
-			uint64_t cap = ix->bhits.cap / 4;
-			const bool wide = expect_wide_regions(ix, n, x, y);
-			run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, nullptr, wide);
-			uint32_t st = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, wide);
-			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+		if (n == 0) { *out = fetch_t4(ix, 0, ix->boffsets, ix->bhits, true); return VSGPU_OK; }
+		const bool wide = expect_wide_regions(ix, n, x, y);
+		uint64_t per = 0;
+		const int chunks = wide ? (per = n, 1) : plan_chunks(n, &per);
+		const uint64_t state_words = t4_state_words(per);
+		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+		CU(ix->boffsets.ensure((n + 1) * 8)); CU(ix->bstate.ensure(state_words * chunks * 8));
+		uint64_t cap = ix->bhits.cap / 4;
+		if (cap == 0) { cap = std::max<uint64_t>((wide ? 64 : 4) * n, 1024); CU(ix->bhits.ensure(cap * 4)); cap = ix->bhits.cap / 4; }
+		uint64_t* dx = ix->bx.as<uint64_t>(); uint64_t* dy = ix->by.as<uint64_t>(); uint32_t* ds = ix->bs.as<uint32_t>();
+		uint64_t* d_off = ix->boffsets.as<uint64_t>();
+		r.reset(new vsgpu_result);
+		r->owner = ix; r->n = n;
+		r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
+		r->hits = (uint32_t*)ix->pinned_acquire(cap * 4, &r->hits_cap);
+		if (!r->offsets || !r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		// inputs on s_in, kernels on the index's stream (chunk c continues the offsets of chunk c-1),
+		// results on s_out as soon as their chunk is done
+		for (int c = 0; c < chunks; c++) {
+			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
+			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
+			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
+			CU(cudaMemcpyAsync(ds + a, sample_ids + a, m * 4, cudaMemcpyHostToDevice, ix->s_in));
+			CU(cudaEventRecord(ix->ev_in[c], ix->s_in));
 		}
-		*out = fetch_t4(ix, n, ix->boffsets, ix->bhits, true);
-	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
+		CU(cudaMemsetAsync(ix->bstate.p, 0, state_words * chunks * 8, ix->stream));
+		for (int c = 0; c < chunks; c++) {
+			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
+			CU(cudaStreamWaitEvent(ix->stream, ix->ev_in[c], 0));
+			CU(launch_t4(ix->dev, m, dx + a, dy + a, ds + a, d_off + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status, wide,
+			             ix->stream, c ? d_off + a : nullptr));
+			CU(cudaEventRecord(ix->ev_k[c], ix->stream));
+		}
+		tr.mark("enqueue");
+		uint64_t done = 0; bool overflow = false;
+		for (int c = 0; c < chunks; c++) {
+			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
+			CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
+			CU(cudaMemcpyAsync(ix->pin_small + c, d_off + a + m, 8, cudaMemcpyDeviceToHost, ix->s_out));
+			CU(cudaEventRecord(ix->ev_out[c], ix->s_out));
+			CU(cudaMemcpyAsync(r->offsets + a, d_off + a, (m + (c == chunks - 1 ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, ix->s_out));
+			CU(cudaEventSynchronize(ix->ev_out[c]));                   // the running total after chunk c: its hits are final
+			const uint64_t total = ix->pin_small[c];
+			if (total > cap) { overflow = true; continue; }
+			if (!overflow && total > done) CU(cudaMemcpyAsync(r->hits + done, ix->bhits.as<uint32_t>() + done, (total - done) * 4, cudaMemcpyDeviceToHost, ix->s_out));
+			done = total;
+		}
+		uint32_t st = read_status(ix, ix->d_status, nullptr, ix->s_out);
+		tr.mark("pipeline");
+		if (overflow) {
+			// the guess for the hit buffer was too small: size it from the total the kernels computed and
+			// run the batch again in one piece (inputs are resident; results are deterministic)
+			uint64_t c2 = ix->bhits.cap / 4;
+			st |= finish_t4(ix, n, dx, dy, ds, ix->boffsets, ix->bstate, ix->bhits, c2, ix->d_status, wide, ix->pin_small[chunks - 1]);
+			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+			*out = fetch_t4(ix, n, ix->boffsets, ix->bhits, true, &tr);
+			return VSGPU_OK;
+		}
+		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+		*out = r.release();
+	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
 uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r ? r->n : 0; }
@@ -522,12 +632,12 @@ int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x,
 	try {
 		std::unique_ptr<vsgpu_batch> b(new vsgpu_batch);
 		b->idx = ix; b->type = type; b->n = n;
-		CU(cudaMalloc((void**)&b->d_status, 4)); CU(cudaMemset(b->d_status, 0, 4));
+		CU(cudaMalloc((void**)&b->d_status, 8)); CU(cudaMemset(b->d_status, 0, 8));
 		b->hx.assign(x, x + n); if (y) b->hy.assign(y, y + n);
 		CU(b->x.ensure(n * 8));
 		CU(cudaMemcpyAsync(b->x.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
 		if (type != 7) { CU(b->y.ensure(n * 8)); CU(cudaMemcpyAsync(b->y.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream)); }
-		if (type == 6) CU(b->out.ensure(n * 8));
+		if (type == 6) { CU(b->out.ensure(n * 12)); if (t6_special(ix)) CU(b->flag.ensure(n * 4)); }
 		if (type == 4) { b->wide_regions = expect_wide_regions(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 8)); }
 		if (type == 7) {
 			std::vector<uint64_t> qh(n);
@@ -548,7 +658,7 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 	if (int rc = check_device(ix)) return rc;
 	try {
 		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
-		if (b->type == 6) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + b->n, b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		if (b->type == 6) { CU(cudaMemsetAsync(b->d_status, 0, 8, ix->stream)); CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + b->n, b->out.as<uint32_t>() + 2 * b->n, b->flag.as<uint32_t>(), 0, b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status, b->wide_regions);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
@@ -562,7 +672,11 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 	try {
 		const uint64_t n = b->n;
 		if (b->type == 6) {
-			fetch_t6(ix, n, b->out.as<uint32_t>(), b->out.as<uint32_t>() + n, b->hx.data(), b->hy.data(), rec_lo, rec_hi, counts, b->d_status);
+			const uint32_t* o = b->out.as<uint32_t>();
+			if (rec_lo) CU(cudaMemcpyAsync(rec_lo, o, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			if (rec_hi) CU(cudaMemcpyAsync(rec_hi, o + n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			if (counts) CU(cudaMemcpyAsync(counts, o + 2 * n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			settle_t6(ix, b->hx.data(), b->hy.data(), counts, b->flag.as<uint32_t>(), b->d_status, ix->stream);
 		} else if (b->type == 7) {
 			if (rec_lo) CU(cudaMemcpyAsync(rec_lo, b->rec.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
 			uint32_t st = read_status(ix, b->d_status);
@@ -598,7 +712,7 @@ int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* ker
 					bytes += 148 + 16ull * (f.t7_hi[rk - 1] - f.t7_lo[rk - 1]);
 				}
 			} else {
-				CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + n, b->d_status, ix->stream));
+				CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + n, nullptr, nullptr, 0, b->d_status, ix->stream));
 				std::vector<uint32_t> o(2 * n); uint64_t total = 0;
 				CU(cudaMemcpyAsync(o.data(), b->out.p, n * 8, cudaMemcpyDeviceToHost, ix->stream));
 				CU(cudaMemcpyAsync(&total, b->offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
