@@ -22,6 +22,8 @@ def main():
     from variantstore_b200 import VariantStoreIndex
     ap = argparse.ArgumentParser()
     ap.add_argument("--chunks", default="0,65536,131072,262144,524288")
+    ap.add_argument("--h2d-streams", default="3,1")
+    ap.add_argument("--user-stream", type=int, default=0, help="1: hand torch's current stream to the index first (as bench.py does)")
     ap.add_argument("--steps", type=int, default=10)
     a = ap.parse_args()
     args = argparse.Namespace(records=1_103_547, samples=2504, fmax=1100, cache_dir=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"),
@@ -32,6 +34,8 @@ def main():
     n = len(x)
     idx = VariantStoreIndex(prefix, device=0)
     lib, h = idx._lib, idx._h
+    if a.user_stream:
+        idx.set_stream(torch.cuda.current_stream().cuda_stream)
     px = torch.from_numpy(x.astype(np.int64)).pin_memory()
     py = torch.from_numpy(y.astype(np.int64)).pin_memory()
     ps = torch.from_numpy(s.astype(np.int32)).pin_memory()
@@ -49,11 +53,12 @@ def main():
         return total
 
     ref = None
-    for chunk in a.chunks.split(","):
+    for chunk, ks in [(c, k) for k in a.h2d_streams.split(",") for c in a.chunks.split(",")]:
         os.environ["VSGPU_CHUNK_REGIONS"] = chunk
+        os.environ["VSGPU_H2D_STREAMS"] = ks
         for _ in range(3):
             t6(); total = t4()
-        out = {"chunk_regions": int(chunk)}
+        out = {"chunk_regions": int(chunk), "h2d_streams": int(ks), "user_stream": a.user_stream}
         for name, fn in (("t6", t6), ("t4", t4)):
             ts = []
             for _ in range(a.steps):

@@ -35,4 +35,21 @@ for mb in (4, 8, 16, 64):
         d.copy_(h, non_blocking=True)
         torch.cuda.synchronize()
     out[f"h2d_sync_each_{mb}MB_us"] = round((time.perf_counter() - t0) / 20 * 1e6, 1)
+# several H2D copies in flight on different streams (the library sends x, y and the sample ids that way)
+for mb in (1, 2, 4, 8):
+    n = mb << 20
+    for k in (1, 2, 3):
+        hs = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(k)]
+        ds = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(k)]
+        ss = [torch.cuda.Stream() for _ in range(k)]
+        for rep in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                for i in range(k):
+                    with torch.cuda.stream(ss[i]):
+                        ds[i].copy_(hs[i], non_blocking=True)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 10
+        out[f"h2d_{mb}MB_x{k}streams_GBps"] = round(n * k / dt / 1e9, 1)
 print(json.dumps(out))

@@ -79,8 +79,12 @@ struct vsgpu_index : vsgpu::HostIndex {
 	// A large call is cut into chunks of regions so that the input copies (s_in), the kernels (stream)
 	// and the result copies (s_out) of different chunks overlap; PCIe is full duplex.
 	static constexpr int kMaxChunks = 16;
-	cudaStream_t s_in = nullptr, s_out = nullptr;
-	cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_out[kMaxChunks] = {};
+	// Host-buffer calls are synchronous, so they run entirely on internal streams: s_k for the kernels
+	// (the caller's stream set with vsgpu_set_stream is for the device-resident batch API) and up to
+	// three input streams (one by default).
+	static constexpr int kInStreams = 3;
+	cudaStream_t s_in[kInStreams] = {}, s_k = nullptr, s_out = nullptr;
+	cudaEvent_t ev_in[kMaxChunks][kInStreams] = {}, ev_k[kMaxChunks] = {}, ev_out[kMaxChunks] = {};
 	uint64_t* pin_small = nullptr;    // page-locked: kMaxChunks running totals + the two status words
 	// page-locked host buffers: a free list for results + two staging areas for t6
 	std::mutex pool_mu;
@@ -106,9 +110,8 @@ struct vsgpu_index : vsgpu::HostIndex {
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
 		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag}) b->release();
-		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
-		if (s_in) cudaStreamDestroy(s_in);
-		if (s_out) cudaStreamDestroy(s_out);
+		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i][0], ev_in[i][1], ev_in[i][2], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
+		for (cudaStream_t st : {s_in[0], s_in[1], s_in[2], s_k, s_out}) if (st) cudaStreamDestroy(st);
 		if (pin_small) cudaFreeHost(pin_small);
 		for (void* p : allocs) cudaFree(p);
 		if (d_status) cudaFree(d_status);
@@ -191,9 +194,8 @@ void upload_index(vsgpu_index* ix) {
 	d.hitmap = nullptr;
 	CU(cudaMalloc((void**)&ix->d_status, 8));
 	CU(cudaMemset(ix->d_status, 0, 8));
-	CU(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
-	CU(cudaStreamCreateWithFlags(&ix->s_out, cudaStreamNonBlocking));
-	for (int i = 0; i < vsgpu_index::kMaxChunks; i++) for (cudaEvent_t* e : {&ix->ev_in[i], &ix->ev_k[i], &ix->ev_out[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+	for (cudaStream_t* st : {&ix->s_in[0], &ix->s_in[1], &ix->s_in[2], &ix->s_k, &ix->s_out}) CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+	for (int i = 0; i < vsgpu_index::kMaxChunks; i++) for (cudaEvent_t* e : {&ix->ev_in[i][0], &ix->ev_in[i][1], &ix->ev_in[i][2], &ix->ev_k[i], &ix->ev_out[i]}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 	CU(cudaHostAlloc((void**)&ix->pin_small, (vsgpu_index::kMaxChunks + 1) * 8, cudaHostAllocDefault));
 	// Sample-major hit map: num_samples rows of row_words words.  Built on the device; skipped (the
 	// kernels then test class bitmaps per entry) when it would not fit the budget:
@@ -232,6 +234,14 @@ uint32_t read_status(vsgpu_index* ix, uint32_t* d_status = nullptr, uint32_t* nf
 	if (st[0] | st[1]) { cudaMemsetAsync(d_status, 0, 8, stream); cudaStreamSynchronize(stream); }
 	if (nflagged) *nflagged = st[1];
 	return st[0];
+}
+
+// input arrays of one chunk go out on this many streams (VSGPU_H2D_STREAMS, 1..3; measured on the
+// B200 boxes: concurrent host->device copies are slower than one after another, profiles/README.md)
+int in_streams() {
+	int k = 1;
+	if (const char* e = getenv("VSGPU_H2D_STREAMS")) k = atoi(e);
+	return std::max(1, std::min(k, (int)vsgpu_index::kInStreams));
 }
 
 // regions per chunk of a large call (VSGPU_CHUNK_REGIONS; 0 = never cut) and the resulting plan
@@ -335,19 +345,20 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n; uint32_t* d_cnt = d_hi + n;
 		uint64_t per = 0;
 		const int chunks = plan_chunks(n, &per);
-		// inputs on s_in, kernels on the index's stream, results on s_out: chunk c's results travel
+		// inputs on s_in, kernels on s_k, results on s_out: chunk c's results travel
 		// while chunk c+1's inputs arrive
+		const int ks = in_streams();
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
-			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
-			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
-			CU(cudaEventRecord(ix->ev_in[c], ix->s_in));
+			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[0]));
+			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[1 % ks]));
+			for (int k = 0; k < std::min(ks, 2); k++) CU(cudaEventRecord(ix->ev_in[c][k], ix->s_in[k]));
 		}
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
-			CU(cudaStreamWaitEvent(ix->stream, ix->ev_in[c], 0));
-			CU(launch_t6(ix->dev, m, dx + a, dy + a, d_lo + a, d_hi + a, counts ? d_cnt + a : nullptr, flag ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a, ix->d_status, ix->stream));
-			CU(cudaEventRecord(ix->ev_k[c], ix->stream));
+			for (int k = 0; k < std::min(ks, 2); k++) CU(cudaStreamWaitEvent(ix->s_k, ix->ev_in[c][k], 0));
+			CU(launch_t6(ix->dev, m, dx + a, dy + a, d_lo + a, d_hi + a, counts ? d_cnt + a : nullptr, flag ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a, ix->d_status, ix->s_k));
+			CU(cudaEventRecord(ix->ev_k[c], ix->s_k));
 			CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
 			if (rec_lo) CU(cudaMemcpyAsync(rec_lo + a, d_lo + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
 			if (rec_hi) CU(cudaMemcpyAsync(rec_hi + a, d_hi + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
@@ -461,22 +472,23 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
 		r->hits = (uint32_t*)ix->pinned_acquire(cap * 4, &r->hits_cap);
 		if (!r->offsets || !r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
-		// inputs on s_in, kernels on the index's stream (chunk c continues the offsets of chunk c-1),
-		// results on s_out as soon as their chunk is done
+		// inputs on s_in, kernels on s_k (chunk c continues the offsets of chunk c-1), results on s_out as
+		// soon as their chunk is done
+		const int ks = in_streams();
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
-			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
-			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in));
-			CU(cudaMemcpyAsync(ds + a, sample_ids + a, m * 4, cudaMemcpyHostToDevice, ix->s_in));
-			CU(cudaEventRecord(ix->ev_in[c], ix->s_in));
+			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[0]));
+			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[1 % ks]));
+			CU(cudaMemcpyAsync(ds + a, sample_ids + a, m * 4, cudaMemcpyHostToDevice, ix->s_in[2 % ks]));
+			for (int k = 0; k < ks; k++) CU(cudaEventRecord(ix->ev_in[c][k], ix->s_in[k]));
 		}
-		CU(cudaMemsetAsync(ix->bstate.p, 0, state_words * chunks * 8, ix->stream));
+		CU(cudaMemsetAsync(ix->bstate.p, 0, state_words * chunks * 8, ix->s_k));
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
-			CU(cudaStreamWaitEvent(ix->stream, ix->ev_in[c], 0));
+			for (int k = 0; k < ks; k++) CU(cudaStreamWaitEvent(ix->s_k, ix->ev_in[c][k], 0));
 			CU(launch_t4(ix->dev, m, dx + a, dy + a, ds + a, d_off + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status, wide,
-			             ix->stream, c ? d_off + a : nullptr));
-			CU(cudaEventRecord(ix->ev_k[c], ix->stream));
+			             ix->s_k, c ? d_off + a : nullptr));
+			CU(cudaEventRecord(ix->ev_k[c], ix->s_k));
 		}
 		tr.mark("enqueue");
 		uint64_t done = 0; bool overflow = false;
