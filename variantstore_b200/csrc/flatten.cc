@@ -19,6 +19,7 @@ uint64_t hash_ref_alt(const char* ref, size_t nref, const char* alt, size_t nalt
 }
 
 void flatten(const SerData& d, FlatIndex& f) {
+	PhaseClock pc;
 	const uint32_t nv = d.num_vertices;
 	const uint32_t ns = d.num_samples;
 	f.ref_length = d.ref_length; f.index_bits = d.index_bits; f.num_samples = ns; f.class_mode = d.class_mode;
@@ -65,7 +66,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 			vhas_nonref[v] = set_pop[c] > vhas_ref[v];
 			vfirst_nonref[v] = set_first_nonref[c];
 			// s_info[i] belongs to the i-th set bit (variant_graph.h:1302-1315); ref is bit 0 -> entry 0
-			if (vhas_ref[v] && d.v_sinfo_begin[v] < d.v_sinfo_begin[v + 1]) vref_index[v] = d.s_index[d.v_sinfo_begin[v]];
+			if (vhas_ref[v] && d.v_sinfo_begin[v] < d.v_sinfo_begin[v + 1]) vref_index[v] = d.v_first_index[v];
 		}
 	} else {
 		f.words_per_set = 0;
@@ -75,7 +76,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 			bool nonref = false;
 			for (uint64_t i = d.v_sinfo_begin[v]; i < d.v_sinfo_begin[v + 1]; i++) {
 				uint32_t id = d.s_sample_id[i];
-				if (id == 0) { if (!vhas_ref[v]) { vhas_ref[v] = 1; vref_index[v] = d.s_index[i]; } }
+				if (id == 0) { if (!vhas_ref[v]) { vhas_ref[v] = 1; vref_index[v] = d.v_ref0_index[v]; } }
 				else { if (!nonref) { nonref = true; vfirst_nonref[v] = id; } f.list_ids.push_back(id); }
 			}
 			if (nonref) { vhas_nonref[v] = 1; vset[v] = next++; f.list_begin.push_back(f.list_ids.size()); }
@@ -100,6 +101,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 		return next;
 	};
 
+	pc.lap("flatten: carrier sets");
 	// ------------------------------------------------------------ backbone
 	f.vertex_bb.assign(nv, kNone);
 	for (uint32_t v = 0, steps = 0;; steps++) {
@@ -118,6 +120,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 	f.bb_set.assign(M, 0);
 	for (uint32_t k = 0; k < M; k++) if (vhas_nonref[f.bb_vertex[k]]) f.bb_set[k] = vset[f.bb_vertex[k]];
 
+	pc.lap("flatten: backbone");
 	// ------------------------------------------------------------ distinct starts <-> loaded index
 	const uint32_t D = f.D = (uint32_t)d.index_ones.size();
 	if (D == 0 || d.node_list.size() != D) fail("index.sdsl and ref_node_id.sdsl disagree");
@@ -132,6 +135,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 	}
 	{ uint32_t distinct = 0; for (uint32_t k = 0; k < M; k++) if (k == 0 || f.vstart[k] != f.vstart[k - 1]) distinct++; if (distinct != D) fail("position index misses backbone starts"); }
 
+	pc.lap("flatten: distinct starts");
 	// ------------------------------------------------------------ per backbone vertex: records + entries
 	auto seq_eq = [&](uint32_t va, uint32_t vb) {   // sequences of two vertices (kNone = "")
 		uint32_t la = va == kNone ? 0 : d.v_length[va], lb = vb == kNone ? 0 : d.v_length[vb];
@@ -222,6 +226,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 	f.marker_bits.assign(f.row_words, 0);
 	for (size_t c = 0; c < f.cent.size(); c++) if (f.cent[c].tgt & kEntMarker) f.marker_bits[c >> 5] |= 1u << (c & 31);
 
+	pc.lap("flatten: records + entries");
 	// suspect duplicates for t6: an earlier record with the same (pos, alt) inside the preceding run
 	// of records whose pos is >= this one's.  Ranges containing a suspect are re-counted on the host
 	// with the literal rule.
@@ -238,6 +243,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 	f.rec_hash.resize(f.R);
 	for (uint32_t r = 0; r < f.R; r++) { seq_str(f.rec_refv[r], sref); seq_str(f.rec_altv[r], salt); f.rec_hash[r] = hash_ref_alt(sref.data(), sref.size(), salt.data(), salt.size()); }
 
+	pc.lap("flatten: suspect dups");
 	// ------------------------------------------------------------ distinct-start level tables
 	f.dinfo.assign(D, 0); f.t7_lo.assign(D, 0); f.t7_hi.assign(D, 0);
 	std::vector<uint32_t> next_branchy(M + 1, M);
@@ -254,6 +260,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 	}
 	f.dlev[D] = DLevel{M, f.R, M ? f.rec_begin[M - 1] : 0, (uint32_t)f.cent.size()};
 
+	pc.lap("flatten: level tables");
 	// ------------------------------------------------------------ back-walk forest
 	// State c (= cur_ref_node_idx) examines node_list[c-1] and moves to c - outdeg; states 0 and 1 end
 	// the walk at vertex 0.  parent < child, so subtree sizes and pre-order times need no recursion.
@@ -274,6 +281,7 @@ void flatten(const SerData& d, FlatIndex& f) {
 			else { f.cent_anc[2 * e] = 1; f.cent_anc[2 * e + 1] = 0; }
 		}
 	}
+	pc.lap("flatten: back-walk forest");
 }
 
 }  // namespace vsgpu

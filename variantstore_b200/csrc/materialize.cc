@@ -39,7 +39,7 @@ void build_host_index(const std::string& prefix, HostIndex& h, int* stage) {
 		for (uint32_t d = f.D; d-- > 0;) if (f.t7_hi[d] > f.t7_lo[d]) { h.t1_fallback_pos = d + 1 < f.D ? f.dstart[d + 1] - 1 : 0xFFFFFFFEu; break; }
 	}
 	// host copies nothing needs again
-	std::vector<uint32_t>().swap(h.ser.s_index); std::vector<uint64_t>().swap(h.ser.sample_vector);
+	std::vector<uint64_t>().swap(h.ser.sample_vector);
 	if (stage) *stage = 2;
 }
 

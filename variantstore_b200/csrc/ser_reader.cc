@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
@@ -87,36 +88,74 @@ struct RrrTables {
 };
 const RrrTables& rrr_tables() { static RrrTables t; return t; }
 
-// Calls sink(bit_position) for every set bit, in ascending order.
-template <class Sink>
-uint64_t decode_rrr127(const std::string& path, Sink&& sink) {
+// Decodes the whole vector into 64-bit words (bit i = word i/64, bit i%64); returns its length in
+// bits.  Blocks are independent once the start of their offset field is known, so a first pass sums
+// the field widths up to every chunk boundary (the file's own pointer samples are not trusted) and
+// the chunks — whole numbers of 127-word spans, so no two threads share an output word — are
+// decoded in parallel.
+uint64_t decode_rrr127(const std::string& path, std::vector<uint64_t>& out) {
 	Mapped m(path);
 	Cursor c{m.p, m.p + m.n, path};
 	const RrrTables& T = rrr_tables();
-	uint64_t size = c.u64();
-	PackedInts bt = read_iv0(c);
-	PackedBits btnr = read_bv(c);
+	const uint64_t size = c.u64();
+	const PackedInts bt = read_iv0(c);
+	const PackedBits btnr = read_bv(c);
 	PackedInts btnrp = read_iv0(c); (void)btnrp;
 	PackedInts rank = read_iv0(c); (void)rank;
-	PackedBits inv = read_bv(c);
-	uint64_t off = 0;
-	for (uint64_t blk = 0, base = 0; base < size; blk++, base += 127) {
-		if (blk >= bt.count) fail("rrr block table too short in " + path);
-		unsigned k = (unsigned)bt[blk];
-		if (k > 127) fail("bad rrr block type in " + path);
-		unsigned w = T.width[k];
-		u128 nr = 0;
-		if (w) { nr = bits_at(btnr.w, btnr.nwords, off, w > 64 ? 64 : w); if (w > 64) nr |= (u128)bits_at(btnr.w, btnr.nwords, off + 64, w - 64) << 64; }
-		off += w;
-		bool flip = (blk / 32) < inv.nbits && inv[blk / 32];
-		unsigned len = (unsigned)std::min<uint64_t>(127, size - base);
-		// unrank: walk the 127 positions, deciding each bit by comparing against C(remaining-1, k)
-		unsigned left = k;
-		for (unsigned p = 0; p < len; p++) {
-			bool one = false;
-			if (left) { const u128 cnt = T.binom[126 - p][left]; if (nr >= cnt) { nr -= cnt; left--; one = true; } }
-			if (one != flip) sink(base + p);
+	const PackedBits inv = read_bv(c);
+	const uint64_t nblocks = (size + 126) / 127;
+	if (nblocks > bt.count) fail("rrr block table too short in " + path);
+	out.assign((size + 63) / 64 + 1, 0);
+	constexpr uint64_t kChunk = 64 * 64;                       // blocks per chunk: 64 superblock pairs = 8128 words
+	const uint64_t nchunks = (nblocks + kChunk - 1) / kChunk;
+	std::vector<uint64_t> chunk_off(nchunks + 1, 0);
+	{
+		uint64_t off = 0;
+		for (uint64_t blk = 0; blk < nblocks; blk++) {
+			if (blk % kChunk == 0) chunk_off[blk / kChunk] = off;
+			const unsigned k = (unsigned)bt[blk];
+			if (k > 127) fail("bad rrr block type in " + path);
+			off += T.width[k];
 		}
+		chunk_off[nchunks] = off;
+		if (off > btnr.nbits) fail("rrr offset stream too short in " + path);
+	}
+	auto work = [&](uint64_t c0, uint64_t c1) {
+		for (uint64_t ch = c0; ch < c1; ch++) {
+			uint64_t off = chunk_off[ch];
+			const uint64_t b1 = std::min(nblocks, (ch + 1) * kChunk);
+			for (uint64_t blk = ch * kChunk; blk < b1; blk++) {
+				const uint64_t base = blk * 127;
+				const unsigned k = (unsigned)bt[blk], w = T.width[k];
+				u128 nr = 0;
+				if (w) { nr = bits_at(btnr.w, btnr.nwords, off, w > 64 ? 64 : w); if (w > 64) nr |= (u128)bits_at(btnr.w, btnr.nwords, off + 64, w - 64) << 64; }
+				off += w;
+				const bool flip = (blk / 32) < inv.nbits && inv[blk / 32];
+				const unsigned len = (unsigned)std::min<uint64_t>(127, size - base);
+				// unrank: walk the positions, deciding each bit by comparing against C(remaining - 1, left)
+				u128 pat = 0;
+				if (k == 127) pat = ~(u128)0 >> 1;
+				else for (unsigned p = 0, left = k; left && p < 127; p++) { const u128 cnt = T.binom[126 - p][left]; if (nr >= cnt) { nr -= cnt; left--; pat |= (u128)1 << p; } }
+				if (flip) pat = ~pat;
+				if (len < 127) pat &= ((u128)1 << len) - 1; else pat &= ~(u128)0 >> 1;
+				if (!pat) continue;
+				// a word is only touched when it receives bits: the neighbouring chunk owns the words after ours
+				const uint64_t wi = base >> 6; const unsigned sh = (unsigned)(base & 63);
+				const uint64_t lo = (uint64_t)pat, hi = (uint64_t)(pat >> 64);
+				const uint64_t w0 = lo << sh, w1 = (sh ? lo >> (64 - sh) : 0) | (hi << sh), w2 = sh ? hi >> (64 - sh) : 0;
+				if (w0) out[wi] |= w0;
+				if (w1) out[wi + 1] |= w1;
+				if (w2) out[wi + 2] |= w2;
+			}
+		}
+	};
+	unsigned nt = (unsigned)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), nchunks);
+	if (nt <= 1) work(0, nchunks);
+	else {
+		std::vector<std::thread> th;
+		const uint64_t per = (nchunks + nt - 1) / nt;
+		for (unsigned t = 0; t < nt; t++) { const uint64_t a0 = t * per, a1 = std::min(nchunks, a0 + per); if (a0 < a1) th.emplace_back(work, a0, a1); }
+		for (auto& t : th) t.join();
 	}
 	return size;
 }
@@ -136,12 +175,15 @@ inline bool skip(const uint8_t*& p, const uint8_t* e, unsigned wt) {
 	return false;
 }
 
+// One decoded block.  Per s_info only the 3 phasing flags are kept (plus the sample id in
+// explicit-id mode); of the `index` fields only the two per vertex that flatten() reads.
 struct BlockSoA {
-	std::vector<uint32_t> id, offset, length, cls; std::vector<uint8_t> has_cls;
-	std::vector<uint64_t> sbegin; std::vector<uint32_t> sindex, ssid; std::vector<uint8_t> sflags, shas_sid;
+	std::vector<uint32_t> id, offset, length, cls, first_index, ref0_index; std::vector<uint8_t> has_cls;
+	std::vector<uint64_t> sbegin; std::vector<uint32_t> ssid; std::vector<uint8_t> sflags;
+	bool any_sid = false, any_cls = false;
 };
 
-void parse_sinfo(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::string& name) {
+void parse_sinfo(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::string& name, uint32_t& first_index, uint32_t& ref0_index, bool& seen_first, bool& seen_ref0) {
 	uint32_t index = 0, sid = 0; uint8_t flags = 0, has = 0;
 	while (p < e) {
 		uint64_t tag, v;
@@ -157,12 +199,20 @@ void parse_sinfo(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::str
 			while (p < e2) { if (!varint(p, e2, x)) fail("bad s_info in " + name); if (!has) { has = 1; sid = (uint32_t)x; } }
 		} else if (!skip(p, e, wt)) fail("bad s_info in " + name);
 	}
-	b.sindex.push_back(index); b.ssid.push_back(sid); b.sflags.push_back(flags); b.shas_sid.push_back(has);
+	if (!seen_first) { seen_first = true; first_index = index; }
+	if (has) {
+		if (sid == 0 && !seen_ref0) { seen_ref0 = true; ref0_index = index; }
+		b.any_sid = true;
+		if (b.ssid.size() < b.sflags.size()) b.ssid.resize(b.sflags.size(), 0);
+		b.ssid.push_back(sid);
+	}
+	b.sflags.push_back(flags);
 }
 
 void parse_vertex(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::string& name) {
 	uint32_t id = 0, off = 0, len = 0, cls = 0; uint8_t has_cls = 0;
-	b.sbegin.push_back(b.sindex.size());
+	uint32_t first_index = 0, ref0_index = 0; bool seen_first = false, seen_ref0 = false;
+	b.sbegin.push_back(b.sflags.size());
 	while (p < e) {
 		uint64_t tag, v;
 		if (!varint(p, e, tag)) fail("bad vertex in " + name);
@@ -174,12 +224,14 @@ void parse_vertex(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::st
 		} else if (wt == 2 && (f == 4 || f == 5)) {
 			if (!varint(p, e, v) || (uint64_t)(e - p) < v) fail("bad vertex in " + name);
 			const uint8_t* e2 = p + v;
-			if (f == 5) parse_sinfo(p, e2, b, name);
+			if (f == 5) parse_sinfo(p, e2, b, name, first_index, ref0_index, seen_first, seen_ref0);
 			else { const uint8_t* q = p; uint64_t x; while (q < e2) { if (!varint(q, e2, x)) fail("bad vertex in " + name); if (!has_cls) { has_cls = 1; cls = (uint32_t)x; } } }
 			p = e2;
 		} else if (!skip(p, e, wt)) fail("bad vertex in " + name);
 	}
 	b.id.push_back(id); b.offset.push_back(off); b.length.push_back(len); b.cls.push_back(cls); b.has_cls.push_back(has_cls);
+	b.first_index.push_back(first_index); b.ref0_index.push_back(ref0_index);
+	if (has_cls) b.any_cls = true;
 }
 
 void inflate_file(const std::string& path, std::vector<uint8_t>& out) {
@@ -224,7 +276,7 @@ void load_block(const std::string& path, BlockSoA& b) {
 		}
 		if (p >= e || !varint(p, e, count)) break;
 	}
-	b.sbegin.push_back(b.sindex.size());
+	b.sbegin.push_back(b.sflags.size());
 }
 
 // ------------------------------------------------------------------ CQF image -> (key, value bit, count)
@@ -300,7 +352,12 @@ void read_cqf(const std::string& path, std::vector<CqfEntry>& out, uint64_t& ndi
 
 }  // namespace
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+PhaseClock::PhaseClock() : on(getenv("VSGPU_TRACE") != nullptr), t0(now_s()) {}
+void PhaseClock::lap(const char* what) { if (!on) return; const double t = now_s(); fprintf(stderr, "[vsgpu trace] open: %-28s %.3f s\n", what, t - t0); t0 = t; }
+
 void load_ser(const std::string& prefix, SerData& d) {
+	PhaseClock pc;
 	// ---- sampleid_map.lst
 	{
 		std::ifstream f(prefix + "/sampleid_map.lst");
@@ -315,12 +372,15 @@ void load_ser(const std::string& prefix, SerData& d) {
 	}
 	// ---- position index
 	{
-		d.index_bits = decode_rrr127(prefix + "/index.sdsl", [&](uint64_t p) { d.index_ones.push_back((uint32_t)p); });
+		std::vector<uint64_t> w;
+		d.index_bits = decode_rrr127(prefix + "/index.sdsl", w);
+		for (uint64_t i = 0; i < w.size(); i++) for (uint64_t bits = w[i]; bits; bits &= bits - 1) d.index_ones.push_back((uint32_t)(i * 64 + __builtin_ctzll(bits)));
 		std::string nm = prefix + "/ref_node_id.sdsl"; Mapped m(nm); Cursor c{m.p, m.p + m.n, nm};
 		PackedInts nl = read_iv0(c);
 		d.node_list.resize(nl.count);
 		for (uint64_t i = 0; i < nl.count; i++) d.node_list[i] = (uint32_t)nl[i];
 	}
+	pc.lap("sample map + position index");
 	// ---- sequence buffer
 	{
 		std::string nm = prefix + "/seq_buffer.sdsl"; Mapped m(nm); Cursor c{m.p, m.p + m.n, nm};
@@ -328,15 +388,15 @@ void load_ser(const std::string& prefix, SerData& d) {
 		d.seq.resize(sb.count);
 		for (uint64_t i = 0; i < sb.count; i++) d.seq[i] = (uint8_t)sb[i];
 	}
+	pc.lap("sequence buffer");
 	// ---- sample classes
 	{
 		std::vector<uint64_t>& w = d.sample_vector;
 		struct stat st; std::string nm = prefix + "/sample_vector.sdsl";
 		if (stat(nm.c_str(), &st) != 0) fail("cannot open " + nm);
-		uint64_t last_word = ~0ULL;
-		d.sample_vector_bits = decode_rrr127(nm, [&](uint64_t p) { uint64_t wi = p >> 6; if (wi != last_word) { if (w.size() <= wi) w.resize(wi + 1, 0); last_word = wi; } w[wi] |= 1ULL << (p & 63); });
-		w.resize((d.sample_vector_bits + 63) / 64 + 1, 0);
+		d.sample_vector_bits = decode_rrr127(nm, w);
 	}
+	pc.lap("sample classes (rrr)");
 	// ---- vertex blocks, decoded in parallel
 	{
 		std::vector<std::string> files;
@@ -351,34 +411,54 @@ void load_ser(const std::string& prefix, SerData& d) {
 		});
 		for (auto& t : th) t.join();
 		if (bad) throw std::runtime_error(err);
-		uint64_t nv = 0, ns = 0;
-		for (auto& b : blocks) { nv += b.id.size(); ns += b.sindex.size(); }
+		pc.lap("vertex blocks: decode");
+		// blocks -> one SoA: offsets first, then every block copies its part in parallel
+		const size_t nb = blocks.size();
+		std::vector<uint64_t> vbase(nb + 1, 0), sbase(nb + 1, 0);
+		for (size_t i = 0; i < nb; i++) { vbase[i + 1] = vbase[i] + blocks[i].id.size(); sbase[i + 1] = sbase[i] + blocks[i].sflags.size(); }
+		const uint64_t nv = vbase[nb], ns = sbase[nb];
+		if (nv >= 0xFFFFFFFFull) fail("too many vertices");
 		d.num_vertices = (uint32_t)nv;
-		d.v_offset.reserve(nv); d.v_length.reserve(nv); d.v_class.reserve(nv); d.v_sinfo_begin.reserve(nv + 1);
-		d.s_index.reserve(ns); d.s_flags.reserve(ns);
 		bool any_sid = false, any_cls = false;
-		for (auto& b : blocks) {
-			for (size_t i = 0; i < b.id.size(); i++) {
-				if (b.id[i] != d.v_offset.size()) fail("vertex ids are not dense/in order in the vertex blocks");
-				d.v_offset.push_back(b.offset[i]); d.v_length.push_back(b.length[i]); d.v_class.push_back(b.cls[i]);
-				any_cls |= b.has_cls[i] != 0;
-				d.v_sinfo_begin.push_back(d.s_index.size() + b.sbegin[i] - b.sbegin[0]);
-			}
-			for (auto h : b.shas_sid) any_sid |= h != 0;
-			d.s_index.insert(d.s_index.end(), b.sindex.begin(), b.sindex.end());
-			d.s_flags.insert(d.s_flags.end(), b.sflags.begin(), b.sflags.end());
-			if (any_sid) { d.s_sample_id.resize(d.s_index.size() - b.ssid.size(), 0); d.s_sample_id.insert(d.s_sample_id.end(), b.ssid.begin(), b.ssid.end()); }
-			b = BlockSoA();
-		}
-		d.v_sinfo_begin.push_back(d.s_index.size());
+		for (auto& b : blocks) { any_sid |= b.any_sid; any_cls |= b.any_cls; }
 		if (any_sid && any_cls) fail("vertex blocks mix sample-class and explicit-id encodings");
 		d.class_mode = !any_sid;
-		if (any_sid) d.s_sample_id.resize(d.s_index.size(), 0);
+		d.v_offset.resize(nv); d.v_length.resize(nv); d.v_class.resize(nv); d.v_sinfo_begin.resize(nv + 1);
+		d.v_first_index.resize(nv); d.v_ref0_index.resize(nv);
+		d.s_flags.resize(ns);
+		if (any_sid) d.s_sample_id.resize(ns);
+		std::atomic<size_t> nextb{0}; std::atomic<bool> order_bad{false};
+		std::vector<std::thread> th2;
+		for (unsigned t = 0; t < nt; t++) th2.emplace_back([&]() {
+			for (size_t i; (i = nextb++) < nb;) {
+				BlockSoA& b = blocks[i];
+				const uint64_t v0 = vbase[i], s0 = sbase[i];
+				for (size_t j = 0; j < b.id.size(); j++) {
+					if (b.id[j] != v0 + j) order_bad = true;
+					d.v_sinfo_begin[v0 + j] = s0 + b.sbegin[j] - b.sbegin[0];
+				}
+				if (!b.id.empty()) {
+					memcpy(&d.v_offset[v0], b.offset.data(), b.id.size() * 4); memcpy(&d.v_length[v0], b.length.data(), b.id.size() * 4);
+					memcpy(&d.v_class[v0], b.cls.data(), b.id.size() * 4);
+					memcpy(&d.v_first_index[v0], b.first_index.data(), b.id.size() * 4); memcpy(&d.v_ref0_index[v0], b.ref0_index.data(), b.id.size() * 4);
+				}
+				if (!b.sflags.empty()) {
+					memcpy(&d.s_flags[s0], b.sflags.data(), b.sflags.size());
+					if (any_sid && !b.ssid.empty()) memcpy(&d.s_sample_id[s0], b.ssid.data(), b.ssid.size() * 4);   // shorter only if its tail had no ids: stays 0
+				}
+				b = BlockSoA();
+			}
+		});
+		for (auto& t : th2) t.join();
+		if (order_bad) fail("vertex ids are not dense/in order in the vertex blocks");
+		d.v_sinfo_begin[nv] = ns;
 	}
+	pc.lap("vertex blocks: concatenate");
 	// ---- topology
 	{
 		std::vector<CqfEntry> ents;
 		read_cqf(prefix + "/adj_list.cqf", ents, d.cqf_distinct);
+		pc.lap("cqf scan");
 		std::vector<uint32_t> aux, lens;
 		auto read_iv32 = [&](const std::string& nm, std::vector<uint32_t>& v) {
 			Mapped m(nm); Cursor c{m.p, m.p + m.n, nm};
@@ -400,21 +480,31 @@ void load_ser(const std::string& prefix, SerData& d) {
 		d.adj_begin.assign(nv + 1, 0);
 		for (uint32_t v = 0; v < nv; v++) d.adj_begin[v + 1] = d.adj_begin[v] + deg[v];
 		d.adj.resize(d.adj_begin[nv]);
-		for (auto& e : ents) {
-			uint32_t* dst = &d.adj[d.adj_begin[e.key]];
-			if (e.inplace) { dst[0] = (uint32_t)e.count; continue; }
-			// Graph::Graph(prefix) (graph.h:162-171) re-inserts the serialised ids into a fresh
-			// std::unordered_set; what the operators then see is that set's iteration order.
+		auto rows = [&](uint64_t i0, uint64_t i1) {
 			std::unordered_set<uint32_t> s;
-			for (uint64_t i = aux_begin[e.count - 1]; i < aux_begin[e.count]; i++) s.insert(aux[i]);
-			uint32_t k = 0;
-			for (uint32_t n : s) dst[k++] = n;
-			if (k != deg[e.key]) {   // duplicate ids inside one aux list: shrink the row
-				for (uint32_t j = k; j < deg[e.key]; j++) dst[j] = UINT32_MAX;
+			for (uint64_t i = i0; i < i1; i++) {
+				const CqfEntry& e = ents[i];
+				uint32_t* dst = &d.adj[d.adj_begin[e.key]];
+				if (e.inplace) { dst[0] = (uint32_t)e.count; continue; }
+				// Graph::Graph(prefix) (graph.h:162-171) re-inserts the serialised ids into a fresh
+				// std::unordered_set; what the operators then see is that set's iteration order.
+				std::unordered_set<uint32_t>().swap(s);               // fresh: the bucket count history is part of the order
+				for (uint64_t j = aux_begin[e.count - 1]; j < aux_begin[e.count]; j++) s.insert(aux[j]);
+				uint32_t k = 0;
+				for (uint32_t n : s) dst[k++] = n;
+				for (uint32_t j = k; j < deg[e.key]; j++) dst[j] = UINT32_MAX;   // duplicate ids inside one aux list: shrink the row
 			}
+		};
+		{
+			const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)(ents.size() / 65536 + 1)));
+			std::vector<std::thread> th;
+			const uint64_t per = (ents.size() + nt - 1) / nt;
+			for (unsigned t = 0; t < nt; t++) { const uint64_t a0 = t * per, a1 = std::min<uint64_t>(ents.size(), a0 + per); if (a0 < a1) th.emplace_back(rows, a0, a1); }
+			for (auto& t : th) t.join();
 		}
 		for (uint32_t n : d.adj) if (n != UINT32_MAX && n >= nv) fail("neighbour id beyond the vertex table");
 	}
+	pc.lap("adjacency rows");
 }
 
 }  // namespace vsgpu

@@ -29,7 +29,8 @@ struct SerData {
 	bool class_mode = true;                     // bit-vector encoding (sampleclass_id present, no sample_id)
 	std::vector<uint32_t> v_offset, v_length, v_class;
 	std::vector<uint64_t> v_sinfo_begin;        // CSR into the s_info arrays, num_vertices + 1
-	std::vector<uint32_t> s_index;              // sample_info.index (kept for the ref entry only; 0 elsewhere)
+	std::vector<uint32_t> v_first_index;        // sample_info.index of the vertex's first s_info (the ref entry in class mode)
+	std::vector<uint32_t> v_ref0_index;         // ... of its first s_info that names sample id 0 (explicit-id mode)
 	std::vector<uint32_t> s_sample_id;          // explicit-id mode only
 	std::vector<uint8_t> s_flags;               // bit0 phase, bit1 gt_1, bit2 gt_2
 
@@ -49,5 +50,12 @@ struct SerData {
 
 // Throws std::runtime_error with a message naming the file that failed.
 void load_ser(const std::string& prefix, SerData& out);
+
+// VSGPU_TRACE=1: wall-clock seconds of the phases of vsgpu_open on stderr
+struct PhaseClock {
+	bool on; double t0;
+	PhaseClock();
+	void lap(const char* what);
+};
 
 }  // namespace vsgpu
