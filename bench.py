@@ -207,9 +207,20 @@ def run_vsgpu(args):
     from variantstore_b200 import Batch, VariantStoreIndex
 
     prefix, meta = ensure_index(args, rank)
+    # vsgpu_open twice: decoding ser/ (and writing the flattened-index cache), then from that cache
+    os.environ.setdefault("VSGPU_INDEX_CACHE", os.path.join(args.cache_dir, "flat"))
+    os.makedirs(os.environ["VSGPU_INDEX_CACHE"], exist_ok=True) if os.environ["VSGPU_INDEX_CACHE"] not in ("0", "1") else None
     t0 = time.time()
     idx = VariantStoreIndex(prefix, device=local)
     open_s = time.time() - t0
+    open_cached_s = None
+    if idx.info.from_cache:
+        open_s, open_cached_s = None, open_s
+    else:
+        idx.close()
+        t0 = time.time()
+        idx = VariantStoreIndex(prefix, device=local)
+        open_cached_s = time.time() - t0 if idx.info.from_cache else None
     idx.set_stream(torch.cuda.current_stream().cuda_stream)
     x, y, s = make_regions(args, meta, rank)
     n = len(x)
@@ -313,7 +324,7 @@ def run_vsgpu(args):
         "dtype": "u32", "data": "synthetic", "config": workload_config(args, meta),
         "by_kernel": {"t6_regions_per_s": n / (t6_ms / 1000), "t4_regions_per_s": n / (walk_ms / 1000),
                       "k_t6_ms": t6_ms, "k_t4_ms": walk_ms, "t6_algorithmic_GBps": algo6 / (t6_ms / 1000) / 1e9,
-                      "t4_hits_per_region": hits_total / n, "index_open_s": open_s, "device_bytes": int(idx.info.device_bytes)},
+                      "t4_hits_per_region": hits_total / n, "index_open_s": open_s, "index_open_cached_s": open_cached_s, "device_bytes": int(idx.info.device_bytes)},
         "roofline": {"bound": "hbm", "kernel": "k_t4", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo4},
         "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -57,6 +57,7 @@ typedef struct vsgpu_info_t {
 	char chr[64];               /* VariantGraph::get_chr */
 	uint32_t walk_markers;      /* walk entries that are out-of-step arrival markers (deletion target listed last) */
 	uint32_t rejoin_carriers;   /* alt entries whose rejoin vertex carries samples itself (rows with VSGPU_HIT_REJOIN) */
+	uint32_t from_cache;        /* 1: the flattened index came from VSGPU_INDEX_CACHE, ser/ was not decoded */
 } vsgpu_info_t;
 
 /* ---- lifecycle -------------------------------------------------------------------------------

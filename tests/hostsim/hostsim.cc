@@ -81,6 +81,7 @@ int vsgpu_info(const vsgpu_index* ix, vsgpu_info_t* o) {
 	o->backbone_vertices = ix->flat.M; o->distinct_starts = ix->flat.D; o->branch_records = ix->flat.R;
 	o->walk_entries = (uint32_t)ix->flat.cent.size(); o->has_suspect_dups = ix->flat.has_suspect_dups;
 	strncpy(o->chr, ix->ser.chr.c_str(), sizeof o->chr - 1);
+	o->from_cache = ix->from_cache ? 1 : 0;
 	for (const auto& e : ix->flat.cent) { if (e.tgt & kEntMarker) o->walk_markers++; else if ((e.tgt & kEntAlt) && (e.tgt & kEntTgtCarriers)) o->rejoin_carriers++; }
 	return VSGPU_OK;
 }

@@ -177,6 +177,28 @@ def test_duplicate_records_and_contig_tail_cuda(tmp_path, monkeypatch):
             assert np.array_equal(cnt, cnt2) and np.array_equal(lo, lo2) and np.array_equal(hi, hi2)
 
 
+def test_index_cache_cuda(tmp_path, monkeypatch):
+    """An index opened from VSGPU_INDEX_CACHE answers exactly like one decoded from ser/."""
+    o = Oracle.synth(str(tmp_path / "ser"), ref_length=400_000, n_records=15_000, n_samples=120, fmax=50, seed=21, cqf_log2=18)
+    monkeypatch.setenv("VSGPU_INDEX_CACHE", str(tmp_path))
+    rng = np.random.default_rng(4)
+    x = np.sort(rng.integers(1, 400_000, 3000)).astype(np.uint64)
+    y = x + rng.choice([10, 1000, 30_000], 3000).astype(np.uint64)
+    s = rng.integers(1, 121, 3000).astype(np.uint32)
+    answers = []
+    for expect in (0, 1):
+        with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+            assert e.info.from_cache == expect
+            off, hits = e.batch_sample_var_in_ref(x, y, s)
+            answers.append((off, hits) + e.batch_var_in_ref(x, y) + e.batch_closest_var(x))
+            if expect:
+                sub = rng.choice(3000, 500, replace=False)
+                bad6, bad4, _ = T.compare_all(o, e, x[sub], y[sub], s[sub])
+                assert not bad6 and not bad4
+                assert _t7_check(o, e, limit=2000)[0] > 0
+    assert all(np.array_equal(p, q) for p, q in zip(*answers))
+
+
 def test_error_paths_cuda(tmp_path):
     from variantstore_b200 import VsgpuError
     prefix = os.path.join(T.GOLDEN, "x_ser")

@@ -127,3 +127,43 @@ def test_duplicate_records_take_the_literal_path(tmp_path):
     x, y, s = T.random_regions(3, 400, 1200, widths=(1, 2, 5, 20, 100, 1000), n_samples=len(names))
     bad6, bad4, _ = T.compare_all(o, e, x, y, s)
     assert not bad6 and not bad4
+
+
+def test_index_cache_round_trip(tmp_path, monkeypatch):
+    """VSGPU_INDEX_CACHE: the loaded + flattened index is written once and read back by later opens
+    (SURVEY.md section 8(f)2); a changed ser/ file, a truncated or a foreign cache file is ignored."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 31, overlap=True)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    x, y, s = T.random_regions(5, 300, 4000, n_samples=len(names))
+    cache_dir = tmp_path / "cache"
+    cache_dir.mkdir()
+    monkeypatch.setenv("VSGPU_INDEX_CACHE", str(cache_dir))
+    e1 = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    assert e1.info.from_cache == 0
+    files = list(cache_dir.iterdir())
+    assert len(files) == 1 and files[0].name.endswith(".vsgpu_cache")
+    e2 = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    assert e2.info.from_cache == 1
+    for f in ("num_vertices", "num_vertices_cqf", "seq_length", "branch_records", "walk_entries", "num_classes", "walk_markers"):
+        assert getattr(e1.info, f) == getattr(e2.info, f)
+    bad6, bad4, _ = T.compare_all(o, e2, x, y, s)
+    assert not bad6 and not bad4
+    assert t7_parity(o, e2) > 0
+    assert e2.get_var_in_ref(1, 4001) == e1.get_var_in_ref(1, 4001)                # rows incl. sample names and phasing
+    assert e2.get_sample_var_in_ref(1, 4001, names[3]) == e1.get_sample_var_in_ref(1, 4001, names[3])
+    # a truncated cache is ignored (and replaced)
+    blob = files[0].read_bytes()
+    files[0].write_bytes(blob[: len(blob) // 2])
+    e3 = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    assert e3.info.from_cache == 0 and files[0].stat().st_size == len(blob)
+    # so is one whose ser/ changed underneath it
+    p = tmp_path / "ser" / "sampleid_map.lst"
+    os.utime(p, ns=(p.stat().st_atime_ns, p.stat().st_mtime_ns + 1_000_000_000))
+    e4 = T.open_engine(str(tmp_path / "ser"), "hostsim")
+    assert e4.info.from_cache == 0
+    assert T.open_engine(str(tmp_path / "ser"), "hostsim").info.from_cache == 1
+    # "1" puts it beside the data
+    monkeypatch.setenv("VSGPU_INDEX_CACHE", "1")
+    T.open_engine(str(tmp_path / "ser"), "hostsim")
+    assert (tmp_path / "ser" / "vsgpu_flat.cache").exists()
+    assert T.open_engine(str(tmp_path / "ser"), "hostsim").info.from_cache == 1

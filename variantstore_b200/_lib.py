@@ -12,7 +12,7 @@ class InfoT(C.Structure):
         ("num_vertices", C.c_uint64), ("num_samples", C.c_uint32), ("num_classes", C.c_uint32),
         ("class_mode", C.c_uint32), ("backbone_vertices", C.c_uint32), ("distinct_starts", C.c_uint32),
         ("branch_records", C.c_uint32), ("walk_entries", C.c_uint32), ("has_suspect_dups", C.c_uint32),
-        ("device_bytes", C.c_uint64), ("chr", C.c_char * 64), ("walk_markers", C.c_uint32), ("rejoin_carriers", C.c_uint32),
+        ("device_bytes", C.c_uint64), ("chr", C.c_char * 64), ("walk_markers", C.c_uint32), ("rejoin_carriers", C.c_uint32), ("from_cache", C.c_uint32),
     ]
 
 

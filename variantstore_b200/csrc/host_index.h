@@ -17,7 +17,12 @@ struct HostIndex {
 	uint32_t last_end = 0;                                  // start + length of the last backbone vertex
 	uint32_t t1_fallback_pos = 0;                           // see DevIndex::t1_fallback_pos
 	std::unordered_map<std::string, uint32_t> name2id;
+	bool from_cache = false;                                // read from VSGPU_INDEX_CACHE instead of decoding ser/
 };
+
+// index_cache.cc: opt-in on-disk cache of everything build_host_index computes
+bool load_index_cache(const std::string& prefix, HostIndex& h);
+void save_index_cache(const std::string& prefix, HostIndex& h);
 
 // load_ser + flatten + derived fields; throws std::runtime_error
 void build_host_index(const std::string& prefix, HostIndex& h, int* stage = nullptr);

@@ -27,19 +27,30 @@ void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& 
 
 void build_host_index(const std::string& prefix, HostIndex& h, int* stage) {
 	if (stage) *stage = 0;
-	load_ser(prefix, h.ser);
-	if (stage) *stage = 1;
-	flatten(h.ser, h.flat);
-	for (uint32_t i = 0; i < h.ser.num_samples; i++) h.name2id[h.ser.sample_names[i]] = i;
-	uint64_t le = (uint64_t)h.flat.vstart[h.flat.M - 1] + h.flat.vlen[h.flat.M - 1];
-	h.last_end = le > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)le;
-	{   // largest d whose first-branchy range is non-empty; the position just before the next start
-		const FlatIndex& f = h.flat;
-		h.t1_fallback_pos = 0;
-		for (uint32_t d = f.D; d-- > 0;) if (f.t7_hi[d] > f.t7_lo[d]) { h.t1_fallback_pos = d + 1 < f.D ? f.dstart[d + 1] - 1 : 0xFFFFFFFEu; break; }
+	PhaseClock pc;
+	h.from_cache = load_index_cache(prefix, h);          // VSGPU_INDEX_CACHE (index_cache.cc); false when unset, stale or unreadable
+	if (h.from_cache) pc.lap("flattened index read from cache");
+	else {
+		load_ser(prefix, h.ser);
+		if (stage) *stage = 1;
+		flatten(h.ser, h.flat);
+		uint64_t le = (uint64_t)h.flat.vstart[h.flat.M - 1] + h.flat.vlen[h.flat.M - 1];
+		h.last_end = le > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)le;
+		{   // largest d whose first-branchy range is non-empty; the position just before the next start
+			const FlatIndex& f = h.flat;
+			h.t1_fallback_pos = 0;
+			for (uint32_t d = f.D; d-- > 0;) if (f.t7_hi[d] > f.t7_lo[d]) { h.t1_fallback_pos = d + 1 < f.D ? f.dstart[d + 1] - 1 : 0xFFFFFFFEu; break; }
+		}
+		// host copies nothing reads after flatten()
+		SerData& s = h.ser;
+		std::vector<uint64_t>().swap(s.sample_vector); std::vector<uint32_t>().swap(s.index_ones); std::vector<uint32_t>().swap(s.node_list);
+		std::vector<uint32_t>().swap(s.v_first_index); std::vector<uint32_t>().swap(s.v_ref0_index);
+		std::vector<uint64_t>().swap(s.adj_begin); std::vector<uint32_t>().swap(s.adj);
+		pc = PhaseClock();
+		save_index_cache(prefix, h);
+		if (getenv("VSGPU_INDEX_CACHE")) pc.lap("flattened index written to cache");
 	}
-	// host copies nothing needs again
-	std::vector<uint64_t>().swap(h.ser.sample_vector);
+	for (uint32_t i = 0; i < h.ser.num_samples; i++) h.name2id[h.ser.sample_names[i]] = i;
 	if (stage) *stage = 2;
 }
 
