@@ -124,6 +124,22 @@ int vsgpu_digest_t1(const vsgpu_index* idx, uint64_t n, const uint32_t* rec_lo, 
 int vsgpu_digest_t4(const vsgpu_index* idx, uint64_t n, const uint64_t* offsets, const uint32_t* hits, int with_samples, uint64_t* digests);
 int vsgpu_digest_t7(const vsgpu_index* idx, uint64_t n, const uint32_t* rec, uint64_t* ncarriers, uint64_t* digests);
 
+/* ---- t6 rows rendered on the device (SURVEY.md §8f "next" row 3) -----------------------------------
+ * get_var_in_ref(vg, idx, x, y, print = true, outfile) — include/query.h:736-784 with print_var
+ * (:43-50) and get_samples (:268-285): the rows of every region as the bytes the reference writes
+ * to `-o` after its header line, produced by a kernel (one warp per row expands the class bitmap /
+ * id list of the row's vertex into "name(gt) " items) instead of the host loop of vsgpu_rows_t6.
+ * Region i owns bytes [offsets[i], offsets[i+1]) of vsgpu_text_bytes; byte-identical to
+ * vsgpu_rows_t6 on the slice vsgpu_query_t6 returns for it.  Returns VSGPU_ESHAPE when the text of
+ * the batch exceeds VSGPU_RENDER_MAX_BYTES (default 2 GiB): split the batch. */
+typedef struct vsgpu_text vsgpu_text;
+int vsgpu_render_t6(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, int with_samples, vsgpu_text** out);
+const char* vsgpu_text_bytes(const vsgpu_text* t);          /* NUL-terminated after the last region */
+const uint64_t* vsgpu_text_offsets(const vsgpu_text* t);    /* n + 1 byte offsets */
+uint64_t vsgpu_text_num_rows(const vsgpu_text* t);          /* rows rendered over all regions */
+float vsgpu_text_kernel_ms(const vsgpu_text* t);            /* device time of the offset + render kernels (CUDA events) */
+void vsgpu_text_free(vsgpu_text* t);
+
 /* ---- device-resident batches (bench harness; replaces the timing loop of src/bm_query.cc:74-135)
  * A batch keeps its regions and results in HBM so a run times the kernels alone.
  * type = 4, 6 or 7.  For type 7 pass refs/alts; for type 4 pass sample_ids. */

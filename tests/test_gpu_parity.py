@@ -199,6 +199,68 @@ def test_index_cache_cuda(tmp_path, monkeypatch):
     assert all(np.array_equal(p, q) for p, q in zip(*answers))
 
 
+def _check_render(o, e, x, y, oracle_regions=60):
+    """device-rendered rows == host-materialised rows of the same slices == the oracle's -o bytes"""
+    lo, hi, cnt = e.batch_var_in_ref(x, y)
+    for ws in (True, False):
+        off, text, rows, ms = e.render_var_in_ref(x, y, with_samples=ws)
+        assert rows == int(cnt.sum()) and len(text) == off[-1] and np.all(np.diff(off.astype(np.int64)) >= 0)
+        for i in range(len(x)):
+            got = text[off[i]:off[i + 1]].decode()
+            assert got.count("\n") == cnt[i]
+            if cnt[i] == hi[i] - lo[i] and lo[i] != NONE:
+                assert got == e.rows_t6_text(int(lo[i]), int(hi[i]), with_samples=ws), (i, x[i], y[i])
+        if ws:
+            for i in list(range(min(oracle_regions, len(x)))):
+                want = o.t6_text(int(x[i]), int(y[i]))
+                want = want.split("Pos\tRef\tAlt\tSamples\n", 1)[1]               # drop the count line and the header
+                assert text[off[i]:off[i + 1]].decode() == want, (i, x[i], y[i])
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_rows_rendered_on_device_cuda(tmp_path, sparse):
+    """the -v rows of t6 produced by a kernel, byte for byte."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 4, overlap=True, sparse=sparse, n_samples=40 if sparse else 12)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"), force_enc=0 if sparse else -1)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        x, y, _ = T.random_regions(9, 300, 4000, widths=(1, 5, 100, 1000, 4000), n_samples=len(names))
+        x = np.concatenate([x, [1, 1, 3999, 4000, 4500]]).astype(np.uint64)
+        y = np.concatenate([y, [4001, 9000, 4001, 4001, 5000]]).astype(np.uint64)
+        _check_render(o, e, x, y)
+        off, text, rows, ms = e.render_var_in_ref(np.zeros(0, np.uint64), np.zeros(0, np.uint64))
+        assert len(off) == 1 and text == b"" and rows == 0
+
+
+def test_rows_rendered_on_device_many_samples_cuda(tmp_path):
+    """chr22-shaped classes (300 samples, 5 bitmap words, long carrier lists) and a batch large enough
+    for several scan CTAs; names of different lengths."""
+    o = Oracle.synth(str(tmp_path / "ser"), ref_length=600_000, n_records=20_000, n_samples=300, fmax=120, seed=8, cqf_log2=19)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        rng = np.random.default_rng(6)
+        x = np.sort(rng.integers(1, 600_000, 5000)).astype(np.uint64)
+        y = x + rng.choice([10, 300, 3000], 5000).astype(np.uint64)
+        _check_render(o, e, x, y, oracle_regions=40)
+
+
+def test_rows_rendered_with_duplicate_records_cuda(tmp_path):
+    """regions whose rows are decided by the literal dedup rule become several segments"""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 2, n_records=60)
+    lines = open(vcf).read().split("\n")
+    body = [l for l in lines if l and not l.startswith("#")]
+    snps = [l for l in body if len(l.split("\t")[3]) == 1 and len(l.split("\t")[4]) == 1]
+    out = []
+    for l in lines:
+        out.append(l)
+        if l in snps[:8]:
+            out.append(l)
+    open(vcf, "w").write("\n".join(out))
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        assert e.info.has_suspect_dups == 1
+        x, y, _ = T.random_regions(3, 250, 1200, widths=(1, 5, 20, 100, 1000, 5000), n_samples=len(names))
+        _check_render(o, e, x, y, oracle_regions=250)
+
+
 def test_error_paths_cuda(tmp_path):
     from variantstore_b200 import VsgpuError
     prefix = os.path.join(T.GOLDEN, "x_ser")

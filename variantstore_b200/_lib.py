@@ -45,6 +45,12 @@ PROTOTYPES = {
     "vsgpu_digest_t6": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, vp]),
     "vsgpu_digest_t4": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, vp]),
     "vsgpu_digest_t7": (C.c_int, [vp, C.c_uint64, vp, vp, vp]),
+    "vsgpu_render_t6": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp)]),
+    "vsgpu_text_bytes": (vp, [vp]),
+    "vsgpu_text_offsets": (u64p, [vp]),
+    "vsgpu_text_num_rows": (C.c_uint64, [vp]),
+    "vsgpu_text_kernel_ms": (C.c_float, [vp]),
+    "vsgpu_text_free": (None, [vp]),
     "vsgpu_batch_create": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, cpp, cpp, C.POINTER(vp)]),
     "vsgpu_batch_run": (C.c_int, [vp]),
     "vsgpu_batch_fetch": (C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
@@ -53,7 +59,7 @@ PROTOTYPES = {
     "vsgpu_batch_free": (None, [vp]),
 }
 # subset a test-only host simulator has to provide
-QUERY_SUBSET = [s for s in PROTOTYPES if not s.startswith("vsgpu_batch") and s != "vsgpu_set_stream"]
+QUERY_SUBSET = [s for s in PROTOTYPES if not s.startswith(("vsgpu_batch", "vsgpu_render", "vsgpu_text")) and s != "vsgpu_set_stream"]
 
 
 def load(path=None, subset=False):

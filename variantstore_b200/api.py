@@ -150,6 +150,22 @@ class VariantStoreIndex:
             self._lib.vsgpu_result_free(r)
         return off, hits
 
+    def render_var_in_ref(self, x, y, with_samples=True):
+        """t6 over arrays with the rows rendered on the device: (offsets[n+1], text bytes, rows,
+        kernel ms).  Region i's rows (print_var lines, query.h:43-50) are text[offsets[i]:offsets[i+1]]."""
+        x, y = _u64(x), _u64(y)
+        n = len(x)
+        t = C.c_void_p()
+        self._check(self._lib.vsgpu_render_t6(self._h, n, _ptr(x), _ptr(y), int(with_samples), C.byref(t)))
+        try:
+            off = np.ctypeslib.as_array(self._lib.vsgpu_text_offsets(t), shape=(n + 1,)).copy()
+            text = C.string_at(self._lib.vsgpu_text_bytes(t), int(off[-1]))
+            rows = int(self._lib.vsgpu_text_num_rows(t))
+            ms = float(self._lib.vsgpu_text_kernel_ms(t))
+        finally:
+            self._lib.vsgpu_text_free(t)
+        return off, text, rows, ms
+
     def batch_closest_var(self, pos):
         """t1 over an array of positions: (rec_lo, rec_hi); both NONE where the operator returns false."""
         pos = _u64(pos)

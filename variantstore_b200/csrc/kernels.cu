@@ -407,6 +407,165 @@ __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, c
 	}
 }
 
+
+// ------------------------------------------------------------------ t6 rows as text, on the device
+// print_var (query.h:43-50) for the records of get_var_in_ref: the carriers of a row are the set
+// bits of its class bitmap (or its id list), each printed as name(gt) with the phasing flags of the
+// matching s_info entry (get_samples, query.h:268-285; get_sample_phasing, variant_graph.h:882-900).
+// Row lengths are static, so every row knows where its text starts; a warp writes one row.
+struct SegCount { uint64_t rows, bytes; };
+__device__ __forceinline__ SegCount seg_count(const uint64_t* __restrict__ tp, const uint32_t* lo, const uint32_t* hi, uint64_t i, uint64_t nseg) {
+	SegCount c{0, 0};
+	if (i < nseg) {
+		const uint32_t a = lo[i], b = hi[i];
+		if (a != kNoneU32 && b > a) { c.rows = b - a; c.bytes = __ldg(tp + b) - __ldg(tp + a); }
+	}
+	return c;
+}
+__device__ __forceinline__ SegCount cta_scan_1024(SegCount mine, SegCount* s_warp, SegCount* total) {   // 256 threads; returns the exclusive prefix of `mine`
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	SegCount inc = mine;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint64_t r = __shfl_up_sync(0xFFFFFFFFu, inc.rows, d), b = __shfl_up_sync(0xFFFFFFFFu, inc.bytes, d);
+		if (lane >= (uint32_t)d) { inc.rows += r; inc.bytes += b; }
+	}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads();
+	SegCount pre{0, 0}, tot{0, 0};
+#pragma unroll
+	for (uint32_t w = 0; w < 8; w++) { if (w < warp) { pre.rows += s_warp[w].rows; pre.bytes += s_warp[w].bytes; } tot.rows += s_warp[w].rows; tot.bytes += s_warp[w].bytes; }
+	__syncthreads();
+	*total = tot;
+	return SegCount{pre.rows + inc.rows - mine.rows, pre.bytes + inc.bytes - mine.bytes};
+}
+// pass 1: per-CTA totals (4 segments per thread)
+__global__ void __launch_bounds__(256) k_seg_sums(const uint64_t* __restrict__ tp, uint64_t nseg, const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, uint64_t* __restrict__ cta_sums) {
+	__shared__ SegCount s_warp[8];
+	SegCount mine{0, 0};
+	const uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+	for (int j = 0; j < 4; j++) { const SegCount c = seg_count(tp, lo, hi, base + j, nseg); mine.rows += c.rows; mine.bytes += c.bytes; }
+	SegCount tot;
+	cta_scan_1024(mine, s_warp, &tot);
+	if (threadIdx.x == 0) { cta_sums[2 * (uint64_t)blockIdx.x] = tot.rows; cta_sums[2 * (uint64_t)blockIdx.x + 1] = tot.bytes; }
+}
+// pass 2: one CTA turns the per-CTA totals into exclusive bases, in place; entry nctas = grand totals
+__global__ void __launch_bounds__(256) k_seg_bases(uint64_t nctas, uint64_t* cta_sums) {
+	__shared__ SegCount s_warp[8];
+	SegCount carry{0, 0};
+	for (uint64_t b0 = 0; b0 < nctas; b0 += 256) {
+		const uint64_t b = b0 + threadIdx.x;
+		SegCount mine{0, 0};
+		if (b < nctas) { mine.rows = cta_sums[2 * b]; mine.bytes = cta_sums[2 * b + 1]; }
+		SegCount tot;
+		const SegCount ex = cta_scan_1024(mine, s_warp, &tot);
+		if (b < nctas) { cta_sums[2 * b] = carry.rows + ex.rows; cta_sums[2 * b + 1] = carry.bytes + ex.bytes; }
+		carry.rows += tot.rows; carry.bytes += tot.bytes;
+	}
+	if (threadIdx.x == 0) { cta_sums[2 * nctas] = carry.rows; cta_sums[2 * nctas + 1] = carry.bytes; }
+}
+// pass 3: exclusive offsets per segment
+__global__ void __launch_bounds__(256) k_seg_offsets(const uint64_t* __restrict__ tp, uint64_t nseg, const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi,
+                                                     const uint64_t* __restrict__ cta_sums, uint64_t nctas, uint64_t* __restrict__ row_off, uint64_t* __restrict__ byte_off) {
+	__shared__ SegCount s_warp[8];
+	SegCount c[4], mine{0, 0};
+	const uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+	for (int j = 0; j < 4; j++) { c[j] = seg_count(tp, lo, hi, base + j, nseg); mine.rows += c[j].rows; mine.bytes += c[j].bytes; }
+	SegCount tot;
+	SegCount ex = cta_scan_1024(mine, s_warp, &tot);
+	ex.rows += cta_sums[2 * (uint64_t)blockIdx.x]; ex.bytes += cta_sums[2 * (uint64_t)blockIdx.x + 1];
+#pragma unroll
+	for (int j = 0; j < 4; j++) { if (base + j < nseg) { row_off[base + j] = ex.rows; byte_off[base + j] = ex.bytes; } ex.rows += c[j].rows; ex.bytes += c[j].bytes; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) { row_off[nseg] = cta_sums[2 * nctas]; byte_off[nseg] = cta_sums[2 * nctas + 1]; }
+}
+
+__device__ __forceinline__ uint32_t name_len(const RenderTables& rt, uint32_t id) { return __ldg(rt.name_off + id + 1) - __ldg(rt.name_off + id); }
+// name(g|g) + blank at `out`; returns the bytes written
+__device__ __forceinline__ uint32_t put_carrier(const RenderTables& rt, char* out, uint32_t id, uint8_t fl) {
+	const uint32_t a = __ldg(rt.name_off + id), n = __ldg(rt.name_off + id + 1) - a;
+	for (uint32_t i = 0; i < n; i++) out[i] = __ldg(rt.name_chars + a + i);
+	out[n] = '('; out[n + 1] = (fl & 2) ? '1' : '0'; out[n + 2] = (fl & 1) ? '|' : '/'; out[n + 3] = (fl & 4) ? '1' : '0'; out[n + 4] = ')'; out[n + 5] = ' ';
+	return n + 6;
+}
+__device__ __forceinline__ void warp_excl2(uint32_t lane, uint32_t a, uint32_t b, uint32_t& ea, uint32_t& eb, uint32_t& ta, uint32_t& tb) {
+	uint32_t ia = a, ib = b;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, ia, d), y = __shfl_up_sync(0xFFFFFFFFu, ib, d); if (lane >= (uint32_t)d) { ia += x; ib += y; } }
+	ea = ia - a; eb = ib - b;
+	ta = __shfl_sync(0xFFFFFFFFu, ia, 31); tb = __shfl_sync(0xFFFFFFFFu, ib, 31);
+}
+
+__global__ void __launch_bounds__(256) k_render(const DevIndex ix, const RenderTables rt, const uint64_t* __restrict__ tp, uint64_t nseg, const uint32_t* __restrict__ seg_lo, int ws,
+                                                const uint64_t* __restrict__ row_off, const uint64_t* __restrict__ byte_off, uint64_t total_rows, char* __restrict__ text) {
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	const uint64_t kBase = 0x0505054E47544341ULL;                      // "ACTGN" + 5,5,5 by 3-bit code: map_int, src/util.cc:32-41
+	for (uint64_t row = warp0; row < total_rows; row += nwarps) {
+		// segment of this row: last s with row_off[s] <= row (empty segments share an offset with their successor)
+		uint64_t a = 0, b = nseg;
+		while (b - a > 1) { const uint64_t m = (a + b) >> 1; if (__ldg(row_off + m) <= row) a = m; else b = m; }
+		const uint32_t lo = __ldg(seg_lo + a);
+		const uint32_t r = lo + (uint32_t)(row - __ldg(row_off + a));
+		const uint64_t t0 = __ldg(tp + r);
+		char* out = text + __ldg(byte_off + a) + (t0 - __ldg(tp + lo));
+		const uint32_t row_bytes = (uint32_t)(__ldg(tp + r + 1) - t0);
+		const uint4 sq = __ldg(rt.rec_seq + r), cr = __ldg(rt.rec_car + r);
+		// ---- "pos\t"
+		uint32_t at = 0;
+		{
+			uint32_t p = __ldg(ix.rec_pos + r), nd = 1;
+			for (uint32_t q = p; q >= 10; q /= 10) nd++;
+			if (lane == 0) { uint32_t q = p; for (uint32_t i = nd; i-- > 0;) { out[i] = (char)('0' + q % 10); q /= 10; } out[nd] = '\t'; }
+			at = nd + 1;
+		}
+		// ---- ref \t alt \t
+		for (uint32_t i = lane; i < sq.y; i += 32) out[at + i] = (char)(kBase >> (8 * (__ldg(rt.seq + sq.x + i) & 7)));
+		at += sq.y;
+		if (lane == 0) out[at] = '\t';
+		at += 1;
+		for (uint32_t i = lane; i < sq.w; i += 32) out[at + i] = (char)(kBase >> (8 * (__ldg(rt.seq + sq.z + i) & 7)));
+		at += sq.w;
+		if (lane == 0) { out[at] = '\t'; out[row_bytes - 1] = '\n'; }
+		at += 1;
+		if (!ws || ((cr.y >> 28) & 4)) continue;                        // no carrier list asked for / the row has none
+		// ---- carriers
+		const uint64_t sbegin = (uint64_t)cr.z | ((uint64_t)cr.w << 32);
+		uint32_t slot0 = 0;                                              // s_info entries consumed so far
+		if (ix.class_mode) {
+			const uint64_t* bits_row = ix.bitmap + (uint64_t)cr.x * ix.words_per_set;
+			for (uint32_t w0 = 0; w0 < ix.words_per_set; w0 += 32) {
+				const uint32_t w = w0 + lane;
+				const uint64_t all = w < ix.words_per_set ? __ldg(bits_row + w) : 0;
+				const uint64_t pr = w == 0 ? all & ~1ULL : all;           // the ref bit owns an s_info entry but is not printed
+				uint32_t bytes = 0;
+				for (uint64_t m = pr; m; m &= m - 1) bytes += name_len(rt, w * 64 + (uint32_t)__ffsll((long long)m) - 1) + 6;
+				uint32_t eslot, ebytes, tslot, tbytes;
+				warp_excl2(lane, (uint32_t)__popcll(all), bytes, eslot, ebytes, tslot, tbytes);
+				uint32_t slot = slot0 + eslot; char* o = out + at + ebytes;
+				for (uint64_t m = all; m; m &= m - 1) {
+					const uint32_t id = w * 64 + (uint32_t)__ffsll((long long)m) - 1;
+					if (id != 0) o += put_carrier(rt, o, id, __ldg(rt.s_flags + sbegin + slot));
+					slot++;
+				}
+				slot0 += tslot; at += tbytes;
+			}
+		} else {
+			const uint32_t cnt = cr.y & 0x0FFFFFFFu;
+			for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+				const uint32_t j = j0 + lane;
+				const uint32_t id = j < cnt ? __ldg(rt.s_sample_id + sbegin + j) : 0;
+				const uint32_t bytes = id ? name_len(rt, id) + 6 : 0;
+				uint32_t e1, ebytes, t1, tbytes;
+				warp_excl2(lane, 0, bytes, e1, ebytes, t1, tbytes);
+				if (id) put_carrier(rt, out + at + ebytes, id, __ldg(rt.s_flags + sbegin + j));
+				at += tbytes;
+			}
+		}
+	}
+}
+
 // ------------------------------------------------------------------ hit map build (once, at vsgpu_open)
 // one warp per walk entry: lanes sweep the words of the entry's carrier set and scatter its bits
 // into the sample rows.
@@ -446,6 +605,23 @@ inline uint32_t grid_for(uint64_t n, uint32_t block, int ctas_per_sm) {
 cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream) {
 	if (ix.num_cent == 0) return cudaSuccess;
 	k_build_hitmap<<<grid_for((uint64_t)ix.num_cent * 32, 256, 8), 256, 0, stream>>>(ix, hitmap);
+	return cudaGetLastError();
+}
+cudaError_t launch_render_offsets(const DevIndex& ix, const RenderTables& rt, uint64_t nseg, const uint32_t* seg_lo, const uint32_t* seg_hi, int with_samples,
+                                  uint64_t* row_off, uint64_t* byte_off, uint64_t* scratch, cudaStream_t stream) {
+	(void)ix;
+	const int ws = with_samples ? 1 : 0;
+	const uint64_t nctas = (nseg + 1023) / 1024;
+	if (nseg == 0) return cudaSuccess;
+	k_seg_sums<<<(uint32_t)nctas, 256, 0, stream>>>(rt.text_prefix[ws], nseg, seg_lo, seg_hi, scratch);
+	k_seg_bases<<<1, 256, 0, stream>>>(nctas, scratch);
+	k_seg_offsets<<<(uint32_t)nctas, 256, 0, stream>>>(rt.text_prefix[ws], nseg, seg_lo, seg_hi, scratch, nctas, row_off, byte_off);
+	return cudaGetLastError();
+}
+cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t nseg, const uint32_t* seg_lo, int with_samples,
+                          const uint64_t* row_off, const uint64_t* byte_off, uint64_t total_rows, char* text, cudaStream_t stream) {
+	if (total_rows == 0) return cudaSuccess;
+	k_render<<<grid_for(total_rows * 32, 256, 8), 256, 0, stream>>>(ix, rt, rt.text_prefix[with_samples ? 1 : 0], nseg, seg_lo, with_samples ? 1 : 0, row_off, byte_off, total_rows, text);
 	return cudaGetLastError();
 }
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts,

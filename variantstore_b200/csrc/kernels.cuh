@@ -39,6 +39,29 @@ struct DevIndex {
 	const uint2* cent_anc;                // per walk entry: pre-order interval of the state examining its source
 };
 
+// Tables for rendering t6 rows as text on the device; uploaded on first use.
+// A row is print_var's line (query.h:43-50): "pos\tref\talt\tname(gt) name(gt) ...\n"; its length
+// depends on the record alone, so text offsets are differences of two prefix arrays.
+struct RenderTables {
+	const uint4* rec_seq;        // R: {ref_off, ref_len, alt_off, alt_len} into `seq`
+	const uint4* rec_car;        // R: {carrier set id, s_info count | row flags << 28, s_info begin lo, hi}
+	const uint64_t* text_prefix[2];   // R + 1 each: bytes of rows [0, r) without / with the carrier list
+	const uint8_t* seq;          // 3-bit base codes, one per byte (seq_buffer.sdsl)
+	const uint8_t* s_flags;      // per s_info: bit0 phase, bit1 gt_1, bit2 gt_2
+	const uint32_t* s_sample_id; // explicit-id mode: per s_info sample id
+	const uint32_t* name_off;    // num_samples + 1 offsets into name_chars
+	const char* name_chars;
+};
+
+// Segment s of a render call = records [seg_lo[s], seg_hi[s]) ((NONE, NONE) = empty).  Three small
+// launches turn the per-segment row and byte counts into exclusive offsets: row_off / byte_off get
+// nseg + 1 entries (the last = totals); `scratch` needs 2 * (ceil(nseg / 1024) + 1) words.
+cudaError_t launch_render_offsets(const DevIndex& ix, const RenderTables& rt, uint64_t nseg, const uint32_t* seg_lo, const uint32_t* seg_hi, int with_samples,
+                                  uint64_t* row_off, uint64_t* byte_off, uint64_t* scratch, cudaStream_t stream);
+// One warp per row writes its text at its final position in `text`.
+cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t nseg, const uint32_t* seg_lo, int with_samples,
+                          const uint64_t* row_off, const uint64_t* byte_off, uint64_t total_rows, char* text, cudaStream_t stream);
+
 // fills `hitmap` (zeroed, num_samples x row_words) from the walk entries and their carrier sets
 cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream);
 

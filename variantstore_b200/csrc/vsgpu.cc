@@ -64,6 +64,15 @@ struct vsgpu_result {
 	uint32_t* hits = nullptr; size_t hits_cap = 0;         // bytes
 };
 
+// Host side of a rendered t6 answer (page-locked, pooled like vsgpu_result).
+struct vsgpu_text {
+	vsgpu_index* owner = nullptr;
+	uint64_t n = 0, nbytes = 0, nrows = 0;
+	char* bytes = nullptr; size_t bytes_cap = 0;
+	uint64_t* offsets = nullptr; size_t offsets_cap = 0;
+	float kernel_ms = 0;
+};
+
 struct vsgpu_index : vsgpu::HostIndex {
 	DevIndex dev;
 	int device = 0;
@@ -86,6 +95,11 @@ struct vsgpu_index : vsgpu::HostIndex {
 	cudaStream_t s_in[kInStreams] = {}, s_k = nullptr, s_out = nullptr;
 	cudaEvent_t ev_in[kMaxChunks][kInStreams] = {}, ev_k[kMaxChunks] = {}, ev_out[kMaxChunks] = {};
 	uint64_t* pin_small = nullptr;    // page-locked: kMaxChunks running totals + the two status words
+	// device-side row rendering: tables uploaded on first use
+	bool render_ready = false;
+	RenderTables render{};
+	DevBuf bseg, brow_off, bbyte_off, bscratch, btext;
+	cudaEvent_t ev_render[2] = {nullptr, nullptr};
 	// page-locked host buffers: a free list for results + two staging areas for t6
 	std::mutex pool_mu;
 	std::vector<std::pair<void*, size_t>> pinned_free;
@@ -109,7 +123,8 @@ struct vsgpu_index : vsgpu::HostIndex {
 		cudaSetDevice(device);
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag}) b->release();
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bseg, &brow_off, &bbyte_off, &bscratch, &btext}) b->release();
+		for (cudaEvent_t e : ev_render) if (e) cudaEventDestroy(e);
 		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i][0], ev_in[i][1], ev_in[i][2], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
 		for (cudaStream_t st : {s_in[0], s_in[1], s_in[2], s_k, s_out}) if (st) cudaStreamDestroy(st);
 		if (pin_small) cudaFreeHost(pin_small);
@@ -632,6 +647,164 @@ int vsgpu_digest_t7(const vsgpu_index* ix, uint64_t n, const uint32_t* rec, uint
 	if (!ix || (n && !rec)) return set_err(VSGPU_EINVAL, "vsgpu_digest_t7: null argument");
 	digests_t7(ix, n, rec, ncarriers, digests);
 	return VSGPU_OK;
+}
+
+// ------------------------------------------------------------------ t6 rows rendered on the device
+namespace {
+// Row lengths and per-record lookups for k_render.  Everything is a function of the index alone.
+void ensure_render_tables(vsgpu_index* ix) {
+	if (ix->render_ready) return;
+	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
+	RenderTables& rt = ix->render;
+	std::vector<uint32_t> name_off(s.num_samples + 1, 0);
+	std::string chars;
+	for (uint32_t i = 0; i < s.num_samples; i++) { chars += s.sample_names[i]; name_off[i + 1] = (uint32_t)chars.size(); }
+	// bytes of the carrier list of every class: sum over non-ref members of len(name) + len("(g|g) ")
+	std::vector<uint64_t> set_bytes; std::vector<uint32_t> set_pop;
+	if (f.class_mode) {
+		set_bytes.assign(f.num_sets, 0); set_pop.assign(f.num_sets, 0);
+		std::atomic<bool> beyond{false};
+		parallel_for(f.num_sets, [&](uint64_t a, uint64_t b) {
+			for (uint64_t c = a; c < b; c++) {
+				uint64_t bytes = 0; uint32_t pop = 0;
+				for (uint32_t w = 0; w < f.words_per_set; w++)
+					for (uint64_t m = f.bitmap[c * f.words_per_set + w]; m; m &= m - 1) {
+						const uint32_t id = w * 64 + (uint32_t)__builtin_ctzll(m); pop++;
+						if (id >= s.num_samples) { beyond = true; continue; }
+						if (id) bytes += name_off[id + 1] - name_off[id] + 6;
+					}
+				set_bytes[c] = bytes; set_pop[c] = pop;
+			}
+		});
+		if (beyond) throw std::runtime_error("a sample class names a sample beyond sampleid_map.lst");
+	}
+	std::vector<uint4> rec_seq(f.R), rec_car(f.R);
+	std::vector<uint64_t> tp0(f.R + 1, 0), tp1(f.R + 1, 0);
+	for (uint32_t r = 0; r < f.R; r++) {
+		const uint32_t v = f.rec_vertex[r], rv = f.rec_refv[r], av = f.rec_altv[r];
+		rec_seq[r] = make_uint4(rv == kNone ? 0 : s.v_offset[rv], rv == kNone ? 0 : s.v_length[rv], av == kNone ? 0 : s.v_offset[av], av == kNone ? 0 : s.v_length[av]);
+		const uint64_t sb = s.v_sinfo_begin[v], sc = s.v_sinfo_begin[v + 1] - sb;
+		if (sc >= (1u << 28)) throw std::runtime_error("vertex " + std::to_string(v) + " has too many s_info entries to render");
+		const uint32_t set = f.class_mode ? s.v_class[v] : 0;
+		rec_car[r] = make_uint4(set, (uint32_t)sc | ((uint32_t)f.rec_flags[r] << 28), (uint32_t)sb, (uint32_t)(sb >> 32));
+		uint32_t digits = 1; for (uint32_t q = f.rec_pos[r]; q >= 10; q /= 10) digits++;
+		const uint64_t hdr = digits + 1 + rec_seq[r].y + 1 + rec_seq[r].w + 1 + 1;
+		uint64_t car = 0;
+		if (!(f.rec_flags[r] & 4)) {
+			if (f.class_mode) {
+				if (set_pop[set] != sc) throw std::runtime_error("vertex " + std::to_string(v) + ": s_info entries differ from the members of its sample class");
+				car = set_bytes[set];
+			} else for (uint64_t i = sb; i < sb + sc; i++) {
+				const uint32_t id = s.s_sample_id[i];
+				if (id >= s.num_samples) throw std::runtime_error("vertex " + std::to_string(v) + " names a sample beyond sampleid_map.lst");
+				if (id) car += name_off[id + 1] - name_off[id] + 6;
+			}
+		}
+		tp0[r + 1] = tp0[r] + hdr; tp1[r + 1] = tp1[r] + hdr + car;
+	}
+	rt.rec_seq = upload(ix, rec_seq); rt.rec_car = upload(ix, rec_car);
+	rt.text_prefix[0] = upload(ix, tp0); rt.text_prefix[1] = upload(ix, tp1);
+	rt.seq = upload(ix, s.seq); rt.s_flags = upload(ix, s.s_flags); rt.s_sample_id = upload(ix, s.s_sample_id);
+	rt.name_off = upload(ix, name_off);
+	std::vector<char> cv(chars.begin(), chars.end());
+	rt.name_chars = upload(ix, cv);
+	for (auto& e : ix->ev_render) CU(cudaEventCreate(&e));
+	ix->render_ready = true;
+}
+}  // namespace
+
+int vsgpu_render_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, int with_samples, vsgpu_text** out) {
+	if (!ix || !out || (n && (!x || !y))) return set_err(VSGPU_EINVAL, "vsgpu_render_t6: null argument");
+	*out = nullptr;
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	std::unique_ptr<vsgpu_text, void (*)(vsgpu_text*)> t(new vsgpu_text, vsgpu_text_free);
+	t->owner = ix; t->n = n;
+	try {
+		ensure_render_tables(ix);
+		cudaStream_t st = ix->s_k;
+		t->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &t->offsets_cap);
+		if (!t->offsets) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		t->offsets[0] = 0;
+		uint64_t nseg = n; const uint32_t* seg_lo = nullptr; const uint32_t* seg_hi = nullptr;
+		std::vector<uint64_t> seg_first;                       // only when a region needs several segments
+		if (n) {
+			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bout.ensure(n * 12));
+			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
+			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
+			uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n;
+			CU(launch_t6(ix->dev, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), d_lo, d_hi, nullptr, nullptr, 0, ix->d_status, st));
+			seg_lo = d_lo; seg_hi = d_hi;
+			if (t6_special(ix)) {
+				// Slices holding a repeated record, or regions past the contig end over tail records, are not
+				// printed whole: the literal rule (query.h:397-414, 758-771) decides their rows, so such a
+				// region becomes several segments (runs of kept records), built on the host.
+				std::vector<uint32_t> lo(n), hi(n), slo, shi, vars;
+				CU(cudaMemcpyAsync(lo.data(), d_lo, n * 4, cudaMemcpyDeviceToHost, st));
+				CU(cudaMemcpyAsync(hi.data(), d_hi, n * 4, cudaMemcpyDeviceToHost, st));
+				CU(cudaStreamSynchronize(st));
+				seg_first.assign(n + 1, 0);
+				for (uint64_t i = 0; i < n; i++) {
+					seg_first[i] = slo.size();
+					if (lo[i] == kNone || hi[i] <= lo[i]) continue;
+					if (!t6_needs_literal(ix, y[i], lo[i], hi[i])) { slo.push_back(lo[i]); shi.push_back(hi[i]); continue; }
+					t6_literal(ix, x[i], y[i], vars);
+					for (size_t a = 0; a < vars.size();) { size_t b = a + 1; while (b < vars.size() && vars[b] == vars[b - 1] + 1) b++; slo.push_back(vars[a]); shi.push_back(vars[b - 1] + 1); a = b; }
+				}
+				seg_first[n] = slo.size();
+				nseg = slo.size();
+				CU(ix->bseg.ensure(std::max<uint64_t>(nseg, 1) * 8));
+				if (nseg) {
+					CU(cudaMemcpyAsync(ix->bseg.p, slo.data(), nseg * 4, cudaMemcpyHostToDevice, st));
+					CU(cudaMemcpyAsync(ix->bseg.as<uint32_t>() + nseg, shi.data(), nseg * 4, cudaMemcpyHostToDevice, st));
+					CU(cudaStreamSynchronize(st));                 // slo / shi go out of scope below
+				}
+				seg_lo = ix->bseg.as<uint32_t>(); seg_hi = seg_lo + nseg;
+			}
+		}
+		uint64_t totals[2] = {0, 0};
+		if (nseg) {
+			CU(ix->brow_off.ensure((nseg + 1) * 8)); CU(ix->bbyte_off.ensure((nseg + 1) * 8)); CU(ix->bscratch.ensure(((nseg + 1023) / 1024 + 1) * 16));
+			CU(cudaEventRecord(ix->ev_render[0], st));
+			CU(launch_render_offsets(ix->dev, ix->render, nseg, seg_lo, seg_hi, with_samples, ix->brow_off.as<uint64_t>(), ix->bbyte_off.as<uint64_t>(), ix->bscratch.as<uint64_t>(), st));
+			CU(cudaMemcpyAsync(&ix->pin_small[0], ix->brow_off.as<uint64_t>() + nseg, 8, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(&ix->pin_small[1], ix->bbyte_off.as<uint64_t>() + nseg, 8, cudaMemcpyDeviceToHost, st));
+			const uint32_t status = read_status(ix, ix->d_status, nullptr, st);
+			if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+			totals[0] = ix->pin_small[0]; totals[1] = ix->pin_small[1];
+		}
+		uint64_t max_bytes = 2ull << 30;
+		if (const char* e = getenv("VSGPU_RENDER_MAX_BYTES")) max_bytes = strtoull(e, nullptr, 10);
+		if (totals[1] > max_bytes) return set_err(VSGPU_ESHAPE, "vsgpu_render_t6: the rows of this batch take " + std::to_string(totals[1]) + " bytes (limit VSGPU_RENDER_MAX_BYTES = " + std::to_string(max_bytes) + "); split the batch");
+		t->nrows = totals[0]; t->nbytes = totals[1];
+		t->bytes = (char*)ix->pinned_acquire(totals[1] + 1, &t->bytes_cap);
+		if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		if (totals[1]) {
+			CU(ix->btext.ensure(totals[1]));
+			CU(launch_render(ix->dev, ix->render, nseg, seg_lo, with_samples, ix->brow_off.as<uint64_t>(), ix->bbyte_off.as<uint64_t>(), totals[0], ix->btext.as<char>(), st));
+			CU(cudaEventRecord(ix->ev_render[1], st));
+			CU(cudaMemcpyAsync(t->bytes, ix->btext.p, totals[1], cudaMemcpyDeviceToHost, st));
+		} else if (nseg) CU(cudaEventRecord(ix->ev_render[1], st));
+		if (nseg && seg_first.empty()) CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+		std::vector<uint64_t> seg_off;
+		if (nseg && !seg_first.empty()) { seg_off.resize(nseg + 1); CU(cudaMemcpyAsync(seg_off.data(), ix->bbyte_off.p, (nseg + 1) * 8, cudaMemcpyDeviceToHost, st)); }
+		CU(cudaStreamSynchronize(st));
+		if (!seg_first.empty()) for (uint64_t i = 0; i <= n; i++) t->offsets[i] = nseg ? seg_off[seg_first[i]] : 0;
+		else if (!nseg) for (uint64_t i = 0; i <= n; i++) t->offsets[i] = 0;
+		t->bytes[totals[1]] = 0;
+		if (nseg) CU(cudaEventElapsedTime(&t->kernel_ms, ix->ev_render[0], ix->ev_render[1]));
+		*out = t.release();
+	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+const char* vsgpu_text_bytes(const vsgpu_text* t) { return t ? t->bytes : nullptr; }
+const uint64_t* vsgpu_text_offsets(const vsgpu_text* t) { return t ? t->offsets : nullptr; }
+uint64_t vsgpu_text_num_rows(const vsgpu_text* t) { return t ? t->nrows : 0; }
+float vsgpu_text_kernel_ms(const vsgpu_text* t) { return t ? t->kernel_ms : 0.f; }
+void vsgpu_text_free(vsgpu_text* t) {
+	if (!t) return;
+	if (t->owner) { t->owner->pinned_release(t->bytes, t->bytes_cap); t->owner->pinned_release(t->offsets, t->offsets_cap); }
+	delete t;
 }
 
 // ------------------------------------------------------------------ device-resident batches
