@@ -482,12 +482,30 @@ __global__ void __launch_bounds__(256) k_seg_offsets(const uint64_t* __restrict_
 }
 
 __device__ __forceinline__ uint32_t name_len(const RenderTables& rt, uint32_t id) { return __ldg(rt.name_off + id + 1) - __ldg(rt.name_off + id); }
-// name(g|g) + blank at `out`; returns the bytes written
-__device__ __forceinline__ uint32_t put_carrier(const RenderTables& rt, char* out, uint32_t id, uint8_t fl) {
+// The carrier lists are staged in shared memory, a window of kRenderWin bytes per warp, and flushed
+// with coalesced 32-bit stores: a lane's items land at byte offsets of their own, and writing them
+// straight to global memory costs one sector transaction per byte.
+constexpr uint32_t kRenderWin = 2048;
+// bytes [b0, b1) of the item "name(g|g) " of sample `id`, to stage[pos + b - b0 ...]
+__device__ __forceinline__ void put_carrier(const RenderTables& rt, uint8_t* stage, uint32_t id, uint8_t fl, uint32_t b0, uint32_t b1) {
 	const uint32_t a = __ldg(rt.name_off + id), n = __ldg(rt.name_off + id + 1) - a;
-	for (uint32_t i = 0; i < n; i++) out[i] = __ldg(rt.name_chars + a + i);
-	out[n] = '('; out[n + 1] = (fl & 2) ? '1' : '0'; out[n + 2] = (fl & 1) ? '|' : '/'; out[n + 3] = (fl & 4) ? '1' : '0'; out[n + 4] = ')'; out[n + 5] = ' ';
-	return n + 6;
+	for (uint32_t b = b0; b < b1; b++) {
+		char c;
+		if (b < n) c = __ldg(rt.name_chars + a + b);
+		else { const uint32_t k = b - n; c = k == 0 ? '(' : k == 1 ? ((fl & 2) ? '1' : '0') : k == 2 ? ((fl & 1) ? '|' : '/') : k == 3 ? ((fl & 4) ? '1' : '0') : k == 4 ? ')' : ' '; }
+		stage[b - b0] = (uint8_t)c;
+	}
+}
+// stage[sh .. sh + len) -> dst[0 .. len), where sh = dst & 3 so that 32-bit words line up on both sides
+__device__ __forceinline__ void flush_window(const uint8_t* stage, uint32_t sh, uint32_t len, char* dst, uint32_t lane) {
+	const uint32_t head = min(len, (4 - sh) & 3);
+	if (lane < head) dst[lane] = (char)stage[sh + lane];
+	const uint32_t nwords = (len - head) >> 2;
+	const uint32_t* sw = (const uint32_t*)(stage + sh + head);
+	uint32_t* dw = (uint32_t*)(dst + head);
+	for (uint32_t i = lane; i < nwords; i += 32) dw[i] = sw[i];
+	const uint32_t done = head + (nwords << 2);
+	if (lane < len - done) dst[done + lane] = (char)stage[sh + done + lane];
 }
 __device__ __forceinline__ void warp_excl2(uint32_t lane, uint32_t a, uint32_t b, uint32_t& ea, uint32_t& eb, uint32_t& ta, uint32_t& tb) {
 	uint32_t ia = a, ib = b;
@@ -499,7 +517,9 @@ __device__ __forceinline__ void warp_excl2(uint32_t lane, uint32_t a, uint32_t b
 
 __global__ void __launch_bounds__(256) k_render(const DevIndex ix, const RenderTables rt, const uint64_t* __restrict__ tp, uint64_t nseg, const uint32_t* __restrict__ seg_lo, int ws,
                                                 const uint64_t* __restrict__ row_off, const uint64_t* __restrict__ byte_off, uint64_t total_rows, char* __restrict__ text) {
+	__shared__ __align__(16) uint8_t s_stage[8][kRenderWin + 16];
 	const uint32_t lane = threadIdx.x & 31;
+	uint8_t* stage = s_stage[threadIdx.x >> 5];
 	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
 	const uint64_t kBase = 0x0505054E47544341ULL;                      // "ACTGN" + 5,5,5 by 3-bit code: map_int, src/util.cc:32-41
 	for (uint64_t row = warp0; row < total_rows; row += nwarps) {
@@ -533,35 +553,46 @@ __global__ void __launch_bounds__(256) k_render(const DevIndex ix, const RenderT
 		// ---- carriers
 		const uint64_t sbegin = (uint64_t)cr.z | ((uint64_t)cr.w << 32);
 		uint32_t slot0 = 0;                                              // s_info entries consumed so far
-		if (ix.class_mode) {
-			const uint64_t* bits_row = ix.bitmap + (uint64_t)cr.x * ix.words_per_set;
-			for (uint32_t w0 = 0; w0 < ix.words_per_set; w0 += 32) {
-				const uint32_t w = w0 + lane;
-				const uint64_t all = w < ix.words_per_set ? __ldg(bits_row + w) : 0;
-				const uint64_t pr = w == 0 ? all & ~1ULL : all;           // the ref bit owns an s_info entry but is not printed
-				uint32_t bytes = 0;
-				for (uint64_t m = pr; m; m &= m - 1) bytes += name_len(rt, w * 64 + (uint32_t)__ffsll((long long)m) - 1) + 6;
-				uint32_t eslot, ebytes, tslot, tbytes;
-				warp_excl2(lane, (uint32_t)__popcll(all), bytes, eslot, ebytes, tslot, tbytes);
-				uint32_t slot = slot0 + eslot; char* o = out + at + ebytes;
-				for (uint64_t m = all; m; m &= m - 1) {
-					const uint32_t id = w * 64 + (uint32_t)__ffsll((long long)m) - 1;
-					if (id != 0) o += put_carrier(rt, o, id, __ldg(rt.s_flags + sbegin + slot));
-					slot++;
+		const uint32_t rounds = ix.class_mode ? (ix.words_per_set + 31) / 32 : ((cr.y & 0x0FFFFFFFu) + 31) / 32;
+		for (uint32_t rd = 0; rd < rounds; rd++) {
+			// this lane's items of the round: class mode = the members of one bitmap word (the ref bit owns an
+			// s_info entry but is not printed); explicit-id mode = one s_info entry
+			uint64_t all = 0; uint32_t base_id = 0, nslots = 0, bytes = 0;
+			if (ix.class_mode) {
+				const uint32_t w = rd * 32 + lane;
+				all = w < ix.words_per_set ? __ldg(ix.bitmap + (uint64_t)cr.x * ix.words_per_set + w) : 0;
+				base_id = w * 64; nslots = (uint32_t)__popcll(all);
+				for (uint64_t m = (w == 0 ? all & ~1ULL : all); m; m &= m - 1) bytes += name_len(rt, base_id + (uint32_t)__ffsll((long long)m) - 1) + 6;
+			} else {
+				const uint32_t j = rd * 32 + lane;
+				if (j < (cr.y & 0x0FFFFFFFu)) { base_id = __ldg(rt.s_sample_id + sbegin + j); all = 1; nslots = 1; if (base_id) bytes = name_len(rt, base_id) + 6; }
+			}
+			uint32_t eslot, ebytes, tslot, tbytes;
+			warp_excl2(lane, nslots, bytes, eslot, ebytes, tslot, tbytes);
+			for (uint32_t win0 = 0; win0 < tbytes; win0 += kRenderWin) {
+				const uint32_t wlen = min(kRenderWin, tbytes - win0);
+				char* dst = out + at + win0;
+				const uint32_t sh = (uint32_t)((uintptr_t)dst & 3);
+				if (bytes && ebytes < win0 + wlen && ebytes + bytes > win0) {
+					uint32_t slot = slot0 + eslot, o = ebytes;
+					for (uint64_t m = all; m; m &= m - 1) {
+						const uint32_t id = ix.class_mode ? base_id + (uint32_t)__ffsll((long long)m) - 1 : base_id;
+						if (id != 0) {
+							const uint32_t len = name_len(rt, id) + 6;
+							if (o + len > win0 && o < win0 + wlen) {
+								const uint32_t b0 = o < win0 ? win0 - o : 0, b1 = min(len, win0 + wlen - o);
+								put_carrier(rt, stage + sh + (o + b0 - win0), id, __ldg(rt.s_flags + sbegin + slot), b0, b1);
+							}
+							o += len;
+						}
+						slot++;
+					}
 				}
-				slot0 += tslot; at += tbytes;
+				__syncwarp();
+				flush_window(stage, sh, wlen, dst, lane);
+				__syncwarp();
 			}
-		} else {
-			const uint32_t cnt = cr.y & 0x0FFFFFFFu;
-			for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-				const uint32_t j = j0 + lane;
-				const uint32_t id = j < cnt ? __ldg(rt.s_sample_id + sbegin + j) : 0;
-				const uint32_t bytes = id ? name_len(rt, id) + 6 : 0;
-				uint32_t e1, ebytes, t1, tbytes;
-				warp_excl2(lane, 0, bytes, e1, ebytes, t1, tbytes);
-				if (id) put_carrier(rt, out + at + ebytes, id, __ldg(rt.s_flags + sbegin + j));
-				at += tbytes;
-			}
+			slot0 += tslot; at += tbytes;
 		}
 	}
 }
