@@ -231,7 +231,7 @@ def test_rows_rendered_on_device_cuda(tmp_path, sparse):
         assert len(off) == 1 and text == b"" and rows == 0
 
 
-def test_rows_rendered_on_device_many_samples_cuda(tmp_path):
+def test_rows_rendered_on_device_many_samples_cuda(tmp_path, monkeypatch):
     """chr22-shaped classes (300 samples, 5 bitmap words, long carrier lists) and a batch large enough
     for several scan CTAs; names of different lengths."""
     o = Oracle.synth(str(tmp_path / "ser"), ref_length=600_000, n_records=20_000, n_samples=300, fmax=120, seed=8, cqf_log2=19)
@@ -240,6 +240,11 @@ def test_rows_rendered_on_device_many_samples_cuda(tmp_path):
         x = np.sort(rng.integers(1, 600_000, 5000)).astype(np.uint64)
         y = x + rng.choice([10, 300, 3000], 5000).astype(np.uint64)
         _check_render(o, e, x, y, oracle_regions=40)
+        # the text leaves the device in chunks while the next chunk is rendered: same bytes
+        whole = e.render_var_in_ref(x, y)
+        monkeypatch.setenv("VSGPU_RENDER_CHUNK_BYTES", "65536")
+        cut = e.render_var_in_ref(x, y)
+        assert np.array_equal(whole[0], cut[0]) and whole[1] == cut[1] and whole[2] == cut[2] and len(whole[1]) > 16 * 65536
 
 
 def test_rows_rendered_with_duplicate_records_cuda(tmp_path):

@@ -516,13 +516,13 @@ __device__ __forceinline__ void warp_excl2(uint32_t lane, uint32_t a, uint32_t b
 }
 
 __global__ void __launch_bounds__(256) k_render(const DevIndex ix, const RenderTables rt, const uint64_t* __restrict__ tp, uint64_t nseg, const uint32_t* __restrict__ seg_lo, int ws,
-                                                const uint64_t* __restrict__ row_off, const uint64_t* __restrict__ byte_off, uint64_t total_rows, char* __restrict__ text) {
+                                                const uint64_t* __restrict__ row_off, const uint64_t* __restrict__ byte_off, uint64_t row_begin, uint64_t row_end, char* __restrict__ text) {
 	__shared__ __align__(16) uint8_t s_stage[8][kRenderWin + 16];
 	const uint32_t lane = threadIdx.x & 31;
 	uint8_t* stage = s_stage[threadIdx.x >> 5];
 	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
 	const uint64_t kBase = 0x0505054E47544341ULL;                      // "ACTGN" + 5,5,5 by 3-bit code: map_int, src/util.cc:32-41
-	for (uint64_t row = warp0; row < total_rows; row += nwarps) {
+	for (uint64_t row = row_begin + warp0; row < row_end; row += nwarps) {
 		// segment of this row: last s with row_off[s] <= row (empty segments share an offset with their successor)
 		uint64_t a = 0, b = nseg;
 		while (b - a > 1) { const uint64_t m = (a + b) >> 1; if (__ldg(row_off + m) <= row) a = m; else b = m; }
@@ -650,9 +650,9 @@ cudaError_t launch_render_offsets(const DevIndex& ix, const RenderTables& rt, ui
 	return cudaGetLastError();
 }
 cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t nseg, const uint32_t* seg_lo, int with_samples,
-                          const uint64_t* row_off, const uint64_t* byte_off, uint64_t total_rows, char* text, cudaStream_t stream) {
-	if (total_rows == 0) return cudaSuccess;
-	k_render<<<grid_for(total_rows * 32, 256, 8), 256, 0, stream>>>(ix, rt, rt.text_prefix[with_samples ? 1 : 0], nseg, seg_lo, with_samples ? 1 : 0, row_off, byte_off, total_rows, text);
+                          const uint64_t* row_off, const uint64_t* byte_off, uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream) {
+	if (row_end <= row_begin) return cudaSuccess;
+	k_render<<<grid_for((row_end - row_begin) * 32, 256, 8), 256, 0, stream>>>(ix, rt, rt.text_prefix[with_samples ? 1 : 0], nseg, seg_lo, with_samples ? 1 : 0, row_off, byte_off, row_begin, row_end, text);
 	return cudaGetLastError();
 }
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts,

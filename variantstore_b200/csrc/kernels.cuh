@@ -58,9 +58,9 @@ struct RenderTables {
 // nseg + 1 entries (the last = totals); `scratch` needs 2 * (ceil(nseg / 1024) + 1) words.
 cudaError_t launch_render_offsets(const DevIndex& ix, const RenderTables& rt, uint64_t nseg, const uint32_t* seg_lo, const uint32_t* seg_hi, int with_samples,
                                   uint64_t* row_off, uint64_t* byte_off, uint64_t* scratch, cudaStream_t stream);
-// One warp per row writes its text at its final position in `text`.
+// One warp per row of [row_begin, row_end) writes its text at its final position in `text`.
 cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t nseg, const uint32_t* seg_lo, int with_samples,
-                          const uint64_t* row_off, const uint64_t* byte_off, uint64_t total_rows, char* text, cudaStream_t stream);
+                          const uint64_t* row_off, const uint64_t* byte_off, uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream);
 
 // fills `hitmap` (zeroed, num_samples x row_words) from the walk entries and their carrier sets
 cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream);

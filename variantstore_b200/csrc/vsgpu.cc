@@ -779,18 +779,41 @@ int vsgpu_render_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64
 		t->nrows = totals[0]; t->nbytes = totals[1];
 		t->bytes = (char*)ix->pinned_acquire(totals[1] + 1, &t->bytes_cap);
 		if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		// segment offsets on the host: the result's region offsets, and where to cut the text into chunks
+		// whose device->host copy overlaps the rendering of the next one
+		size_t ro_cap = 0, bo_cap = 0;
+		uint64_t* ro = nullptr; uint64_t* bo = nullptr;
+		struct Temps { vsgpu_index* ix; uint64_t*& a; size_t& ac; uint64_t*& b; size_t& bc; ~Temps() { ix->pinned_release(a, ac); ix->pinned_release(b, bc); } } temps{ix, ro, ro_cap, bo, bo_cap};
+		if (nseg) {
+			ro = (uint64_t*)ix->pinned_acquire((nseg + 1) * 8, &ro_cap); bo = (uint64_t*)ix->pinned_acquire((nseg + 1) * 8, &bo_cap);
+			if (!ro || !bo) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+			CU(cudaMemcpyAsync(ro, ix->brow_off.p, (nseg + 1) * 8, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(bo, ix->bbyte_off.p, (nseg + 1) * 8, cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+		}
 		if (totals[1]) {
 			CU(ix->btext.ensure(totals[1]));
-			CU(launch_render(ix->dev, ix->render, nseg, seg_lo, with_samples, ix->brow_off.as<uint64_t>(), ix->bbyte_off.as<uint64_t>(), totals[0], ix->btext.as<char>(), st));
+			uint64_t chunk_bytes = 32ull << 20;
+			if (const char* e = getenv("VSGPU_RENDER_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+			const int chunks = (int)std::min<uint64_t>(vsgpu_index::kMaxChunks, (totals[1] + chunk_bytes - 1) / chunk_bytes);
+			uint64_t s0 = 0;
+			for (int c = 0; c < chunks && s0 < nseg; c++) {
+				uint64_t s1 = nseg;
+				if (c + 1 < chunks) { const uint64_t target = totals[1] / chunks * (c + 1); s1 = std::lower_bound(bo + s0 + 1, bo + nseg, target) - bo; }
+				if (s1 <= s0) continue;
+				CU(launch_render(ix->dev, ix->render, nseg, seg_lo, with_samples, ix->brow_off.as<uint64_t>(), ix->bbyte_off.as<uint64_t>(), ro[s0], ro[s1], ix->btext.as<char>(), st));
+				CU(cudaEventRecord(ix->ev_k[c], st));
+				CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
+				if (bo[s1] > bo[s0]) CU(cudaMemcpyAsync(t->bytes + bo[s0], ix->btext.as<char>() + bo[s0], bo[s1] - bo[s0], cudaMemcpyDeviceToHost, ix->s_out));
+				s0 = s1;
+			}
 			CU(cudaEventRecord(ix->ev_render[1], st));
-			CU(cudaMemcpyAsync(t->bytes, ix->btext.p, totals[1], cudaMemcpyDeviceToHost, st));
-		} else if (nseg) CU(cudaEventRecord(ix->ev_render[1], st));
-		if (nseg && seg_first.empty()) CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-		std::vector<uint64_t> seg_off;
-		if (nseg && !seg_first.empty()) { seg_off.resize(nseg + 1); CU(cudaMemcpyAsync(seg_off.data(), ix->bbyte_off.p, (nseg + 1) * 8, cudaMemcpyDeviceToHost, st)); }
-		CU(cudaStreamSynchronize(st));
-		if (!seg_first.empty()) for (uint64_t i = 0; i <= n; i++) t->offsets[i] = nseg ? seg_off[seg_first[i]] : 0;
-		else if (!nseg) for (uint64_t i = 0; i <= n; i++) t->offsets[i] = 0;
+			CU(cudaStreamSynchronize(ix->s_out));
+			CU(cudaStreamSynchronize(st));
+		} else if (nseg) { CU(cudaEventRecord(ix->ev_render[1], st)); CU(cudaStreamSynchronize(st)); }
+		if (!nseg) for (uint64_t i = 0; i <= n; i++) t->offsets[i] = 0;
+		else if (seg_first.empty()) memcpy(t->offsets, bo, (n + 1) * 8);
+		else for (uint64_t i = 0; i <= n; i++) t->offsets[i] = bo[seg_first[i]];
 		t->bytes[totals[1]] = 0;
 		if (nseg) CU(cudaEventElapsedTime(&t->kernel_ms, ix->ev_render[0], ix->ev_render[1]));
 		*out = t.release();
