@@ -71,7 +71,13 @@ int main(int argc, char** argv) {
 		for (uint64_t i = 0; i < n && rc == 0; i++) {
 			// the reference prints the t4 label when its is_empty gate fires (query.h:746)
 			printf("Number of variants %s: %u\n", lo[i] == VSGPU_NONE ? "get_sample_var_in_ref" : "get_var_in_ref", cnt[i]);
-			if (verbose) { char* text = nullptr; uint64_t nr; if (vsgpu_rows_t6(idx, lo[i], hi[i], 1, &text, &nr) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
+		}
+		if (verbose && rc == 0 && n) {
+			// every call of the reference truncates and rewrites -o (query.h:774-781), so what is left on disk
+			// are the rows of the last region: rendered on the device, written once
+			vsgpu_text* text = nullptr;
+			rc = vsgpu_render_t6(idx, 1, &x[n - 1], &y[n - 1], 1, &text);
+			if (rc == 0) { write_rows(outfile, vsgpu_text_bytes(text), true); vsgpu_text_free(text); }
 		}
 	} else if (type == 4) {
 		uint32_t sid = 0;
