@@ -24,7 +24,7 @@ using namespace logic;
 
 // counts[i] = rows the reference returns when that is the slice length; regions whose slice needs the
 // literal dedup rule (a suspect duplicate inside, or a region running past the contig end over tail
-// records — DESIGN.md section 7) are appended to `flagged` (count in status[1]) for the host to re-count.
+// records — DESIGN.md section 9) are appended to `flagged` (count in status[1]) for the host to re-count.
 __global__ void __launch_bounds__(256) k_t6(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                             const uint64_t* __restrict__ ys, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi,
                                             uint32_t* __restrict__ counts, uint32_t* __restrict__ flagged, uint32_t flag_base, uint32_t* status) {
