@@ -28,7 +28,7 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "four-barriers", "tile-64", "chunked-calls"])
+@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "tile-64", "chunked-calls"])
 def walk_path(request, monkeypatch):
     """The t4 kernel paths: the sample-major hit map with one thread per region (default), the
     per-entry class-bitmap test used when the map does not fit the memory budget, and the
@@ -43,9 +43,7 @@ def walk_path(request, monkeypatch):
     monkeypatch.delenv("VSGPU_T4_PIPE", raising=False)
     monkeypatch.delenv("VSGPU_T4_TILE", raising=False)
     if request.param == "cta-per-tile":
-        monkeypatch.setenv("VSGPU_T4_PIPE", "0")        # k_t4 instead of the persistent pipelined kernels
-    if request.param == "four-barriers":
-        monkeypatch.setenv("VSGPU_T4_PIPE", "1")        # k_t4p instead of the one-barrier k_t4q
+        monkeypatch.setenv("VSGPU_T4_PIPE", "0")        # k_t4 instead of the persistent pipelined k_t4p
     if request.param == "tile-64":
         monkeypatch.setenv("VSGPU_T4_TILE", "64")       # more, smaller tiles: deeper look-back
     if request.param == "class-bitmaps":

@@ -6,10 +6,14 @@ run() {
 import json,sys
 b=json.loads(sys.stdin.readline()); print('$*', 'k_t4_ms', round(b['by_kernel']['k_t4_ms'],4), 'k_t6_ms', round(b['by_kernel']['k_t6_ms'],4), 'value', round(b['value']/1e9,2), 'e2e', round(b['e2e']['value']/1e9,2))"
 }
-run VSGPU_T4_PIPE=2
+
 run VSGPU_T4_PIPE=1
-run VSGPU_T4_PIPE=2 VSGPU_T4_MINCTAS=8
-run VSGPU_T4_PIPE=2 VSGPU_T4_TILE=128
-run VSGPU_T4_PIPE=2 VSGPU_T4_TILE=64
+
+
+
 run VSGPU_T4_PIPE=1 VSGPU_T4_TILE=128
-run VSGPU_T4_PIPE=2
+
+run VSGPU_T4_PIPE=1
+run VSGPU_T4_PIPE=1 VSGPU_T4_TILE=128
+run VSGPU_T4_PIPE=1 VSGPU_T4_TILE=64
+run VSGPU_T4_PIPE=0

@@ -336,84 +336,6 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 	}
 }
 
-// ------------------------------------------------------------------ t4, persistent + pipelined, one barrier per round
-// k_t4p spends a fifth of its stall samples at its four CTA barriers per round (ncu source page,
-// profiles/README.md).  Here only the one the CTA-wide scan needs is left: the ticket of the next
-// round is fetched a round ahead, the per-warp sums alternate between two buffers, and every warp
-// runs the look-back of the previous tile itself (the same 32 state words, served by L2) instead
-// of waiting for warp 0 to broadcast the result.
-template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
-__global__ void __launch_bounds__(kTile, kMinCtas) k_t4q(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
-                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
-                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                               uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr) {
-	__shared__ uint32_t s_hits[2][kTile * kKeep];
-	__shared__ uint32_t s_warp[2][kTile / 32];
-	__shared__ uint32_t s_tile[2];
-	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t ntiles = (uint32_t)((n + kTile - 1) / kTile);
-	volatile uint64_t* state = tile_state + 1;
-	if (threadIdx.x == 0) s_tile[0] = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);   // tiles start in ticket order
-	__syncthreads();
-	uint32_t p_tile = 0xFFFFFFFFu, p_cnt = 0, p_pre = 0; uint64_t p_agg = 0;   // what this thread still owes for the previous tile
-	for (uint32_t round = 0;; round++) {
-		const uint32_t buf = round & 1;
-		const uint32_t tile = s_tile[buf];
-		const bool has = tile < ntiles;
-		uint32_t cnt = 0, pre = 0; uint64_t agg = 0;
-		if (has) {
-			if (threadIdx.x == 0) s_tile[buf ^ 1] = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);   // next round's tile, read after the barrier below
-			// ---- walk this thread's region of the new tile
-			const uint64_t i = (uint64_t)tile * kTile + threadIdx.x;
-			SmemSink<kTile, kKeep> sink{s_hits[buf] + threadIdx.x, 0};
-			if (i < n) {
-				const uint64_t x = xs[i]; const uint32_t s = sample[i];
-				if (x < 1 || s == 0 || s >= ix.num_samples) atomicOr(status, kStatusBadRegion);
-				else walk_any(ix, x, ys[i], s, sink);
-			}
-			cnt = sink.n;
-			uint32_t incl = cnt;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-			if (lane == 31) s_warp[buf][warp] = incl;
-			__syncthreads();                                   // the only barrier of the round
-			uint32_t wpre = 0;
-#pragma unroll
-			for (uint32_t w = 0; w < kTile / 32; w++) { const uint32_t v = s_warp[buf][w]; if (w < warp) wpre += v; agg += v; }
-			pre = wpre + incl - cnt;
-			if (threadIdx.x == 0) state[tile] = tile == 0 ? (kFlagIncl | (chunk_base(base_ptr) + agg)) : (kFlagAgg | agg);      // publish the count now; the prefix later
-		}
-		// ---- finish the previous tile: look-back (every warp for itself), then the ordered write
-		if (p_tile != 0xFFFFFFFFu) {
-			uint64_t excl = 0;
-			if (p_tile == 0) excl = chunk_base(base_ptr);
-			else {
-				for (int64_t idx = (int64_t)p_tile - 1;; idx -= 32) {
-					const int64_t j = idx - lane;
-					uint64_t st = j >= 0 ? state[j] : kFlagIncl;
-					while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0)) { if ((st >> 62) == 0) st = state[j]; }
-					const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
-					const uint64_t v = st & kValMask;
-					if (incl_mask) { const uint32_t first = (uint32_t)__ffs((int)incl_mask) - 1; excl += warp_sum(lane <= first ? v : 0); break; }
-					excl += warp_sum(v);
-				}
-				if (threadIdx.x == 0) state[p_tile] = kFlagIncl | (excl + p_agg);
-			}
-			const uint64_t i = (uint64_t)p_tile * kTile + threadIdx.x;
-			if (i < n) {
-				const uint64_t off = excl + p_pre;
-				offsets[i] = off;
-				if (i == n - 1) offsets[n] = off + p_cnt;
-				if (off + p_cnt > cap) atomicOr(status, kStatusOverflow);
-				else if (p_cnt <= kKeep) { const uint32_t* src = s_hits[buf ^ 1] + threadIdx.x; for (uint32_t j = 0; j < p_cnt; j++) hits[off + j] = src[j * kTile]; }
-				else { DirectSink direct{hits + off, 0}; walk_any(ix, xs[i], ys[i], sample[i], direct); }   // more hits than the staging holds: walk again, straight into place
-			}
-		}
-		if (!has) break;
-		p_tile = tile; p_cnt = cnt; p_pre = pre; p_agg = agg;
-	}
-}
-
 // ------------------------------------------------------------------ t4, one warp per region
 // For batches of few, wide regions (the scan-bound end of the width sweep): eight regions per CTA,
 // every warp runs the setup in lock step and then the cooperative scan above; up to kKeepW hits per
@@ -769,16 +691,9 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 	static int min_ctas = 0;                       // tuning knob: registers per thread follow from it
 	if (!min_ctas) { const char* e = getenv("VSGPU_T4_MINCTAS"); min_ctas = e ? atoi(e) : 6; }
 #define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status, base_ptr
-	const char* pe = getenv("VSGPU_T4_PIPE");      // 2: persistent pipelined kernel with one barrier per round (default), 1: k_t4p, 0: one CTA per tile
-	const int pipe = pe ? atoi(pe) : 2;
+	const char* pe = getenv("VSGPU_T4_PIPE");      // 1: persistent pipelined kernel (default), 0: one CTA per tile
+	const int pipe = pe ? atoi(pe) : 1;
 	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each
-	else if (pipe == 2) {
-		const uint32_t tiles = (uint32_t)((n + tile - 1) / tile);
-		if (tile == 128) k_t4q<128, 12, kScratchHits><<<min(tiles, grid_for((uint64_t)tiles * 128, 128, 12)), 128, 0, stream>>>(VSGPU_T4_ARGS);
-		else if (tile == 64) k_t4q<64, 24, kScratchHits><<<min(tiles, grid_for((uint64_t)tiles * 64, 64, 24)), 64, 0, stream>>>(VSGPU_T4_ARGS);
-		else if (min_ctas == 8) k_t4q<256, 8, kScratchHits><<<min(tiles, grid_for((uint64_t)tiles * 256, 256, 8)), 256, 0, stream>>>(VSGPU_T4_ARGS);
-		else k_t4q<256, 6, kScratchHits><<<min(tiles, grid_for((uint64_t)tiles * 256, 256, 6)), 256, 0, stream>>>(VSGPU_T4_ARGS);
-	}
 	else if (pipe) {
 		const uint32_t tiles = (uint32_t)((n + tile - 1) / tile);
 		if (tile == 128) k_t4p<128, 12, kScratchHits><<<min(tiles, grid_for((uint64_t)tiles * 128, 128, 12)), 128, 0, stream>>>(VSGPU_T4_ARGS);
