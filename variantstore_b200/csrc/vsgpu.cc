@@ -486,7 +486,10 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		r.reset(new vsgpu_result);
 		r->owner = ix; r->n = n;
 		r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
-		r->hits = (uint32_t*)ix->pinned_acquire(cap * 4, &r->hits_cap);
+		// page-locked room for the hit codes is a guess too (the device buffer may be far larger than this
+		// batch needs); a batch that outgrows it gets an exact buffer and one copy at the end
+		const uint64_t host_cap = std::min<uint64_t>(cap, std::max<uint64_t>(8 * n, 1u << 18));
+		r->hits = (uint32_t*)ix->pinned_acquire(host_cap * 4, &r->hits_cap);
 		if (!r->offsets || !r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
 		// inputs on s_in, kernels on s_k (chunk c continues the offsets of chunk c-1), results on s_out as
 		// soon as their chunk is done
@@ -507,7 +510,7 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			CU(cudaEventRecord(ix->ev_k[c], ix->s_k));
 		}
 		tr.mark("enqueue");
-		uint64_t done = 0; bool overflow = false;
+		uint64_t done = 0; bool overflow = false, host_small = false;
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
 			CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
@@ -517,7 +520,8 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			CU(cudaEventSynchronize(ix->ev_out[c]));                   // the running total after chunk c: its hits are final
 			const uint64_t total = ix->pin_small[c];
 			if (total > cap) { overflow = true; continue; }
-			if (!overflow && total > done) CU(cudaMemcpyAsync(r->hits + done, ix->bhits.as<uint32_t>() + done, (total - done) * 4, cudaMemcpyDeviceToHost, ix->s_out));
+			if (total > host_cap) { host_small = true; continue; }
+			if (!overflow && !host_small && total > done) CU(cudaMemcpyAsync(r->hits + done, ix->bhits.as<uint32_t>() + done, (total - done) * 4, cudaMemcpyDeviceToHost, ix->s_out));
 			done = total;
 		}
 		uint32_t st = read_status(ix, ix->d_status, nullptr, ix->s_out);
@@ -532,6 +536,14 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			return VSGPU_OK;
 		}
 		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+		if (host_small) {
+			const uint64_t total = ix->pin_small[chunks - 1];
+			ix->pinned_release(r->hits, r->hits_cap);
+			r->hits = (uint32_t*)ix->pinned_acquire(total * 4, &r->hits_cap);
+			if (!r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+			CU(cudaMemcpyAsync(r->hits, ix->bhits.p, total * 4, cudaMemcpyDeviceToHost, ix->s_out));
+			CU(cudaStreamSynchronize(ix->s_out));
+		}
 		*out = r.release();
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
