@@ -234,6 +234,20 @@ def test_rows_rendered_on_device_cuda(tmp_path, sparse):
         assert len(off) == 1 and text == b"" and rows == 0
 
 
+def test_rows_rendered_with_long_and_mixed_names_cuda(tmp_path):
+    """items of up to 15 bytes come from per-sample templates; longer names (and a mix) take the generic path"""
+    for k, fmt in enumerate(["a_rather_long_sample_name_{:04d}", "n{:d}", "x{:09d}"]):          # 30-char, 2..3-char, 10-char names (items of 36, 8-9, 16 bytes)
+        d = tmp_path / str(k)
+        fa, vcf, names = T.write_fuzz_inputs(str(d), 6 + k, n_samples=14, name_fmt=fmt)
+        if k == 1:                                                                                  # mix short and long names in one index
+            txt = open(vcf).read().replace("n7\t", "the_seventh_sample_of_fourteen\t")
+            open(vcf, "w").write(txt)
+        o = Oracle.construct(fa, vcf, str(d / "ser"))
+        with T.open_engine(str(d / "ser"), "cuda") as e:
+            x, y, _ = T.random_regions(2, 120, 4000, widths=(5, 100, 1000, 4000), n_samples=len(names))
+            _check_render(o, e, x, y, oracle_regions=120)
+
+
 def test_rows_rendered_on_device_many_samples_cuda(tmp_path, monkeypatch):
     """chr22-shaped classes (300 samples, 5 bitmap words, long carrier lists) and a batch large enough
     for several scan CTAs; names of different lengths."""

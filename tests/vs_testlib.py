@@ -219,12 +219,12 @@ class Oracle:
 
 
 # ----------------------------------------------------------------------------- synthetic VCF text
-def write_fuzz_inputs(dirpath, seed, ref_len=4000, n_records=260, n_samples=12, overlap=False, sparse=False, chrom="f"):
+def write_fuzz_inputs(dirpath, seed, ref_len=4000, n_records=260, n_samples=12, overlap=False, sparse=False, chrom="f", name_fmt="S{:03d}"):
     """The fuzz shapes of SURVEY.md §4: SNPs (some bi-allelic), small insertions and deletions with
     abutting / adjacent sites; `overlap` lets a record start inside the previous record's REF span."""
     rnd = random.Random(seed)
     ref = "".join(rnd.choice("ACGT") for _ in range(ref_len))
-    names = [f"S{i:03d}" for i in range(1, n_samples + 1)]
+    names = [name_fmt.format(i) for i in range(1, n_samples + 1)]
     lines = ["##fileformat=VCFv4.1", '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">',
              "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names)]
     pos = rnd.randint(2, 12)

@@ -486,8 +486,24 @@ __device__ __forceinline__ uint32_t name_len(const RenderTables& rt, uint32_t id
 // with coalesced 32-bit stores: a lane's items land at byte offsets of their own, and writing them
 // straight to global memory costs one sector transaction per byte.
 constexpr uint32_t kRenderWin = 2048;
-// bytes [b0, b1) of the item "name(g|g) " of sample `id`, to stage[pos + b - b0 ...]
+// bytes [b0, b1) of the item "name(g|g) " of sample `id`, to stage[0 .. b1 - b0).  Items of up to 15
+// bytes come from a 16-byte template per sample ("name(0|0) ", length in byte 15): one load, the
+// genotype characters patched in by XOR, bytes peeled off with static shifts; longer names take the
+// character-by-character path.
 __device__ __forceinline__ void put_carrier(const RenderTables& rt, uint8_t* stage, uint32_t id, uint8_t fl, uint32_t b0, uint32_t b1) {
+	const uint4 t = __ldg(rt.item16 + id);
+	const uint32_t len = t.w >> 24;
+	if (len) {
+		uint64_t lo = t.x | ((uint64_t)t.y << 32), hi = t.z | ((uint64_t)(t.w & 0x00FFFFFFu) << 32);
+		const uint32_t delta = ((fl & 2) ? 1u : 0u) | ((fl & 1) ? 0u : (uint32_t)('/' ^ '|') << 8) | ((fl & 4) ? 1u << 16 : 0u);
+		const uint32_t sh = 8 * (len - 5);                          // the genotype starts right after "name("
+		if (sh < 64) { lo ^= (uint64_t)delta << sh; if (sh > 40) hi ^= (uint64_t)delta >> (64 - sh); }
+		else hi ^= (uint64_t)delta << (sh - 64);
+#pragma unroll
+		for (uint32_t j = 0; j < 15; j++)
+			if (j >= b0 && j < b1) stage[j - b0] = (uint8_t)(j < 8 ? lo >> (8 * j) : hi >> (8 * (j - 8)));
+		return;
+	}
 	const uint32_t a = __ldg(rt.name_off + id), n = __ldg(rt.name_off + id + 1) - a;
 	for (uint32_t b = b0; b < b1; b++) {
 		char c;

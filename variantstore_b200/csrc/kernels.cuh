@@ -51,6 +51,7 @@ struct RenderTables {
 	const uint32_t* s_sample_id; // explicit-id mode: per s_info sample id
 	const uint32_t* name_off;    // num_samples + 1 offsets into name_chars
 	const char* name_chars;
+	const uint4* item16;         // num_samples: "name(0|0) " + its length in byte 15 when that fits 15 bytes, else zeros
 };
 
 // Segment s of a render call = records [seg_lo[s], seg_hi[s]) ((NONE, NONE) = empty).  Three small

@@ -718,6 +718,15 @@ void ensure_render_tables(vsgpu_index* ix) {
 	rt.text_prefix[0] = upload(ix, tp0); rt.text_prefix[1] = upload(ix, tp1);
 	rt.seq = upload(ix, s.seq); rt.s_flags = upload(ix, s.s_flags); rt.s_sample_id = upload(ix, s.s_sample_id);
 	rt.name_off = upload(ix, name_off);
+	std::vector<uint4> item16(s.num_samples, make_uint4(0, 0, 0, 0));
+	for (uint32_t i = 0; i < s.num_samples; i++) {
+		const std::string item = s.sample_names[i] + "(0|0) ";
+		if (item.size() > 15) continue;
+		uint8_t b[16] = {0};
+		memcpy(b, item.data(), item.size()); b[15] = (uint8_t)item.size();
+		memcpy(&item16[i], b, 16);
+	}
+	rt.item16 = upload(ix, item16);
 	std::vector<char> cv(chars.begin(), chars.end());
 	rt.name_chars = upload(ix, cv);
 	for (auto& e : ix->ev_render) CU(cudaEventCreate(&e));
