@@ -28,7 +28,7 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "tile-64", "chunked-calls"])
+@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "tile-256", "chunked-calls"])
 def walk_path(request, monkeypatch):
     """The t4 kernel paths: the sample-major hit map with one thread per region (default), the
     per-entry class-bitmap test used when the map does not fit the memory budget, and the
@@ -44,8 +44,8 @@ def walk_path(request, monkeypatch):
     monkeypatch.delenv("VSGPU_T4_TILE", raising=False)
     if request.param == "cta-per-tile":
         monkeypatch.setenv("VSGPU_T4_PIPE", "0")        # k_t4 instead of the persistent pipelined k_t4p
-    if request.param == "tile-64":
-        monkeypatch.setenv("VSGPU_T4_TILE", "64")       # more, smaller tiles: deeper look-back
+    if request.param == "tile-256":
+        monkeypatch.setenv("VSGPU_T4_TILE", "256")      # fewer, larger tiles than the default 64
     if request.param == "class-bitmaps":
         monkeypatch.setenv("VSGPU_DISABLE_HITMAP", "1")
     elif request.param == "warp-cooperative":
