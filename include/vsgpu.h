@@ -140,6 +140,19 @@ uint64_t vsgpu_text_num_rows(const vsgpu_text* t);          /* rows rendered ove
 float vsgpu_text_kernel_ms(const vsgpu_text* t);            /* device time of the offset + render kernels (CUDA events) */
 void vsgpu_text_free(vsgpu_text* t);
 
+/* ---- t2: query_sample_from_ref(vg, idx, pos_x, pos_y, sample) — include/query.h:120-189 (SURVEY.md §8f "next" row 4) ---
+ * The sample's sequence over the reference interval [x[i], y[i]): region i owns bytes
+ * [offsets[i], offsets[i+1]) of vsgpu_text_bytes (what the reference writes to `-o` before its
+ * newline).  vsgpu_text_status()[i] = 1 where the reference call ends in an uncaught
+ * std::out_of_range from std::string::substr (query.h:163,167 — e.g. x = 0, or x right behind a
+ * deletion whose target the neighbour scan meets first); the region's sequence is then empty.
+ * sample_ids are sampleid_map ids (1..num_samples-1).  Returns VSGPU_ESHAPE when the index cannot
+ * serve t2 (backbone sequences not contiguous in seq_buffer.sdsl) or the batch exceeds
+ * VSGPU_RENDER_MAX_BYTES. */
+int vsgpu_query_t2(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out);
+const uint8_t* vsgpu_text_status(const vsgpu_text* t);      /* n bytes (t2 results; NULL for rendered t6 rows) */
+const float* vsgpu_text_stage_ms(const vsgpu_text* t);      /* t2: device time of the count, plan and copy launches (CUDA events); their sum = vsgpu_text_kernel_ms */
+
 /* ---- device-resident batches (bench harness; replaces the timing loop of src/bm_query.cc:74-135)
  * A batch keeps its regions and results in HBM so a run times the kernels alone.
  * type = 4, 6 or 7.  For type 7 pass refs/alts; for type 4 pass sample_ids. */

@@ -256,6 +256,9 @@ struct QueryLog { std::string out; std::string err; };   // stdout count lines /
 Graph::vertex get_prev_vertex_with_sample(const VariantGraph* vg, const Index* idx, uint64_t pos,
                                           const std::string& sample_id, uint64_t& ref_pos,
                                           uint64_t& sample_pos, bool* ub = nullptr);     // :57-113
+std::string query_sample_from_ref(const VariantGraph* vg, const Index* idx, uint64_t x, uint64_t y,
+                                  const std::string& sample_id, bool print = false,
+                                  const std::string& outfile = "", bool* ub = nullptr);   // :120-189
 bool get_samples(const Vertex* v, const VariantGraph* vg,
                  std::vector<std::pair<std::string, std::string>>& sample_ids);       // :268-285
 bool next_variant_in_ref(const VariantGraph* vg, const Index* idx, uint64_t pos, std::vector<Variant>& vars,

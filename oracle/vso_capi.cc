@@ -183,6 +183,48 @@ int vso_batch_t7(void* hp, uint64_t n, const uint64_t* pos, const char* const* r
 	} catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// query_sample_from_ref (query.h:120-189).  status[i]: 0 = a sequence came back, 1 = the call ended in
+// std::out_of_range (the reference process would terminate).  lengths / digests describe the sequence;
+// `text` (nullable) receives the sequences joined by '\n' (malloc'd).
+int vso_batch_t2(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids,
+                 uint64_t* lengths, uint64_t* digests, uint8_t* status, uint8_t* ub, char** text) {
+	Handle* h = (Handle*)hp;
+	try {
+		std::string all;
+		for (uint64_t i = 0; i < n; i++) {
+			bool u = false;
+			std::string name = h->vg->get_sample_name(sample_ids[i]);
+			std::string seq; uint8_t st = 0;
+			try { seq = query_sample_from_ref(h->vg.get(), h->idx.get(), x[i], y[i], name, false, "", &u); }
+			catch (const std::out_of_range&) { seq.clear(); st = 1; }
+			lengths[i] = seq.size();
+			if (digests) digests[i] = fnv1a(kFnvInit, seq.data(), seq.size());
+			if (status) status[i] = st;
+			if (ub) ub[i] = u;
+			if (text) { all += seq; all += '\n'; }
+		}
+		if (text) *text = dup_str(all);
+		return 0;
+	} catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+int vso_batch_t2_mt(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, uint64_t* lengths, int nthreads) {
+	Handle* h = (Handle*)hp;
+	if (nthreads < 1) nthreads = 1;
+	std::vector<std::thread> th; std::vector<int> rc(nthreads, 0);
+	for (int t = 0; t < nthreads; t++) th.emplace_back([&, t]() {
+		try {
+			for (uint64_t i = t; i < n; i += nthreads) {
+				std::string name = h->vg->get_sample_name(sample_ids[i]);
+				try { lengths[i] = query_sample_from_ref(h->vg.get(), h->idx.get(), x[i], y[i], name).size(); }
+				catch (const std::out_of_range&) { lengths[i] = 0; }
+			}
+		} catch (const std::exception&) { rc[t] = -1; }
+	});
+	for (auto& t : th) t.join();
+	for (int r : rc) if (r) return r;
+	return 0;
+}
+
 // closest_var (query.h:441-483): found flag, row count, digest of the rows
 int vso_batch_t1(void* hp, uint64_t n, const uint64_t* pos, uint8_t* found, uint64_t* counts, uint64_t* digests, int with_samples) {
 	Handle* h = (Handle*)hp;

@@ -64,6 +64,48 @@ Graph::vertex get_prev_vertex_with_sample(const VariantGraph* vg, const Index* i
 	return v_find;
 }
 
+// Sample's sequence in ref coordinates [pos_x, pos_y) (query.h:120-189).  std::string::substr throws
+// std::out_of_range exactly where the reference's does (:163, :167) — the reference does not catch it,
+// so its process terminates; callers of the oracle catch it and report "threw".
+std::string query_sample_from_ref(const VariantGraph* vg, const Index* idx, const uint64_t pos_x, const uint64_t pos_y,
+                                  const std::string& sample_id, bool print, const std::string& outfile, bool* ub) {
+	std::string seq = "";
+	uint64_t ref_pos = 0, sample_pos = 0;
+	Graph::vertex closest_v = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, ref_pos, sample_pos, ub);
+	VariantGraph::PathIterator it = vg->find(closest_v, sample_id);
+	bool record_seq = false;
+	std::string temp;
+	while (!it.done()) {
+		temp.assign(vg->get_sequence(*(*it)));
+		uint64_t l = (*it)->length;
+		uint64_t next_ref_pos = ref_pos + l;
+		VariantGraph::BfsIterator bfs_it = vg->find((*it)->vertex_id, 1);
+		++bfs_it;
+		while (!bfs_it.done()) {          // FIRST ref-carrying neighbour wins (:143-151) — t4 takes the last
+			Graph::vertex v = (*bfs_it)->vertex_id;
+			SampleInfo sample;
+			if (vg->get_sample_from_vertex_if_exists(v, REF, sample)) { next_ref_pos = sample.index; break; }
+			++bfs_it;
+		}
+		if (record_seq == true && next_ref_pos < pos_y) {
+			seq += temp;
+		} else if (record_seq == true && next_ref_pos >= pos_y) {
+			seq += temp.substr(0, pos_y - ref_pos);
+			break;
+		} else if (next_ref_pos >= pos_x && next_ref_pos < pos_y) {
+			record_seq = true;
+			seq += temp.substr(pos_x - ref_pos);
+		} else if (next_ref_pos >= pos_x && next_ref_pos >= pos_y) {
+			seq = temp.substr(pos_x - ref_pos, pos_y - pos_x);
+			break;
+		}
+		++it;
+		ref_pos = next_ref_pos;
+	}
+	if (print) { std::ofstream out; out.open(outfile); out << seq << std::endl; out.close(); }
+	return seq;
+}
+
 bool get_samples(const Vertex* v, const VariantGraph* vg, std::vector<std::pair<std::string, std::string>>& sample_ids) {   // :268-285
 	bool is_var = false;
 	sample_ids = {};

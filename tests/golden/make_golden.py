@@ -15,6 +15,28 @@ sys.path.insert(0, os.path.dirname(HERE))
 import vs_testlib as T  # noqa: E402
 from vs_testlib import Oracle  # noqa: E402
 
+
+
+def consensus(fa, vcf, sample_col=9):
+    """Independent of the oracle: the FASTA with every record applied whose genotype names an alt allele
+    (what query_sample_from_ref returns over the whole contig when no two records overlap)."""
+    import gzip
+    ref = open(fa).read().split("\n", 1)[1].replace("\n", "")
+    opener = gzip.open if vcf.endswith(".gz") else open
+    pieces, cur = [], 0
+    for line in opener(vcf, "rt"):
+        if line.startswith("#"):
+            continue
+        r = line.rstrip("\n").split("\t")
+        pos, alleles = int(r[1]) - 1, [int(g) for g in r[sample_col].split(":")[0].replace("/", "|").split("|") if g != "." and int(g) > 0]
+        if not alleles:
+            continue
+        assert ref[pos:pos + len(r[3])] == r[3] and pos >= cur
+        pieces += [ref[cur:pos], r[4].split(",")[alleles[0] - 1]]
+        cur = pos + len(r[3])
+    return ref, "".join(pieces) + ref[cur:]
+
+
 out = {}
 for name, fa, vcf, log2 in [("x", "x.fa", "x.vcf.gz", 12), ("xsmall", "x.small.fa", "x.small.vcf", 10)]:
     prefix = os.path.join(HERE, name + "_ser")
@@ -26,6 +48,16 @@ for name, fa, vcf, log2 in [("x", "x.fa", "x.vcf.gz", 12), ("xsmall", "x.small.f
     for x, y in regions:
         ex["t6"][f"{x}:{y}"] = o.t6_text(x, y)
         ex["t4"][f"{x}:{y}"] = o.t4_text(x, y, "1")[0]
+    # t2 (query_sample_from_ref) for sample "1": status 1 = the reference's substr throws
+    ex["t2"] = []
+    for x, y in regions + [(0, 5), (58, 60), (57, 60), (ref_len, ref_len + 50), (ref_len + 10, ref_len + 20)]:
+        ln, dg, st, ub, seqs = o.batch_t2([x], [y], [1], want_text=True)
+        ex["t2"].append({"x": x, "y": y, "status": int(st[0]), "seq": seqs[0]})
+    if name == "x":       # single-sample fixture without overlapping records: pinned by an independent consensus
+        ref, cons = consensus(os.path.join(T.REF_DATA, fa), os.path.join(T.REF_DATA, vcf))
+        whole = [q for q in ex["t2"] if (q["x"], q["y"]) == (1, ref_len + 1)][0]
+        assert whole["status"] == 0 and whole["seq"] == cons, "oracle t2 != VCF consensus"
+        ex["t2_consensus_sha1"] = __import__("hashlib").sha1(cons.encode()).hexdigest()
     for p, r, a in o.all_variants() + [(58, "G", "GT"), (11, "C", "T")]:
         ex["t7"][f"{p}|{r}|{a}"] = o.t7_text(p, r, a)
     out[name] = ex

@@ -18,8 +18,12 @@
 using namespace vsgpu;
 
 struct vsgpu_result { std::vector<uint64_t> offsets; std::vector<uint32_t> hits; };
+struct vsgpu_text { std::string bytes; std::vector<uint64_t> offsets; std::vector<uint8_t> status; };
 struct vsgpu_index : HostIndex {
 	DevIndex dev;
+	T2Tables t2{};
+	std::vector<uint32_t> bbs;
+	std::string seq_ascii;
 	std::vector<uint32_t> bucket;
 	std::vector<uint2> t7;
 	std::vector<uint32_t> hitmap;
@@ -68,10 +72,47 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 		}
 		d.hitmap = ix->hitmap.data();
 	}
+	ix->bbs.assign(f.vstart.begin(), f.vstart.end()); ix->bbs.push_back(ix->last_end);
+	static const char kBase[8] = {'A', 'C', 'T', 'G', 'N', 5, 5, 5};
+	ix->seq_ascii.resize(ix->ser.seq.size() + 16, 0);
+	for (size_t i = 0; i < ix->ser.seq.size(); i++) ix->seq_ascii[i] = kBase[ix->ser.seq[i] & 7];
+	ix->t2.bbs = ix->bbs.data(); ix->t2.nrp1 = f.nrp1.data(); ix->t2.first_reach = f.first_reach.data();
+	ix->t2.cent_seq = (const uint2*)f.cent_seq.data(); ix->t2.seq_ascii = ix->seq_ascii.data();
 	*out = ix.release();
 	return VSGPU_OK;
 }
 void vsgpu_close(vsgpu_index* ix) { delete ix; }
+
+// t2 through the same two passes as the kernels: count, then copy records, then the copy itself
+int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) {
+	if (!ix->flat.t2_ok) return set_err(VSGPU_ESHAPE, "vsgpu_query_t2: " + ix->flat.t2_why);
+	std::unique_ptr<vsgpu_text> t(new vsgpu_text);
+	t->offsets.assign(n + 1, 0); t->status.assign(n + 1, 0);
+	for (uint64_t i = 0; i < n; i++) {
+		if (s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "vsgpu_query_t2: sample id out of range");
+		logic::T2CountSink cs{0, 0, 0, 0};
+		uint32_t st = logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], cs); cs.flush();
+		t->status[i] = (uint8_t)st;
+		if (!st && cs.nrec) {
+			std::vector<uint4> recs(cs.nrec);
+			logic::T2WriteSink ws{0, 0, recs.data(), t->bytes.size()};
+			logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], ws); ws.flush();
+			if (ws.out != recs.data() + cs.nrec) return set_err(VSGPU_EINVAL, "hostsim: t2 count and write passes disagree");
+			t->bytes.resize(t->bytes.size() + cs.bytes);
+			for (const uint4& r : recs) memcpy(&t->bytes[r.z | ((uint64_t)r.w << 32)], ix->seq_ascii.data() + r.x, r.y);
+		}
+		t->offsets[i + 1] = t->bytes.size();
+	}
+	*out = t.release();
+	return VSGPU_OK;
+}
+const char* vsgpu_text_bytes(const vsgpu_text* t) { return t->bytes.c_str(); }
+const uint64_t* vsgpu_text_offsets(const vsgpu_text* t) { return t->offsets.data(); }
+const uint8_t* vsgpu_text_status(const vsgpu_text* t) { return t->status.data(); }
+uint64_t vsgpu_text_num_rows(const vsgpu_text* t) { return t->offsets.size() - 1; }
+float vsgpu_text_kernel_ms(const vsgpu_text*) { return 0.f; }
+const float* vsgpu_text_stage_ms(const vsgpu_text*) { static const float z[3] = {0, 0, 0}; return z; }
+void vsgpu_text_free(vsgpu_text* t) { delete t; }
 
 int vsgpu_info(const vsgpu_index* ix, vsgpu_info_t* o) {
 	memset(o, 0, sizeof *o);

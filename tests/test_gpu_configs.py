@@ -134,6 +134,17 @@ def test_full_size_chr22_shape_cuda(tmp_path):
         assert np.array_equal(np.concatenate([offa[:-1], offb + offa[-1]]), off)
         da = e.digest_t4(off, hits, with_samples=False)
         assert np.bitwise_xor.reduce(da) == np.bitwise_xor.reduce(np.concatenate([e.digest_t4(offa, hitsa, False), e.digest_t4(offb, hitsb, False)]))
+        # t2 (query_sample_from_ref): oracle on a subsample; the whole batch (~1 GB of sequence) as two halves
+        bad2, _ = T.compare_t2(o, e, x[sub[:1500]], y[sub[:1500]], s[sub[:1500]])
+        assert not bad2
+        soff, stext, sst, _ = e.batch_sample_seq_in_ref(x, y, s)
+        sl = np.diff(soff.astype(np.int64))
+        assert int(sst.sum()) < n // 100 and np.all(sl[sst == 1] == 0)
+        assert np.all(np.abs(sl[sst == 0] - 1000) <= 64) and 999.0 < sl[sst == 0].mean() < 1001.0   # ref interval +- the sample's indels
+        soa, sta_, ssa, _ = e.batch_sample_seq_in_ref(x[:h], y[:h], s[:h])
+        sob, stb_, ssb, _ = e.batch_sample_seq_in_ref(x[h:], y[h:], s[h:])
+        assert sta_ + stb_ == stext and np.array_equal(np.concatenate([soa[:-1], sob + soa[-1]]), soff)
+        del stext, sta_, stb_
         # t6 slice algebra on sorted equal-width regions: bounds are monotone, counts add up over a split at any y
         ok = lo != NONE
         assert np.all(np.diff(lo[ok].astype(np.int64)) >= 0) and np.all(np.diff(hi[ok].astype(np.int64)) >= 0)

@@ -7,6 +7,7 @@ import pytest
 
 import vs_testlib as T
 from vs_testlib import Oracle
+from variantstore_b200.api import VsgpuError
 
 pytestmark = pytest.mark.gpu
 NONE = 0xFFFFFFFF
@@ -67,6 +68,9 @@ def test_fuzz_parity_cuda(tmp_path, seed, overlap, sparse, walk_path):
         assert 0 < hits < total
         pos = np.concatenate([np.arange(1, 300), np.random.default_rng(seed).integers(1, 4000, 500), [3999, 4000, 4001, 5000]]).astype(np.uint64)
         assert not T.compare_t1(o, e, pos)
+        x[:8] = np.arange(8)                                     # t2 has no pos-0 check: x = 0 throws inside substr
+        bad2, threw = T.compare_t2(o, e, x, y, s)
+        assert not bad2 and threw >= 1
 
 
 def test_golden_fixture_cuda():
@@ -86,6 +90,15 @@ def test_golden_fixture_cuda():
         assert e.samples_has_var(14, "G", "A") == []
         found, rows = e.closest_var(20)
         assert found and [(v.var_pos, v.ref, v.alt) for v in rows] == [(9, "G", "A")]   # first variant of the mirrored window [6, 34], not the nearest
+        # t2: sample "1" over 10:20 — C>T at 10 and G>A at 14 applied to CTTGGAAATT
+        assert e.query_sample_from_ref(10, 20, "1") == "TTTGAAAATT"
+        exp = __import__("json").load(open(os.path.join(T.GOLDEN, "expected.json")))
+        for q in exp["x"]["t2"]:
+            if q["status"]:
+                with pytest.raises(IndexError):
+                    e.query_sample_from_ref(q["x"], q["y"], "1")
+            else:
+                assert e.query_sample_from_ref(q["x"], q["y"], "1") == q["seq"]
 
 
 def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
@@ -115,6 +128,8 @@ def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
         assert len(b4.timings_ms()) == 1 and b4.stats()[1] == 1 and b6.stats()[0] == 288 * n
         # size-independent properties: slices are monotone in x for sorted regions of equal width,
         # a t4 answer never has more rows than twice the t6 slice (+ the start / rejoin rows)
+        bad2, _ = T.compare_t2(o, e, x[sub], y[sub], s[sub])       # up to 100 kb per region: several 4 KB copy records each
+        assert not bad2
         same_w = (y - x == 1000) & (lo != NONE)
         assert np.all(np.diff(lo[same_w].astype(np.int64)) >= 0)
         assert np.all(np.diff(off).astype(np.int64) <= 2 * (hi.astype(np.int64) - lo) + 2)
@@ -281,6 +296,38 @@ def test_rows_rendered_with_duplicate_records_cuda(tmp_path):
         assert e.info.has_suspect_dups == 1
         x, y, _ = T.random_regions(3, 250, 1200, widths=(1, 5, 20, 100, 1000, 5000), n_samples=len(names))
         _check_render(o, e, x, y, oracle_regions=250)
+
+
+def test_sample_sequences_cuda(tmp_path, monkeypatch):
+    """t2 (query_sample_from_ref) beyond the fuzz regions: every sample over sliding windows of an
+    overlapping-deletion graph (the starts right behind a deletion throw in the reference), whole-contig
+    regions, split invariance of a batch, and the byte limit."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 53, overlap=True, n_records=320)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"))
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        starts = np.arange(0, 4003, 2, dtype=np.uint64)
+        x = np.tile(np.concatenate([starts, starts]), len(names))
+        y = x + np.tile(np.concatenate([np.full(len(starts), 37), np.full(len(starts), 5000)]).astype(np.uint64), len(names))
+        s = np.repeat(np.arange(1, len(names) + 1, dtype=np.uint32), 2 * len(starts))
+        bad2, threw = T.compare_t2(o, e, x, y, s)
+        assert not bad2 and threw > len(names)
+        off, text, st, ms = e.batch_sample_seq_in_ref(x, y, s)
+        h = len(x) // 3
+        offa, texta, sta, _ = e.batch_sample_seq_in_ref(x[:h], y[:h], s[:h])
+        offb, textb, stb, _ = e.batch_sample_seq_in_ref(x[h:], y[h:], s[h:])
+        assert texta + textb == text and np.array_equal(np.concatenate([offa[:-1], offb + offa[-1]]), off)
+        assert np.array_equal(np.concatenate([sta, stb]), st) and ms > 0
+        assert set(text) <= set(b"ACGTN")
+        off0, text0, st0, _ = e.batch_sample_seq_in_ref([], [], [])
+        assert len(off0) == 1 and off0[0] == 0 and text0 == b""
+        monkeypatch.setenv("VSGPU_RENDER_MAX_BYTES", "1000")
+        with pytest.raises(VsgpuError) as ei:
+            e.batch_sample_seq_in_ref(x, y, s)
+        assert ei.value.code == -3
+        monkeypatch.delenv("VSGPU_RENDER_MAX_BYTES")
+        with pytest.raises(VsgpuError) as ei:
+            e.batch_sample_seq_in_ref([5], [50], [len(names) + 1])
+        assert ei.value.code == -1
 
 
 def test_error_paths_cuda(tmp_path):

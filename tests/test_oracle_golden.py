@@ -60,7 +60,29 @@ def test_committed_fixture_matches_expected():
         for key, text in ex["t7"].items():
             p, r, a = key.split("|")
             assert o.t7_text(int(p), r, a) == text, (name, key)
+        for q in ex["t2"]:
+            ln, dg, st, ub, seqs = o.batch_t2([q["x"]], [q["y"]], [1], want_text=True)
+            assert (int(st[0]), seqs[0]) == (q["status"], q["seq"]), (name, q["x"], q["y"])
         o.close()
+
+
+def test_sample_sequence_equals_vcf_consensus():
+    """query_sample_from_ref over the whole contig of data/x.* (one sample, no overlapping records) =
+    the FASTA with the sample's alt alleles applied — computed without the oracle by
+    tests/golden/make_golden.py::consensus and committed as a SHA-1; recomputed here when the
+    reference's data directory is present."""
+    import hashlib
+    o = Oracle.open(os.path.join(T.GOLDEN, "x_ser"))
+    seq = o.batch_t2([1], [o.info()["ref_length"] + 1], [1], want_text=True)[4][0]
+    assert hashlib.sha1(seq.encode()).hexdigest() == EXPECTED["x"]["t2_consensus_sha1"]
+    assert len(seq) == 1005 and seq[9:19] == "TTTGAAAATT"      # C>T at 10, G>A at 14 on CTTGGAAATT
+    if os.path.isdir(T.REF_DATA):
+        src = open(os.path.join(T.GOLDEN, "make_golden.py")).read()
+        ns = {}
+        exec(src[src.index("def consensus"):src.index("out = {}")], ns)
+        ref, cons = ns["consensus"](os.path.join(T.REF_DATA, "x.fa"), os.path.join(T.REF_DATA, "x.vcf.gz"))
+        assert cons == seq and len(ref) == 1001
+    o.close()
 
 
 def test_known_answers_x():

@@ -49,6 +49,9 @@ def test_fuzz_parity(tmp_path, seed, overlap, sparse, walk_path):
     # closest_var (t1): every position of the contig's head, a random spread, and past the end
     pos = np.concatenate([np.arange(1, 400), np.random.default_rng(seed).integers(1, 4000, 600), [3999, 4000, 4001, 5000]]).astype(np.uint64)
     assert not T.compare_t1(o, e, pos)
+    # query_sample_from_ref (t2): the same regions, byte for byte, incl. the calls that throw
+    bad2, _ = T.compare_t2(o, e, x, y, s)
+    assert not bad2
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
@@ -67,6 +70,10 @@ def test_exhaustive_windows_reach_the_rare_walk_entries(tmp_path, seed, walk_pat
     assert not bad6 and not bad4
     off, hits = e.batch_sample_var_in_ref(x, y, s)
     assert e.info.walk_markers > 0
+    # t2 on every third window: regions starting right behind a deletion whose target the neighbour
+    # scan meets first make the reference's substr throw (status 1) — those must agree too
+    bad2, threw = T.compare_t2(o, e, x[::3], y[::3], s[::3])
+    assert not bad2 and threw > 0
     if e.info.rejoin_carriers:
         assert int(((hits & 0x40000000) != 0).sum()) > 0
 
@@ -91,6 +98,15 @@ def test_edges_of_the_contig(tmp_path):
     s = np.array([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12], np.uint32)
     bad6, bad4, _ = T.compare_all(o, e, x, y, s)
     assert not bad6 and not bad4
+    # t2 has no gate and no pos-0 check: x = 0, empty and inverted regions, regions past the contig end
+    x2 = np.concatenate([x, [0, 0, 5, 50, 4000, 4001, 7000, 1, 2**33]]).astype(np.uint64)
+    y2 = np.concatenate([y, [5, 0, 5, 10, 2**40, 4002, 7001, 2**33, 2**34]]).astype(np.uint64)
+    s2 = np.concatenate([s, [1, 2, 3, 4, 5, 6, 7, 8, 9]]).astype(np.uint32)
+    bad2, threw = T.compare_t2(o, e, x2, y2, s2)
+    assert not bad2 and threw >= 1
+    assert e.query_sample_from_ref(1, 4001, names[2]) == o.batch_t2([1], [4001], [3], want_text=True)[4][0]
+    with pytest.raises(IndexError):
+        e.query_sample_from_ref(0, 5, names[0])
 
 
 def test_synthetic_generator_parity(tmp_path):
@@ -106,6 +122,8 @@ def test_synthetic_generator_parity(tmp_path):
         bad6, bad4, _ = T.compare_all(o, e, x, y, s)
         assert not bad6 and not bad4
         assert t7_parity(o, e) > 0
+        bad2, _ = T.compare_t2(o, e, x, y, s)
+        assert not bad2
 
 
 def test_duplicate_records_take_the_literal_path(tmp_path):
@@ -149,6 +167,7 @@ def test_index_cache_round_trip(tmp_path, monkeypatch):
     bad6, bad4, _ = T.compare_all(o, e2, x, y, s)
     assert not bad6 and not bad4
     assert t7_parity(o, e2) > 0
+    assert not T.compare_t2(o, e2, x, y, s)[0]
     assert e2.get_var_in_ref(1, 4001) == e1.get_var_in_ref(1, 4001)                # rows incl. sample names and phasing
     assert e2.get_sample_var_in_ref(1, 4001, names[3]) == e1.get_sample_var_in_ref(1, 4001, names[3])
     # a truncated cache is ignored (and replaced)

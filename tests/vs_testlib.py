@@ -74,6 +74,8 @@ class Oracle:
             L.vso_batch_t6.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t4.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t1.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
+            L.vso_batch_t2.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+            L.vso_batch_t2_mt.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t6_mt.argtypes = [vp, u64, vp, vp, vp, C.c_int]
             L.vso_batch_t4_mt.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t7.argtypes = [vp, u64, vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), vp, vp, vp]
@@ -193,12 +195,32 @@ class Oracle:
             raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
         return found, cnt, dig
 
+    def batch_t2(self, x, y, sample_ids, want_text=False):
+        """query_sample_from_ref: (lengths, digests, status, ub[, list of sequences]); status 1 = the
+        reference call ends in std::out_of_range."""
+        x, y = np.ascontiguousarray(x, np.uint64), np.ascontiguousarray(y, np.uint64)
+        s = np.ascontiguousarray(sample_ids, np.uint32)
+        n = len(x)
+        ln, dig, st, ub = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        tp = C.c_void_p(0)
+        rc = self.lib().vso_batch_t2(self.h, n, x.ctypes.data, y.ctypes.data, s.ctypes.data, ln.ctypes.data, dig.ctypes.data,
+                                     st.ctypes.data, ub.ctypes.data, C.byref(tp) if want_text else None)
+        if rc != 0:
+            raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
+        if want_text:
+            seqs = self._text(tp.value).split("\n")[:n]
+            return ln, dig, st, ub, seqs
+        return ln, dig, st, ub
+
     def timed_counts(self, qtype, x, y, sample_ids=None, nthreads=1):
         """Counts only, optionally over several worker threads (bench timing arms)."""
         x, y = np.ascontiguousarray(x, np.uint64), np.ascontiguousarray(y, np.uint64)
         cnt = np.zeros(len(x), np.uint64)
         if qtype == 6:
             rc = self.lib().vso_batch_t6_mt(self.h, len(x), x.ctypes.data, y.ctypes.data, cnt.ctypes.data, nthreads)
+        elif qtype == 2:
+            s = np.ascontiguousarray(sample_ids, np.uint32)
+            rc = self.lib().vso_batch_t2_mt(self.h, len(x), x.ctypes.data, y.ctypes.data, s.ctypes.data, cnt.ctypes.data, nthreads)
         else:
             s = np.ascontiguousarray(sample_ids, np.uint32)
             rc = self.lib().vso_batch_t4_mt(self.h, len(x), x.ctypes.data, y.ctypes.data, s.ctypes.data, cnt.ctypes.data, nthreads)
@@ -297,6 +319,20 @@ def compare_t1(oracle, eng, pos, with_samples=True):
     efound = lo != 0xFFFFFFFF
     bad = (efound != (f == 1)) | ((f == 1) & ((c != ec) | (d != ed)))
     return [int(i) for i in np.nonzero(bad)[0]]
+
+
+def compare_t2(oracle, eng, x, y, s, skip_ub=True):
+    """query_sample_from_ref on both sides, byte for byte; returns (mismatching indices, regions where
+    the reference throws std::out_of_range)."""
+    ln, dg, st, ub, seqs = oracle.batch_t2(x, y, s, want_text=True)
+    off, text, est, _ = eng.batch_sample_seq_in_ref(x, y, s)
+    bad = []
+    for i in range(len(seqs)):
+        if skip_ub and ub[i]:
+            continue
+        if est[i] != st[i] or int(off[i + 1] - off[i]) != int(ln[i]) or text[off[i]:off[i + 1]] != seqs[i].encode():
+            bad.append(i)
+    return bad, int(st.sum())
 
 
 def compare_all(oracle, eng, x, y, s, with_samples=True, skip_ub=True):

@@ -51,6 +51,9 @@ PROTOTYPES = {
     "vsgpu_text_num_rows": (C.c_uint64, [vp]),
     "vsgpu_text_kernel_ms": (C.c_float, [vp]),
     "vsgpu_text_free": (None, [vp]),
+    "vsgpu_query_t2": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
+    "vsgpu_text_status": (vp, [vp]),
+    "vsgpu_text_stage_ms": (C.POINTER(C.c_float), [vp]),
     "vsgpu_batch_create": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, cpp, cpp, C.POINTER(vp)]),
     "vsgpu_batch_run": (C.c_int, [vp]),
     "vsgpu_batch_fetch": (C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
@@ -59,7 +62,7 @@ PROTOTYPES = {
     "vsgpu_batch_free": (None, [vp]),
 }
 # subset a test-only host simulator has to provide
-QUERY_SUBSET = [s for s in PROTOTYPES if not s.startswith(("vsgpu_batch", "vsgpu_render", "vsgpu_text")) and s != "vsgpu_set_stream"]
+QUERY_SUBSET = [s for s in PROTOTYPES if not s.startswith(("vsgpu_batch", "vsgpu_render")) and s != "vsgpu_set_stream"]
 
 
 def load(path=None, subset=False):

@@ -4,6 +4,8 @@ Names, argument meaning and error behaviour follow the reference:
   get_var_in_ref(pos_x, pos_y)                 query.h:736-784   (t6)
   get_sample_var_in_ref(pos_x, pos_y, sample)  query.h:618-729   (t4)
   samples_has_var(pos, ref, alt)               query.h:792-823   (t7)
+  query_sample_from_ref(pos_x, pos_y, sample)  query.h:120-189   (t2)
+  closest_var(pos)                             query.h:441-483   (t1)
 plus batched forms that take whole arrays of regions — the reason this engine exists.
 Positions are 1-based, regions are [pos_x, pos_y).
 """
@@ -165,6 +167,31 @@ class VariantStoreIndex:
         finally:
             self._lib.vsgpu_text_free(t)
         return off, text, rows, ms
+
+    def batch_sample_seq_in_ref(self, x, y, sample_ids):
+        """t2 over arrays (query_sample_from_ref, query.h:120-189): (offsets[n+1], bytes, status, kernel ms).
+        Region i's sequence is bytes[offsets[i]:offsets[i+1]]; status[i] = 1 where the reference call
+        ends in std::out_of_range."""
+        x, y = _u64(x), _u64(y)
+        s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        n = len(x)
+        t = C.c_void_p()
+        self._check(self._lib.vsgpu_query_t2(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(t)))
+        try:
+            off = np.ctypeslib.as_array(self._lib.vsgpu_text_offsets(t), shape=(n + 1,)).copy()
+            text = C.string_at(self._lib.vsgpu_text_bytes(t), int(off[-1]))
+            status = np.frombuffer(C.string_at(self._lib.vsgpu_text_status(t), n), np.uint8).copy() if n else np.zeros(0, np.uint8)
+            ms = float(self._lib.vsgpu_text_kernel_ms(t))
+        finally:
+            self._lib.vsgpu_text_free(t)
+        return off, text, status, ms
+
+    def query_sample_from_ref(self, pos_x: int, pos_y: int, sample_id: str) -> str:
+        """query.h:120-189.  Raises IndexError where the reference's substr throws std::out_of_range."""
+        off, text, status, _ = self.batch_sample_seq_in_ref([pos_x], [pos_y], [self.sample_id(sample_id)])
+        if status[0]:
+            raise IndexError("basic_string::substr: __pos > this->size() (query.h:163,167)")
+        return text.decode()
 
     def batch_closest_var(self, pos):
         """t1 over an array of positions: (rec_lo, rec_hi); both NONE where the operator returns false."""

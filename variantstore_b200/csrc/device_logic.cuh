@@ -337,5 +337,193 @@ VSGPU_HD void walk_any(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t 
 	else walk_region(ix, x64, y64, s, sink);
 }
 
+// ------------------------------------------------------------------ t2: query_sample_from_ref (query.h:120-189)
+// The reference walks the sample's path vertex by vertex from the vertex get_prev_vertex_with_sample
+// returns, keeping (ref_pos, next_ref_pos) and cutting the vertex sequences with four rules
+// (:157-173).  Here the path is taken stretch by stretch: between two walk entries the sample takes,
+// it follows the backbone, whose sequences are contiguous in seq_buffer, so a whole stretch is at
+// most three pieces (a clipped first vertex, whole vertices, a clipped last one) and the vertices
+// where recording starts / ends come from `first_reach` instead of a per-vertex loop.
+
+// get_prev_vertex_with_sample (query.h:57-113) for back-walk state `cur`: the walk entry it stops on,
+// or kNoneU32 when it reaches the start of the contig.
+VSGPU_HD uint32_t back_walk(const DevIndex& ix, uint32_t s, uint64_t cur) {
+	if (ix.hitmap) {
+		if (cur < 2 || cur > ix.D) return kNoneU32;
+		const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
+		const uint64_t info = ldg(ix.dinfo + (cur - 1));
+		const uint32_t t = ldg(ix.dtin + cur);
+		const uint32_t pos = (uint32_t)info + ((uint32_t)(info >> 32) & 0xFFFF);     // entries below pos are candidates
+		if (pos == 0) return kNoneU32;
+		uint32_t w = (pos - 1) >> 5;
+		uint32_t m = ldg(row + w) & (0xFFFFFFFFu >> (31 - ((pos - 1) & 31)));
+		for (;;) {
+			while (m == 0 && w > 0) { w--; m = ldg(row + w); }
+			if (m == 0) return kNoneU32;
+			const uint32_t b = 31 - clz32(m);
+			m &= ~(1u << b);
+			const uint32_t p = (w << 5) + b;
+			const uint2 a = ldg(ix.cent_anc + p);
+			if (a.x <= t && t <= a.y) return p;                                      // last carrier of the nearest examined vertex
+		}
+	}
+	uint32_t c_found = kNoneU32;
+	for (;;) {
+		if (cur > ix.D) cur = 0;
+		if (cur <= 1) break;
+		const uint64_t info = ldg(ix.dinfo + (cur - 1));
+		const uint32_t cb = (uint32_t)info, ncar = (uint32_t)(info >> 32) & 0xFFFF, deg = (uint32_t)(info >> 48);
+		for (uint32_t c = cb; c < cb + ncar; c++) if (member(ix, s, ldg(&ix.cent[c].z))) c_found = c;
+		cur -= deg;
+		if (c_found != kNoneU32) break;
+	}
+	return c_found;
+}
+
+// first walk entry in [c, limit) whose target the sample carries (markers are not edges), or kNoneU32
+VSGPU_HD uint32_t next_carried(const DevIndex& ix, uint32_t s, uint32_t c, uint32_t limit) {
+	if (c >= limit) return kNoneU32;
+	if (ix.hitmap) {
+		const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
+		uint32_t w = c >> 5;
+		uint32_t m = ldg(row + w) & (0xFFFFFFFFu << (c & 31));
+		while (m == 0) { w++; if ((w << 5) >= limit) return kNoneU32; m = ldg(row + w); }
+		const uint32_t ci = (w << 5) + ctz32(m);
+		return ci < limit ? ci : kNoneU32;
+	}
+	for (; c < limit; c++) { const uint4 e = ldg(ix.cent + c); if (!(e.y & kEntMarker) && member(ix, s, e.z)) return c; }
+	return kNoneU32;
+}
+
+struct T2State { bool rec; uint64_t x, y; uint32_t e_x, e_y; };
+
+// The four rules of query.h:157-173 on one vertex: `off`/`l` = its sequence in seq_buffer, rp = ref_pos
+// on arrival, nrp = next_ref_pos.  0: go on, 1: the walk ends, 2: substr throws std::out_of_range.
+template <class Sink>
+VSGPU_HD int t2_apply(T2State& st, uint32_t off, uint32_t l, uint64_t rp, uint64_t nrp, Sink& sink) {
+	if (st.rec) {
+		if (nrp < st.y) { sink.seg(off, l); return 0; }                             // :157-159
+		const uint64_t cnt = st.y - rp;                                            // :160-163 substr(0, pos_y - ref_pos)
+		sink.seg(off, cnt < l ? (uint32_t)cnt : l);
+		return 1;
+	}
+	if (nrp < st.x) return 0;
+	const uint64_t start = st.x - rp;                                            // substr(pos_x - ref_pos ...): throws past the end
+	if (start > l) return 2;
+	const uint32_t avail = l - (uint32_t)start;
+	if (nrp < st.y) { st.rec = true; sink.seg(off + (uint32_t)start, avail); return 0; }   // :164-167
+	const uint64_t cnt = st.y - st.x;                                            // :168-172 substr(pos_x - ref_pos, pos_y - pos_x)
+	sink.seg(off + (uint32_t)start, cnt < avail ? (uint32_t)cnt : avail);
+	return 1;
+}
+
+// first backbone index j >= k with nrp1[j] >= v, where e = number of distinct starts < v; M: none.
+// first_reach answers it unless the vertex it names was bypassed by a detour (then the answer lies a
+// few vertices ahead: nrp1[j] >= start of P[j+1]).
+VSGPU_HD uint32_t t2_first_ge(const DevIndex& ix, const T2Tables& t2, uint32_t k, uint32_t e, uint64_t v) {
+	const uint32_t fr = ldg(t2.first_reach + e);
+	if (fr >= k && e < ix.D) return fr;
+	for (uint32_t j = fr > k ? fr : k; j < ix.M; j++) if ((uint64_t)ldg(t2.nrp1 + j) >= v) return j;
+	return ix.M;
+}
+
+// backbone vertices [k_a, k_b] visited in order, arriving at P[k_a] with ref_pos
+template <class Sink>
+VSGPU_HD int t2_stretch(const DevIndex& ix, const T2Tables& t2, T2State& st, uint32_t k_a, uint32_t k_b, uint64_t ref_pos, Sink& sink) {
+	uint32_t k = k_a;
+	if (!st.rec) {
+		const uint32_t j = t2_first_ge(ix, t2, k_a, st.e_x, st.x);
+		if (j > k_b) return 0;
+		const uint64_t rp = j == k_a ? ref_pos : (uint64_t)ldg(t2.nrp1 + j - 1);
+		const uint32_t b0 = ldg(t2.bbs + j), b1 = ldg(t2.bbs + j + 1);
+		const int r = t2_apply(st, b0 - 1, b1 - b0, rp, ldg(t2.nrp1 + j), sink);
+		if (r) return r;
+		k = j + 1;
+		if (k > k_b) return 0;
+	}
+	const uint32_t j = t2_first_ge(ix, t2, k, st.e_y, st.y);
+	const uint32_t b0 = ldg(t2.bbs + k);
+	if (j > k_b) { sink.seg(b0 - 1, ldg(t2.bbs + k_b + 1) - b0); return 0; }        // whole vertices, one piece
+	const uint32_t bj = ldg(t2.bbs + j), bj1 = ldg(t2.bbs + j + 1);
+	if (j > k) sink.seg(b0 - 1, bj - b0);
+	const uint64_t rp = j == k_a ? ref_pos : (uint64_t)ldg(t2.nrp1 + j - 1);
+	return t2_apply(st, bj - 1, bj1 - bj, rp, ldg(t2.nrp1 + j), sink);
+}
+
+// returns 0, or kT2Throw when the reference call ends in std::out_of_range (nothing is emitted then)
+template <class Sink>
+VSGPU_HD uint32_t t2_walk(const DevIndex& ix, const T2Tables& t2, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	const uint32_t xc = clamp_pos(x64), yc = clamp_pos(y64);
+	uint32_t rk, e_y;                                                           // rank(x); number of starts < y
+	rank_le2(ix, xc, yc ? yc - 1 : 0, rk, e_y);
+	if (!yc) e_y = 0;
+	uint32_t e_x = rk;                                                          // number of starts < x
+	if (rk >= 1 && ldg(ix.dstart + rk - 1) == xc) e_x = rk - 1;
+	T2State st{false, x64, y64, e_x, e_y};
+	// entries whose source starts at or after max(x, y) are never reached: the vertex before ends the walk
+	const uint4 dl = ldg(ix.dlev + (e_x > e_y ? e_x : e_y));
+	const uint32_t limit = dl.w, k_last = dl.x;
+	// ---- get_prev_vertex_with_sample (query.h:57-113); Index::find(pos, rank) index.h:135-148
+	const uint64_t cur = x64 >= ix.index_bits ? ix.D - 1 : (rk ? rk - 1 : 0);
+	const uint32_t c_found = back_walk(ix, s, cur);
+	uint32_t cur_k, c;
+	uint64_t ref_pos;
+	if (c_found != kNoneU32) {
+		const uint4 e = ldg(ix.cent + c_found);
+		ref_pos = e.w;                                                            // index of the last ref-carrying neighbour seen (:93-95)
+		if (e.y & kEntAlt) {
+			const uint2 sq = ldg(t2.cent_seq + c_found);
+			const uint32_t tk = e.y & kEntTgtMask;
+			const uint64_t nrp = tk == kEntTgtMask ? ref_pos + sq.y : (uint64_t)ldg(t2.bbs + tk);
+			const int r = t2_apply(st, sq.x, sq.y, ref_pos, nrp, sink);
+			if (r) return r == 2 ? kT2Throw : 0;
+			if (tk == kEntTgtMask) return 0;                                        // the path ends on this vertex
+			cur_k = tk; ref_pos = nrp;
+		} else cur_k = e.y & kEntTgtMask;
+		c = c_found + 1;
+	} else { cur_k = ldg(&ix.dlev[0].x); ref_pos = 1; c = 0; }
+	// ---- the path: backbone stretches between the walk entries the sample takes
+	for (;;) {
+		const uint32_t ci = next_carried(ix, s, c, limit);
+		if (ci == kNoneU32) break;
+		c = ci + 1;
+		const uint4 e = ldg(ix.cent + ci);
+		if (e.x < cur_k) continue;                                                // hidden behind a taken detour / an earlier sibling
+		int r = t2_stretch(ix, t2, st, cur_k, e.x, ref_pos, sink);
+		if (r) return r == 2 ? kT2Throw : 0;
+		ref_pos = ldg(t2.nrp1 + e.x);
+		if (e.y & kEntAlt) {
+			const uint2 sq = ldg(t2.cent_seq + ci);
+			const uint32_t tk = e.y & kEntTgtMask;
+			const uint64_t nrp = tk == kEntTgtMask ? ref_pos + sq.y : (uint64_t)ldg(t2.bbs + tk);
+			r = t2_apply(st, sq.x, sq.y, ref_pos, nrp, sink);
+			if (r) return r == 2 ? kT2Throw : 0;
+			if (tk == kEntTgtMask) return 0;
+			cur_k = tk; ref_pos = nrp;
+		} else cur_k = e.y & kEntTgtMask;
+	}
+	uint32_t k_b = k_last ? k_last - 1 : 0;
+	if (k_b < cur_k) k_b = cur_k;
+	if (k_b > ix.M - 1) k_b = ix.M - 1;
+	if (cur_k > k_b) return 0;
+	const int r = t2_stretch(ix, t2, st, cur_k, k_b, ref_pos, sink);
+	return r == 2 ? kT2Throw : 0;
+}
+
+// Pieces of one region's answer, merged while they are contiguous in seq_buffer and cut into copy
+// records of at most kT2Chunk bytes.  Count: how many records / bytes.  Write: the records themselves.
+struct T2CountSink {
+	uint32_t off, len; uint32_t nrec; uint64_t bytes;
+	VSGPU_HD void flush() { if (len) { nrec += (len + kT2Chunk - 1) / kT2Chunk; bytes += len; len = 0; } }
+	VSGPU_HD void seg(uint32_t o, uint32_t l) { if (!l) return; if (len && off + len == o) { len += l; return; } flush(); off = o; len = l; }
+};
+struct T2WriteSink {
+	uint32_t off, len; uint4* out; uint64_t dst;
+	VSGPU_HD void flush() {
+		while (len) { const uint32_t l = len < kT2Chunk ? len : kT2Chunk; *out++ = make_uint4(off, l, (uint32_t)dst, (uint32_t)(dst >> 32)); off += l; dst += l; len -= l; }
+	}
+	VSGPU_HD void seg(uint32_t o, uint32_t l) { if (!l) return; if (len && off + len == o) { len += l; return; } flush(); off = o; len = l; }
+};
+
 }  // namespace logic
 }  // namespace vsgpu

@@ -157,6 +157,13 @@ void flatten(const SerData& d, FlatIndex& f) {
 		uint32_t nrp = f.vstart[k] + f.vlen[k], nref = kNone;
 		for (uint64_t i = out_begin(v); i < out_end(v); i++) { uint32_t n = d.adj[i]; if (n != UINT32_MAX && vhas_ref[n]) { nrp = vref_index[n]; nref = n; } }
 		f.bb_nrp.push_back(nrp); f.bb_nref.push_back(nref);
+		{   // t2: the first ref-carrying neighbour sets next_ref_pos and the scan stops (query.h:143-151)
+			uint32_t n1 = f.vstart[k] + f.vlen[k];
+			for (uint64_t i = out_begin(v); i < out_end(v); i++) { uint32_t n = d.adj[i]; if (n != UINT32_MAX && vhas_ref[n]) { n1 = vref_index[n]; break; } }
+			f.nrp1.push_back(n1);
+			if (f.vlen[k] && d.v_offset[v] != (uint64_t)f.vstart[k] - 1 && f.t2_ok) { f.t2_ok = false; f.t2_why = "sequence of backbone vertex " + std::to_string(v) + " is not at offset start - 1 of seq_buffer"; }
+			if (k + 1 < M && n1 < f.vstart[k + 1] && f.t2_ok) { f.t2_ok = false; f.t2_why = "backbone vertex " + std::to_string(v) + " has a ref neighbour behind its successor"; }
+		}
 		const size_t rec0 = f.rec_k.size();
 		for (uint64_t i = out_begin(v); i < out_end(v); i++) {
 			const uint32_t n = d.adj[i];
@@ -197,10 +204,13 @@ void flatten(const SerData& d, FlatIndex& f) {
 					else { uint32_t tk = f.vertex_bb[nn]; e.tgt = kEntAlt | tk | (f.bb_set[tk] ? kEntTgtCarriers : 0); }
 				}
 				f.cent.push_back(e); f.cent_vertex.push_back(n); ncar[k]++;
+				if (n_bb) { f.cent_seq.push_back(0); f.cent_seq.push_back(0); }
+				else { f.cent_seq.push_back(d.v_offset[n]); f.cent_seq.push_back(d.v_length[n]); }
 			}
 		}
 		if (k + 1 < M && nrp != f.vstart[k + 1]) {        // arrival at P[k+1] along the backbone is out of step
 			f.cent.push_back(CEntry{k, kEntMarker | (k + 1), 0, nrp}); f.cent_vertex.push_back(kNone);
+			f.cent_seq.push_back(0); f.cent_seq.push_back(0);
 		}
 		// ---- t7: which records survive the dedup of a fresh next_variant_in_ref call (:397-414)
 		std::vector<size_t> kept;
@@ -260,6 +270,15 @@ void flatten(const SerData& d, FlatIndex& f) {
 	}
 	f.dlev[D] = DLevel{M, f.R, M ? f.rec_begin[M - 1] : 0, (uint32_t)f.cent.size()};
 
+	// t2: first backbone index whose nrp1 reaches each distinct start (prefix maxima are monotone)
+	f.first_reach.assign(D + 1, M);
+	{
+		uint32_t j = 0, pm = 0;     // pm = max nrp1[0..j)
+		for (uint32_t i = 0; i <= D; i++) {
+			while (j < M && (i < D ? std::max(pm, f.nrp1[j]) < f.dstart[i] : std::max(pm, f.nrp1[j]) <= f.dstart[D - 1])) { pm = std::max(pm, f.nrp1[j]); j++; }
+			f.first_reach[i] = j;     // first j with nrp1[j] >= dstart[i]  (M: none)
+		}
+	}
 	pc.lap("flatten: level tables");
 	// ------------------------------------------------------------ back-walk forest
 	// State c (= cur_ref_node_idx) examines node_list[c-1] and moves to c - outdeg; states 0 and 1 end

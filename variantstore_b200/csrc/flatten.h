@@ -70,6 +70,17 @@ struct FlatIndex {
 	std::vector<uint32_t> dtin;           // D + 1: Euler-tour entry time of back-walk state c
 	std::vector<uint32_t> cent_anc;       // 2 per walk entry: [tin, last] of the state that examines its source vertex (1,0: never examined)
 
+	// t2 (query_sample_from_ref, query.h:120-189): next_ref_pos computed at P[k] from the FIRST ref-carrying
+	// neighbour (:143-151; t4 takes the last), the sequence of every walk entry's alt target, and per
+	// distinct start d the first backbone index j with nrp1[j] >= dstart[d] (D + 1 entries; the last =
+	// first j with nrp1[j] > dstart[D-1]).  t2_ok: backbone sequences are contiguous in seq_buffer
+	// (offset = start - 1) and nrp1[k] >= vstart[k+1] everywhere; otherwise t2 is refused (t2_why).
+	std::vector<uint32_t> nrp1;           // M
+	std::vector<uint32_t> first_reach;    // D + 1
+	std::vector<uint32_t> cent_seq;       // 2 per walk entry: {seq offset, length} of an alt target (0,0 otherwise)
+	bool t2_ok = true;
+	std::string t2_why;
+
 	// t6/t7 branch records, (backbone index, out-order) order
 	std::vector<uint32_t> rec_k, rec_vertex, rec_pos, rec_refv, rec_altv;   // *_v: vertex whose sequence is the string, kNone = ""
 	std::vector<uint8_t> rec_flags;       // bit0: kept by a fresh next_variant_in_ref call (t7); bit1: suspect duplicate (t6)

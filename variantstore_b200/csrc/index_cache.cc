@@ -24,7 +24,7 @@ namespace vsgpu {
 namespace {
 
 constexpr uint64_t kMagic = 0x3143464750475356ULL;   // "VSGPGFC1"
-constexpr uint32_t kLayoutVersion = 1;               // bump whenever SerData / FlatIndex / the walk-entry encoding changes
+constexpr uint32_t kLayoutVersion = 2;                // bump whenever SerData / FlatIndex / the walk-entry encoding changes
 constexpr uint64_t kEndMark = 0x444E455F43465356ULL;
 
 struct Writer {
@@ -65,6 +65,7 @@ void archive(A& a, HostIndex& h) {
 	a.vec(f.rec_k); a.vec(f.rec_vertex); a.vec(f.rec_pos); a.vec(f.rec_refv); a.vec(f.rec_altv); a.vec(f.rec_flags); a.vec(f.rec_hash); a.vec(f.rec_dup_prefix);
 	a.vec(f.bitmap); a.vec(f.list_begin); a.vec(f.list_ids);
 	a.pod(h.last_end); a.pod(h.t1_fallback_pos);
+	a.vec(f.nrp1); a.vec(f.first_reach); a.vec(f.cent_seq); a.pod(f.t2_ok); a.str(f.t2_why);
 }
 
 uint64_t mix(uint64_t h, const void* p, size_t n) { return fnv1a(h, p, n); }
@@ -123,7 +124,7 @@ bool load_index_cache(const std::string& prefix, HostIndex& h) {
 	if (ok) {   // cross-checks the kernels rely on; a cache that fails them is treated as absent
 		const FlatIndex& x = h.flat;
 		ok = x.M > 0 && x.bb_vertex.size() == x.M && x.vstart.size() == x.M && x.rec_begin.size() == (size_t)x.M + 1 && x.dstart.size() == x.D && x.dlev.size() == (size_t)x.D + 1
-		     && x.rec_pos.size() == x.R && x.cent_anc.size() == 2 * x.cent.size() && h.ser.sample_names.size() == h.ser.num_samples && h.ser.v_sinfo_begin.size() == (size_t)h.ser.num_vertices + 1;
+		     && x.rec_pos.size() == x.R && x.cent_anc.size() == 2 * x.cent.size() && x.cent_seq.size() == 2 * x.cent.size() && x.nrp1.size() == x.M && x.first_reach.size() == (size_t)x.D + 1 && h.ser.sample_names.size() == h.ser.num_samples && h.ser.v_sinfo_begin.size() == (size_t)h.ser.num_vertices + 1;
 	}
 	if (!ok) { h.ser = SerData(); h.flat = FlatIndex(); h.last_end = 0; h.t1_fallback_pos = 0; }
 	return ok;

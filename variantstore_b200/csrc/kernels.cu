@@ -638,6 +638,78 @@ __global__ void __launch_bounds__(256) k_build_hitmap(const DevIndex ix, uint32_
 	}
 }
 
+// ------------------------------------------------------------------ t2: query_sample_from_ref (query.h:120-189)
+// count: one thread per region walks the sample's path (logic::t2_walk) and counts copy records and
+// bytes; the CTA reduces them into cta_sums (k_seg_bases then scans those in place).
+__global__ void __launch_bounds__(256) k_t2_count(const DevIndex ix, const T2Tables t2, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
+                                                  const uint32_t* __restrict__ sample, uint2* __restrict__ cnt, uint8_t* __restrict__ status,
+                                                  uint64_t* __restrict__ cta_sums, uint32_t* gstatus) {
+	__shared__ SegCount s_warp[8];
+	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	SegCount mine{0, 0};
+	if (i < n) {
+		const uint32_t s = sample[i];
+		uint32_t st = 0;
+		T2CountSink sink{0, 0, 0, 0};
+		if (s == 0 || s >= ix.num_samples) atomicOr(gstatus, kStatusBadRegion);
+		else { st = t2_walk(ix, t2, xs[i], ys[i], s, sink); sink.flush(); }
+		if (st) { sink.nrec = 0; sink.bytes = 0; }
+		cnt[i] = make_uint2(sink.nrec, (uint32_t)sink.bytes);
+		status[i] = (uint8_t)st;
+		mine.rows = sink.nrec; mine.bytes = sink.bytes;
+	}
+	SegCount tot;
+	cta_scan_1024(mine, s_warp, &tot);
+	if (threadIdx.x == 0) { cta_sums[2 * (uint64_t)blockIdx.x] = tot.rows; cta_sums[2 * (uint64_t)blockIdx.x + 1] = tot.bytes; }
+}
+// plan: byte offset of every region (exclusive scan of the counts) and its copy records, written at
+// their final index so the records of the batch are in region order.
+__global__ void __launch_bounds__(256) k_t2_plan(const DevIndex ix, const T2Tables t2, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
+                                                 const uint32_t* __restrict__ sample, const uint2* __restrict__ cnt, const uint64_t* __restrict__ cta_sums,
+                                                 uint64_t nctas, uint64_t* __restrict__ offsets, uint4* __restrict__ recs) {
+	__shared__ SegCount s_warp[8];
+	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	SegCount mine{0, 0};
+	if (i < n) { const uint2 c = cnt[i]; mine.rows = c.x; mine.bytes = c.y; }
+	SegCount tot;
+	SegCount ex = cta_scan_1024(mine, s_warp, &tot);
+	ex.rows += cta_sums[2 * (uint64_t)blockIdx.x]; ex.bytes += cta_sums[2 * (uint64_t)blockIdx.x + 1];
+	if (i < n) {
+		offsets[i] = ex.bytes;
+		if (mine.rows) {
+			T2WriteSink sink{0, 0, recs + ex.rows, ex.bytes};
+			t2_walk(ix, t2, xs[i], ys[i], sample[i], sink);
+			sink.flush();
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = cta_sums[2 * nctas + 1];
+}
+// copy: one warp per record; 32-bit stores aligned on the destination, the source words funnel-shifted
+// into place (seq_ascii is padded so that reading one word past a piece stays inside the buffer).
+__global__ void __launch_bounds__(256) k_t2_copy(const T2Tables t2, const uint4* __restrict__ recs, const uint64_t* __restrict__ nrecs_ptr, char* __restrict__ text) {
+	const uint64_t nrecs = *nrecs_ptr;
+	const uint32_t lane = threadIdx.x & 31;
+	for (uint64_t r = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5; r < nrecs; r += ((uint64_t)gridDim.x * 256) >> 5) {
+		const uint4 rec = __ldg(recs + r);
+		const char* src = t2.seq_ascii + rec.x;
+		char* dst = text + (rec.z | ((uint64_t)rec.w << 32));
+		const uint32_t len = rec.y;
+		const uint32_t head = min(len, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+		if (lane < head) dst[lane] = __ldg(src + lane);
+		const uint32_t nwords = (len - head) >> 2;
+		const char* s2 = src + head;
+		const uint32_t sh = ((uintptr_t)s2 & 3) * 8;
+		const uint32_t* sw = (const uint32_t*)(s2 - ((uintptr_t)s2 & 3));
+		uint32_t* dw = (uint32_t*)(dst + head);
+		for (uint32_t i = lane; i < nwords; i += 32) {
+			const uint32_t lo = __ldg(sw + i), hi = __ldg(sw + i + 1);
+			dw[i] = __funnelshift_r(lo, hi, sh);
+		}
+		const uint32_t done = head + (nwords << 2);
+		if (lane < len - done) dst[done + lane] = __ldg(src + done + lane);
+	}
+}
+
 inline uint32_t grid_for(uint64_t n, uint32_t block, int ctas_per_sm) {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
@@ -685,6 +757,27 @@ cudaError_t launch_t1(const DevIndex& ix, uint64_t n, const uint64_t* pos, uint3
 cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const uint64_t* qhash, uint32_t* rec, uint32_t* status, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	k_t7<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, pos, qhash, rec, status);
+	return cudaGetLastError();
+}
+uint64_t t2_ctas(uint64_t n) { return (n + 255) / 256; }
+cudaError_t launch_t2_count(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
+                            uint2* cnt, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	const uint64_t nctas = t2_ctas(n);
+	k_t2_count<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, n, x, y, sample, cnt, status, cta_sums, gstatus);
+	k_seg_bases<<<1, 256, 0, stream>>>(nctas, cta_sums);
+	return cudaGetLastError();
+}
+cudaError_t launch_t2_plan(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
+                           const uint2* cnt, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	const uint64_t nctas = t2_ctas(n);
+	k_t2_plan<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, n, x, y, sample, cnt, cta_sums, nctas, offsets, recs);
+	return cudaGetLastError();
+}
+cudaError_t launch_t2_copy(const T2Tables& t2, const uint4* recs, const uint64_t* nrecs_ptr, uint64_t nrecs_hint, char* text, cudaStream_t stream) {
+	if (nrecs_hint == 0) return cudaSuccess;
+	k_t2_copy<<<grid_for(nrecs_hint * 32, 256, 8), 256, 0, stream>>>(t2, recs, nrecs_ptr, text);
 	return cudaGetLastError();
 }
 static uint32_t t4_tile() {                // regions per tile (tuning knob, read per launch)

@@ -54,6 +54,28 @@ struct RenderTables {
 	const uint4* item16;         // num_samples: "name(0|0) " + its length in byte 15 when that fits 15 bytes, else zeros
 };
 
+// Tables of t2 = query_sample_from_ref (include/query.h:120-189); uploaded on first use.
+struct T2Tables {
+	const uint32_t* bbs;          // M + 1: backbone starts, bbs[M] = end of the last backbone vertex
+	const uint32_t* nrp1;         // M: next_ref_pos computed at P[k] (first ref-carrying neighbour, query.h:143-151)
+	const uint32_t* first_reach;  // D + 1: first backbone index j with nrp1[j] >= dstart[d]
+	const uint2* cent_seq;        // per walk entry: {seq offset, length} of its alt target
+	const char* seq_ascii;        // seq_buffer.sdsl as ASCII (A C T G N, util.cc:32-41), padded by 16 bytes
+};
+constexpr uint32_t kT2Chunk = 4096;       // longest piece of sequence one copy record moves
+constexpr uint32_t kT2Throw = 1;          // per-region status: the reference call ends in std::out_of_range (substr, query.h:163,167)
+// t2 runs as four launches over n regions (CTA b owns regions [256 b, 256 b + 256)):
+//   count : walk every region, write cnt[i] = {copy records, bytes} and status[i]; per-CTA sums into cta_sums[2 b]
+//   bases : exclusive scan of the per-CTA sums in place (entry nctas = totals)          -> launch_t2_offsets
+//   plan  : offsets[i] (bytes) from the scans, walk again and write the copy records {src, len, dst lo, dst hi}
+//   copy  : one warp per copy record moves its piece of seq_ascii to its final place in `text`
+uint64_t t2_ctas(uint64_t n);
+cudaError_t launch_t2_count(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
+                            uint2* cnt, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream);
+cudaError_t launch_t2_plan(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
+                           const uint2* cnt, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, cudaStream_t stream);
+cudaError_t launch_t2_copy(const T2Tables& t2, const uint4* recs, const uint64_t* nrecs_ptr, uint64_t nrecs_hint, char* text, cudaStream_t stream);
+
 // Segment s of a render call = records [seg_lo[s], seg_hi[s]) ((NONE, NONE) = empty).  Three small
 // launches turn the per-segment row and byte counts into exclusive offsets: row_off / byte_off get
 // nseg + 1 entries (the last = totals); `scratch` needs 2 * (ceil(nseg / 1024) + 1) words.

@@ -70,7 +70,9 @@ struct vsgpu_text {
 	uint64_t n = 0, nbytes = 0, nrows = 0;
 	char* bytes = nullptr; size_t bytes_cap = 0;
 	uint64_t* offsets = nullptr; size_t offsets_cap = 0;
+	uint8_t* status = nullptr; size_t status_cap = 0;     // t2 only
 	float kernel_ms = 0;
+	float stage_ms[3] = {0, 0, 0};                        // t2 only: count (+ scan of CTA sums), plan, copy
 };
 
 struct vsgpu_index : vsgpu::HostIndex {
@@ -99,6 +101,11 @@ struct vsgpu_index : vsgpu::HostIndex {
 	bool render_ready = false;
 	RenderTables render{};
 	DevBuf bseg, brow_off, bbyte_off, bscratch, btext;
+	// t2 (query_sample_from_ref): tables uploaded on first use
+	bool t2_ready = false;
+	T2Tables t2{};
+	DevBuf bcnt, bst8, brecs;
+	cudaEvent_t ev_t2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_render[2] = {nullptr, nullptr};
 	// page-locked host buffers: a free list for results + two staging areas for t6
 	std::mutex pool_mu;
@@ -123,8 +130,9 @@ struct vsgpu_index : vsgpu::HostIndex {
 		cudaSetDevice(device);
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bseg, &brow_off, &bbyte_off, &bscratch, &btext}) b->release();
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs}) b->release();
 		for (cudaEvent_t e : ev_render) if (e) cudaEventDestroy(e);
+		for (cudaEvent_t e : ev_t2) if (e) cudaEventDestroy(e);
 		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i][0], ev_in[i][1], ev_in[i][2], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
 		for (cudaStream_t st : {s_in[0], s_in[1], s_in[2], s_k, s_out}) if (st) cudaStreamDestroy(st);
 		if (pin_small) cudaFreeHost(pin_small);
@@ -845,10 +853,92 @@ const char* vsgpu_text_bytes(const vsgpu_text* t) { return t ? t->bytes : nullpt
 const uint64_t* vsgpu_text_offsets(const vsgpu_text* t) { return t ? t->offsets : nullptr; }
 uint64_t vsgpu_text_num_rows(const vsgpu_text* t) { return t ? t->nrows : 0; }
 float vsgpu_text_kernel_ms(const vsgpu_text* t) { return t ? t->kernel_ms : 0.f; }
+const uint8_t* vsgpu_text_status(const vsgpu_text* t) { return t ? t->status : nullptr; }
+const float* vsgpu_text_stage_ms(const vsgpu_text* t) { return t ? t->stage_ms : nullptr; }
 void vsgpu_text_free(vsgpu_text* t) {
 	if (!t) return;
-	if (t->owner) { t->owner->pinned_release(t->bytes, t->bytes_cap); t->owner->pinned_release(t->offsets, t->offsets_cap); }
+	if (t->owner) { t->owner->pinned_release(t->bytes, t->bytes_cap); t->owner->pinned_release(t->offsets, t->offsets_cap); t->owner->pinned_release(t->status, t->status_cap); }
 	delete t;
+}
+
+// ------------------------------------------------------------------ t2: query_sample_from_ref
+namespace {
+void ensure_t2_tables(vsgpu_index* ix) {
+	if (ix->t2_ready) return;
+	const FlatIndex& f = ix->flat;
+	if (!f.t2_ok) throw std::invalid_argument("vsgpu_query_t2: " + f.t2_why);
+	T2Tables& t = ix->t2;
+	std::vector<uint32_t> bbs(f.vstart.begin(), f.vstart.end());
+	bbs.push_back(ix->last_end);
+	t.bbs = upload(ix, bbs); t.nrp1 = upload(ix, f.nrp1); t.first_reach = upload(ix, f.first_reach);
+	t.cent_seq = (const uint2*)upload(ix, f.cent_seq);
+	static const char kBase[8] = {'A', 'C', 'T', 'G', 'N', 5, 5, 5};   // util.cc:32-41 (map_int)
+	std::vector<char> ascii(ix->ser.seq.size() + 16, 0);
+	parallel_for(ix->ser.seq.size(), [&](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; i++) ascii[i] = kBase[ix->ser.seq[i] & 7]; });
+	t.seq_ascii = upload(ix, ascii);
+	for (auto& e : ix->ev_t2) CU(cudaEventCreate(&e));
+	ix->t2_ready = true;
+}
+}  // namespace
+
+int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out) {
+	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t2: null argument");
+	*out = nullptr;
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	std::unique_ptr<vsgpu_text, void (*)(vsgpu_text*)> t(new vsgpu_text, vsgpu_text_free);
+	t->owner = ix; t->n = n;
+	try {
+		ensure_t2_tables(ix);
+		cudaStream_t st = ix->s_k;
+		t->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &t->offsets_cap);
+		t->status = (uint8_t*)ix->pinned_acquire(n + 1, &t->status_cap);
+		if (!t->offsets || !t->status) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		uint64_t totals[2] = {0, 0};
+		const uint64_t nctas = t2_ctas(n);
+		if (n) {
+			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+			CU(ix->bcnt.ensure(n * 8)); CU(ix->bst8.ensure(n)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->bbyte_off.ensure((n + 1) * 8));
+			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
+			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
+			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
+			CU(cudaEventRecord(ix->ev_t2[0], st));
+			CU(launch_t2_count(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bst8.as<uint8_t>(),
+			                   ix->bscratch.as<uint64_t>(), ix->d_status, st));
+			CU(cudaEventRecord(ix->ev_t2[1], st));
+			CU(cudaMemcpyAsync(ix->pin_small, ix->bscratch.as<uint64_t>() + 2 * nctas, 16, cudaMemcpyDeviceToHost, st));
+			const uint32_t status = read_status(ix, ix->d_status, nullptr, st);
+			if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "vsgpu_query_t2: sample id out of range");
+			totals[0] = ix->pin_small[0]; totals[1] = ix->pin_small[1];
+		}
+		uint64_t max_bytes = 2ull << 30;
+		if (const char* e = getenv("VSGPU_RENDER_MAX_BYTES")) max_bytes = strtoull(e, nullptr, 10);
+		if (totals[1] > max_bytes) return set_err(VSGPU_ESHAPE, "vsgpu_query_t2: the sequences of this batch take " + std::to_string(totals[1]) + " bytes (limit VSGPU_RENDER_MAX_BYTES = " + std::to_string(max_bytes) + "); split the batch");
+		t->nbytes = totals[1]; t->nrows = n;
+		t->bytes = (char*)ix->pinned_acquire(totals[1] + 1, &t->bytes_cap);
+		if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		if (n) {
+			CU(ix->brecs.ensure(std::max<uint64_t>(totals[0], 1) * 16)); CU(ix->btext.ensure(totals[1] + 16));
+			CU(cudaEventRecord(ix->ev_t2[2], st));
+			CU(launch_t2_plan(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bscratch.as<uint64_t>(),
+			                  ix->bbyte_off.as<uint64_t>(), ix->brecs.as<uint4>(), st));
+			CU(cudaEventRecord(ix->ev_t2[3], st));
+			CU(launch_t2_copy(ix->t2, ix->brecs.as<uint4>(), ix->bscratch.as<uint64_t>() + 2 * nctas, totals[0], ix->btext.as<char>(), st));
+			CU(cudaEventRecord(ix->ev_t2[4], st));
+			CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(t->status, ix->bst8.p, n, cudaMemcpyDeviceToHost, st));
+			if (totals[1]) CU(cudaMemcpyAsync(t->bytes, ix->btext.p, totals[1], cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			CU(cudaEventElapsedTime(&t->stage_ms[0], ix->ev_t2[0], ix->ev_t2[1]));
+			CU(cudaEventElapsedTime(&t->stage_ms[1], ix->ev_t2[2], ix->ev_t2[3]));
+			CU(cudaEventElapsedTime(&t->stage_ms[2], ix->ev_t2[3], ix->ev_t2[4]));
+			t->kernel_ms = t->stage_ms[0] + t->stage_ms[1] + t->stage_ms[2];
+		} else t->offsets[0] = 0;
+		t->bytes[totals[1]] = 0;
+		*out = t.release();
+	} catch (const std::invalid_argument& e) { return set_err(VSGPU_ESHAPE, e.what());
+	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
 }
 
 // ------------------------------------------------------------------ device-resident batches
