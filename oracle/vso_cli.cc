@@ -43,7 +43,8 @@ int main(int argc, char** argv) {
 			bool verbose = flag(argc, argv, "-v");
 			auto t0 = std::chrono::steady_clock::now();
 			for (size_t i = 0; i < regions.size(); i++) {
-				if (type == 4) get_sample_var_in_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);
+				if (type == 2) query_sample_from_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);
+				else if (type == 4) get_sample_var_in_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);
 				else if (type == 6) get_var_in_ref(&vg, &idx, regions[i].first, regions[i].second, verbose, outfile);
 				else if (type == 7) {
 					auto alts = read_sequences(arg(argc, argv, "-a", "")), refs = read_sequences(arg(argc, argv, "-b", ""));

@@ -90,14 +90,15 @@ int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	t->offsets.assign(n + 1, 0); t->status.assign(n + 1, 0);
 	for (uint64_t i = 0; i < n; i++) {
 		if (s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "vsgpu_query_t2: sample id out of range");
-		logic::T2CountSink cs{0, 0, 0, 0};
+		logic::T2CountSink cs{0, 0, 0, 0, nullptr, 0};
 		uint32_t st = logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], cs); cs.flush();
 		t->status[i] = (uint8_t)st;
 		if (!st && cs.nrec) {
 			std::vector<uint4> recs(cs.nrec);
-			logic::T2WriteSink ws{0, 0, recs.data(), t->bytes.size()};
+			std::vector<uint32_t> tile_first((t->bytes.size() + cs.bytes) / kT2Tile + 2, 0);
+			logic::T2WriteSink ws{0, 0, recs.data(), t->bytes.size(), recs.data(), tile_first.data()};
 			logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], ws); ws.flush();
-			if (ws.out != recs.data() + cs.nrec) return set_err(VSGPU_EINVAL, "hostsim: t2 count and write passes disagree");
+			if (ws.out != recs.data() + cs.nrec || ws.dst != t->bytes.size() + cs.bytes) return set_err(VSGPU_EINVAL, "hostsim: t2 count and write passes disagree");
 			t->bytes.resize(t->bytes.size() + cs.bytes);
 			for (const uint4& r : recs) memcpy(&t->bytes[r.z | ((uint64_t)r.w << 32)], ix->seq_ascii.data() + r.x, r.y);
 		}

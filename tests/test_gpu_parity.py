@@ -356,7 +356,8 @@ def test_cli_front_end_matches_reference_cli_lines(tmp_path):
     subprocess.run(["make", "-s", "vs_oracle"], cwd=T.ORACLE_DIR, check=True)
     subprocess.run(["make", "-s", "../vsgpu_query"], cwd=T.CSRC_DIR, check=True)
     cases = [["-t", "6", "-r", "10:105"], ["-t", "6", "-r", "30:40,10:105,2000:3000,466:470"], ["-t", "4", "-s", "1", "-r", "14:105,660:700"],
-             ["-t", "7", "-r", "10", "-b", "C", "-a", "T"], ["-t", "7", "-r", "58", "-b", "", "-a", "T"]]
+             ["-t", "7", "-r", "10", "-b", "C", "-a", "T"], ["-t", "7", "-r", "58", "-b", "", "-a", "T"],
+             ["-t", "2", "-s", "1", "-r", "10:105"], ["-t", "2", "-s", "1", "-r", "1:1002,660:700,55:62"]]
     for i, c in enumerate(cases):
         outs = []
         for exe, tag in ((cli, "gpu"), (ref, "cpu")):

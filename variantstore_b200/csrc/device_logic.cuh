@@ -510,17 +510,24 @@ VSGPU_HD uint32_t t2_walk(const DevIndex& ix, const T2Tables& t2, uint64_t x64, 
 	return r == 2 ? kT2Throw : 0;
 }
 
-// Pieces of one region's answer, merged while they are contiguous in seq_buffer and cut into copy
-// records of at most kT2Chunk bytes.  Count: how many records / bytes.  Write: the records themselves.
+// Pieces of one region's answer, merged while they are contiguous in seq_buffer: one copy record
+// {src, len, dst lo, dst hi} per maximal run.  Count: how many records / bytes.  Write: the records
+// themselves plus, for every kT2Tile-byte boundary of the output a record covers, its index in
+// tile_first (the copy kernel starts each tile from there; every boundary below the total is covered
+// by exactly one record because the records tile the output without gaps).
 struct T2CountSink {
-	uint32_t off, len; uint32_t nrec; uint64_t bytes;
-	VSGPU_HD void flush() { if (len) { nrec += (len + kT2Chunk - 1) / kT2Chunk; bytes += len; len = 0; } }
+	uint32_t off, len; uint32_t nrec; uint64_t bytes; uint2* keep; uint64_t stride;   // keep: nullable
+	VSGPU_HD void flush() { if (len) { if (keep && nrec < kT2Keep) keep[nrec * stride] = make_uint2(off, len); nrec++; bytes += len; len = 0; } }
 	VSGPU_HD void seg(uint32_t o, uint32_t l) { if (!l) return; if (len && off + len == o) { len += l; return; } flush(); off = o; len = l; }
 };
 struct T2WriteSink {
-	uint32_t off, len; uint4* out; uint64_t dst;
+	uint32_t off, len; uint4* out; uint64_t dst; const uint4* base; uint32_t* tile_first;
 	VSGPU_HD void flush() {
-		while (len) { const uint32_t l = len < kT2Chunk ? len : kT2Chunk; *out++ = make_uint4(off, l, (uint32_t)dst, (uint32_t)(dst >> 32)); off += l; dst += l; len -= l; }
+		if (!len) return;
+		*out = make_uint4(off, len, (uint32_t)dst, (uint32_t)(dst >> 32));
+		const uint32_t r = (uint32_t)(out - base);
+		for (uint64_t b = (dst + kT2Tile - 1) / kT2Tile, e = (dst + len - 1) / kT2Tile; b <= e; b++) tile_first[b] = r;
+		out++; dst += len; len = 0;
 	}
 	VSGPU_HD void seg(uint32_t o, uint32_t l) { if (!l) return; if (len && off + len == o) { len += l; return; } flush(); off = o; len = l; }
 };

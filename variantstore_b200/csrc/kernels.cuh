@@ -60,21 +60,27 @@ struct T2Tables {
 	const uint32_t* nrp1;         // M: next_ref_pos computed at P[k] (first ref-carrying neighbour, query.h:143-151)
 	const uint32_t* first_reach;  // D + 1: first backbone index j with nrp1[j] >= dstart[d]
 	const uint2* cent_seq;        // per walk entry: {seq offset, length} of its alt target
-	const char* seq_ascii;        // seq_buffer.sdsl as ASCII (A C T G N, util.cc:32-41), padded by 16 bytes
+	const char* seq_ascii;        // seq_buffer.sdsl as ASCII (A C T G N, util.cc:32-41); 64 readable bytes before and after
 };
-constexpr uint32_t kT2Chunk = 4096;       // longest piece of sequence one copy record moves
+constexpr uint32_t kT2Tile = 512;         // bytes of output one warp of the copy kernel writes per step (16 per lane)
+constexpr uint32_t kT2Keep = 16;          // copy records per region the count pass keeps for the plan pass (more: the plan pass walks again)
 constexpr uint32_t kT2Throw = 1;          // per-region status: the reference call ends in std::out_of_range (substr, query.h:163,167)
 // t2 runs as four launches over n regions (CTA b owns regions [256 b, 256 b + 256)):
-//   count : walk every region, write cnt[i] = {copy records, bytes} and status[i]; per-CTA sums into cta_sums[2 b]
+//   count : walk every region, write cnt[i] = {copy records, bytes}, status[i] and the first kT2Keep pieces {src, len}
+//           of the region into keep[k * n + i]; per-CTA sums into cta_sums[2 b]
 //   bases : exclusive scan of the per-CTA sums in place (entry nctas = totals)          -> launch_t2_offsets
 //   plan  : offsets[i] (bytes) from the scans, walk again and write the copy records {src, len, dst lo, dst hi}
-//   copy  : one warp per copy record moves its piece of seq_ascii to its final place in `text`
+//           and tile_first[t] = the record covering output byte t * kT2Tile
+//   copy  : one warp per kT2Tile bytes of `text`; a lane finds the record of its 16 bytes starting from
+//           tile_first and stores them with one 128-bit store (k_t2_copy); the 16-byte chunks in which a
+//           record starts are built by one thread per record (k_t2_seams)
 uint64_t t2_ctas(uint64_t n);
 cudaError_t launch_t2_count(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                            uint2* cnt, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream);
+                            uint2* cnt, uint2* keep, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream);
 cudaError_t launch_t2_plan(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                           const uint2* cnt, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, cudaStream_t stream);
-cudaError_t launch_t2_copy(const T2Tables& t2, const uint4* recs, const uint64_t* nrecs_ptr, uint64_t nrecs_hint, char* text, cudaStream_t stream);
+                           const uint2* cnt, const uint2* keep, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, uint32_t* tile_first, cudaStream_t stream);
+// `totals` = {records, bytes} on the device (entry nctas of the scanned CTA sums); text must have room for bytes rounded up to kT2Tile
+cudaError_t launch_t2_copy(const T2Tables& t2, const uint4* recs, const uint32_t* tile_first, const uint64_t* totals, uint64_t recs_hint, uint64_t bytes_hint, char* text, cudaStream_t stream);
 
 // Segment s of a render call = records [seg_lo[s], seg_hi[s]) ((NONE, NONE) = empty).  Three small
 // launches turn the per-segment row and byte counts into exclusive offsets: row_off / byte_off get

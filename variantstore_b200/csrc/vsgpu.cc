@@ -104,7 +104,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 	// t2 (query_sample_from_ref): tables uploaded on first use
 	bool t2_ready = false;
 	T2Tables t2{};
-	DevBuf bcnt, bst8, brecs;
+	DevBuf bcnt, bst8, brecs, btile, bkeep;
 	cudaEvent_t ev_t2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_render[2] = {nullptr, nullptr};
 	// page-locked host buffers: a free list for results + two staging areas for t6
@@ -130,7 +130,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 		cudaSetDevice(device);
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs}) b->release();
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs, &btile, &bkeep}) b->release();
 		for (cudaEvent_t e : ev_render) if (e) cudaEventDestroy(e);
 		for (cudaEvent_t e : ev_t2) if (e) cudaEventDestroy(e);
 		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i][0], ev_in[i][1], ev_in[i][2], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
@@ -873,9 +873,10 @@ void ensure_t2_tables(vsgpu_index* ix) {
 	t.bbs = upload(ix, bbs); t.nrp1 = upload(ix, f.nrp1); t.first_reach = upload(ix, f.first_reach);
 	t.cent_seq = (const uint2*)upload(ix, f.cent_seq);
 	static const char kBase[8] = {'A', 'C', 'T', 'G', 'N', 5, 5, 5};   // util.cc:32-41 (map_int)
-	std::vector<char> ascii(ix->ser.seq.size() + 16, 0);
-	parallel_for(ix->ser.seq.size(), [&](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; i++) ascii[i] = kBase[ix->ser.seq[i] & 7]; });
-	t.seq_ascii = upload(ix, ascii);
+	// 64 bytes of padding on both sides: the copy kernel reads whole aligned 16-byte vectors around a piece
+	std::vector<char> ascii(ix->ser.seq.size() + 128, 0);
+	parallel_for(ix->ser.seq.size(), [&](uint64_t a, uint64_t b) { for (uint64_t i = a; i < b; i++) ascii[64 + i] = kBase[ix->ser.seq[i] & 7]; });
+	t.seq_ascii = upload(ix, ascii) + 64;
 	for (auto& e : ix->ev_t2) CU(cudaEventCreate(&e));
 	ix->t2_ready = true;
 }
@@ -898,12 +899,12 @@ int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		const uint64_t nctas = t2_ctas(n);
 		if (n) {
 			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
-			CU(ix->bcnt.ensure(n * 8)); CU(ix->bst8.ensure(n)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->bbyte_off.ensure((n + 1) * 8));
+			CU(ix->bcnt.ensure(n * 8)); CU(ix->bst8.ensure(n)); CU(ix->bkeep.ensure(n * 8 * kT2Keep)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->bbyte_off.ensure((n + 1) * 8));
 			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
 			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
 			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
 			CU(cudaEventRecord(ix->ev_t2[0], st));
-			CU(launch_t2_count(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bst8.as<uint8_t>(),
+			CU(launch_t2_count(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bkeep.as<uint2>(), ix->bst8.as<uint8_t>(),
 			                   ix->bscratch.as<uint64_t>(), ix->d_status, st));
 			CU(cudaEventRecord(ix->ev_t2[1], st));
 			CU(cudaMemcpyAsync(ix->pin_small, ix->bscratch.as<uint64_t>() + 2 * nctas, 16, cudaMemcpyDeviceToHost, st));
@@ -918,12 +919,13 @@ int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		t->bytes = (char*)ix->pinned_acquire(totals[1] + 1, &t->bytes_cap);
 		if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
 		if (n) {
-			CU(ix->brecs.ensure(std::max<uint64_t>(totals[0], 1) * 16)); CU(ix->btext.ensure(totals[1] + 16));
+			CU(ix->brecs.ensure(std::max<uint64_t>(totals[0], 1) * 16)); CU(ix->btext.ensure(totals[1] + kT2Tile));
+			CU(ix->btile.ensure((totals[1] / kT2Tile + 2) * 4));
 			CU(cudaEventRecord(ix->ev_t2[2], st));
-			CU(launch_t2_plan(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bscratch.as<uint64_t>(),
-			                  ix->bbyte_off.as<uint64_t>(), ix->brecs.as<uint4>(), st));
+			CU(launch_t2_plan(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bkeep.as<uint2>(), ix->bscratch.as<uint64_t>(),
+			                  ix->bbyte_off.as<uint64_t>(), ix->brecs.as<uint4>(), ix->btile.as<uint32_t>(), st));
 			CU(cudaEventRecord(ix->ev_t2[3], st));
-			CU(launch_t2_copy(ix->t2, ix->brecs.as<uint4>(), ix->bscratch.as<uint64_t>() + 2 * nctas, totals[0], ix->btext.as<char>(), st));
+			CU(launch_t2_copy(ix->t2, ix->brecs.as<uint4>(), ix->btile.as<uint32_t>(), ix->bscratch.as<uint64_t>() + 2 * nctas, totals[0], totals[1], ix->btext.as<char>(), st));
 			CU(cudaEventRecord(ix->ev_t2[4], st));
 			CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
 			CU(cudaMemcpyAsync(t->status, ix->bst8.p, n, cudaMemcpyDeviceToHost, st));
