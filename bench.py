@@ -188,7 +188,8 @@ def workload_config(args, meta):
                         f"{args.regions} random {args.width} bp regions per GPU sorted by start; one step = t6 + t4 over all regions",
             "regions_per_gpu": args.regions, "region_width": args.width, "records": args.records, "samples": args.samples,
             "sharding": "one contig shard per GPU, regions routed by the host, no collective on the data path",
-            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+            "l2": "256 MiB buffer written between timed steps (L2 flush)",
+            "e2e_coordinates": "u64 (vsgpu_query_t6 / _t4)" if getattr(args, "e2e_u64", False) else "u32 (vsgpu_query_t6_u32 / _t4_u32)"}
 
 
 def run_vsgpu(args):
@@ -268,18 +269,23 @@ def run_vsgpu(args):
     value = 2 * n * world / (ms_per_step / 1000)
 
     # ---- end to end through the C ABI with host buffers (pinned inputs), H2D + kernels + D2H each step
-    px = torch.from_numpy(x.astype(np.int64)).pin_memory()
-    py = torch.from_numpy(y.astype(np.int64)).pin_memory()
-    ps = torch.from_numpy(s.astype(np.int32)).pin_memory()
     lib, h = idx._lib, idx._h
+    # region bounds go in as 32-bit arrays (vsgpu_query_t6_u32 / _t4_u32: the reference parses them with
+    # std::stoi, commands.cc:76-80), which halves the bytes over PCIe; --e2e-u64 uses the 64-bit entry points
+    cdt = np.int64 if args.e2e_u64 else np.int32
+    px = torch.from_numpy(x.astype(cdt)).pin_memory()
+    py = torch.from_numpy(y.astype(cdt)).pin_memory()
+    ps = torch.from_numpy(s.astype(np.int32)).pin_memory()
+    q6 = lib.vsgpu_query_t6 if args.e2e_u64 else lib.vsgpu_query_t6_u32
+    q4 = lib.vsgpu_query_t4 if args.e2e_u64 else lib.vsgpu_query_t4_u32
     plo, phi, pcnt = (torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(3))      # page-locked result arrays
     vp = C.c_void_p
 
     def e2e_step():
-        rc = lib.vsgpu_query_t6(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(plo.data_ptr()), vp(phi.data_ptr()), vp(pcnt.data_ptr()))
+        rc = q6(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(plo.data_ptr()), vp(phi.data_ptr()), vp(pcnt.data_ptr()))
         assert rc == 0, lib.vsgpu_last_error()
         r = vp()
-        rc = lib.vsgpu_query_t4(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(ps.data_ptr()), C.byref(r))
+        rc = q4(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(ps.data_ptr()), C.byref(r))
         assert rc == 0, lib.vsgpu_last_error()
         total = int(lib.vsgpu_result_offsets(r)[n])
         lib.vsgpu_result_free(r)
@@ -299,8 +305,9 @@ def run_vsgpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = 2 * n * world / e2e_s
-    h2d = n * 16 + n * 20
-    d2h = n * 8 + (n + 1) * 8 + hits_total * 4          # t6 lo+hi; t4 offsets + hit codes
+    cb = 8 if args.e2e_u64 else 4
+    h2d = n * 2 * cb + n * (2 * cb + 4)                  # t6 x, y; t4 x, y, sample ids
+    d2h = n * 12 + (n + 1) * 8 + hits_total * 4         # t6 lo, hi, counts; t4 offsets + hit codes
 
     if rank != 0:
         if dist is not None:
@@ -358,6 +365,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="regions per type per step of the reference arm")
     ap.add_argument("--cpu-sample-single", type=int, default=2_000, help="regions per type of the single-thread cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-u64", action="store_true", help="end-to-end arm through the 64-bit coordinate entry points instead of the 32-bit ones")
     ap.add_argument("--cache-dir", default=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"))
     args = ap.parse_args()
     import __graft_entry__

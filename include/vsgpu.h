@@ -84,11 +84,18 @@ const char* vsgpu_sample_name(const vsgpu_index* idx, uint32_t id);
 int vsgpu_query_t6(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y,
                    uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts);
 
+/* The same with 32-bit coordinates: region bounds are parsed with std::stoi (src/commands.cc:76-80), so
+ * they fit, and half as many bytes cross PCIe; a small kernel widens them in HBM. */
+int vsgpu_query_t6_u32(vsgpu_index* idx, uint64_t n, const uint32_t* x, const uint32_t* y,
+                       uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts);
+
 /* ---- t4: get_sample_var_in_ref(vg, idx, pos_x, pos_y, sample) — include/query.h:618-729 ---------
  * Result = CSR: offsets[n+1] into hits[]; each hit is a walk-entry code (VSGPU_HIT_*), in the
  * order the reference pushes the rows.  sample_ids are sampleid_map ids (1..num_samples-1). */
 int vsgpu_query_t4(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y,
                    const uint32_t* sample_ids, vsgpu_result** out);
+int vsgpu_query_t4_u32(vsgpu_index* idx, uint64_t n, const uint32_t* x, const uint32_t* y,
+                       const uint32_t* sample_ids, vsgpu_result** out);   /* 32-bit coordinates, see vsgpu_query_t6_u32 */
 uint64_t vsgpu_result_num_queries(const vsgpu_result* r);
 const uint64_t* vsgpu_result_offsets(const vsgpu_result* r);   /* n + 1 */
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r);

@@ -159,6 +159,14 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	*out = r.release();
 	return VSGPU_OK;
 }
+int vsgpu_query_t6_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uint32_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts) {
+	std::vector<uint64_t> x64(x, x + n), y64(y, y + n);
+	return vsgpu_query_t6(ix, n, x64.data(), y64.data(), lo, hi, counts);
+}
+int vsgpu_query_t4_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uint32_t* y, const uint32_t* s, vsgpu_result** out) {
+	std::vector<uint64_t> x64(x, x + n), y64(y, y + n);
+	return vsgpu_query_t4(ix, n, x64.data(), y64.data(), s, out);
+}
 uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r->offsets.size() - 1; }
 const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r->offsets.data(); }
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r->hits.data(); }

@@ -117,6 +117,11 @@ def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
         assert not bad6 and not bad4
         lo, hi, cnt = e.batch_var_in_ref(x, y)
         off, hits = e.batch_sample_var_in_ref(x, y, s)
+        # the 32-bit coordinate entry points (vsgpu_query_t6_u32 / _t4_u32) give the same answers
+        lo32, hi32, cnt32 = e.batch_var_in_ref(x.astype(np.uint32), y.astype(np.uint32))
+        off32, hits32 = e.batch_sample_var_in_ref(x.astype(np.uint32), y.astype(np.uint32), s)
+        assert np.array_equal(lo, lo32) and np.array_equal(hi, hi32) and np.array_equal(cnt, cnt32)
+        assert np.array_equal(off, off32) and np.array_equal(hits, hits32)
         b6, b4 = Batch(e, 6, x, y), Batch(e, 4, x, y, sample_ids=s)
         for _ in range(2):
             b6.run()

@@ -104,6 +104,13 @@ def test_edges_of_the_contig(tmp_path):
     s2 = np.concatenate([s, [1, 2, 3, 4, 5, 6, 7, 8, 9]]).astype(np.uint32)
     bad2, threw = T.compare_t2(o, e, x2, y2, s2)
     assert not bad2 and threw >= 1
+    # 32-bit coordinate entry points: same answers as the 64-bit ones
+    lo, hi, cnt = e.batch_var_in_ref(x, y)
+    lo32, hi32, cnt32 = e.batch_var_in_ref(x.astype(np.uint32), y.astype(np.uint32))
+    assert np.array_equal(lo, lo32) and np.array_equal(hi, hi32) and np.array_equal(cnt, cnt32)
+    off, hits = e.batch_sample_var_in_ref(x, y, s)
+    off32, hits32 = e.batch_sample_var_in_ref(x.astype(np.uint32), y.astype(np.uint32), s)
+    assert np.array_equal(off, off32) and np.array_equal(hits, hits32)
     assert e.query_sample_from_ref(1, 4001, names[2]) == o.batch_t2([1], [4001], [3], want_text=True)[4][0]
     with pytest.raises(IndexError):
         e.query_sample_from_ref(0, 5, names[0])

@@ -30,6 +30,8 @@ PROTOTYPES = {
     "vsgpu_sample_name": (C.c_char_p, [vp, C.c_uint32]),
     "vsgpu_query_t6": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp]),
     "vsgpu_query_t4": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
+    "vsgpu_query_t6_u32": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp]),
+    "vsgpu_query_t4_u32": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
     "vsgpu_result_num_queries": (C.c_uint64, [vp]),
     "vsgpu_result_offsets": (u64p, [vp]),
     "vsgpu_result_hits": (u32p, [vp]),

@@ -60,6 +60,10 @@ def _u64(a):
     return np.ascontiguousarray(a, dtype=np.uint64)
 
 
+def _is_u32(a):
+    return isinstance(a, np.ndarray) and a.dtype == np.uint32
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -130,20 +134,29 @@ class VariantStoreIndex:
 
     # ---- batched operators
     def batch_var_in_ref(self, x, y):
-        """t6 over arrays: returns (rec_lo, rec_hi, counts)."""
-        x, y = _u64(x), _u64(y)
+        """t6 over arrays: returns (rec_lo, rec_hi, counts).  uint32 arrays go through the 32-bit entry
+        point (half the bytes over PCIe), anything else as 64-bit."""
         n = len(x)
         lo, hi, cnt = (np.zeros(n, np.uint32) for _ in range(3))
+        if _is_u32(x) and _is_u32(y):
+            x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+            self._check(self._lib.vsgpu_query_t6_u32(self._h, n, _ptr(x), _ptr(y), _ptr(lo), _ptr(hi), _ptr(cnt)))
+            return lo, hi, cnt
+        x, y = _u64(x), _u64(y)
         self._check(self._lib.vsgpu_query_t6(self._h, n, _ptr(x), _ptr(y), _ptr(lo), _ptr(hi), _ptr(cnt)))
         return lo, hi, cnt
 
     def batch_sample_var_in_ref(self, x, y, sample_ids):
-        """t4 over arrays: returns (offsets[n+1], hit codes)."""
-        x, y = _u64(x), _u64(y)
+        """t4 over arrays: returns (offsets[n+1], hit codes).  uint32 coordinate arrays use the 32-bit entry point."""
         s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
         n = len(x)
         r = C.c_void_p()
-        self._check(self._lib.vsgpu_query_t4(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(r)))
+        if _is_u32(x) and _is_u32(y):
+            x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+            self._check(self._lib.vsgpu_query_t4_u32(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(r)))
+        else:
+            x, y = _u64(x), _u64(y)
+            self._check(self._lib.vsgpu_query_t4(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(r)))
         try:
             off = np.ctypeslib.as_array(self._lib.vsgpu_result_offsets(r), shape=(n + 1,)).copy()
             total = int(off[-1])

@@ -638,6 +638,10 @@ __global__ void __launch_bounds__(256) k_build_hitmap(const DevIndex ix, uint32_
 	}
 }
 
+__global__ void __launch_bounds__(256) k_widen(uint64_t n, const uint32_t* __restrict__ x32, const uint32_t* __restrict__ y32, uint64_t* __restrict__ x, uint64_t* __restrict__ y) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) { x[i] = x32[i]; y[i] = y32[i]; }
+}
+
 // ------------------------------------------------------------------ t2: query_sample_from_ref (query.h:120-189)
 // count: one thread per region walks the sample's path (logic::t2_walk) and counts copy records and
 // bytes; the CTA reduces them into cta_sums (k_seg_bases then scans those in place).
@@ -844,6 +848,11 @@ cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t n
                           const uint64_t* row_off, const uint64_t* byte_off, uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream) {
 	if (row_end <= row_begin) return cudaSuccess;
 	k_render<<<grid_for((row_end - row_begin) * 32, 256, 8), 256, 0, stream>>>(ix, rt, rt.text_prefix[with_samples ? 1 : 0], nseg, seg_lo, with_samples ? 1 : 0, row_off, byte_off, row_begin, row_end, text);
+	return cudaGetLastError();
+}
+cudaError_t launch_widen(uint64_t n, const uint32_t* x32, const uint32_t* y32, uint64_t* x, uint64_t* y, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	k_widen<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, x32, y32, x, y);
 	return cudaGetLastError();
 }
 cudaError_t launch_t6(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* lo, uint32_t* hi, uint32_t* counts,

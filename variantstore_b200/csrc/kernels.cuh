@@ -94,6 +94,9 @@ cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t n
 // fills `hitmap` (zeroed, num_samples x row_words) from the walk entries and their carrier sets
 cudaError_t launch_build_hitmap(const DevIndex& ix, uint32_t* hitmap, cudaStream_t stream);
 
+// 32-bit host coordinates widened to the 64-bit arrays the query kernels read
+cudaError_t launch_widen(uint64_t n, const uint32_t* x32, const uint32_t* y32, uint64_t* x, uint64_t* y, cudaStream_t stream);
+
 // All launchers enqueue on `stream` and return the CUDA error of the launch.
 // `status` is two words: [0] status bits, [1] number of entries appended to a t6 `flagged` list.
 // t6 writes the record slice of every region as two arrays lo[n], hi[n]; optionally counts[n] (slice

@@ -86,7 +86,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 	double entries_per_base = 0;      // walk entries per covered base
 	uint32_t* d_status = nullptr;     // two words: status bits, length of the t6 flagged list
 	std::mutex mu;
-	DevBuf bx, by, bs, bout, boffsets, bhits, bstate, bhash, brec, bflag;
+	DevBuf bx, by, bs, bout, boffsets, bhits, bstate, bhash, brec, bflag, bx32, by32;
 	// A large call is cut into chunks of regions so that the input copies (s_in), the kernels (stream)
 	// and the result copies (s_out) of different chunks overlap; PCIe is full duplex.
 	static constexpr int kMaxChunks = 16;
@@ -130,7 +130,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 		cudaSetDevice(device);
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs, &btile, &bkeep}) b->release();
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bx32, &by32, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs, &btile, &bkeep}) b->release();
 		for (cudaEvent_t e : ev_render) if (e) cudaEventDestroy(e);
 		for (cudaEvent_t e : ev_t2) if (e) cudaEventDestroy(e);
 		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i][0], ev_in[i][1], ev_in[i][2], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
@@ -343,7 +343,8 @@ bool t6_special(const vsgpu_index* ix) { return ix->flat.has_suspect_dups || ix-
 
 // Reads the status words on `stream` (synchronising it), raises on a bad region and re-counts the
 // regions the kernel flagged.
-void settle_t6(vsgpu_index* ix, const uint64_t* x, const uint64_t* y, uint32_t* counts, const uint32_t* d_flag, uint32_t* d_status, cudaStream_t stream) {
+extern "C++" template <class T>
+void settle_t6(vsgpu_index* ix, const T* x, const T* y, uint32_t* counts, const uint32_t* d_flag, uint32_t* d_status, cudaStream_t stream) {
 	uint32_t nflag = 0;
 	const uint32_t st = read_status(ix, d_status, &nflag, stream);
 	if (st & kStatusBadRegion) throw std::invalid_argument("Can't find node corresponding to pos 0");   // index.h:151-154 aborts
@@ -355,7 +356,13 @@ void settle_t6(vsgpu_index* ix, const uint64_t* x, const uint64_t* y, uint32_t* 
 }
 }  // namespace
 
-int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts) {
+namespace {
+// Host-buffer calls take the coordinates as 64-bit (the reference's uint64_t arguments) or 32-bit
+// (they are parsed with std::stoi, commands.cc:76-80, so they fit): the 32-bit form halves the bytes
+// that cross PCIe, and a small kernel widens them in HBM in front of the query kernel.
+extern "C++" template <class T>
+int query_t6_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts) {
+	constexpr bool k32 = sizeof(T) == 4;
 	if (!ix || (n && (!x || !y))) return set_err(VSGPU_EINVAL, "vsgpu_query_t6: null argument");
 	if (n == 0) return VSGPU_OK;
 	if (int rc = check_device(ix)) return rc;
@@ -364,8 +371,10 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	try {
 		const bool flag = counts && t6_special(ix);
 		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bout.ensure(n * 12));
+		if (k32) { CU(ix->bx32.ensure(n * 4)); CU(ix->by32.ensure(n * 4)); }
 		if (flag) CU(ix->bflag.ensure(n * 4));
 		uint64_t* dx = ix->bx.as<uint64_t>(); uint64_t* dy = ix->by.as<uint64_t>();
+		T* sx = k32 ? ix->bx32.as<T>() : (T*)dx; T* sy = k32 ? ix->by32.as<T>() : (T*)dy;      // where the host arrays land
 		uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n; uint32_t* d_cnt = d_hi + n;
 		uint64_t per = 0;
 		const int chunks = plan_chunks(n, &per);
@@ -374,13 +383,14 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		const int ks = in_streams();
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
-			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[0]));
-			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[1 % ks]));
+			CU(cudaMemcpyAsync(sx + a, x + a, m * sizeof(T), cudaMemcpyHostToDevice, ix->s_in[0]));
+			CU(cudaMemcpyAsync(sy + a, y + a, m * sizeof(T), cudaMemcpyHostToDevice, ix->s_in[1 % ks]));
 			for (int k = 0; k < std::min(ks, 2); k++) CU(cudaEventRecord(ix->ev_in[c][k], ix->s_in[k]));
 		}
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
 			for (int k = 0; k < std::min(ks, 2); k++) CU(cudaStreamWaitEvent(ix->s_k, ix->ev_in[c][k], 0));
+			if (k32) CU(launch_widen(m, (const uint32_t*)sx + a, (const uint32_t*)sy + a, dx + a, dy + a, ix->s_k));
 			CU(launch_t6(ix->dev, m, dx + a, dy + a, d_lo + a, d_hi + a, counts ? d_cnt + a : nullptr, flag ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a, ix->d_status, ix->s_k));
 			CU(cudaEventRecord(ix->ev_k[c], ix->s_k));
 			CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
@@ -395,6 +405,9 @@ int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
+}  // namespace
+int vsgpu_query_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts) { return query_t6_impl(ix, n, x, y, rec_lo, rec_hi, counts); }
+int vsgpu_query_t6_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uint32_t* y, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts) { return query_t6_impl(ix, n, x, y, rec_lo, rec_hi, counts); }
 
 // ------------------------------------------------------------------ t4
 namespace {
@@ -434,7 +447,8 @@ uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64
 namespace {
 // Does this batch look like "few, wide regions" (the scan-bound end of the width sweep)?  Decided from
 // a sample of the region widths and the index's walk-entry density; such batches get a warp per region.
-bool expect_wide_regions(const vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y) {
+extern "C++" template <class T>
+bool expect_wide_regions(const vsgpu_index* ix, uint64_t n, const T* x, const T* y) {
 	if (n == 0) return false;
 	const uint64_t step = std::max<uint64_t>(1, n / 1024);
 	// the widest sampled region, in walk entries: beyond the kernel's threshold the batch is launched
@@ -472,7 +486,10 @@ vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const
 }
 }  // namespace
 
-int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out) {
+namespace {
+extern "C++" template <class T>
+int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uint32_t* sample_ids, vsgpu_result** out) {
+	constexpr bool k32 = sizeof(T) == 4;
 	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t4: null argument");
 	*out = nullptr;
 	if (int rc = check_device(ix)) return rc;
@@ -486,10 +503,12 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		const int chunks = wide ? (per = n, 1) : plan_chunks(n, &per);
 		const uint64_t state_words = t4_state_words(per);
 		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+		if (k32) { CU(ix->bx32.ensure(n * 4)); CU(ix->by32.ensure(n * 4)); }
 		CU(ix->boffsets.ensure((n + 1) * 8)); CU(ix->bstate.ensure(state_words * chunks * 8));
 		uint64_t cap = ix->bhits.cap / 4;
 		if (cap == 0) { cap = std::max<uint64_t>((wide ? 64 : 4) * n, 1024); CU(ix->bhits.ensure(cap * 4)); cap = ix->bhits.cap / 4; }
 		uint64_t* dx = ix->bx.as<uint64_t>(); uint64_t* dy = ix->by.as<uint64_t>(); uint32_t* ds = ix->bs.as<uint32_t>();
+		T* sx = k32 ? ix->bx32.as<T>() : (T*)dx; T* sy = k32 ? ix->by32.as<T>() : (T*)dy;
 		uint64_t* d_off = ix->boffsets.as<uint64_t>();
 		r.reset(new vsgpu_result);
 		r->owner = ix; r->n = n;
@@ -504,8 +523,8 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		const int ks = in_streams();
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
-			CU(cudaMemcpyAsync(dx + a, x + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[0]));
-			CU(cudaMemcpyAsync(dy + a, y + a, m * 8, cudaMemcpyHostToDevice, ix->s_in[1 % ks]));
+			CU(cudaMemcpyAsync(sx + a, x + a, m * sizeof(T), cudaMemcpyHostToDevice, ix->s_in[0]));
+			CU(cudaMemcpyAsync(sy + a, y + a, m * sizeof(T), cudaMemcpyHostToDevice, ix->s_in[1 % ks]));
 			CU(cudaMemcpyAsync(ds + a, sample_ids + a, m * 4, cudaMemcpyHostToDevice, ix->s_in[2 % ks]));
 			for (int k = 0; k < ks; k++) CU(cudaEventRecord(ix->ev_in[c][k], ix->s_in[k]));
 		}
@@ -513,6 +532,7 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
 			for (int k = 0; k < ks; k++) CU(cudaStreamWaitEvent(ix->s_k, ix->ev_in[c][k], 0));
+			if (k32) CU(launch_widen(m, (const uint32_t*)sx + a, (const uint32_t*)sy + a, dx + a, dy + a, ix->s_k));
 			CU(launch_t4(ix->dev, m, dx + a, dy + a, ds + a, d_off + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status, wide,
 			             ix->s_k, c ? d_off + a : nullptr));
 			CU(cudaEventRecord(ix->ev_k[c], ix->s_k));
@@ -556,6 +576,9 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
+}  // namespace
+int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out) { return query_t4_impl(ix, n, x, y, sample_ids, out); }
+int vsgpu_query_t4_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample_ids, vsgpu_result** out) { return query_t4_impl(ix, n, x, y, sample_ids, out); }
 uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r ? r->n : 0; }
 const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r ? r->offsets : nullptr; }
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r ? r->hits : nullptr; }
