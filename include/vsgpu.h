@@ -157,6 +157,14 @@ void vsgpu_text_free(vsgpu_text* t);
  * serve t2 (backbone sequences not contiguous in seq_buffer.sdsl) or the batch exceeds
  * VSGPU_RENDER_MAX_BYTES. */
 int vsgpu_query_t2(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out);
+/* ---- t3: query_sample_from_sample(vg, idx, pos_x, pos_y, sample) — include/query.h:195-261 ------------------
+ * The sample's sequence over [x[i], y[i]) of the sample's OWN coordinates (the `index` fields
+ * fix_sample_indexes writes, variant_graph.h:1883-1997).  Same result object as t2; status 1 = substr
+ * throws (query.h:235,239), status 2 = the reference never returns: its loop at :209-214 repeats
+ * get_prev_vertex_with_sample from a position that maps to itself (any x at or just behind one of
+ * the sample's variants).  The first call reads the vertex blocks of ser/ a second time (vsgpu_open
+ * does not keep the per-carrier indexes) and uploads them: 4 bytes per genotype entry. */
+int vsgpu_query_t3(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out);
 const uint8_t* vsgpu_text_status(const vsgpu_text* t);      /* n bytes (t2 results; NULL for rendered t6 rows) */
 const float* vsgpu_text_stage_ms(const vsgpu_text* t);      /* t2: device time of the count, plan and copy launches (CUDA events); their sum = vsgpu_text_kernel_ms */
 

@@ -259,6 +259,9 @@ Graph::vertex get_prev_vertex_with_sample(const VariantGraph* vg, const Index* i
 std::string query_sample_from_ref(const VariantGraph* vg, const Index* idx, uint64_t x, uint64_t y,
                                   const std::string& sample_id, bool print = false,
                                   const std::string& outfile = "", bool* ub = nullptr);   // :120-189
+std::string query_sample_from_sample(const VariantGraph* vg, const Index* idx, uint64_t x, uint64_t y,
+                                     const std::string& sample_id, bool print = false,
+                                     const std::string& outfile = "", bool* ub = nullptr, bool* hang = nullptr);   // :195-261
 bool get_samples(const Vertex* v, const VariantGraph* vg,
                  std::vector<std::pair<std::string, std::string>>& sample_ids);       // :268-285
 bool next_variant_in_ref(const VariantGraph* vg, const Index* idx, uint64_t pos, std::vector<Variant>& vars,

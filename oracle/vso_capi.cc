@@ -207,6 +207,30 @@ int vso_batch_t2(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, con
 		return 0;
 	} catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+// query_sample_from_sample (query.h:195-261).  status: 0 = a sequence came back, 1 = std::out_of_range,
+// 2 = the loop at :209-214 never ends (the reference hangs).
+int vso_batch_t3(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids,
+                 uint64_t* lengths, uint64_t* digests, uint8_t* status, uint8_t* ub, char** text) {
+	Handle* h = (Handle*)hp;
+	try {
+		std::string all;
+		for (uint64_t i = 0; i < n; i++) {
+			bool u = false, hang = false;
+			std::string name = h->vg->get_sample_name(sample_ids[i]);
+			std::string seq; uint8_t st = 0;
+			try { seq = query_sample_from_sample(h->vg.get(), h->idx.get(), x[i], y[i], name, false, "", &u, &hang); }
+			catch (const std::out_of_range&) { seq.clear(); st = 1; }
+			if (hang) { seq.clear(); st = 2; }
+			lengths[i] = seq.size();
+			if (digests) digests[i] = fnv1a(kFnvInit, seq.data(), seq.size());
+			if (status) status[i] = st;
+			if (ub) ub[i] = u;
+			if (text) { all += seq; all += '\n'; }
+		}
+		if (text) *text = dup_str(all);
+		return 0;
+	} catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 int vso_batch_t2_mt(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, uint64_t* lengths, int nthreads) {
 	Handle* h = (Handle*)hp;
 	if (nthreads < 1) nthreads = 1;

@@ -106,6 +106,48 @@ std::string query_sample_from_ref(const VariantGraph* vg, const Index* idx, cons
 	return seq;
 }
 
+// Sample's sequence in the sample's own coordinates [pos_x, pos_y) (query.h:195-261).  The loop at
+// :209-214 repeats get_prev_vertex_with_sample from the ref position of the vertex found; when that
+// position maps to itself the reference never leaves the loop — detected here (the chain of positions
+// is deterministic, so revisiting one means it cycles) and reported through *hang.
+std::string query_sample_from_sample(const VariantGraph* vg, const Index* idx, const uint64_t pos_x, const uint64_t pos_y,
+                                     const std::string& sample_id, bool print, const std::string& outfile, bool* ub, bool* hang) {
+	std::string seq = "";
+	uint64_t ref_pos = 0, sample_pos = 0;
+	Graph::vertex closest_v = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, ref_pos, sample_pos, ub);
+	std::vector<uint64_t> seen;
+	while (sample_pos >= pos_x && closest_v > 0) {
+		uint64_t pos = ref_pos;
+		if (std::find(seen.begin(), seen.end(), pos) != seen.end()) { if (hang) *hang = true; return ""; }
+		seen.push_back(pos);
+		closest_v = get_prev_vertex_with_sample(vg, idx, pos, sample_id, ref_pos, sample_pos, ub);
+	}
+	VariantGraph::PathIterator it = vg->find(closest_v, sample_id);
+	bool record_seq = false;
+	std::string temp;
+	while (!it.done()) {
+		temp.assign(vg->get_sequence(*(*it)));
+		uint64_t l = (*it)->length;
+		uint64_t next_sample_pos = sample_pos + l;
+		if (record_seq == true && next_sample_pos < pos_y) {
+			seq += temp;
+		} else if (record_seq == true && next_sample_pos >= pos_y) {
+			seq += temp.substr(0, pos_y - sample_pos);
+			break;
+		} else if (next_sample_pos >= pos_x && next_sample_pos < pos_y) {
+			record_seq = true;
+			seq += temp.substr(pos_x - sample_pos);
+		} else if (next_sample_pos >= pos_x && next_sample_pos >= pos_y) {
+			seq = temp.substr(pos_x - sample_pos, pos_y - pos_x);
+			break;
+		}
+		++it;
+		sample_pos = next_sample_pos;
+	}
+	if (print) { std::ofstream out; out.open(outfile); out << seq << std::endl; out.close(); }
+	return seq;
+}
+
 bool get_samples(const Vertex* v, const VariantGraph* vg, std::vector<std::pair<std::string, std::string>>& sample_ids) {   // :268-285
 	bool is_var = false;
 	sample_ids = {};

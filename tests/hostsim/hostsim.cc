@@ -22,6 +22,8 @@ struct vsgpu_text { std::string bytes; std::vector<uint64_t> offsets; std::vecto
 struct vsgpu_index : HostIndex {
 	DevIndex dev;
 	T2Tables t2{};
+	T3Tables t3{};
+	std::vector<uint64_t> sidx_begin; std::vector<uint32_t> sidx, sid;
 	std::vector<uint32_t> bbs;
 	std::string seq_ascii;
 	std::vector<uint32_t> bucket;
@@ -84,20 +86,44 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 void vsgpu_close(vsgpu_index* ix) { delete ix; }
 
 // t2 through the same two passes as the kernels: count, then copy records, then the copy itself
-int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) {
+static int query_seq(vsgpu_index* ix, bool t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out);
+int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) { return query_seq(ix, false, n, x, y, s, out); }
+int vsgpu_query_t3(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) {
+	if (ix->sidx_begin.empty()) {     // same construction as ensure_t3_tables of libvsgpu
+		const FlatIndex& f = ix->flat; const SerData& sd = ix->ser;
+		std::vector<uint32_t> sindex;
+		try { load_sample_indexes(ix->prefix, sd.v_sinfo_begin.back(), sindex); } catch (const std::exception& e) { return set_err(VSGPU_ESHAPE, e.what()); }
+		const size_t E = f.cent.size();
+		ix->sidx_begin.assign(E + 1, 0);
+		for (size_t c = 0; c < E; c++) { const uint32_t v = f.cent_vertex[c]; ix->sidx_begin[c + 1] = ix->sidx_begin[c] + (v == kNone ? 0 : sd.v_sinfo_begin[v + 1] - sd.v_sinfo_begin[v]); }
+		ix->sidx.resize(ix->sidx_begin[E]); if (!f.class_mode) ix->sid.resize(ix->sidx_begin[E]);
+		for (size_t c = 0; c < E; c++) {
+			const uint32_t v = f.cent_vertex[c];
+			if (v == kNone) continue;
+			const uint64_t s0 = sd.v_sinfo_begin[v], cnt = sd.v_sinfo_begin[v + 1] - s0;
+			memcpy(ix->sidx.data() + ix->sidx_begin[c], sindex.data() + s0, cnt * 4);
+			if (!f.class_mode) memcpy(ix->sid.data() + ix->sidx_begin[c], sd.s_sample_id.data() + s0, cnt * 4);
+		}
+		ix->t3.sidx_begin = ix->sidx_begin.data(); ix->t3.sidx = ix->sidx.data(); ix->t3.sid = f.class_mode ? nullptr : ix->sid.data();
+		ix->t3.first_index = f.vstart[f.dlev[0].k];
+	}
+	return query_seq(ix, true, n, x, y, s, out);
+}
+static int query_seq(vsgpu_index* ix, bool t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) {
 	if (!ix->flat.t2_ok) return set_err(VSGPU_ESHAPE, "vsgpu_query_t2: " + ix->flat.t2_why);
 	std::unique_ptr<vsgpu_text> t(new vsgpu_text);
 	t->offsets.assign(n + 1, 0); t->status.assign(n + 1, 0);
 	for (uint64_t i = 0; i < n; i++) {
 		if (s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "vsgpu_query_t2: sample id out of range");
 		logic::T2CountSink cs{0, 0, 0, 0, nullptr, 0};
-		uint32_t st = logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], cs); cs.flush();
+		uint32_t st = t3 ? logic::t3_walk(ix->dev, ix->t2, ix->t3, x[i], y[i], s[i], cs) : logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], cs); cs.flush();
 		t->status[i] = (uint8_t)st;
 		if (!st && cs.nrec) {
 			std::vector<uint4> recs(cs.nrec);
 			std::vector<uint32_t> tile_first((t->bytes.size() + cs.bytes) / kT2Tile + 2, 0);
 			logic::T2WriteSink ws{0, 0, recs.data(), t->bytes.size(), recs.data(), tile_first.data()};
-			logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], ws); ws.flush();
+			if (t3) logic::t3_walk(ix->dev, ix->t2, ix->t3, x[i], y[i], s[i], ws); else logic::t2_walk(ix->dev, ix->t2, x[i], y[i], s[i], ws);
+			ws.flush();
 			if (ws.out != recs.data() + cs.nrec || ws.dst != t->bytes.size() + cs.bytes) return set_err(VSGPU_EINVAL, "hostsim: t2 count and write passes disagree");
 			t->bytes.resize(t->bytes.size() + cs.bytes);
 			for (const uint4& r : recs) memcpy(&t->bytes[r.z | ((uint64_t)r.w << 32)], ix->seq_ascii.data() + r.x, r.y);

@@ -71,6 +71,8 @@ def test_fuzz_parity_cuda(tmp_path, seed, overlap, sparse, walk_path):
         x[:8] = np.arange(8)                                     # t2 has no pos-0 check: x = 0 throws inside substr
         bad2, threw = T.compare_t2(o, e, x, y, s)
         assert not bad2 and threw >= 1
+        bad3, odd3 = T.compare_t3(o, e, x, y, s)                 # sample coordinates: incl. the regions the reference hangs on
+        assert not bad3 and (sparse or odd3 >= 1)
 
 
 def test_golden_fixture_cuda():
@@ -133,8 +135,10 @@ def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
         assert len(b4.timings_ms()) == 1 and b4.stats()[1] == 1 and b6.stats()[0] == 288 * n
         # size-independent properties: slices are monotone in x for sorted regions of equal width,
         # a t4 answer never has more rows than twice the t6 slice (+ the start / rejoin rows)
-        bad2, _ = T.compare_t2(o, e, x[sub], y[sub], s[sub])       # up to 100 kb per region: several 4 KB copy records each
+        bad2, _ = T.compare_t2(o, e, x[sub], y[sub], s[sub])       # up to 100 kb per region
         assert not bad2
+        bad3, _ = T.compare_t3(o, e, x[sub], y[sub], s[sub])
+        assert not bad3
         same_w = (y - x == 1000) & (lo != NONE)
         assert np.all(np.diff(lo[same_w].astype(np.int64)) >= 0)
         assert np.all(np.diff(off).astype(np.int64) <= 2 * (hi.astype(np.int64) - lo) + 2)
@@ -316,6 +320,12 @@ def test_sample_sequences_cuda(tmp_path, monkeypatch):
         s = np.repeat(np.arange(1, len(names) + 1, dtype=np.uint32), 2 * len(starts))
         bad2, threw = T.compare_t2(o, e, x, y, s)
         assert not bad2 and threw > len(names)
+        bad3, odd3 = T.compare_t3(o, e, x, y, s)
+        assert not bad3 and odd3 > len(names)
+        st3 = e.batch_sample_seq_in_sample(x, y, s)[2]
+        i2 = int(np.nonzero(st3 == 2)[0][0])
+        with pytest.raises(RuntimeError):
+            e.query_sample_from_sample(int(x[i2]), int(y[i2]), names[int(s[i2]) - 1])
         off, text, st, ms = e.batch_sample_seq_in_ref(x, y, s)
         h = len(x) // 3
         offa, texta, sta, _ = e.batch_sample_seq_in_ref(x[:h], y[:h], s[:h])
@@ -362,7 +372,8 @@ def test_cli_front_end_matches_reference_cli_lines(tmp_path):
     subprocess.run(["make", "-s", "../vsgpu_query"], cwd=T.CSRC_DIR, check=True)
     cases = [["-t", "6", "-r", "10:105"], ["-t", "6", "-r", "30:40,10:105,2000:3000,466:470"], ["-t", "4", "-s", "1", "-r", "14:105,660:700"],
              ["-t", "7", "-r", "10", "-b", "C", "-a", "T"], ["-t", "7", "-r", "58", "-b", "", "-a", "T"],
-             ["-t", "2", "-s", "1", "-r", "10:105"], ["-t", "2", "-s", "1", "-r", "1:1002,660:700,55:62"]]
+             ["-t", "2", "-s", "1", "-r", "10:105"], ["-t", "2", "-s", "1", "-r", "1:1002,660:700,55:62"],
+             ["-t", "3", "-s", "1", "-r", "1:1001,466:470,57:60"]]
     for i, c in enumerate(cases):
         outs = []
         for exe, tag in ((cli, "gpu"), (ref, "cpu")):

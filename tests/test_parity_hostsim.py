@@ -52,6 +52,10 @@ def test_fuzz_parity(tmp_path, seed, overlap, sparse, walk_path):
     # query_sample_from_ref (t2): the same regions, byte for byte, incl. the calls that throw
     bad2, _ = T.compare_t2(o, e, x, y, s)
     assert not bad2
+    # query_sample_from_sample (t3): the sample's own coordinates; includes the regions for which the
+    # reference never returns (status 2) and those whose substr throws (status 1)
+    bad3, odd3 = T.compare_t3(o, e, x, y, s)
+    assert not bad3 and (sparse or odd3 > 0)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
@@ -74,6 +78,8 @@ def test_exhaustive_windows_reach_the_rare_walk_entries(tmp_path, seed, walk_pat
     # scan meets first make the reference's substr throw (status 1) — those must agree too
     bad2, threw = T.compare_t2(o, e, x[::3], y[::3], s[::3])
     assert not bad2 and threw > 0
+    bad3, odd3 = T.compare_t3(o, e, x[1::3], y[1::3], s[1::3])
+    assert not bad3 and odd3 > 0
     if e.info.rejoin_carriers:
         assert int(((hits & 0x40000000) != 0).sum()) > 0
 
@@ -104,6 +110,8 @@ def test_edges_of_the_contig(tmp_path):
     s2 = np.concatenate([s, [1, 2, 3, 4, 5, 6, 7, 8, 9]]).astype(np.uint32)
     bad2, threw = T.compare_t2(o, e, x2, y2, s2)
     assert not bad2 and threw >= 1
+    bad3, odd3 = T.compare_t3(o, e, x2, y2, s2)
+    assert not bad3 and odd3 >= 1
     # 32-bit coordinate entry points: same answers as the 64-bit ones
     lo, hi, cnt = e.batch_var_in_ref(x, y)
     lo32, hi32, cnt32 = e.batch_var_in_ref(x.astype(np.uint32), y.astype(np.uint32))
@@ -131,6 +139,8 @@ def test_synthetic_generator_parity(tmp_path):
         assert t7_parity(o, e) > 0
         bad2, _ = T.compare_t2(o, e, x, y, s)
         assert not bad2
+        bad3, _ = T.compare_t3(o, e, x, y, s)
+        assert not bad3
 
 
 def test_duplicate_records_take_the_literal_path(tmp_path):
@@ -175,6 +185,7 @@ def test_index_cache_round_trip(tmp_path, monkeypatch):
     assert not bad6 and not bad4
     assert t7_parity(o, e2) > 0
     assert not T.compare_t2(o, e2, x, y, s)[0]
+    assert not T.compare_t3(o, e2, x, y, s)[0]        # t3 re-reads ser/ for the per-carrier indexes even when the index came from the cache
     assert e2.get_var_in_ref(1, 4001) == e1.get_var_in_ref(1, 4001)                # rows incl. sample names and phasing
     assert e2.get_sample_var_in_ref(1, 4001, names[3]) == e1.get_sample_var_in_ref(1, 4001, names[3])
     # a truncated cache is ignored (and replaced)

@@ -75,6 +75,7 @@ class Oracle:
             L.vso_batch_t4.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t1.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t2.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+            L.vso_batch_t3.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
             L.vso_batch_t2_mt.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t6_mt.argtypes = [vp, u64, vp, vp, vp, C.c_int]
             L.vso_batch_t4_mt.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
@@ -195,7 +196,11 @@ class Oracle:
             raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
         return found, cnt, dig
 
-    def batch_t2(self, x, y, sample_ids, want_text=False):
+    def batch_t3(self, x, y, sample_ids, want_text=False):
+        """query_sample_from_sample: like batch_t2; status 2 = the reference never leaves its loop."""
+        return self.batch_t2(x, y, sample_ids, want_text, fn="vso_batch_t3")
+
+    def batch_t2(self, x, y, sample_ids, want_text=False, fn="vso_batch_t2"):
         """query_sample_from_ref: (lengths, digests, status, ub[, list of sequences]); status 1 = the
         reference call ends in std::out_of_range."""
         x, y = np.ascontiguousarray(x, np.uint64), np.ascontiguousarray(y, np.uint64)
@@ -203,7 +208,7 @@ class Oracle:
         n = len(x)
         ln, dig, st, ub = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
         tp = C.c_void_p(0)
-        rc = self.lib().vso_batch_t2(self.h, n, x.ctypes.data, y.ctypes.data, s.ctypes.data, ln.ctypes.data, dig.ctypes.data,
+        rc = getattr(self.lib(), fn)(self.h, n, x.ctypes.data, y.ctypes.data, s.ctypes.data, ln.ctypes.data, dig.ctypes.data,
                                      st.ctypes.data, ub.ctypes.data, C.byref(tp) if want_text else None)
         if rc != 0:
             raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
@@ -321,18 +326,28 @@ def compare_t1(oracle, eng, pos, with_samples=True):
     return [int(i) for i in np.nonzero(bad)[0]]
 
 
-def compare_t2(oracle, eng, x, y, s, skip_ub=True):
+def compare_t3(oracle, eng, x, y, s, skip_ub=True):
+    """query_sample_from_sample on both sides; returns (mismatching indices, regions where the reference
+    throws or never returns)."""
+    return compare_t2(oracle, eng, x, y, s, skip_ub, t3=True)
+
+
+def compare_t2(oracle, eng, x, y, s, skip_ub=True, t3=False):
     """query_sample_from_ref on both sides, byte for byte; returns (mismatching indices, regions where
     the reference throws std::out_of_range)."""
-    ln, dg, st, ub, seqs = oracle.batch_t2(x, y, s, want_text=True)
-    off, text, est, _ = eng.batch_sample_seq_in_ref(x, y, s)
+    if t3:
+        ln, dg, st, ub, seqs = oracle.batch_t3(x, y, s, want_text=True)
+        off, text, est, _ = eng.batch_sample_seq_in_sample(x, y, s)
+    else:
+        ln, dg, st, ub, seqs = oracle.batch_t2(x, y, s, want_text=True)
+        off, text, est, _ = eng.batch_sample_seq_in_ref(x, y, s)
     bad = []
     for i in range(len(seqs)):
         if skip_ub and ub[i]:
             continue
         if est[i] != st[i] or int(off[i + 1] - off[i]) != int(ln[i]) or text[off[i]:off[i + 1]] != seqs[i].encode():
             bad.append(i)
-    return bad, int(st.sum())
+    return bad, int((st != 0).sum())
 
 
 def compare_all(oracle, eng, x, y, s, with_samples=True, skip_ub=True):

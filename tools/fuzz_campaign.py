@@ -2,7 +2,7 @@
 """Long-running parity campaign on the CPU: for every seed in [lo, hi) and each of the four fuzz shapes
 (overlapping deletions x explicit-id encoding), random record / sample counts, construct with the
 oracle, open with the engine's loader + flattener + kernel logic compiled for the host (test-only
-simulator), and compare t6, t4, closest_var and t2 (sample sequences) on random regions.  usage: fuzz_campaign.py LO HI
+simulator), and compare t6, t4, closest_var, t2 and t3 (sample sequences in ref / sample coordinates) on random regions.  usage: fuzz_campaign.py LO HI
 Round 1: seeds 0..299 = 1 200 graphs, 480 000 t6 + t4 region queries, 360 000 closest_var: 0 mismatches."""
 import sys, os, tempfile, shutil, json, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,7 +12,7 @@ import vs_testlib as T
 from vs_testlib import Oracle
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
 bad = []
-n_t2 = n_threw = 0
+n_t2 = n_threw = n_odd3 = 0
 t0 = time.time()
 for seed in range(lo, hi):
     for overlap in (False, True):
@@ -32,6 +32,9 @@ for seed in range(lo, hi):
                 x[:4] = [0, 0, 1, 4100]
                 b2, threw = T.compare_t2(o, e, x, y, s)
                 n_t2 += len(x); n_threw += threw
+                b3, odd3 = T.compare_t3(o, e, x, y, s)
+                n_odd3 += odd3
+                b2 = b2 + [("t3", i) for i in b3]
                 if b6 or b4 or b1 or b2:
                     bad.append(dict(seed=seed, overlap=overlap, sparse=sparse, nrec=nrec, ns=ns, b6=b6[:5], b4=b4[:5], b1=b1[:5], b2=b2[:5]))
                     print("MISMATCH", bad[-1], flush=True)
@@ -40,4 +43,4 @@ for seed in range(lo, hi):
                 shutil.rmtree(d, ignore_errors=True)
     if seed % 10 == 0:
         print("seed", seed, "elapsed", round(time.time() - t0), "bad", len(bad), flush=True)
-print("DONE", lo, hi, "bad", len(bad), "t2 regions", n_t2, "of which the reference throws", n_threw)
+print("DONE", lo, hi, "bad", len(bad), "t2 regions", n_t2, "of which the reference throws", n_threw, "; t3 on the same regions, reference throws or hangs on", n_odd3)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--shapes", default="1000:1000000,100:1000000,10000:100000,100000:10000,1000000:1000")
     ap.add_argument("--oracle-sample", type=int, default=300)
     ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--t3", action="store_true", help="query_sample_from_sample (sample coordinates) instead of query_sample_from_ref")
     a = ap.parse_args()
     args = argparse.Namespace(records=1_103_547, samples=2504, fmax=1100, cache_dir=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"),
                               regions=1_000_000, width=1000)
@@ -48,7 +49,9 @@ def main():
         x = np.sort(rng.integers(max(1, meta["pos_lo"]), meta["ref_length"] - width, n)).astype(np.uint64)
         y = x + np.uint64(width)
         s = rng.integers(1, args.samples + 1, n).astype(np.uint32)
-        off, text, st, _ = idx.batch_sample_seq_in_ref(x, y, s)
+        t_first = time.perf_counter()
+        off, text, st, _ = (idx.batch_sample_seq_in_sample if a.t3 else idx.batch_sample_seq_in_ref)(x, y, s)
+        t_first = time.perf_counter() - t_first
         px = torch.from_numpy(x.astype(np.int64)).pin_memory()
         py = torch.from_numpy(y.astype(np.int64)).pin_memory()
         ps = torch.from_numpy(s.astype(np.int32)).pin_memory()
@@ -56,7 +59,7 @@ def main():
         for _ in range(a.reps):
             t = C.c_void_p()
             t0 = time.perf_counter()
-            rc = lib.vsgpu_query_t2(h, n, C.c_void_p(px.data_ptr()), C.c_void_p(py.data_ptr()), C.c_void_p(ps.data_ptr()), C.byref(t))
+            rc = (lib.vsgpu_query_t3 if a.t3 else lib.vsgpu_query_t2)(h, n, C.c_void_p(px.data_ptr()), C.c_void_p(py.data_ptr()), C.c_void_p(ps.data_ptr()), C.byref(t))
             ts.append(time.perf_counter() - t0)
             assert rc == 0
             sm = lib.vsgpu_text_stage_ms(t)
@@ -65,7 +68,7 @@ def main():
         stages = np.median(np.array(stages), axis=0)
         nbytes = int(off[-1])
         kms = float(stages.sum())
-        out = {"config": "t2 sample sequences in ref coordinates", "width": width, "regions": n, "text_bytes": nbytes, "threw": int(st.sum()),
+        out = {"config": "t3 sample sequences in sample coordinates" if a.t3 else "t2 sample sequences in ref coordinates", "first_call_s": round(t_first, 3), "width": width, "regions": n, "text_bytes": nbytes, "threw": int((st == 1).sum()), "reference_hangs": int((st == 2).sum()),
                "count_ms": round(float(stages[0]), 4), "plan_ms": round(float(stages[1]), 4), "copy_ms": round(float(stages[2]), 4),
                "kernels_ms": round(kms, 4), "regions_per_s_kernels": round(n / (kms / 1e3)),
                "copy_GBps_algorithmic": round(2 * nbytes / (stages[2] / 1e3) / 1e9, 1), "copy_frac_of_hbm_peak": round(2 * nbytes / (stages[2] / 1e3) / 1e9 / hbm, 3),
@@ -76,7 +79,7 @@ def main():
             m = min(n, a.oracle_sample)
             sub = rng.choice(n, m, replace=False)
             t0 = time.perf_counter()
-            ln, dg, ost, ub, seqs = oracle.batch_t2(x[sub], y[sub], s[sub], want_text=True)
+            ln, dg, ost, ub, seqs = (oracle.batch_t3 if a.t3 else oracle.batch_t2)(x[sub], y[sub], s[sub], want_text=True)
             dt = time.perf_counter() - t0
             for j, i in enumerate(sub):
                 assert int(ost[j]) == int(st[i]) and seqs[j].encode() == text[off[i]:off[i + 1]], (int(x[i]), int(y[i]), int(s[i]))

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "vsgpu_text_kernel_ms": (C.c_float, [vp]),
     "vsgpu_text_free": (None, [vp]),
     "vsgpu_query_t2": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
+    "vsgpu_query_t3": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
     "vsgpu_text_status": (vp, [vp]),
     "vsgpu_text_stage_ms": (C.POINTER(C.c_float), [vp]),
     "vsgpu_batch_create": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, cpp, cpp, C.POINTER(vp)]),

@@ -181,7 +181,21 @@ class VariantStoreIndex:
             self._lib.vsgpu_text_free(t)
         return off, text, rows, ms
 
-    def batch_sample_seq_in_ref(self, x, y, sample_ids):
+    def batch_sample_seq_in_sample(self, x, y, sample_ids):
+        """t3 over arrays (query_sample_from_sample, query.h:195-261): like batch_sample_seq_in_ref with the
+        regions in the sample's own coordinates; status 2 = the reference never returns."""
+        return self.batch_sample_seq_in_ref(x, y, sample_ids, _fn="vsgpu_query_t3")
+
+    def query_sample_from_sample(self, pos_x: int, pos_y: int, sample_id: str) -> str:
+        """query.h:195-261.  IndexError where substr throws; RuntimeError where the reference would spin forever."""
+        off, text, status, _ = self.batch_sample_seq_in_sample([pos_x], [pos_y], [self.sample_id(sample_id)])
+        if status[0] == 1:
+            raise IndexError("basic_string::substr: __pos > this->size() (query.h:235,239)")
+        if status[0] == 2:
+            raise RuntimeError("the reference does not terminate for this region (query.h:209-214)")
+        return text.decode()
+
+    def batch_sample_seq_in_ref(self, x, y, sample_ids, _fn="vsgpu_query_t2"):
         """t2 over arrays (query_sample_from_ref, query.h:120-189): (offsets[n+1], bytes, status, kernel ms).
         Region i's sequence is bytes[offsets[i]:offsets[i+1]]; status[i] = 1 where the reference call
         ends in std::out_of_range."""
@@ -189,7 +203,7 @@ class VariantStoreIndex:
         s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
         n = len(x)
         t = C.c_void_p()
-        self._check(self._lib.vsgpu_query_t2(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(t)))
+        self._check(getattr(self._lib, _fn)(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(t)))
         try:
             off = np.ctypeslib.as_array(self._lib.vsgpu_text_offsets(t), shape=(n + 1,)).copy()
             text = C.string_at(self._lib.vsgpu_text_bytes(t), int(off[-1]))

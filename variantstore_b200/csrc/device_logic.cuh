@@ -510,6 +510,146 @@ VSGPU_HD uint32_t t2_walk(const DevIndex& ix, const T2Tables& t2, uint64_t x64, 
 	return r == 2 ? kT2Throw : 0;
 }
 
+// ------------------------------------------------------------------ t3: query_sample_from_sample (query.h:195-261)
+// Same answer shape as t2, but the cutting rules run on the sample's own coordinate: it starts from
+// the sample's `index` in the vertex get_prev_vertex_with_sample returns and grows by the length of
+// every vertex on the path, so along a backbone stretch it is monotone and the vertices where
+// recording starts / ends come from one rank each.
+
+// sample_info.index of sample s in the target vertex of walk entry c (s is a carrier of it)
+VSGPU_HD uint32_t sample_index_at(const DevIndex& ix, const T3Tables& t3, uint32_t c, uint32_t s) {
+	const uint64_t b = ldg(t3.sidx_begin + c);
+	if (ix.class_mode) {                                   // s_info[i] belongs to the i-th set bit of the class (variant_graph.h:1302-1315)
+		const uint64_t* row = ix.bitmap + (uint64_t)ldg(&ix.cent[c].z) * ix.words_per_set;
+		uint32_t r = 0;
+		for (uint32_t w = 0; w < (s >> 6); w++) r += (uint32_t)
+#if defined(__CUDA_ARCH__)
+			__popcll(ldg(row + w));
+#else
+			__builtin_popcountll(row[w]);
+#endif
+		const uint64_t last = ldg(row + (s >> 6)) & (((uint64_t)1 << (s & 63)) - 1);
+#if defined(__CUDA_ARCH__)
+		r += (uint32_t)__popcll(last);
+#else
+		r += (uint32_t)__builtin_popcountll(last);
+#endif
+		return ldg(t3.sidx + b + r);
+	}
+	for (uint64_t i = b, e = ldg(t3.sidx_begin + c + 1); i < e; i++) if (ldg(t3.sid + i) == s) return ldg(t3.sidx + i);
+	return 0;
+}
+
+struct PrevHit { uint32_t c; uint64_t ref_pos, sample_pos; };
+// get_prev_vertex_with_sample (query.h:57-113) with all three outputs
+VSGPU_HD PrevHit prev_with_sample(const DevIndex& ix, const T3Tables& t3, uint64_t pos, uint32_t s) {
+	const uint32_t rk = rank_le(ix, clamp_pos(pos));
+	const uint64_t cur = pos >= ix.index_bits ? ix.D - 1 : (rk ? rk - 1 : 0);
+	PrevHit h;
+	h.c = back_walk(ix, s, cur);
+	if (h.c == kNoneU32) { h.ref_pos = 1; h.sample_pos = t3.first_index; }
+	else { h.ref_pos = ldg(&ix.cent[h.c].w); h.sample_pos = sample_index_at(ix, t3, h.c, s); }
+	return h;
+}
+
+// first backbone index k >= k_a with sp + (start of P[k+1] - start of P[k_a]) >= v; M: none
+VSGPU_HD uint32_t t3_first_ge(const DevIndex& ix, const T2Tables& t2, uint32_t k_a, uint64_t sp, uint64_t v) {
+	const uint64_t base = ldg(t2.bbs + k_a);
+	if (v <= sp || v - sp + base <= (uint64_t)ldg(t2.bbs + k_a + 1)) return k_a;
+	const uint64_t V = v - sp + base;                      // first k with start of P[k+1] >= V
+	if (V > (uint64_t)ix.last_end) return ix.M;
+	const uint32_t e = rank_le(ix, (uint32_t)V - 1);       // number of distinct starts < V
+	if (e >= ix.D) return ix.M - 1;                        // only the end of the last vertex reaches V
+	const uint32_t j = ldg(&ix.dlev[e].x);                 // first backbone vertex starting at or after V
+	return j ? j - 1 : 0;
+}
+
+template <class Sink>
+VSGPU_HD int t3_stretch(const DevIndex& ix, const T2Tables& t2, T2State& st, uint32_t k_a, uint32_t k_b, uint64_t sp, Sink& sink) {
+	const uint32_t base = ldg(t2.bbs + k_a);
+	uint32_t k = k_a;
+	if (!st.rec) {
+		uint32_t j = t3_first_ge(ix, t2, k_a, sp, st.x);
+		if (j < k_a) j = k_a;
+		if (j > k_b) return 0;
+		const uint32_t b0 = ldg(t2.bbs + j), b1 = ldg(t2.bbs + j + 1);
+		const uint64_t spj = sp + (b0 - base);
+		const int r = t2_apply(st, b0 - 1, b1 - b0, spj, spj + (b1 - b0), sink);
+		if (r) return r;
+		k = j + 1;
+		if (k > k_b) return 0;
+	}
+	uint32_t j = t3_first_ge(ix, t2, k_a, sp, st.y);
+	if (j < k) j = k;
+	const uint32_t b0 = ldg(t2.bbs + k);
+	if (j > k_b) { sink.seg(b0 - 1, ldg(t2.bbs + k_b + 1) - b0); return 0; }
+	const uint32_t bj = ldg(t2.bbs + j), bj1 = ldg(t2.bbs + j + 1);
+	if (j > k) sink.seg(b0 - 1, bj - b0);
+	const uint64_t spj = sp + (bj - base);
+	return t2_apply(st, bj - 1, bj1 - bj, spj, spj + (bj1 - bj), sink);
+}
+
+// returns 0, kT2Throw (substr throws) or kT3Hang (the reference never leaves the loop at :209-214)
+template <class Sink>
+VSGPU_HD uint32_t t3_walk(const DevIndex& ix, const T2Tables& t2, const T3Tables& t3, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	PrevHit h = prev_with_sample(ix, t3, x64, s);
+	// :209-214: step back from the ref position of the vertex found while its sample position is >= x.
+	// The chain of positions is deterministic; Brent's test finds the cycle the reference would spin in.
+	uint64_t saved = ~(uint64_t)0;
+	for (uint32_t steps = 0, power = 1; h.sample_pos >= x64 && h.c != kNoneU32;) {
+		const uint64_t pos = h.ref_pos;
+		if (pos == saved) return kT3Hang;
+		if (++steps == power) { saved = pos; power <<= 1; steps = 0; }
+		h = prev_with_sample(ix, t3, pos, s);
+	}
+	T2State st{false, x64, y64, 0, 0};
+	const uint64_t m = x64 > y64 ? x64 : y64;
+	uint32_t cur_k, c;
+	uint64_t sp = h.sample_pos;
+	if (h.c != kNoneU32) {
+		const uint4 e = ldg(ix.cent + h.c);
+		if (e.y & kEntAlt) {
+			const uint2 sq = ldg(t2.cent_seq + h.c);
+			const uint32_t tk = e.y & kEntTgtMask;
+			const int r = t2_apply(st, sq.x, sq.y, sp, sp + sq.y, sink);
+			if (r) return r == 2 ? kT2Throw : 0;
+			if (tk == kEntTgtMask) return 0;
+			cur_k = tk; sp += sq.y;
+		} else cur_k = e.y & kEntTgtMask;
+		c = h.c + 1;
+	} else { cur_k = ldg(&ix.dlev[0].x); c = 0; }
+	for (;;) {
+		// without another entry taken, the backbone from here ends the walk at k_end
+		const uint32_t k_end = t3_first_ge(ix, t2, cur_k, sp, m);
+		const uint32_t limit = k_end < ix.M ? ldg(ix.cent_begin_k + k_end + 1) : ix.num_cent;
+		uint32_t ci;
+		uint4 e = make_uint4(0, 0, 0, 0);
+		for (;;) {                                             // next entry the sample takes that is not hidden behind cur_k
+			ci = next_carried(ix, s, c, limit);
+			if (ci == kNoneU32) break;
+			c = ci + 1;
+			e = ldg(ix.cent + ci);
+			if (e.x >= cur_k) break;
+		}
+		if (ci == kNoneU32) {
+			const uint32_t k_b = k_end < ix.M ? k_end : ix.M - 1;
+			const int r = t3_stretch(ix, t2, st, cur_k, k_b, sp, sink);
+			return r == 2 ? kT2Throw : 0;
+		}
+		int r = t3_stretch(ix, t2, st, cur_k, e.x, sp, sink);
+		if (r) return r == 2 ? kT2Throw : 0;
+		sp += ldg(t2.bbs + e.x + 1) - ldg(t2.bbs + cur_k);
+		if (e.y & kEntAlt) {
+			const uint2 sq = ldg(t2.cent_seq + ci);
+			const uint32_t tk = e.y & kEntTgtMask;
+			r = t2_apply(st, sq.x, sq.y, sp, sp + sq.y, sink);
+			if (r) return r == 2 ? kT2Throw : 0;
+			if (tk == kEntTgtMask) return 0;
+			cur_k = tk; sp += sq.y;
+		} else cur_k = e.y & kEntTgtMask;
+	}
+}
+
 // Pieces of one region's answer, merged while they are contiguous in seq_buffer: one copy record
 // {src, len, dst lo, dst hi} per maximal run.  Count: how many records / bytes.  Write: the records
 // themselves plus, for every kT2Tile-byte boundary of the output a record covers, its index in

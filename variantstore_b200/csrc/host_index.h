@@ -17,6 +17,7 @@ struct HostIndex {
 	uint32_t last_end = 0;                                  // start + length of the last backbone vertex
 	uint32_t t1_fallback_pos = 0;                           // see DevIndex::t1_fallback_pos
 	std::unordered_map<std::string, uint32_t> name2id;
+	std::string prefix;                                     // the ser/ directory (operators that need a second pass over it: t3)
 	bool from_cache = false;                                // read from VSGPU_INDEX_CACHE instead of decoding ser/
 };
 

@@ -645,7 +645,8 @@ __global__ void __launch_bounds__(256) k_widen(uint64_t n, const uint32_t* __res
 // ------------------------------------------------------------------ t2: query_sample_from_ref (query.h:120-189)
 // count: one thread per region walks the sample's path (logic::t2_walk) and counts copy records and
 // bytes; the CTA reduces them into cta_sums (k_seg_bases then scans those in place).
-__global__ void __launch_bounds__(256) k_t2_count(const DevIndex ix, const T2Tables t2, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
+template <bool kT3>
+__global__ void __launch_bounds__(256) k_t2_count(const DevIndex ix, const T2Tables t2, const T3Tables t3, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
                                                   const uint32_t* __restrict__ sample, uint2* __restrict__ cnt, uint2* __restrict__ keep, uint8_t* __restrict__ status,
                                                   uint64_t* __restrict__ cta_sums, uint32_t* gstatus) {
 	__shared__ SegCount s_warp[8];
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(256) k_t2_count(const DevIndex ix, const T2Tab
 		uint32_t st = 0;
 		T2CountSink sink{0, 0, 0, 0, keep + i, n};
 		if (s == 0 || s >= ix.num_samples) atomicOr(gstatus, kStatusBadRegion);
-		else { st = t2_walk(ix, t2, xs[i], ys[i], s, sink); sink.flush(); }
+		else { st = kT3 ? t3_walk(ix, t2, t3, xs[i], ys[i], s, sink) : t2_walk(ix, t2, xs[i], ys[i], s, sink); sink.flush(); }
 		if (st) { sink.nrec = 0; sink.bytes = 0; }
 		cnt[i] = make_uint2(sink.nrec, (uint32_t)sink.bytes);
 		status[i] = (uint8_t)st;
@@ -668,7 +669,8 @@ __global__ void __launch_bounds__(256) k_t2_count(const DevIndex ix, const T2Tab
 }
 // plan: byte offset of every region (exclusive scan of the counts) and its copy records, written at
 // their final index so the records of the batch are in region order.
-__global__ void __launch_bounds__(256) k_t2_plan(const DevIndex ix, const T2Tables t2, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
+template <bool kT3>
+__global__ void __launch_bounds__(256) k_t2_plan(const DevIndex ix, const T2Tables t2, const T3Tables t3, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
                                                  const uint32_t* __restrict__ sample, const uint2* __restrict__ cnt, const uint2* __restrict__ keep, const uint64_t* __restrict__ cta_sums,
                                                  uint64_t nctas, uint64_t* __restrict__ offsets, uint4* __restrict__ recs, uint32_t* __restrict__ tile_first) {
 	__shared__ SegCount s_warp[8];
@@ -685,7 +687,7 @@ __global__ void __launch_bounds__(256) k_t2_plan(const DevIndex ix, const T2Tabl
 			if (mine.rows <= kT2Keep) {                               // the pieces the count pass kept
 				for (uint32_t k = 0; k < (uint32_t)mine.rows; k++) { const uint2 p = __ldg(keep + k * n + i); sink.off = p.x; sink.len = p.y; sink.flush(); }
 			} else {
-				t2_walk(ix, t2, xs[i], ys[i], sample[i], sink);
+				if (kT3) t3_walk(ix, t2, t3, xs[i], ys[i], sample[i], sink); else t2_walk(ix, t2, xs[i], ys[i], sample[i], sink);
 				sink.flush();
 			}
 		}
@@ -873,18 +875,21 @@ cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const
 }
 uint64_t t2_ctas(uint64_t n) { return (n + 255) / 256; }
 cudaError_t launch_t2_count(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                            uint2* cnt, uint2* keep, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream) {
+                            uint2* cnt, uint2* keep, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream, const T3Tables* t3) {
 	if (n == 0) return cudaSuccess;
 	const uint64_t nctas = t2_ctas(n);
-	k_t2_count<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, n, x, y, sample, cnt, keep, status, cta_sums, gstatus);
+	if (t3) k_t2_count<true><<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, *t3, n, x, y, sample, cnt, keep, status, cta_sums, gstatus);
+	else k_t2_count<false><<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, T3Tables{}, n, x, y, sample, cnt, keep, status, cta_sums, gstatus);
 	k_seg_bases<<<1, 256, 0, stream>>>(nctas, cta_sums);
 	return cudaGetLastError();
 }
 cudaError_t launch_t2_plan(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                           const uint2* cnt, const uint2* keep, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, uint32_t* tile_first, cudaStream_t stream) {
+                           const uint2* cnt, const uint2* keep, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, uint32_t* tile_first, cudaStream_t stream,
+                           const T3Tables* t3) {
 	if (n == 0) return cudaSuccess;
 	const uint64_t nctas = t2_ctas(n);
-	k_t2_plan<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, n, x, y, sample, cnt, keep, cta_sums, nctas, offsets, recs, tile_first);
+	if (t3) k_t2_plan<true><<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, *t3, n, x, y, sample, cnt, keep, cta_sums, nctas, offsets, recs, tile_first);
+	else k_t2_plan<false><<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, T3Tables{}, n, x, y, sample, cnt, keep, cta_sums, nctas, offsets, recs, tile_first);
 	return cudaGetLastError();
 }
 cudaError_t launch_t2_copy(const T2Tables& t2, const uint4* recs, const uint32_t* tile_first, const uint64_t* totals, uint64_t recs_hint, uint64_t bytes_hint, char* text, cudaStream_t stream) {

@@ -62,6 +62,15 @@ struct T2Tables {
 	const uint2* cent_seq;        // per walk entry: {seq offset, length} of its alt target
 	const char* seq_ascii;        // seq_buffer.sdsl as ASCII (A C T G N, util.cc:32-41); 64 readable bytes before and after
 };
+// Extra tables of t3 = query_sample_from_sample (include/query.h:195-261): sample_info.index of every carrier of
+// every walk entry's target vertex, in s_info order (uploaded on first use; read back from ser/ by a second pass).
+struct T3Tables {
+	const uint64_t* sidx_begin;   // num_cent + 1
+	const uint32_t* sidx;         // sample_info.index per carrier
+	const uint32_t* sid;          // explicit-id mode: sample id per carrier (nullptr in class mode)
+	uint32_t first_index;         // REF's index in node_list[0] (where a walk from the contig start begins)
+};
+constexpr uint32_t kT3Hang = 2;           // per-region status: the loop of query.h:209-214 never ends (the reference hangs)
 constexpr uint32_t kT2Tile = 512;         // bytes of output one warp of the copy kernel writes per step (16 per lane)
 constexpr uint32_t kT2Keep = 16;          // copy records per region the count pass keeps for the plan pass (more: the plan pass walks again)
 constexpr uint32_t kT2Throw = 1;          // per-region status: the reference call ends in std::out_of_range (substr, query.h:163,167)
@@ -76,9 +85,10 @@ constexpr uint32_t kT2Throw = 1;          // per-region status: the reference ca
 //           record starts are built by one thread per record (k_t2_seams)
 uint64_t t2_ctas(uint64_t n);
 cudaError_t launch_t2_count(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                            uint2* cnt, uint2* keep, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream);
+                            uint2* cnt, uint2* keep, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream, const T3Tables* t3 = nullptr);
 cudaError_t launch_t2_plan(const DevIndex& ix, const T2Tables& t2, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                           const uint2* cnt, const uint2* keep, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, uint32_t* tile_first, cudaStream_t stream);
+                           const uint2* cnt, const uint2* keep, const uint64_t* cta_sums, uint64_t* offsets, uint4* recs, uint32_t* tile_first, cudaStream_t stream,
+                           const T3Tables* t3 = nullptr);   // t3 != nullptr: the same launches walk in the sample's own coordinates (t3)
 // `totals` = {records, bytes} on the device (entry nctas of the scanned CTA sums); text must have room for bytes rounded up to kT2Tile
 cudaError_t launch_t2_copy(const T2Tables& t2, const uint4* recs, const uint32_t* tile_first, const uint64_t* totals, uint64_t recs_hint, uint64_t bytes_hint, char* text, cudaStream_t stream);
 

@@ -26,6 +26,7 @@ void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& 
 }
 
 void build_host_index(const std::string& prefix, HostIndex& h, int* stage) {
+	h.prefix = prefix;
 	if (stage) *stage = 0;
 	PhaseClock pc;
 	h.from_cache = load_index_cache(prefix, h);          // VSGPU_INDEX_CACHE (index_cache.cc); false when unset, stale or unreadable

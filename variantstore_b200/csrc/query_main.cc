@@ -1,6 +1,6 @@
 // vsgpu_query — front-end with the reference's `variantstore query` flags
 // (src/variantstore.cc:101-134, src/commands.cc:113-215):
-//   -p <ser prefix> -t <2|4|6|7> -r <beg[:end][,...]> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]
+//   -p <ser prefix> -t <2|3|4|6|7> -r <beg[:end][,...]> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]
 // -m is accepted and ignored (both modes give identical results; only the reference's paging differs).
 // Unlike query_main's per-region loop the whole region list goes to the GPU as one batch; the lines
 // printed per region are the reference's.
@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
 	int a0 = (argc > 1 && !strcmp(argv[1], "query")) ? 2 : 1;
 	argc -= a0 - 1; argv += a0 - 1;
 	const char* prefix = opt(argc, argv, "-p", nullptr); const char* tstr = opt(argc, argv, "-t", nullptr); const char* rstr = opt(argc, argv, "-r", nullptr);
-	if (!prefix || !tstr || !rstr) { fprintf(stderr, "usage: vsgpu_query [query] -p <prefix> -t <2|4|6|7> -r <regions> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]\n"); return 1; }
+	if (!prefix || !tstr || !rstr) { fprintf(stderr, "usage: vsgpu_query [query] -p <prefix> -t <2|3|4|6|7> -r <regions> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]\n"); return 1; }
 	const int type = atoi(tstr);
 	const std::string outfile = opt(argc, argv, "-o", ""), sample = opt(argc, argv, "-s", "");
 	const bool verbose = flag(argc, argv, "-v");
@@ -93,18 +93,19 @@ int main(int argc, char** argv) {
 			}
 			vsgpu_result_free(res);
 		}
-	} else if (type == 2) {
-		// query_sample_from_ref prints nothing; with -v every call rewrites -o with "<sequence>\n"
+	} else if (type == 2 || type == 3) {
+		// query_sample_from_ref / query_sample_from_sample print nothing; with -v every call rewrites -o with "<sequence>\n"
 		// (query.h:180-186), so the file ends up holding the last region's.  Where the reference's substr
 		// throws std::out_of_range its process terminates there: same message, same kind of exit.
 		uint32_t sid = 0;
 		if (vsgpu_sample_id(idx, sample.c_str(), &sid) != 0) { fprintf(stderr, "%s\n", vsgpu_last_error()); return 2; }
 		std::vector<uint32_t> s(n, sid);
 		vsgpu_text* text = nullptr;
-		rc = vsgpu_query_t2(idx, n, x.data(), y.data(), s.data(), &text);
+		rc = type == 2 ? vsgpu_query_t2(idx, n, x.data(), y.data(), s.data(), &text) : vsgpu_query_t3(idx, n, x.data(), y.data(), s.data(), &text);
 		if (rc == 0) {
 			const uint64_t* off = vsgpu_text_offsets(text); const char* bytes = vsgpu_text_bytes(text); const uint8_t* st = vsgpu_text_status(text);
 			for (uint64_t i = 0; i < n; i++) {
+				if (st[i] == 2) { fprintf(stderr, "region %lu:%lu: the reference never returns from query_sample_from_sample (query.h:209-214)\n", (unsigned long)x[i], (unsigned long)y[i]); vsgpu_text_free(text); vsgpu_close(idx); return 3; }
 				if (st[i]) { fprintf(stderr, "terminate called after throwing an instance of 'std::out_of_range'\n  what():  basic_string::substr: __pos > this->size()\n"); vsgpu_text_free(text); vsgpu_close(idx); return 134; }
 				if (verbose) { std::string t(bytes + off[i], bytes + off[i + 1]); t += "\n"; write_rows(outfile, t.c_str(), false); }
 			}

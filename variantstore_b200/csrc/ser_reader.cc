@@ -181,6 +181,7 @@ struct BlockSoA {
 	std::vector<uint32_t> id, offset, length, cls, first_index, ref0_index; std::vector<uint8_t> has_cls;
 	std::vector<uint64_t> sbegin; std::vector<uint32_t> ssid; std::vector<uint8_t> sflags;
 	bool any_sid = false, any_cls = false;
+	bool keep_index = false; std::vector<uint32_t> sindex;    // sample_info.index of every s_info (only when asked for)
 };
 
 void parse_sinfo(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::string& name, uint32_t& first_index, uint32_t& ref0_index, bool& seen_first, bool& seen_ref0) {
@@ -207,6 +208,7 @@ void parse_sinfo(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::str
 		b.ssid.push_back(sid);
 	}
 	b.sflags.push_back(flags);
+	if (b.keep_index) b.sindex.push_back(index);
 }
 
 void parse_vertex(const uint8_t* p, const uint8_t* e, BlockSoA& b, const std::string& name) {
@@ -505,6 +507,30 @@ void load_ser(const std::string& prefix, SerData& d) {
 		for (uint32_t n : d.adj) if (n != UINT32_MAX && n >= nv) fail("neighbour id beyond the vertex table");
 	}
 	pc.lap("adjacency rows");
+}
+
+// sample_info.index of every s_info, in the order of SerData::v_sinfo_begin: a second pass over the
+// vertex blocks, made only by the operators that work in a sample's own coordinates (t3); vsgpu_open
+// keeps just the first index of every vertex.
+void load_sample_indexes(const std::string& prefix, uint64_t expect, std::vector<uint32_t>& out) {
+	std::vector<std::string> files;
+	for (uint64_t b = 0;; b++) { std::string nm = prefix + "/vertex_list_" + std::to_string(b) + ".proto"; struct stat st; if (stat(nm.c_str(), &st) != 0) break; files.push_back(nm); }
+	std::vector<BlockSoA> blocks(files.size());
+	for (auto& b : blocks) b.keep_index = true;
+	std::atomic<size_t> next{0}; std::string err; std::atomic<bool> bad{false};
+	unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), (unsigned)std::max<size_t>(files.size(), 1));
+	std::vector<std::thread> th;
+	for (unsigned t = 0; t < nt; t++) th.emplace_back([&]() {
+		for (size_t i; (i = next++) < files.size();) { try { load_block(files[i], blocks[i]); } catch (const std::exception& e) { if (!bad.exchange(true)) err = e.what(); } }
+	});
+	for (auto& t : th) t.join();
+	if (bad) throw std::runtime_error(err);
+	uint64_t total = 0;
+	for (auto& b : blocks) total += b.sindex.size();
+	if (total != expect) fail("vertex blocks changed since the index was opened (" + std::to_string(total) + " sample entries, expected " + std::to_string(expect) + ")");
+	out.resize(total);
+	uint64_t at = 0;
+	for (auto& b : blocks) { if (!b.sindex.empty()) memcpy(&out[at], b.sindex.data(), b.sindex.size() * 4); at += b.sindex.size(); b = BlockSoA(); }
 }
 
 }  // namespace vsgpu

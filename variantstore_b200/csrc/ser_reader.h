@@ -51,6 +51,10 @@ struct SerData {
 // Throws std::runtime_error with a message naming the file that failed.
 void load_ser(const std::string& prefix, SerData& out);
 
+// sample_info.index of every s_info in SerData order (second pass over vertex_list_<k>.proto); `expect`
+// = v_sinfo_begin.back()
+void load_sample_indexes(const std::string& prefix, uint64_t expect, std::vector<uint32_t>& out);
+
 // VSGPU_TRACE=1: wall-clock seconds of the phases of vsgpu_open on stderr
 struct PhaseClock {
 	bool on; double t0;

@@ -105,6 +105,8 @@ struct vsgpu_index : vsgpu::HostIndex {
 	bool t2_ready = false;
 	T2Tables t2{};
 	DevBuf bcnt, bst8, brecs, btile, bkeep;
+	bool t3_ready = false;
+	T3Tables t3{};
 	cudaEvent_t ev_t2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_render[2] = {nullptr, nullptr};
 	// page-locked host buffers: a free list for results + two staging areas for t6
@@ -905,7 +907,36 @@ void ensure_t2_tables(vsgpu_index* ix) {
 }
 }  // namespace
 
-int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out) {
+namespace {
+// t3 on top of the t2 tables: sample_info.index of every carrier of every walk entry's target vertex.
+// vsgpu_open keeps only the first index of a vertex, so the vertex blocks are decoded a second time.
+void ensure_t3_tables(vsgpu_index* ix) {
+	ensure_t2_tables(ix);
+	if (ix->t3_ready) return;
+	const FlatIndex& f = ix->flat; const SerData& sd = ix->ser;
+	std::vector<uint32_t> sindex;
+	try { load_sample_indexes(ix->prefix, sd.v_sinfo_begin.back(), sindex); }
+	catch (const std::exception& e) { throw std::invalid_argument(std::string("vsgpu_query_t3: ") + e.what()); }
+	const size_t E = f.cent.size();
+	std::vector<uint64_t> begin(E + 1, 0);
+	for (size_t c = 0; c < E; c++) { const uint32_t v = f.cent_vertex[c]; begin[c + 1] = begin[c] + (v == kNone ? 0 : sd.v_sinfo_begin[v + 1] - sd.v_sinfo_begin[v]); }
+	std::vector<uint32_t> sidx(begin[E]), sid(f.class_mode ? 0 : begin[E]);
+	parallel_for(E, [&](uint64_t a, uint64_t b) {
+		for (uint64_t c = a; c < b; c++) {
+			const uint32_t v = f.cent_vertex[c];
+			if (v == kNone) continue;
+			const uint64_t s0 = sd.v_sinfo_begin[v], cnt = sd.v_sinfo_begin[v + 1] - s0;
+			memcpy(sidx.data() + begin[c], sindex.data() + s0, cnt * 4);
+			if (!f.class_mode) memcpy(sid.data() + begin[c], sd.s_sample_id.data() + s0, cnt * 4);
+		}
+	});
+	ix->t3.sidx_begin = upload(ix, begin); ix->t3.sidx = upload(ix, sidx);
+	ix->t3.sid = f.class_mode ? nullptr : upload(ix, sid);
+	ix->t3.first_index = f.vstart[f.dlev[0].k];
+	ix->t3_ready = true;
+}
+
+int query_seq_impl(vsgpu_index* ix, bool t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out) {
 	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t2: null argument");
 	*out = nullptr;
 	if (int rc = check_device(ix)) return rc;
@@ -913,7 +944,8 @@ int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	std::unique_ptr<vsgpu_text, void (*)(vsgpu_text*)> t(new vsgpu_text, vsgpu_text_free);
 	t->owner = ix; t->n = n;
 	try {
-		ensure_t2_tables(ix);
+		if (t3) ensure_t3_tables(ix); else ensure_t2_tables(ix);
+		const T3Tables* t3p = t3 ? &ix->t3 : nullptr;
 		cudaStream_t st = ix->s_k;
 		t->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &t->offsets_cap);
 		t->status = (uint8_t*)ix->pinned_acquire(n + 1, &t->status_cap);
@@ -928,7 +960,7 @@ int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
 			CU(cudaEventRecord(ix->ev_t2[0], st));
 			CU(launch_t2_count(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bkeep.as<uint2>(), ix->bst8.as<uint8_t>(),
-			                   ix->bscratch.as<uint64_t>(), ix->d_status, st));
+			                   ix->bscratch.as<uint64_t>(), ix->d_status, st, t3p));
 			CU(cudaEventRecord(ix->ev_t2[1], st));
 			CU(cudaMemcpyAsync(ix->pin_small, ix->bscratch.as<uint64_t>() + 2 * nctas, 16, cudaMemcpyDeviceToHost, st));
 			const uint32_t status = read_status(ix, ix->d_status, nullptr, st);
@@ -946,7 +978,7 @@ int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			CU(ix->btile.ensure((totals[1] / kT2Tile + 2) * 4));
 			CU(cudaEventRecord(ix->ev_t2[2], st));
 			CU(launch_t2_plan(ix->dev, ix->t2, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint2>(), ix->bkeep.as<uint2>(), ix->bscratch.as<uint64_t>(),
-			                  ix->bbyte_off.as<uint64_t>(), ix->brecs.as<uint4>(), ix->btile.as<uint32_t>(), st));
+			                  ix->bbyte_off.as<uint64_t>(), ix->brecs.as<uint4>(), ix->btile.as<uint32_t>(), st, t3p));
 			CU(cudaEventRecord(ix->ev_t2[3], st));
 			CU(launch_t2_copy(ix->t2, ix->brecs.as<uint4>(), ix->btile.as<uint32_t>(), ix->bscratch.as<uint64_t>() + 2 * nctas, totals[0], totals[1], ix->btext.as<char>(), st));
 			CU(cudaEventRecord(ix->ev_t2[4], st));
@@ -965,6 +997,9 @@ int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
+}  // namespace
+int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out) { return query_seq_impl(ix, false, n, x, y, sample_ids, out); }
+int vsgpu_query_t3(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out) { return query_seq_impl(ix, true, n, x, y, sample_ids, out); }
 
 // ------------------------------------------------------------------ device-resident batches
 int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids,
