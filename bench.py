@@ -44,7 +44,8 @@ def ensure_index(args, rank):
     """Synthetic ser/ for this rank's contig shard, built once per box with the oracle's construct
     restatement (construction is out of scope for the engine and the reference binary cannot be
     built here) and cached under --cache-dir for the other arm / later runs."""
-    key = hashlib.sha1(f"v3|{args.records}|{args.samples}|{args.fmax}|{rank}".encode()).hexdigest()[:12]
+    fix_idx = bool(getattr(args, "fix_idx", False))     # run fix_sample_indexes (variant_graph.h:1883-1997) as the reference's construct does; only t3 reads those fields
+    key = hashlib.sha1((f"v3|{args.records}|{args.samples}|{args.fmax}|{rank}" + ("|fixed" if fix_idx else "")).encode()).hexdigest()[:12]
     prefix = os.path.join(args.cache_dir, f"shard_{key}", "ser")
     done = os.path.join(prefix, ".done")
     if not os.path.exists(done):
@@ -56,7 +57,7 @@ def ensure_index(args, rank):
         pos_lo = int(POS_LO * min(1.0, scale)) if scale < 1 else POS_LO
         o = T.Oracle.synth(prefix, chr_name=str(22 - rank if rank < 22 else rank), ref_length=ref_len, pos_lo=max(2, pos_lo),
                            pos_hi=ref_len - 60_000 if ref_len > 200_000 else ref_len - 1000, n_records=args.records,
-                           n_samples=args.samples, fmax=args.fmax, seed=2022 + rank, cqf_log2=25, fix_idx=False, gzip_level=1)
+                           n_samples=args.samples, fmax=args.fmax, seed=2022 + rank, cqf_log2=25, fix_idx=fix_idx, gzip_level=1)
         info = getattr(o, 'construct_info', None) or o.info()
         o.close()
         with open(done, "w") as f:

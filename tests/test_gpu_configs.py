@@ -145,8 +145,10 @@ def test_full_size_chr22_shape_cuda(tmp_path):
         sob, stb_, ssb, _ = e.batch_sample_seq_in_ref(x[h:], y[h:], s[h:])
         assert sta_ + stb_ == stext and np.array_equal(np.concatenate([soa[:-1], sob + soa[-1]]), soff)
         del stext, sta_, stb_
-        # t3 (sample coordinates; the per-carrier indexes come from a second pass over ser/): oracle subsample
-        bad3, _ = T.compare_t3(o, e, x[sub[:1500]], y[sub[:1500]], s[sub[:1500]])
+        # t3 (sample coordinates; the per-carrier indexes come from a second pass over ser/).  This synthetic index
+        # is built without fix_sample_indexes, so a t3 walk starts from an unfixed sample position far from x and
+        # the oracle needs about half a second per region: a handful of regions only
+        bad3, _ = T.compare_t3(o, e, x[sub[:16]], y[sub[:16]], s[sub[:16]])
         assert not bad3
         # t6 slice algebra on sorted equal-width regions: bounds are monotone, counts add up over a split at any y
         ok = lo != NONE

@@ -137,7 +137,7 @@ def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
         # a t4 answer never has more rows than twice the t6 slice (+ the start / rejoin rows)
         bad2, _ = T.compare_t2(o, e, x[sub], y[sub], s[sub])       # up to 100 kb per region
         assert not bad2
-        bad3, _ = T.compare_t3(o, e, x[sub], y[sub], s[sub])
+        bad3, _ = T.compare_t3(o, e, x[sub[:200]], y[sub[:200]], s[sub[:200]])
         assert not bad3
         same_w = (y - x == 1000) & (lo != NONE)
         assert np.all(np.diff(lo[same_w].astype(np.int64)) >= 0)

@@ -30,8 +30,9 @@ def main():
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--t3", action="store_true", help="query_sample_from_sample (sample coordinates) instead of query_sample_from_ref")
     a = ap.parse_args()
+    # t3 reads the per-carrier sample positions: the index is then built with fix_sample_indexes, as the reference's construct does
     args = argparse.Namespace(records=1_103_547, samples=2504, fmax=1100, cache_dir=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"),
-                              regions=1_000_000, width=1000)
+                              regions=1_000_000, width=1000, fix_idx=a.t3)
     torch.cuda.set_device(0)
     prefix, meta = bench.ensure_index(args, 0)
     idx = VariantStoreIndex(prefix, device=0)
