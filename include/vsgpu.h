@@ -165,6 +165,17 @@ int vsgpu_query_t2(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64
  * the sample's variants).  The first call reads the vertex blocks of ser/ a second time (vsgpu_open
  * does not keep the per-carrier indexes) and uploads them: 4 bytes per genotype entry. */
 int vsgpu_query_t3(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out);
+/* ---- t5: get_sample_var_in_sample(vg, idx, pos_x, pos_y, sample) — include/query.h:490-612 -----------------
+ * The sample's variants over [x[i], y[i]) of its own coordinates.  Result = the CSR of t4 (same hit
+ * codes, in the reference's push order) plus vsgpu_result_status()[i] = 2 where the reference never
+ * returns (the loop at :505-510 is the one of t3).  Rows: vsgpu_rows_t5 / vsgpu_digest_t5 — the t4 row of
+ * the same code with var_pos = ref_pos for an insertion and the sample's own position in the vertex
+ * otherwise (:556-579).  Like t3, the first call reads the vertex blocks of ser/ a second time. */
+int vsgpu_query_t5(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out);
+const uint8_t* vsgpu_result_status(const vsgpu_result* r);      /* n bytes (t5 results; NULL for t4) */
+float vsgpu_result_kernel_ms(const vsgpu_result* r);            /* t5: device time of the count and write launches (CUDA events) */
+int vsgpu_rows_t5(const vsgpu_index* idx, const uint32_t* hits, uint64_t nhits, uint32_t sample_id, int with_samples, char** text);
+int vsgpu_digest_t5(const vsgpu_index* idx, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* sample_ids, int with_samples, uint64_t* digests);
 const uint8_t* vsgpu_text_status(const vsgpu_text* t);      /* n bytes (t2 results; NULL for rendered t6 rows) */
 const float* vsgpu_text_stage_ms(const vsgpu_text* t);      /* t2: device time of the count, plan and copy launches (CUDA events); their sum = vsgpu_text_kernel_ms */
 

@@ -272,6 +272,10 @@ std::vector<Variant> get_sample_var_in_ref(const VariantGraph* vg, const Index* 
                                            const std::string& sample_id, bool print = false,
                                            const std::string& outfile = "", QueryLog* log = nullptr,
                                            bool* ub = nullptr);                      // :618-729
+std::vector<Variant> get_sample_var_in_sample(const VariantGraph* vg, const Index* idx, uint64_t x, uint64_t y,
+                                              const std::string& sample_id, bool print = false,
+                                              const std::string& outfile = "", QueryLog* log = nullptr,
+                                              bool* ub = nullptr, bool* hang = nullptr);   // :490-612
 std::vector<Variant> get_var_in_ref(const VariantGraph* vg, const Index* idx, uint64_t x, uint64_t y,
                                     bool print = false, const std::string& outfile = "",
                                     QueryLog* log = nullptr);                        // :736-784

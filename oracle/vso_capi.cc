@@ -167,6 +167,36 @@ int vso_batch_t4(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, con
 		return 0;
 	} catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+// get_sample_var_in_sample (query.h:490-612): status 2 = the reference never returns (no rows then)
+int vso_batch_t5(void* hp, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids,
+                 uint64_t* counts, uint64_t* digests, uint8_t* status, uint8_t* ub, int with_samples) {
+	Handle* h = (Handle*)hp;
+	try {
+		QueryLog log;
+		for (uint64_t i = 0; i < n; i++) {
+			log.out.clear();
+			bool u = false, hang = false;
+			std::string name = h->vg->get_sample_name(sample_ids[i]);
+			auto vars = get_sample_var_in_sample(h->vg.get(), h->idx.get(), x[i], y[i], name, false, "", &log, &u, &hang);
+			counts[i] = vars.size();
+			if (digests) digests[i] = rows_digest(vars, with_samples != 0);
+			if (status) status[i] = hang ? 2 : 0;
+			if (ub) ub[i] = u;
+		}
+		return 0;
+	} catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+char* vso_query_t5_text(void* hp, uint64_t x, uint64_t y, const char* sample) {
+	Handle* h = (Handle*)hp;
+	try {
+		QueryLog log; bool hang = false;
+		auto vars = get_sample_var_in_sample(h->vg.get(), h->idx.get(), x, y, sample, false, "", &log, nullptr, &hang);
+		if (hang) return dup_str("HANG\n");
+		std::string t = log.out + "Pos\tRef\tAlt\tSamples\n";
+		for (auto& v : vars) row_text(v, true, t);
+		return dup_str(t);
+	} catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
 // refs/alts: n NUL-terminated strings each.  found[i] = 1 when a record matched; counts = carriers.
 int vso_batch_t7(void* hp, uint64_t n, const uint64_t* pos, const char* const* refs, const char* const* alts,
                  uint8_t* found, uint64_t* counts, uint64_t* digests) {

@@ -45,6 +45,7 @@ int main(int argc, char** argv) {
 			for (size_t i = 0; i < regions.size(); i++) {
 				if (type == 2) query_sample_from_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);
 				else if (type == 3) { bool hang = false; query_sample_from_sample(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile, nullptr, &hang); if (hang) { fprintf(stderr, "does not terminate\n"); return 3; } }
+				else if (type == 5) { bool hang = false; get_sample_var_in_sample(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile, nullptr, nullptr, &hang); if (hang) { fprintf(stderr, "does not terminate\n"); return 3; } }
 				else if (type == 4) get_sample_var_in_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);
 				else if (type == 6) get_var_in_ref(&vg, &idx, regions[i].first, regions[i].second, verbose, outfile);
 				else if (type == 7) {

@@ -256,6 +256,76 @@ bool closest_var(const VariantGraph* vg, const Index* idx, const uint64_t pos, s
 	return true;
 }
 
+// All variants of a sample over [pos_x, pos_y) of the sample's own coordinates (query.h:490-612).  Same
+// start as query_sample_from_sample, incl. the loop that may never end (*hang).
+std::vector<Variant> get_sample_var_in_sample(const VariantGraph* vg, const Index* idx, const uint64_t pos_x, const uint64_t pos_y,
+                                              const std::string& sample_id, bool print, const std::string& outfile, QueryLog* log,
+                                              bool* ub, bool* hang) {
+	std::vector<Variant> vars;
+	uint64_t ref_pos = 0, sample_pos = 0;
+	Graph::vertex closest_v = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, ref_pos, sample_pos, ub);
+	std::vector<uint64_t> seen;
+	while (sample_pos >= pos_x && closest_v > 0) {
+		uint64_t pos = ref_pos;
+		if (std::find(seen.begin(), seen.end(), pos) != seen.end()) { if (hang) *hang = true; return vars; }
+		seen.push_back(pos);
+		closest_v = get_prev_vertex_with_sample(vg, idx, pos, sample_id, ref_pos, sample_pos, ub);
+	}
+	closest_v = idx->find(ref_pos);                     // start from the ref node at ref_pos (:513)
+	SampleInfo sample;
+	uint64_t seq_len = 0;
+	if (vg->get_sample_from_vertex_if_exists(closest_v, REF, sample)) { seq_len = ref_pos - sample.index; ref_pos = sample.index; }
+	else err(log, "reference node is expected to be found!");
+	sample_pos = sample_pos - seq_len;
+	VariantGraph::PathIterator it = vg->find(closest_v, sample_id);
+	std::string cur_ref;
+	while (!it.done()) {
+		if (sample_pos >= pos_y) break;
+		Graph::vertex cur_v = (*it)->vertex_id;
+		Variant var;
+		uint64_t l = (*it)->length;
+		uint64_t next_ref_pos = ref_pos + l;
+		uint64_t next_sample_pos = sample_pos + l;
+		std::string next_ref;
+		VariantGraph::BfsIterator bfs_it = vg->find((*it)->vertex_id, 1);
+		++bfs_it;
+		while (!bfs_it.done()) {          // last ref-carrying neighbour wins (:541-549)
+			Graph::vertex v = (*bfs_it)->vertex_id;
+			if (vg->get_sample_from_vertex_if_exists(v, REF, sample)) { next_ref_pos = sample.index; next_ref = vg->get_sequence(*(*bfs_it)); }
+			++bfs_it;
+		}
+		if (sample_pos > pos_x && vg->get_sample_from_vertex_if_exists(cur_v, sample_id, sample)) {
+			std::string alt;
+			if (ref_pos == next_ref_pos) {                                   // insertion :556-562
+				cur_ref = "";
+				alt = vg->get_sequence(*(*it));
+				var.var_pos = ref_pos; var.var_pos_set = true;
+			} else if (vg->get_sample_from_vertex_if_exists(cur_v, REF, sample)) {   // deletion :564-573
+				alt = "";
+				vg->get_sample_from_vertex_if_exists(cur_v, sample_id, sample);
+				var.var_pos = sample.index; var.var_pos_set = true;
+				Graph::vertex v = idx->find(ref_pos - 1);
+				cur_ref = vg->get_sequence(vg->get_vertex(v));
+			} else {                                                         // substitution :574-579
+				alt = vg->get_sequence(*(*it));
+				vg->get_sample_from_vertex_if_exists(cur_v, sample_id, sample);
+				var.var_pos = sample.index; var.var_pos_set = true;
+			}
+			var.alt = alt;
+			var.ref = cur_ref;
+			get_samples((*it), vg, var.samples);
+			vars.push_back(var);
+		}
+		cur_ref = next_ref;
+		ref_pos = next_ref_pos;
+		sample_pos = next_sample_pos;
+		++it;
+	}
+	say(log, "Number of variants get_sample_var_in_sample: " + std::to_string(vars.size()) + "\n");
+	if (print) dump_vars(vars, outfile);
+	return vars;
+}
+
 std::vector<Variant> get_sample_var_in_ref(const VariantGraph* vg, const Index* idx, const uint64_t pos_x,
                                            const uint64_t pos_y, const std::string& sample_id, bool print,
                                            const std::string& outfile, QueryLog* log, bool* ub) {   // :618-729

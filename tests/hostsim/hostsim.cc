@@ -17,7 +17,7 @@
 
 using namespace vsgpu;
 
-struct vsgpu_result { std::vector<uint64_t> offsets; std::vector<uint32_t> hits; };
+struct vsgpu_result { std::vector<uint64_t> offsets; std::vector<uint32_t> hits; std::vector<uint8_t> status; };
 struct vsgpu_text { std::string bytes; std::vector<uint64_t> offsets; std::vector<uint8_t> status; };
 struct vsgpu_index : HostIndex {
 	DevIndex dev;
@@ -88,10 +88,10 @@ void vsgpu_close(vsgpu_index* ix) { delete ix; }
 // t2 through the same two passes as the kernels: count, then copy records, then the copy itself
 static int query_seq(vsgpu_index* ix, bool t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out);
 int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) { return query_seq(ix, false, n, x, y, s, out); }
-int vsgpu_query_t3(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) {
+static int ensure_t3(vsgpu_index* ix) {
 	if (ix->sidx_begin.empty()) {     // same construction as ensure_t3_tables of libvsgpu
 		const FlatIndex& f = ix->flat; const SerData& sd = ix->ser;
-		std::vector<uint32_t> sindex;
+		std::vector<uint32_t>& sindex = ix->sindex;
 		try { load_sample_indexes(ix->prefix, sd.v_sinfo_begin.back(), sindex); } catch (const std::exception& e) { return set_err(VSGPU_ESHAPE, e.what()); }
 		const size_t E = f.cent.size();
 		ix->sidx_begin.assign(E + 1, 0);
@@ -107,8 +107,37 @@ int vsgpu_query_t3(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		ix->t3.sidx_begin = ix->sidx_begin.data(); ix->t3.sidx = ix->sidx.data(); ix->t3.sid = f.class_mode ? nullptr : ix->sid.data();
 		ix->t3.first_index = f.vstart[f.dlev[0].k];
 	}
+	return VSGPU_OK;
+}
+int vsgpu_query_t3(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) {
+	if (int rc = ensure_t3(ix)) return rc;
 	return query_seq(ix, true, n, x, y, s, out);
 }
+int vsgpu_query_t5(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_result** out) {
+	if (!ix->flat.t2_ok) return set_err(VSGPU_ESHAPE, "vsgpu_query_t5: " + ix->flat.t2_why);
+	if (int rc = ensure_t3(ix)) return rc;
+	std::unique_ptr<vsgpu_result> r(new vsgpu_result);
+	r->offsets.assign(n + 1, 0); r->status.assign(n + 1, 0);
+	VecSink sink{&r->hits};
+	for (uint64_t i = 0; i < n; i++) {
+		if (s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "vsgpu_query_t5: sample id out of range");
+		const size_t before = r->hits.size();
+		const uint32_t st = logic::t5_walk(ix->dev, ix->t2, ix->t3, x[i], y[i], s[i], sink);
+		if (st) r->hits.resize(before);
+		r->status[i] = (uint8_t)st;
+		r->offsets[i + 1] = r->hits.size();
+	}
+	*out = r.release();
+	return VSGPU_OK;
+}
+const uint8_t* vsgpu_result_status(const vsgpu_result* r) { return r->status.empty() ? nullptr : r->status.data(); }
+float vsgpu_result_kernel_ms(const vsgpu_result*) { return 0.f; }
+int vsgpu_rows_t5(const vsgpu_index* ix, const uint32_t* hits, uint64_t nhits, uint32_t sample, int ws, char** text) {
+	std::string s;
+	for (uint64_t i = 0; i < nhits; i++) t5_row(ix, hits[i], sample, ws != 0, s);
+	*text = dup_text(s); return VSGPU_OK;
+}
+int vsgpu_digest_t5(const vsgpu_index* ix, uint64_t n, const uint64_t* off, const uint32_t* hits, const uint32_t* samples, int ws, uint64_t* d) { digests_t5(ix, n, off, hits, samples, ws != 0, d); return VSGPU_OK; }
 static int query_seq(vsgpu_index* ix, bool t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, vsgpu_text** out) {
 	if (!ix->flat.t2_ok) return set_err(VSGPU_ESHAPE, "vsgpu_query_t2: " + ix->flat.t2_why);
 	std::unique_ptr<vsgpu_text> t(new vsgpu_text);

@@ -150,6 +150,8 @@ def test_full_size_chr22_shape_cuda(tmp_path):
         # the oracle needs about half a second per region: a handful of regions only
         bad3, _ = T.compare_t3(o, e, x[sub[:16]], y[sub[:16]], s[sub[:16]])
         assert not bad3
+        bad5, _ = T.compare_t5(o, e, x[sub[:16]], y[sub[:16]], s[sub[:16]])
+        assert not bad5
         # t6 slice algebra on sorted equal-width regions: bounds are monotone, counts add up over a split at any y
         ok = lo != NONE
         assert np.all(np.diff(lo[ok].astype(np.int64)) >= 0) and np.all(np.diff(hi[ok].astype(np.int64)) >= 0)

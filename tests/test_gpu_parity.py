@@ -73,6 +73,8 @@ def test_fuzz_parity_cuda(tmp_path, seed, overlap, sparse, walk_path):
         assert not bad2 and threw >= 1
         bad3, odd3 = T.compare_t3(o, e, x, y, s)                 # sample coordinates: incl. the regions the reference hangs on
         assert not bad3 and (sparse or odd3 >= 1)
+        bad5, _ = T.compare_t5(o, e, x, y, s)
+        assert not bad5
 
 
 def test_golden_fixture_cuda():
@@ -139,6 +141,8 @@ def test_synthetic_1000g_shape_cuda(tmp_path, walk_path):
         assert not bad2
         bad3, _ = T.compare_t3(o, e, x[sub[:200]], y[sub[:200]], s[sub[:200]])
         assert not bad3
+        bad5, _ = T.compare_t5(o, e, x[sub[:200]], y[sub[:200]], s[sub[:200]])
+        assert not bad5
         same_w = (y - x == 1000) & (lo != NONE)
         assert np.all(np.diff(lo[same_w].astype(np.int64)) >= 0)
         assert np.all(np.diff(off).astype(np.int64) <= 2 * (hi.astype(np.int64) - lo) + 2)
@@ -322,6 +326,12 @@ def test_sample_sequences_cuda(tmp_path, monkeypatch):
         assert not bad2 and threw > len(names)
         bad3, odd3 = T.compare_t3(o, e, x, y, s)
         assert not bad3 and odd3 > len(names)
+        bad5, odd5 = T.compare_t5(o, e, x, y, s)
+        assert not bad5 and odd5 > len(names)
+        off5, hits5, st5, ms5 = e.batch_sample_var_in_sample(x, y, s)
+        o5a, h5a, s5a, _ = e.batch_sample_var_in_sample(x[:h], y[:h], s[:h])
+        o5b, h5b, s5b, _ = e.batch_sample_var_in_sample(x[h:], y[h:], s[h:])
+        assert np.array_equal(np.concatenate([h5a, h5b]), hits5) and np.array_equal(np.concatenate([o5a[:-1], o5b + o5a[-1]]), off5) and ms5 > 0
         st3 = e.batch_sample_seq_in_sample(x, y, s)[2]
         i2 = int(np.nonzero(st3 == 2)[0][0])
         with pytest.raises(RuntimeError):
@@ -373,7 +383,7 @@ def test_cli_front_end_matches_reference_cli_lines(tmp_path):
     cases = [["-t", "6", "-r", "10:105"], ["-t", "6", "-r", "30:40,10:105,2000:3000,466:470"], ["-t", "4", "-s", "1", "-r", "14:105,660:700"],
              ["-t", "7", "-r", "10", "-b", "C", "-a", "T"], ["-t", "7", "-r", "58", "-b", "", "-a", "T"],
              ["-t", "2", "-s", "1", "-r", "10:105"], ["-t", "2", "-s", "1", "-r", "1:1002,660:700,55:62"],
-             ["-t", "3", "-s", "1", "-r", "1:1001,466:470,57:60"]]
+             ["-t", "3", "-s", "1", "-r", "1:1001,466:470,57:60"], ["-t", "5", "-s", "1", "-r", "1:1001,466:600"]]
     for i, c in enumerate(cases):
         outs = []
         for exe, tag in ((cli, "gpu"), (ref, "cpu")):

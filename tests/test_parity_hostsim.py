@@ -56,6 +56,9 @@ def test_fuzz_parity(tmp_path, seed, overlap, sparse, walk_path):
     # reference never returns (status 2) and those whose substr throws (status 1)
     bad3, odd3 = T.compare_t3(o, e, x, y, s)
     assert not bad3 and (sparse or odd3 > 0)
+    # get_sample_var_in_sample (t5): rows with var_pos in the sample's coordinates
+    bad5, _ = T.compare_t5(o, e, x, y, s)
+    assert not bad5
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
@@ -80,6 +83,10 @@ def test_exhaustive_windows_reach_the_rare_walk_entries(tmp_path, seed, walk_pat
     assert not bad2 and threw > 0
     bad3, odd3 = T.compare_t3(o, e, x[1::3], y[1::3], s[1::3])
     assert not bad3 and odd3 > 0
+    bad5, odd5 = T.compare_t5(o, e, x[2::3], y[2::3], s[2::3])
+    assert not bad5 and odd5 > 0
+    off5, hits5, st5, _ = e.batch_sample_var_in_sample(x[2::3], y[2::3], s[2::3])
+    assert len(hits5) > 0
     if e.info.rejoin_carriers:
         assert int(((hits & 0x40000000) != 0).sum()) > 0
 
@@ -112,6 +119,11 @@ def test_edges_of_the_contig(tmp_path):
     assert not bad2 and threw >= 1
     bad3, odd3 = T.compare_t3(o, e, x2, y2, s2)
     assert not bad3 and odd3 >= 1
+    bad5, _ = T.compare_t5(o, e, x2, y2, s2)
+    assert not bad5
+    rows = e.get_sample_var_in_sample(1, 4001, names[2])
+    want = o.t5_text(1, 4001, names[2]).split("Pos\tRef\tAlt\tSamples\n", 1)[1]
+    assert "".join(f"{v.var_pos}\t{v.ref}\t{v.alt}\t" + "".join(f"{a}({b}) " for a, b in v.samples) + "\n" for v in rows) == want and len(rows) > 10
     # 32-bit coordinate entry points: same answers as the 64-bit ones
     lo, hi, cnt = e.batch_var_in_ref(x, y)
     lo32, hi32, cnt32 = e.batch_var_in_ref(x.astype(np.uint32), y.astype(np.uint32))
@@ -141,6 +153,8 @@ def test_synthetic_generator_parity(tmp_path):
         assert not bad2
         bad3, _ = T.compare_t3(o, e, x, y, s)
         assert not bad3
+        bad5, _ = T.compare_t5(o, e, x, y, s)
+        assert not bad5
 
 
 def test_duplicate_records_take_the_literal_path(tmp_path):

@@ -75,6 +75,9 @@ class Oracle:
             L.vso_batch_t4.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t1.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t2.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+            L.vso_batch_t5.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+            L.vso_query_t5_text.restype = vp
+            L.vso_query_t5_text.argtypes = [vp, u64, u64, C.c_char_p]
             L.vso_batch_t3.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
             L.vso_batch_t2_mt.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int]
             L.vso_batch_t6_mt.argtypes = [vp, u64, vp, vp, vp, C.c_int]
@@ -186,6 +189,20 @@ class Oracle:
         if rc != 0:
             raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
         return cnt, dig, ub
+
+    def t5_text(self, x, y, sample):
+        return self._text(self.lib().vso_query_t5_text(self.h, x, y, sample.encode()))
+
+    def batch_t5(self, x, y, sample_ids, with_samples=True):
+        """get_sample_var_in_sample: (counts, digests, status, ub); status 2 = the reference never returns."""
+        x, y = np.ascontiguousarray(x, np.uint64), np.ascontiguousarray(y, np.uint64)
+        s = np.ascontiguousarray(sample_ids, np.uint32)
+        n = len(x)
+        cnt, dig, st, ub = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        rc = self.lib().vso_batch_t5(self.h, n, x.ctypes.data, y.ctypes.data, s.ctypes.data, cnt.ctypes.data, dig.ctypes.data, st.ctypes.data, ub.ctypes.data, int(with_samples))
+        if rc != 0:
+            raise RuntimeError("oracle: " + self.lib().vso_last_error().decode())
+        return cnt, dig, st, ub
 
     def batch_t1(self, pos, with_samples=True):
         pos = np.ascontiguousarray(pos, np.uint64)
@@ -324,6 +341,20 @@ def compare_t1(oracle, eng, pos, with_samples=True):
     efound = lo != 0xFFFFFFFF
     bad = (efound != (f == 1)) | ((f == 1) & ((c != ec) | (d != ed)))
     return [int(i) for i in np.nonzero(bad)[0]]
+
+
+def compare_t5(oracle, eng, x, y, s, with_samples=True, skip_ub=True):
+    """get_sample_var_in_sample on both sides (row counts, row digests, "never returns" flags); returns
+    (mismatching indices, regions the reference hangs on)."""
+    oc, od, ost, ub = oracle.batch_t5(x, y, s, with_samples)
+    off, hits, est, _ = eng.batch_sample_var_in_sample(x, y, s)
+    ed = eng.digest_t5(off, hits, s, with_samples)
+    ec = np.diff(off)
+    ok = ost == 0
+    mism = (ost != est) | (ok & ((oc != ec) | (od != ed))) | (~ok & (ec != 0))
+    if skip_ub:
+        mism &= ub == 0
+    return [int(i) for i in np.nonzero(mism)[0]], int((ost != 0).sum())
 
 
 def compare_t3(oracle, eng, x, y, s, skip_ub=True):

@@ -2,7 +2,7 @@
 """Long-running parity campaign on the CPU: for every seed in [lo, hi) and each of the four fuzz shapes
 (overlapping deletions x explicit-id encoding), random record / sample counts, construct with the
 oracle, open with the engine's loader + flattener + kernel logic compiled for the host (test-only
-simulator), and compare t6, t4, closest_var, t2 and t3 (sample sequences in ref / sample coordinates) on random regions.  usage: fuzz_campaign.py LO HI
+simulator), and compare t6, t4, closest_var, t2 / t3 (sample sequences in ref / sample coordinates) and t5 (a sample's variants in its own coordinates) on random regions.  usage: fuzz_campaign.py LO HI
 Round 1: seeds 0..299 = 1 200 graphs, 480 000 t6 + t4 region queries, 360 000 closest_var: 0 mismatches."""
 import sys, os, tempfile, shutil, json, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -34,7 +34,8 @@ for seed in range(lo, hi):
                 n_t2 += len(x); n_threw += threw
                 b3, odd3 = T.compare_t3(o, e, x, y, s)
                 n_odd3 += odd3
-                b2 = b2 + [("t3", i) for i in b3]
+                b5, _ = T.compare_t5(o, e, x, y, s)
+                b2 = b2 + [("t3", i) for i in b3] + [("t5", i) for i in b5]
                 if b6 or b4 or b1 or b2:
                     bad.append(dict(seed=seed, overlap=overlap, sparse=sparse, nrec=nrec, ns=ns, b6=b6[:5], b4=b4[:5], b1=b1[:5], b2=b2[:5]))
                     print("MISMATCH", bad[-1], flush=True)

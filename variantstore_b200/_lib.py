@@ -55,6 +55,11 @@ PROTOTYPES = {
     "vsgpu_text_free": (None, [vp]),
     "vsgpu_query_t2": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
     "vsgpu_query_t3": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
+    "vsgpu_query_t5": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
+    "vsgpu_result_status": (vp, [vp]),
+    "vsgpu_result_kernel_ms": (C.c_float, [vp]),
+    "vsgpu_rows_t5": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(vp)]),
+    "vsgpu_digest_t5": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.c_int, vp]),
     "vsgpu_text_status": (vp, [vp]),
     "vsgpu_text_stage_ms": (C.POINTER(C.c_float), [vp]),
     "vsgpu_batch_create": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, cpp, cpp, C.POINTER(vp)]),

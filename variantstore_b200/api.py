@@ -5,6 +5,8 @@ Names, argument meaning and error behaviour follow the reference:
   get_sample_var_in_ref(pos_x, pos_y, sample)  query.h:618-729   (t4)
   samples_has_var(pos, ref, alt)               query.h:792-823   (t7)
   query_sample_from_ref(pos_x, pos_y, sample)  query.h:120-189   (t2)
+  query_sample_from_sample(...)                query.h:195-261   (t3)
+  get_sample_var_in_sample(...)                query.h:490-612   (t5)
   closest_var(pos)                             query.h:441-483   (t1)
 plus batched forms that take whole arrays of regions — the reason this engine exists.
 Positions are 1-based, regions are [pos_x, pos_y).
@@ -180,6 +182,42 @@ class VariantStoreIndex:
         finally:
             self._lib.vsgpu_text_free(t)
         return off, text, rows, ms
+
+    def batch_sample_var_in_sample(self, x, y, sample_ids):
+        """t5 over arrays (get_sample_var_in_sample, query.h:490-612): (offsets[n+1], hit codes, status, kernel ms);
+        status 2 = the reference never returns."""
+        x, y = _u64(x), _u64(y)
+        s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        n = len(x)
+        r = C.c_void_p()
+        self._check(self._lib.vsgpu_query_t5(self._h, n, _ptr(x), _ptr(y), _ptr(s), C.byref(r)))
+        try:
+            off = np.ctypeslib.as_array(self._lib.vsgpu_result_offsets(r), shape=(n + 1,)).copy()
+            total = int(off[-1])
+            hits = np.ctypeslib.as_array(self._lib.vsgpu_result_hits(r), shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+            status = np.frombuffer(C.string_at(self._lib.vsgpu_result_status(r), n), np.uint8).copy() if n else np.zeros(0, np.uint8)
+            ms = float(self._lib.vsgpu_result_kernel_ms(r))
+        finally:
+            self._lib.vsgpu_result_free(r)
+        return off, hits, status, ms
+
+    def digest_t5(self, offsets, hits, sample_ids, with_samples=True):
+        n = len(offsets) - 1
+        d = np.zeros(n, np.uint64)
+        hits = np.ascontiguousarray(hits, np.uint32)
+        s = np.ascontiguousarray(sample_ids, np.uint32)
+        self._check(self._lib.vsgpu_digest_t5(self._h, n, _ptr(offsets), _ptr(hits), _ptr(s), int(with_samples), _ptr(d)))
+        return d
+
+    def get_sample_var_in_sample(self, pos_x: int, pos_y: int, sample_id: str) -> List[Variant]:
+        """query.h:490-612.  RuntimeError where the reference would spin forever."""
+        sid = self.sample_id(sample_id)
+        off, hits, status, _ = self.batch_sample_var_in_sample([pos_x], [pos_y], [sid])
+        if status[0] == 2:
+            raise RuntimeError("the reference does not terminate for this region (query.h:505-510)")
+        p = C.c_void_p()
+        self._check(self._lib.vsgpu_rows_t5(self._h, _ptr(hits), len(hits), sid, 1, C.byref(p)))
+        return _parse_rows(self._take_text(p))
 
     def batch_sample_seq_in_sample(self, x, y, sample_ids):
         """t3 over arrays (query_sample_from_sample, query.h:195-261): like batch_sample_seq_in_ref with the

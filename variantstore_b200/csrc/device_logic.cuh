@@ -650,6 +650,54 @@ VSGPU_HD uint32_t t3_walk(const DevIndex& ix, const T2Tables& t2, const T3Tables
 	}
 }
 
+// ------------------------------------------------------------------ t5: get_sample_var_in_sample (query.h:490-612)
+// Same start as t3 (incl. the loop that may never end), then the walk of t4 — but from the backbone
+// vertex holding ref_pos (:513), gated on the sample's own coordinate: a vertex carrying the sample is
+// reported when x < sample_pos < y on arrival (:531, :553; sample_pos only grows along the path).
+// Emits the same hit codes as t4; the row rules differ only in var_pos (host_index.h: t5_row).
+template <class Sink>
+VSGPU_HD uint32_t t5_walk(const DevIndex& ix, const T2Tables& t2, const T3Tables& t3, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+	PrevHit h = prev_with_sample(ix, t3, x64, s);
+	uint64_t saved = ~(uint64_t)0;
+	for (uint32_t steps = 0, power = 1; h.sample_pos >= x64 && h.c != kNoneU32;) {
+		const uint64_t pos = h.ref_pos;
+		if (pos == saved) return kT3Hang;
+		if (++steps == power) { saved = pos; power <<= 1; steps = 0; }
+		h = prev_with_sample(ix, t3, pos, s);
+	}
+	// closest_v = idx->find(ref_pos) (:513, index.h:119-133); seq_len = ref_pos - its start (:517-520)
+	uint32_t rk = h.ref_pos >= ix.index_bits ? ix.D : rank_le(ix, clamp_pos(h.ref_pos));
+	if (rk < 1) rk = 1;
+	uint32_t cur_k = ldg(&ix.dlev[rk - 1].x);
+	uint64_t sp = h.sample_pos - (h.ref_pos - (uint64_t)ldg(t2.bbs + cur_k));
+	uint32_t c = ldg(ix.cent_begin_k + cur_k);
+	for (;;) {
+		if (sp >= y64) return 0;                                 // :531
+		// the first backbone vertex from here at which sample_pos has reached y: entries from it on are never taken
+		const uint32_t k_end = t3_first_ge(ix, t2, cur_k, sp, y64);
+		const uint32_t limit = k_end < ix.M ? ldg(ix.cent_begin_k + k_end + 1) : ix.num_cent;
+		uint32_t ci;
+		uint4 e = make_uint4(0, 0, 0, 0);
+		for (;;) {
+			ci = next_carried(ix, s, c, limit);
+			if (ci == kNoneU32) return 0;
+			c = ci + 1;
+			e = ldg(ix.cent + ci);
+			if (e.x >= cur_k) break;                               // else hidden behind a taken detour / an earlier sibling
+		}
+		sp += ldg(t2.bbs + e.x + 1) - ldg(t2.bbs + cur_k);       // sample_pos on arrival at the entry's target
+		if (sp >= y64) return 0;
+		if (sp > x64) sink.emit(ci);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask) return 0;
+			sp += ldg(&t2.cent_seq[ci].y);
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && sp > x64 && sp < y64) sink.emit(ci | kHitRejoin);
+			cur_k = tk;
+		} else cur_k = e.y & kEntTgtMask;
+	}
+}
+
 // Pieces of one region's answer, merged while they are contiguous in seq_buffer: one copy record
 // {src, len, dst lo, dst hi} per maximal run.  Count: how many records / bytes.  Write: the records
 // themselves plus, for every kT2Tile-byte boundary of the output a record covers, its index in

@@ -18,6 +18,7 @@ struct HostIndex {
 	uint32_t t1_fallback_pos = 0;                           // see DevIndex::t1_fallback_pos
 	std::unordered_map<std::string, uint32_t> name2id;
 	std::string prefix;                                     // the ser/ directory (operators that need a second pass over it: t3)
+	std::vector<uint32_t> sindex;                           // sample_info.index per s_info (second pass over ser/, on the first t3 / t5 call)
 	bool from_cache = false;                                // read from VSGPU_INDEX_CACHE instead of decoding ser/
 };
 
@@ -34,6 +35,10 @@ void append_seq(const HostIndex* ix, uint32_t v, std::string& out);
 void append_carriers(const HostIndex* ix, uint32_t v, std::string& out);
 void t6_row(const HostIndex* ix, uint32_t r, bool with_samples, std::string& out);
 void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& out);
+// t5 row (get_sample_var_in_sample, query.h:553-590): the t4 row of the same hit code with var_pos in the sample's coordinates
+void t5_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool with_samples, std::string& out);
+void digests_t5(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* samples, bool with_samples, uint64_t* digests);
+uint32_t host_sample_index(const HostIndex* ix, uint32_t vertex, uint32_t sample);
 bool push_rule(const HostIndex* ix, const std::vector<uint32_t>& vars, uint32_t r);
 uint32_t host_rank(const FlatIndex& f, uint64_t pos);
 void t6_literal(const HostIndex* ix, uint64_t x, uint64_t y, std::vector<uint32_t>& vars);

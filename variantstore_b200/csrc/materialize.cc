@@ -156,9 +156,28 @@ bool t6_needs_literal(const HostIndex* ix, uint64_t y, uint32_t lo, uint32_t hi)
 	return false;
 }
 
-// t4 row from a hit code: emission rules of get_sample_var_in_ref (query.h:677-710)
-void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& out) {
+// sample_info.index of `sample` in `vertex` (HostIndex::sindex must be loaded): s_info[i] belongs to the
+// i-th set bit of the vertex's class, or to the i-th listed id (variant_graph.h:1296-1326)
+uint32_t host_sample_index(const HostIndex* ix, uint32_t vertex, uint32_t sample) {
 	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
+	const uint64_t b = s.v_sinfo_begin[vertex], e = s.v_sinfo_begin[vertex + 1];
+	if (f.class_mode) {
+		const uint64_t* row = &f.bitmap[(uint64_t)s.v_class[vertex] * f.words_per_set];
+		uint64_t r = 0;
+		for (uint32_t w = 0; w < (sample >> 6); w++) r += (uint64_t)__builtin_popcountll(row[w]);
+		r += (uint64_t)__builtin_popcountll(row[sample >> 6] & (((uint64_t)1 << (sample & 63)) - 1));
+		return b + r < e ? ix->sindex[b + r] : 0;
+	}
+	for (uint64_t i = b; i < e; i++) if (s.s_sample_id[i] == sample) return ix->sindex[i];
+	return 0;
+}
+
+// Row of a t4 / t5 hit code: emission rules of get_sample_var_in_ref (query.h:677-710) and, with
+// sample != kNone, of get_sample_var_in_sample (:553-590) — the same three cases with var_pos = ref_pos
+// for an insertion and the sample's own position in the vertex otherwise.
+static void hit_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool with_samples, std::string& out) {
+	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
+	const bool t5 = sample != kNone;
 	const uint32_t c = code & VSGPU_HIT_ENTRY_MASK;
 	const CEntry& e = f.cent[c];
 	uint32_t u, ref_pos, cur_ref_v; bool cur_ref_empty = false, u_is_bb; uint32_t u_k = kNone;
@@ -179,18 +198,20 @@ void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& 
 		next_ref_pos = tk == kEntTgtNone ? (uint64_t)ref_pos + s.v_length[u] : f.vstart[tk];
 	}
 	std::string ref, alt; uint64_t pos;
-	if (ref_pos == next_ref_pos) { pos = (uint64_t)ref_pos - 1; append_seq(ix, u, alt); }                 // insertion
+	if (ref_pos == next_ref_pos) { pos = t5 ? (uint64_t)ref_pos : (uint64_t)ref_pos - 1; append_seq(ix, u, alt); }   // insertion
 	else if (u_is_bb) {                                                                                   // deletion: cur_ref = seq(find(ref_pos - 1))
 		uint64_t p = ref_pos > 1 ? ref_pos - 1 : 1;
 		uint32_t rk = p >= f.index_bits ? f.D : host_rank(f, p);
 		if (rk < 1) rk = 1;
 		uint32_t wk = f.dlev[rk - 1].k;
-		append_seq(ix, f.bb_vertex[wk], ref); pos = f.vstart[wk];
-	} else { pos = ref_pos; if (!cur_ref_empty) append_seq(ix, cur_ref_v, ref); append_seq(ix, u, alt); } // substitution
+		append_seq(ix, f.bb_vertex[wk], ref); pos = t5 ? host_sample_index(ix, u, sample) : f.vstart[wk];
+	} else { pos = t5 ? host_sample_index(ix, u, sample) : ref_pos; if (!cur_ref_empty) append_seq(ix, cur_ref_v, ref); append_seq(ix, u, alt); } // substitution
 	out += std::to_string(pos); out += '\t'; out += ref; out += '\t'; out += alt; out += '\t';
 	if (with_samples) append_carriers(ix, u, out);
 	out += '\n';
 }
+void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& out) { hit_row(ix, code, kNone, with_samples, out); }
+void t5_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool with_samples, std::string& out) { hit_row(ix, code, sample, with_samples, out); }
 
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
 	const unsigned char* p = (const unsigned char*)data;
@@ -286,6 +307,17 @@ void digests_t4(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const 
 		for (uint64_t i = a; i < b; i++) {
 			uint64_t h = kFnvInit;
 			for (uint64_t j = offsets[i]; j < offsets[i + 1]; j++) { row.clear(); t4_row(ix, hits[j], with_samples, row); h = fnv1a(h, row.data(), row.size()); }
+			digests[i] = h;
+		}
+	});
+}
+
+void digests_t5(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* samples, bool with_samples, uint64_t* digests) {
+	parallel_for(n, [&](uint64_t a, uint64_t b) {
+		std::string row;
+		for (uint64_t i = a; i < b; i++) {
+			uint64_t h = kFnvInit;
+			for (uint64_t j = offsets[i]; j < offsets[i + 1]; j++) { row.clear(); t5_row(ix, hits[j], samples[i], with_samples, row); h = fnv1a(h, row.data(), row.size()); }
 			digests[i] = h;
 		}
 	});

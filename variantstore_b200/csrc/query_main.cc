@@ -1,6 +1,6 @@
 // vsgpu_query — front-end with the reference's `variantstore query` flags
 // (src/variantstore.cc:101-134, src/commands.cc:113-215):
-//   -p <ser prefix> -t <2|3|4|6|7> -r <beg[:end][,...]> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]
+//   -p <ser prefix> -t <2|3|4|5|6|7> -r <beg[:end][,...]> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]
 // -m is accepted and ignored (both modes give identical results; only the reference's paging differs).
 // Unlike query_main's per-region loop the whole region list goes to the GPU as one batch; the lines
 // printed per region are the reference's.
@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
 	int a0 = (argc > 1 && !strcmp(argv[1], "query")) ? 2 : 1;
 	argc -= a0 - 1; argv += a0 - 1;
 	const char* prefix = opt(argc, argv, "-p", nullptr); const char* tstr = opt(argc, argv, "-t", nullptr); const char* rstr = opt(argc, argv, "-r", nullptr);
-	if (!prefix || !tstr || !rstr) { fprintf(stderr, "usage: vsgpu_query [query] -p <prefix> -t <2|3|4|6|7> -r <regions> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]\n"); return 1; }
+	if (!prefix || !tstr || !rstr) { fprintf(stderr, "usage: vsgpu_query [query] -p <prefix> -t <2|3|4|5|6|7> -r <regions> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]\n"); return 1; }
 	const int type = atoi(tstr);
 	const std::string outfile = opt(argc, argv, "-o", ""), sample = opt(argc, argv, "-s", "");
 	const bool verbose = flag(argc, argv, "-v");
@@ -90,6 +90,21 @@ int main(int argc, char** argv) {
 			for (uint64_t i = 0; i < n; i++) {
 				printf("Number of variants get_sample_var_in_ref: %lu\n", (unsigned long)(off[i + 1] - off[i]));
 				if (verbose) { char* text = nullptr; if (vsgpu_rows_t4(idx, hits + off[i], off[i + 1] - off[i], 1, &text) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
+			}
+			vsgpu_result_free(res);
+		}
+	} else if (type == 5) {
+		uint32_t sid = 0;
+		if (vsgpu_sample_id(idx, sample.c_str(), &sid) != 0) { fprintf(stderr, "%s\n", vsgpu_last_error()); return 2; }
+		std::vector<uint32_t> s(n, sid);
+		vsgpu_result* res = nullptr;
+		rc = vsgpu_query_t5(idx, n, x.data(), y.data(), s.data(), &res);
+		if (rc == 0) {
+			const uint64_t* off = vsgpu_result_offsets(res); const uint32_t* hits = vsgpu_result_hits(res); const uint8_t* st = vsgpu_result_status(res);
+			for (uint64_t i = 0; i < n; i++) {
+				if (st[i] == 2) { fprintf(stderr, "region %lu:%lu: the reference never returns from get_sample_var_in_sample (query.h:505-510)\n", (unsigned long)x[i], (unsigned long)y[i]); vsgpu_result_free(res); vsgpu_close(idx); return 3; }
+				printf("Number of variants get_sample_var_in_sample: %lu\n", (unsigned long)(off[i + 1] - off[i]));
+				if (verbose) { char* text = nullptr; if (vsgpu_rows_t5(idx, hits + off[i], off[i + 1] - off[i], sid, 1, &text) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
 			}
 			vsgpu_result_free(res);
 		}

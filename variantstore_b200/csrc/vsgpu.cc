@@ -62,6 +62,8 @@ struct vsgpu_result {
 	uint64_t n = 0;
 	uint64_t* offsets = nullptr; size_t offsets_cap = 0;   // bytes
 	uint32_t* hits = nullptr; size_t hits_cap = 0;         // bytes
+	uint8_t* status = nullptr; size_t status_cap = 0;      // t5 only
+	float kernel_ms = 0;                                   // t5 only
 };
 
 // Host side of a rendered t6 answer (page-locked, pooled like vsgpu_result).
@@ -586,7 +588,7 @@ const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r ? r->offs
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r ? r->hits : nullptr; }
 void vsgpu_result_free(vsgpu_result* r) {
 	if (!r) return;
-	if (r->owner) { r->owner->pinned_release(r->offsets, r->offsets_cap); r->owner->pinned_release(r->hits, r->hits_cap); }
+	if (r->owner) { r->owner->pinned_release(r->offsets, r->offsets_cap); r->owner->pinned_release(r->hits, r->hits_cap); r->owner->pinned_release(r->status, r->status_cap); }
 	delete r;
 }
 
@@ -914,7 +916,7 @@ void ensure_t3_tables(vsgpu_index* ix) {
 	ensure_t2_tables(ix);
 	if (ix->t3_ready) return;
 	const FlatIndex& f = ix->flat; const SerData& sd = ix->ser;
-	std::vector<uint32_t> sindex;
+	std::vector<uint32_t>& sindex = ix->sindex;            // kept on the host too: t5 rows print the sample's position
 	try { load_sample_indexes(ix->prefix, sd.v_sinfo_begin.back(), sindex); }
 	catch (const std::exception& e) { throw std::invalid_argument(std::string("vsgpu_query_t3: ") + e.what()); }
 	const size_t E = f.cent.size();
@@ -998,6 +1000,77 @@ int query_seq_impl(vsgpu_index* ix, bool t3, uint64_t n, const uint64_t* x, cons
 	return VSGPU_OK;
 }
 }  // namespace
+// ------------------------------------------------------------------ t5: get_sample_var_in_sample
+int vsgpu_query_t5(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out) {
+	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t5: null argument");
+	*out = nullptr;
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	std::unique_ptr<vsgpu_result, void (*)(vsgpu_result*)> r(new vsgpu_result, vsgpu_result_free);
+	r->owner = ix; r->n = n;
+	try {
+		ensure_t3_tables(ix);
+		cudaStream_t st = ix->s_k;
+		r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
+		r->status = (uint8_t*)ix->pinned_acquire(n + 1, &r->status_cap);
+		if (!r->offsets || !r->status) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		r->offsets[0] = 0;
+		if (n) {
+			const uint64_t nctas = (n + 255) / 256;
+			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+			CU(ix->bcnt.ensure(n * 4)); CU(ix->bst8.ensure(n)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->boffsets.ensure((n + 1) * 8));
+			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
+			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
+			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
+			CU(cudaEventRecord(ix->ev_t2[0], st));
+			CU(launch_t5_count(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bst8.as<uint8_t>(),
+			                   ix->bscratch.as<uint64_t>(), ix->d_status, st));
+			CU(cudaEventRecord(ix->ev_t2[1], st));
+			CU(cudaMemcpyAsync(ix->pin_small, ix->bscratch.as<uint64_t>() + 2 * nctas, 8, cudaMemcpyDeviceToHost, st));
+			const uint32_t status = read_status(ix, ix->d_status, nullptr, st);
+			if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "vsgpu_query_t5: sample id out of range");
+			const uint64_t total = ix->pin_small[0];
+			CU(ix->bhits.ensure(std::max<uint64_t>(total, 1) * 4));
+			r->hits = (uint32_t*)ix->pinned_acquire(std::max<uint64_t>(total, 1) * 4, &r->hits_cap);
+			if (!r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+			CU(cudaEventRecord(ix->ev_t2[2], st));
+			CU(launch_t5_write(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bscratch.as<uint64_t>(),
+			                   ix->boffsets.as<uint64_t>(), ix->bhits.as<uint32_t>(), st));
+			CU(cudaEventRecord(ix->ev_t2[3], st));
+			CU(cudaMemcpyAsync(r->offsets, ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+			CU(cudaMemcpyAsync(r->status, ix->bst8.p, n, cudaMemcpyDeviceToHost, st));
+			if (total) CU(cudaMemcpyAsync(r->hits, ix->bhits.p, total * 4, cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			float a = 0, b = 0;
+			CU(cudaEventElapsedTime(&a, ix->ev_t2[0], ix->ev_t2[1])); CU(cudaEventElapsedTime(&b, ix->ev_t2[2], ix->ev_t2[3]));
+			r->kernel_ms = a + b;
+		}
+		*out = r.release();
+	} catch (const std::invalid_argument& e) { return set_err(VSGPU_ESHAPE, e.what());
+	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+const uint8_t* vsgpu_result_status(const vsgpu_result* r) { return r ? r->status : nullptr; }
+float vsgpu_result_kernel_ms(const vsgpu_result* r) { return r ? r->kernel_ms : 0.f; }
+int vsgpu_rows_t5(const vsgpu_index* ix, const uint32_t* hits, uint64_t nhits, uint32_t sample_id, int with_samples, char** text) {
+	if (!ix || !text || (nhits && !hits)) return set_err(VSGPU_EINVAL, "vsgpu_rows_t5: null argument");
+	if (ix->sindex.empty() && nhits) return set_err(VSGPU_EINVAL, "vsgpu_rows_t5: no t5 query has run on this index");
+	if (sample_id == 0 || sample_id >= ix->ser.num_samples) return set_err(VSGPU_EINVAL, "vsgpu_rows_t5: sample id out of range");
+	std::string s;
+	for (uint64_t i = 0; i < nhits; i++) {
+		if ((hits[i] & VSGPU_HIT_ENTRY_MASK) >= ix->flat.cent.size()) return set_err(VSGPU_EINVAL, "vsgpu_rows_t5: hit code out of range");
+		t5_row(ix, hits[i], sample_id, with_samples != 0, s);
+	}
+	*text = dup_text(s);
+	return *text ? VSGPU_OK : set_err(VSGPU_ENOMEM, "out of memory");
+}
+int vsgpu_digest_t5(const vsgpu_index* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* sample_ids, int with_samples, uint64_t* digests) {
+	if (!ix || (n && (!offsets || !digests || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_digest_t5: null argument");
+	if (ix->sindex.empty() && n && offsets[n]) return set_err(VSGPU_EINVAL, "vsgpu_digest_t5: no t5 query has run on this index");
+	digests_t5(ix, n, offsets, hits, sample_ids, with_samples != 0, digests);
+	return VSGPU_OK;
+}
+
 int vsgpu_query_t2(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out) { return query_seq_impl(ix, false, n, x, y, sample_ids, out); }
 int vsgpu_query_t3(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_text** out) { return query_seq_impl(ix, true, n, x, y, sample_ids, out); }
 
