@@ -329,6 +329,7 @@ def test_sample_sequences_cuda(tmp_path, monkeypatch):
         bad5, odd5 = T.compare_t5(o, e, x, y, s)
         assert not bad5 and odd5 > len(names)
         off5, hits5, st5, ms5 = e.batch_sample_var_in_sample(x, y, s)
+        h = len(x) // 3
         o5a, h5a, s5a, _ = e.batch_sample_var_in_sample(x[:h], y[:h], s[:h])
         o5b, h5b, s5b, _ = e.batch_sample_var_in_sample(x[h:], y[h:], s[h:])
         assert np.array_equal(np.concatenate([h5a, h5b]), hits5) and np.array_equal(np.concatenate([o5a[:-1], o5b + o5a[-1]]), off5) and ms5 > 0
