@@ -195,7 +195,7 @@ int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* ker
 /* Device time (ms) of each kernel of the last run, from CUDA events on the launch stream
  * (t6/t7: 1 kernel; t4: walk, scan, gather).  Synchronises. */
 int vsgpu_batch_timings(vsgpu_batch* b, float* ms, uint32_t cap, uint32_t* n);
-void vsgpu_batch_free(vsgpu_batch* b);
+void vsgpu_batch_free(vsgpu_batch* b);                         /* before vsgpu_close of its index: a batch points into it */
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ plus batched forms that take whole arrays of regions — the reason this engine 
 Positions are 1-based, regions are [pos_x, pos_y).
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -96,6 +97,7 @@ class VariantStoreIndex:
         if rc != 0:
             raise VsgpuError(rc, self._lib.vsgpu_last_error().decode())
         self._h = h
+        self._batches = weakref.WeakSet()     # device-resident batches must be freed before the index they point into
         info = _lib.InfoT()
         self._lib.vsgpu_info(self._h, C.byref(info))
         self.info = info
@@ -103,6 +105,8 @@ class VariantStoreIndex:
 
     def close(self):
         if getattr(self, "_h", None):
+            for b in list(getattr(self, "_batches", ())):
+                b.close()
             self._lib.vsgpu_close(self._h)
             self._h = None
 
@@ -375,6 +379,7 @@ class Batch:
         index._check(self._lib.vsgpu_batch_create(index._h, qtype, self.n, _ptr(x), _ptr(y) if y is not None else None,
                                                   _ptr(s) if s is not None else None, ra, aa, C.byref(h)))
         self._h = h
+        index._batches.add(self)
 
     def run(self):
         self._ix._check(self._lib.vsgpu_batch_run(self._h))

@@ -148,6 +148,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 
 struct vsgpu_batch {
 	vsgpu_index* idx = nullptr;
+	int device = 0;                  // copied from the index: freeing a batch must not touch an index that may be gone
 	int type = 0; uint64_t n = 0;
 	DevBuf x, y, s, hash, out, offsets, hits, state, rec, flag;
 	uint64_t hits_cap = 0;
@@ -157,7 +158,7 @@ struct vsgpu_batch {
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint32_t* d_status = nullptr;    // per batch: several batches may be in flight on one index
 	bool wide_regions = false;
-	~vsgpu_batch() { if (idx) cudaSetDevice(idx->device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec, &flag}) b->release(); }
+	~vsgpu_batch() { if (idx) cudaSetDevice(device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec, &flag}) b->release(); }
 };
 
 namespace {
@@ -1084,7 +1085,7 @@ int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x,
 	std::lock_guard<std::mutex> g(ix->mu);
 	try {
 		std::unique_ptr<vsgpu_batch> b(new vsgpu_batch);
-		b->idx = ix; b->type = type; b->n = n;
+		b->idx = ix; b->device = ix->device; b->type = type; b->n = n;
 		CU(cudaMalloc((void**)&b->d_status, 8)); CU(cudaMemset(b->d_status, 0, 8));
 		b->hx.assign(x, x + n); if (y) b->hy.assign(y, y + n);
 		CU(b->x.ensure(n * 8));
