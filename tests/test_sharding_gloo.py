@@ -28,15 +28,19 @@ def _worker(rank, world, port, prefixes, owner, queries, out_path):
     sys.path.insert(0, T.ROOT)
     sys.path.insert(0, os.path.join(T.ROOT, "tests"))
     from variantstore_b200 import VariantStoreIndex, load_library
-    from variantstore_b200.sharding import ShardedIndex, distributed_var_in_ref
+    from variantstore_b200.sharding import ShardedIndex, distributed_sample_seq, distributed_var_in_ref
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     lib = load_library(T.HOSTSIM_SO, subset=True)
     mine = {c: p for c, p in prefixes.items() if owner[c] == rank}
     sh = ShardedIndex(mine, lambda p: VariantStoreIndex(p, lib=lib))
-    contigs, x, y = queries
+    contigs, x, y, snames = queries
     res = distributed_var_in_ref(dist, sh, owner, contigs if rank == 0 else None, x if rank == 0 else None, y if rank == 0 else None)
+    seqs = distributed_sample_seq(dist, sh, owner, contigs if rank == 0 else None, x if rank == 0 else None, y if rank == 0 else None,
+                                  snames if rank == 0 else None)
     if rank == 0:
         np.save(out_path, res)
+        import pickle
+        pickle.dump(seqs, open(out_path + ".t2", "wb"))
     dist.barrier()
     sh.close()
     dist.destroy_process_group()
@@ -58,12 +62,23 @@ def test_two_process_sharded_queries(tmp_path):
     contigs = [names[i] for i in rng.integers(0, 3, n)]
     x = rng.integers(1, 3900, n).astype(np.uint64)
     y = x + rng.choice([1, 5, 100, 1000], n).astype(np.uint64)
+    snames = [f"S{int(i):03d}" for i in rng.integers(1, 13, n)]
     port = 29500 + os.getpid() % 400
     out_path = str(tmp_path / "res.npy")
-    mp.spawn(_worker, args=(2, port, prefixes, owner, (contigs, x, y), out_path), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, prefixes, owner, (contigs, x, y, snames), out_path), nprocs=2, join=True)
     got = np.load(out_path)
     want = np.zeros(n, np.uint64)
     for c in names:
         idx = np.nonzero(np.array(contigs) == c)[0]
         want[idx] = oracles[c].batch_t6(x[idx], y[idx])[0]
     assert np.array_equal(got.astype(np.uint64), want)
+    # the routed t2 answers (sample sequences) equal the oracle's, contig by contig
+    import pickle
+    seqs, status = pickle.load(open(out_path + ".t2", "rb"))
+    for c in names:
+        idx = np.nonzero(np.array(contigs) == c)[0]
+        sid = np.array([int(snames[i][1:]) for i in idx], np.uint32)
+        ln, dg, st, ub, want_seqs = oracles[c].batch_t2(x[idx], y[idx], sid, want_text=True)
+        for j, i in enumerate(idx):
+            if not ub[j]:
+                assert status[i] == st[j] and seqs[i] == want_seqs[j].encode(), (c, int(x[i]), int(y[i]), snames[i])

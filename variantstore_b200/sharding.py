@@ -62,9 +62,49 @@ class ShardedIndex:
                 texts[i] = sh.rows_t4_text(hits[off[j]:off[j + 1]])
         return counts, texts
 
+    def sample_seq(self, contigs, x, y, sample_names, own_coordinates=False) -> Tuple[List[bytes], np.ndarray]:
+        """t2 (or, with own_coordinates, t3) for this process's regions: the sequences and the status bytes."""
+        x, y = np.asarray(x, np.uint64), np.asarray(y, np.uint64)
+        seqs = [b""] * len(x)
+        status = np.zeros(len(x), np.uint8)
+        for name, idx in self._by_contig(contigs):
+            sh = self.shards[name]
+            sid = np.array([sh.sample_id(sample_names[i]) for i in idx], np.uint32)
+            fn = sh.batch_sample_seq_in_sample if own_coordinates else sh.batch_sample_seq_in_ref
+            off, text, st, _ = fn(x[idx], y[idx], sid)
+            status[idx] = st
+            for j, i in enumerate(idx):
+                seqs[i] = text[off[j]:off[j + 1]]
+        return seqs, status
+
     def close(self):
         for s in self.shards.values():
             s.close()
+
+
+def distributed_sample_seq(dist, sharded: ShardedIndex, owner: Dict[str, int], contigs, x, y, sample_names, own_coordinates=False):
+    """t2 / t3 over a routed region list: rank 0 scatters (contig, x, y, sample) by owner, every rank answers
+    its part from its own shards, rank 0 gathers sequences + status bytes and restores the order."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == 0:
+        parts = route(contigs, owner, world)
+        payload = [([contigs[i] for i in p], np.asarray(x)[p], np.asarray(y)[p], [sample_names[i] for i in p]) for p in parts]
+    else:
+        parts, payload = None, [None] * world
+    mine = [None]
+    dist.scatter_object_list(mine, payload, src=0)
+    c, xs, ys, names = mine[0]
+    local = sharded.sample_seq(c, xs, ys, names, own_coordinates)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(local, gathered, dst=0)
+    if rank != 0:
+        return None
+    seqs, status = [b""] * len(x), np.zeros(len(x), np.uint8)
+    for p, (sq, st) in zip(parts, gathered):
+        for j, i in enumerate(p):
+            seqs[i] = sq[j]
+        status[p] = st
+    return seqs, status
 
 
 def distributed_var_in_ref(dist, sharded: ShardedIndex, owner: Dict[str, int], contigs, x, y):
