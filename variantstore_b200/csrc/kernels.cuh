@@ -74,10 +74,10 @@ constexpr uint32_t kT3Hang = 2;           // per-region status: the loop of quer
 constexpr uint32_t kT2Tile = 512;         // bytes of output one warp of the copy kernel writes per step (16 per lane)
 constexpr uint32_t kT2Keep = 16;          // copy records per region the count pass keeps for the plan pass (more: the plan pass walks again)
 constexpr uint32_t kT2Throw = 1;          // per-region status: the reference call ends in std::out_of_range (substr, query.h:163,167)
-// t2 runs as four launches over n regions (CTA b owns regions [256 b, 256 b + 256)):
+// t2 runs as five launches over n regions (count and plan: CTA b owns regions [256 b, 256 b + 256)):
 //   count : walk every region, write cnt[i] = {copy records, bytes}, status[i] and the first kT2Keep pieces {src, len}
 //           of the region into keep[k * n + i]; per-CTA sums into cta_sums[2 b]
-//   bases : exclusive scan of the per-CTA sums in place (entry nctas = totals)          -> launch_t2_offsets
+//   bases : exclusive scan of the per-CTA sums in place (entry nctas = totals); launched by launch_t2_count
 //   plan  : offsets[i] (bytes) from the scans, walk again and write the copy records {src, len, dst lo, dst hi}
 //           and tile_first[t] = the record covering output byte t * kT2Tile
 //   copy  : one warp per kT2Tile bytes of `text`; a lane finds the record of its 16 bytes starting from
