@@ -277,6 +277,7 @@ def run_vsgpu(args):
     px = torch.from_numpy(x.astype(cdt)).pin_memory()
     py = torch.from_numpy(y.astype(cdt)).pin_memory()
     ps = torch.from_numpy(s.astype(np.int32)).pin_memory()
+    px64, py64 = (px, py) if args.e2e_u64 else (torch.from_numpy(x.astype(np.int64)).pin_memory(), torch.from_numpy(y.astype(np.int64)).pin_memory())
     q6 = lib.vsgpu_query_t6 if args.e2e_u64 else lib.vsgpu_query_t6_u32
     q4 = lib.vsgpu_query_t4 if args.e2e_u64 else lib.vsgpu_query_t4_u32
     plo, phi, pcnt = (torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(3))      # page-locked result arrays
@@ -339,6 +340,27 @@ def run_vsgpu(args):
         "gpu_launches": (launches6 + launches4) * args.steps,
         "clocks": sampler.summary(),
     }
+    if world == 1 and not args.no_other_ops:
+        # Reported beside the headline, never part of it: the widened operator t2 (a sample's sequence over the same
+        # regions) through its C-ABI call — device time of its kernels and end to end.
+        try:
+            ms, ts, nbytes = [], [], 0
+            for rep in range(4):
+                t = vp()
+                t0 = time.perf_counter()
+                rc = lib.vsgpu_query_t2(h, n, vp(px64.data_ptr()), vp(py64.data_ptr()), vp(ps.data_ptr()), C.byref(t))
+                dt = time.perf_counter() - t0
+                assert rc == 0, lib.vsgpu_last_error()
+                if rep:
+                    ts.append(dt)
+                    ms.append(float(lib.vsgpu_text_kernel_ms(t)))
+                nbytes = int(lib.vsgpu_text_offsets(t)[n])
+                lib.vsgpu_text_free(t)
+            line["other_ops"] = {"t2_query_sample_from_ref": {"regions_per_s_kernels": n / (float(np.median(ms)) / 1e3), "kernels_ms": float(np.median(ms)),
+                                                              "regions_per_s_e2e": n / float(np.median(ts)), "sequence_bytes": nbytes,
+                                                              "copy_algorithmic_bytes": 2 * nbytes}}
+        except Exception as ex:
+            line["other_ops"] = {"failed": str(ex)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             nq, times, load_s = cpu_sample(args, prefix, meta, 1, args.cpu_sample_single)
@@ -366,6 +388,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="regions per type per step of the reference arm")
     ap.add_argument("--cpu-sample-single", type=int, default=2_000, help="regions per type of the single-thread cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-ops", action="store_true", help="skip the t2 side measurement")
     ap.add_argument("--e2e-u64", action="store_true", help="end-to-end arm through the 64-bit coordinate entry points instead of the 32-bit ones")
     ap.add_argument("--cache-dir", default=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"))
     args = ap.parse_args()
