@@ -71,3 +71,28 @@ def test_sample_count_mismatch(ser_copy):
     open(p, "w").write("\n".join(lines[:2] + lines[3:]))       # drop one "<name> <id>" row
     with pytest.raises(VsgpuError):
         open_hostsim(ser_copy)
+
+
+def test_sample_coordinate_operators_need_the_vertex_blocks_again(ser_copy):
+    """t3 / t5 read the per-carrier sample positions by a second pass over vertex_list_<k>.proto on
+    their first call: blocks that vanished or changed since vsgpu_open are an error, not a wrong answer;
+    t2 (which needs nothing new from disk) keeps working."""
+    import numpy as np
+    from variantstore_b200 import VsgpuError
+    e = open_hostsim(ser_copy)
+    assert e.query_sample_from_ref(10, 20, "1") == "TTTGAAAATT"
+    victim = os.path.join(ser_copy, "vertex_list_0.proto")
+    os.rename(victim, victim + ".away")
+    for call in (lambda: e.batch_sample_seq_in_sample([10], [20], [1]), lambda: e.batch_sample_var_in_sample([10], [20], [1])):
+        with pytest.raises(VsgpuError) as ei:
+            call()
+        assert ei.value.code == -3
+    assert e.query_sample_from_ref(10, 20, "1") == "TTTGAAAATT"
+    os.rename(victim + ".away", victim)
+    off, text, st, _ = e.batch_sample_seq_in_sample([1], [1001], [1])      # the tables are built now
+    assert st[0] == 0 and len(text) == 1000
+    off5, hits5, st5, _ = e.batch_sample_var_in_sample([1], [1001], [1])
+    assert st5[0] == 0 and len(hits5) == 74
+    with pytest.raises(VsgpuError):
+        e.batch_sample_var_in_sample([1], [1001], [2])                     # sample id out of range (one sample)
+    e.close()
