@@ -64,88 +64,95 @@ Graph::vertex get_prev_vertex_with_sample(const VariantGraph* vg, const Index* i
 	return v_find;
 }
 
-// Sample's sequence in ref coordinates [pos_x, pos_y) (query.h:120-189).  std::string::substr throws
-// std::out_of_range exactly where the reference's does (:163, :167) — the reference does not catch it,
-// so its process terminates; callers of the oracle catch it and report "threw".
-std::string query_sample_from_ref(const VariantGraph* vg, const Index* idx, const uint64_t pos_x, const uint64_t pos_y,
-                                  const std::string& sample_id, bool print, const std::string& outfile, bool* ub) {
-	std::string seq = "";
-	uint64_t ref_pos = 0, sample_pos = 0;
-	Graph::vertex closest_v = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, ref_pos, sample_pos, ub);
-	VariantGraph::PathIterator it = vg->find(closest_v, sample_id);
-	bool record_seq = false;
-	std::string temp;
-	while (!it.done()) {
-		temp.assign(vg->get_sequence(*(*it)));
-		uint64_t l = (*it)->length;
-		uint64_t next_ref_pos = ref_pos + l;
-		VariantGraph::BfsIterator bfs_it = vg->find((*it)->vertex_id, 1);
-		++bfs_it;
-		while (!bfs_it.done()) {          // FIRST ref-carrying neighbour wins (:143-151) — t4 takes the last
-			Graph::vertex v = (*bfs_it)->vertex_id;
-			SampleInfo sample;
-			if (vg->get_sample_from_vertex_if_exists(v, REF, sample)) { next_ref_pos = sample.index; break; }
-			++bfs_it;
-		}
-		if (record_seq == true && next_ref_pos < pos_y) {
-			seq += temp;
-		} else if (record_seq == true && next_ref_pos >= pos_y) {
-			seq += temp.substr(0, pos_y - ref_pos);
-			break;
-		} else if (next_ref_pos >= pos_x && next_ref_pos < pos_y) {
-			record_seq = true;
-			seq += temp.substr(pos_x - ref_pos);
-		} else if (next_ref_pos >= pos_x && next_ref_pos >= pos_y) {
-			seq = temp.substr(pos_x - ref_pos, pos_y - pos_x);
-			break;
-		}
-		++it;
-		ref_pos = next_ref_pos;
-	}
-	if (print) { std::ofstream out; out.open(outfile); out << seq << std::endl; out.close(); }
-	return seq;
+// ---- helpers shared by the sequence / sample-coordinate operators (t2, t3, t5) ----------------------
+
+// out-neighbours of v in the order the reference's radius-1 BFS meets them (the iterator's first element is v itself)
+static VariantGraph::BfsIterator neighbours_of(const VariantGraph* vg, Graph::vertex v) {
+	VariantGraph::BfsIterator it = vg->find(v, 1);
+	++it;
+	return it;
 }
 
-// Sample's sequence in the sample's own coordinates [pos_x, pos_y) (query.h:195-261).  The loop at
-// :209-214 repeats get_prev_vertex_with_sample from the ref position of the vertex found; when that
-// position maps to itself the reference never leaves the loop — detected here (the chain of positions
-// is deterministic, so revisiting one means it cycles) and reported through *hang.
+// The four cutting rules both sequence operators apply to every vertex of the sample's path
+// (query.h:157-173 in ref coordinates, :229-245 in sample coordinates): `at` = the running position on
+// arrival, `next` = the position behind the vertex.  std::string::substr throws std::out_of_range
+// exactly where the reference's calls do; the reference does not catch it (its process terminates),
+// callers of the oracle do and report "threw".
+struct SeqWindow {
+	uint64_t lo, hi;
+	bool open = false;             // record_seq
+	std::string out;
+	bool take(const std::string& vseq, uint64_t at, uint64_t next) {   // true: the walk is over
+		const bool reaches_hi = next >= hi;
+		if (open) {
+			if (!reaches_hi) { out += vseq; return false; }
+			out += vseq.substr(0, hi - at);
+			return true;
+		}
+		if (next < lo) return false;
+		if (!reaches_hi) { open = true; out += vseq.substr(lo - at); return false; }
+		out = vseq.substr(lo - at, hi - lo);
+		return true;
+	}
+};
+
+static void write_sequence(const std::string& seq, const std::string& outfile) {   // :180-186, :252-258
+	std::ofstream out; out.open(outfile); out << seq << std::endl; out.close();
+}
+
+// Start of t3 / t5 (query.h:201-214, :496-510): get_prev_vertex_with_sample from pos_x, repeated from
+// the ref position of the vertex found while its sample position is still >= pos_x.  When that ref
+// position maps to itself the reference never leaves the loop; the chain of positions is
+// deterministic, so seeing one twice means exactly that (`hang`).
+struct SampleStart { Graph::vertex v; uint64_t ref_pos = 0, sample_pos = 0; bool hang = false; };
+static SampleStart start_before(const VariantGraph* vg, const Index* idx, uint64_t pos_x, const std::string& sample_id, bool* ub) {
+	SampleStart st;
+	st.v = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, st.ref_pos, st.sample_pos, ub);
+	std::vector<uint64_t> tried;
+	while (st.sample_pos >= pos_x && st.v > 0) {
+		const uint64_t from = st.ref_pos;
+		if (std::find(tried.begin(), tried.end(), from) != tried.end()) { st.hang = true; break; }
+		tried.push_back(from);
+		st.v = get_prev_vertex_with_sample(vg, idx, from, sample_id, st.ref_pos, st.sample_pos, ub);
+	}
+	return st;
+}
+
+// t2 — sample's sequence over ref positions [pos_x, pos_y) (query.h:120-189).  next_ref_pos of a vertex
+// is the index of the FIRST ref-carrying out-neighbour (:143-151; t4 and t5 take the last one).
+std::string query_sample_from_ref(const VariantGraph* vg, const Index* idx, const uint64_t pos_x, const uint64_t pos_y,
+                                  const std::string& sample_id, bool print, const std::string& outfile, bool* ub) {
+	uint64_t ref_pos = 0, sample_pos = 0;
+	const Graph::vertex from = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, ref_pos, sample_pos, ub);
+	SeqWindow w{pos_x, pos_y};
+	for (VariantGraph::PathIterator it = vg->find(from, sample_id); !it.done(); ++it) {
+		uint64_t next_ref_pos = ref_pos + (*it)->length;
+		for (VariantGraph::BfsIterator nb = neighbours_of(vg, (*it)->vertex_id); !nb.done(); ++nb) {
+			SampleInfo info;
+			if (vg->get_sample_from_vertex_if_exists((*nb)->vertex_id, REF, info)) { next_ref_pos = info.index; break; }
+		}
+		if (w.take(vg->get_sequence(*(*it)), ref_pos, next_ref_pos)) break;
+		ref_pos = next_ref_pos;
+	}
+	if (print) write_sequence(w.out, outfile);
+	return w.out;
+}
+
+// t3 — the same over [pos_x, pos_y) of the sample's own coordinates (query.h:195-261): the running
+// position starts at the sample's index in the start vertex and grows by the length of every vertex.
 std::string query_sample_from_sample(const VariantGraph* vg, const Index* idx, const uint64_t pos_x, const uint64_t pos_y,
                                      const std::string& sample_id, bool print, const std::string& outfile, bool* ub, bool* hang) {
-	std::string seq = "";
-	uint64_t ref_pos = 0, sample_pos = 0;
-	Graph::vertex closest_v = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, ref_pos, sample_pos, ub);
-	std::vector<uint64_t> seen;
-	while (sample_pos >= pos_x && closest_v > 0) {
-		uint64_t pos = ref_pos;
-		if (std::find(seen.begin(), seen.end(), pos) != seen.end()) { if (hang) *hang = true; return ""; }
-		seen.push_back(pos);
-		closest_v = get_prev_vertex_with_sample(vg, idx, pos, sample_id, ref_pos, sample_pos, ub);
-	}
-	VariantGraph::PathIterator it = vg->find(closest_v, sample_id);
-	bool record_seq = false;
-	std::string temp;
-	while (!it.done()) {
-		temp.assign(vg->get_sequence(*(*it)));
-		uint64_t l = (*it)->length;
-		uint64_t next_sample_pos = sample_pos + l;
-		if (record_seq == true && next_sample_pos < pos_y) {
-			seq += temp;
-		} else if (record_seq == true && next_sample_pos >= pos_y) {
-			seq += temp.substr(0, pos_y - sample_pos);
-			break;
-		} else if (next_sample_pos >= pos_x && next_sample_pos < pos_y) {
-			record_seq = true;
-			seq += temp.substr(pos_x - sample_pos);
-		} else if (next_sample_pos >= pos_x && next_sample_pos >= pos_y) {
-			seq = temp.substr(pos_x - sample_pos, pos_y - pos_x);
-			break;
-		}
-		++it;
+	const SampleStart st = start_before(vg, idx, pos_x, sample_id, ub);
+	if (st.hang) { if (hang) *hang = true; return ""; }
+	SeqWindow w{pos_x, pos_y};
+	uint64_t sample_pos = st.sample_pos;
+	for (VariantGraph::PathIterator it = vg->find(st.v, sample_id); !it.done(); ++it) {
+		const uint64_t next_sample_pos = sample_pos + (*it)->length;
+		if (w.take(vg->get_sequence(*(*it)), sample_pos, next_sample_pos)) break;
 		sample_pos = next_sample_pos;
 	}
-	if (print) { std::ofstream out; out.open(outfile); out << seq << std::endl; out.close(); }
-	return seq;
+	if (print) write_sequence(w.out, outfile);
+	return w.out;
 }
 
 bool get_samples(const Vertex* v, const VariantGraph* vg, std::vector<std::pair<std::string, std::string>>& sample_ids) {   // :268-285
@@ -256,74 +263,58 @@ bool closest_var(const VariantGraph* vg, const Index* idx, const uint64_t pos, s
 	return true;
 }
 
-// All variants of a sample over [pos_x, pos_y) of the sample's own coordinates (query.h:490-612).  Same
-// start as query_sample_from_sample, incl. the loop that may never end (*hang).
+// t5 — a sample's variants over [pos_x, pos_y) of its own coordinates (query.h:490-612).  Start as t3
+// (incl. the loop that may never end), then from the backbone vertex holding ref_pos (:513) along the
+// sample's path: a vertex carrying the sample is a row when pos_x < sample_pos (strictly) on arrival,
+// the walk stops at sample_pos >= pos_y.  next_ref_pos / next_ref come from the LAST ref-carrying
+// out-neighbour (:541-549).
 std::vector<Variant> get_sample_var_in_sample(const VariantGraph* vg, const Index* idx, const uint64_t pos_x, const uint64_t pos_y,
                                               const std::string& sample_id, bool print, const std::string& outfile, QueryLog* log,
                                               bool* ub, bool* hang) {
-	std::vector<Variant> vars;
-	uint64_t ref_pos = 0, sample_pos = 0;
-	Graph::vertex closest_v = get_prev_vertex_with_sample(vg, idx, pos_x, sample_id, ref_pos, sample_pos, ub);
-	std::vector<uint64_t> seen;
-	while (sample_pos >= pos_x && closest_v > 0) {
-		uint64_t pos = ref_pos;
-		if (std::find(seen.begin(), seen.end(), pos) != seen.end()) { if (hang) *hang = true; return vars; }
-		seen.push_back(pos);
-		closest_v = get_prev_vertex_with_sample(vg, idx, pos, sample_id, ref_pos, sample_pos, ub);
-	}
-	closest_v = idx->find(ref_pos);                     // start from the ref node at ref_pos (:513)
-	SampleInfo sample;
-	uint64_t seq_len = 0;
-	if (vg->get_sample_from_vertex_if_exists(closest_v, REF, sample)) { seq_len = ref_pos - sample.index; ref_pos = sample.index; }
-	else err(log, "reference node is expected to be found!");
-	sample_pos = sample_pos - seq_len;
-	VariantGraph::PathIterator it = vg->find(closest_v, sample_id);
-	std::string cur_ref;
-	while (!it.done()) {
+	std::vector<Variant> rows;
+	const SampleStart st = start_before(vg, idx, pos_x, sample_id, ub);
+	if (st.hang) { if (hang) *hang = true; return rows; }
+	uint64_t ref_pos = st.ref_pos, sample_pos = st.sample_pos;
+	const Graph::vertex first = idx->find(ref_pos);
+	SampleInfo info;
+	if (vg->get_sample_from_vertex_if_exists(first, REF, info)) {       // :515-522: back to the start of that vertex
+		sample_pos -= ref_pos - info.index;
+		ref_pos = info.index;
+	} else err(log, "reference node is expected to be found!");
+	std::string ref_before;                                            // cur_ref
+	for (VariantGraph::PathIterator it = vg->find(first, sample_id); !it.done(); ++it) {
 		if (sample_pos >= pos_y) break;
-		Graph::vertex cur_v = (*it)->vertex_id;
-		Variant var;
-		uint64_t l = (*it)->length;
-		uint64_t next_ref_pos = ref_pos + l;
-		uint64_t next_sample_pos = sample_pos + l;
+		const Vertex* cur = *it;
+		uint64_t next_ref_pos = ref_pos + cur->length;
 		std::string next_ref;
-		VariantGraph::BfsIterator bfs_it = vg->find((*it)->vertex_id, 1);
-		++bfs_it;
-		while (!bfs_it.done()) {          // last ref-carrying neighbour wins (:541-549)
-			Graph::vertex v = (*bfs_it)->vertex_id;
-			if (vg->get_sample_from_vertex_if_exists(v, REF, sample)) { next_ref_pos = sample.index; next_ref = vg->get_sequence(*(*bfs_it)); }
-			++bfs_it;
-		}
-		if (sample_pos > pos_x && vg->get_sample_from_vertex_if_exists(cur_v, sample_id, sample)) {
-			std::string alt;
+		for (VariantGraph::BfsIterator nb = neighbours_of(vg, cur->vertex_id); !nb.done(); ++nb)
+			if (vg->get_sample_from_vertex_if_exists((*nb)->vertex_id, REF, info)) { next_ref_pos = info.index; next_ref = vg->get_sequence(*(*nb)); }
+		SampleInfo mine;
+		if (sample_pos > pos_x && vg->get_sample_from_vertex_if_exists(cur->vertex_id, sample_id, mine)) {
+			Variant row;
+			row.var_pos_set = true;
 			if (ref_pos == next_ref_pos) {                                   // insertion :556-562
-				cur_ref = "";
-				alt = vg->get_sequence(*(*it));
-				var.var_pos = ref_pos; var.var_pos_set = true;
-			} else if (vg->get_sample_from_vertex_if_exists(cur_v, REF, sample)) {   // deletion :564-573
-				alt = "";
-				vg->get_sample_from_vertex_if_exists(cur_v, sample_id, sample);
-				var.var_pos = sample.index; var.var_pos_set = true;
-				Graph::vertex v = idx->find(ref_pos - 1);
-				cur_ref = vg->get_sequence(vg->get_vertex(v));
+				ref_before = "";
+				row.alt = vg->get_sequence(*cur);
+				row.var_pos = ref_pos;
+			} else if (vg->get_sample_from_vertex_if_exists(cur->vertex_id, REF, info)) {   // deletion :564-573
+				row.var_pos = mine.index;
+				ref_before = vg->get_sequence(vg->get_vertex(idx->find(ref_pos - 1)));
 			} else {                                                         // substitution :574-579
-				alt = vg->get_sequence(*(*it));
-				vg->get_sample_from_vertex_if_exists(cur_v, sample_id, sample);
-				var.var_pos = sample.index; var.var_pos_set = true;
+				row.alt = vg->get_sequence(*cur);
+				row.var_pos = mine.index;
 			}
-			var.alt = alt;
-			var.ref = cur_ref;
-			get_samples((*it), vg, var.samples);
-			vars.push_back(var);
+			row.ref = ref_before;
+			get_samples(cur, vg, row.samples);
+			rows.push_back(row);
 		}
-		cur_ref = next_ref;
+		ref_before = next_ref;
 		ref_pos = next_ref_pos;
-		sample_pos = next_sample_pos;
-		++it;
+		sample_pos += cur->length;
 	}
-	say(log, "Number of variants get_sample_var_in_sample: " + std::to_string(vars.size()) + "\n");
-	if (print) dump_vars(vars, outfile);
-	return vars;
+	say(log, "Number of variants get_sample_var_in_sample: " + std::to_string(rows.size()) + "\n");
+	if (print) dump_vars(rows, outfile);
+	return rows;
 }
 
 std::vector<Variant> get_sample_var_in_ref(const VariantGraph* vg, const Index* idx, const uint64_t pos_x,
