@@ -43,7 +43,8 @@ int main(int argc, char** argv) {
 			bool verbose = flag(argc, argv, "-v");
 			auto t0 = std::chrono::steady_clock::now();
 			for (size_t i = 0; i < regions.size(); i++) {
-				if (type == 2) query_sample_from_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);
+				if (type == 1) { std::vector<Variant> var; closest_var(&vg, &idx, regions[i].first, var, verbose, outfile); }
+				else if (type == 2) query_sample_from_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);
 				else if (type == 3) { bool hang = false; query_sample_from_sample(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile, nullptr, &hang); if (hang) { fprintf(stderr, "does not terminate\n"); return 3; } }
 				else if (type == 5) { bool hang = false; get_sample_var_in_sample(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile, nullptr, nullptr, &hang); if (hang) { fprintf(stderr, "does not terminate\n"); return 3; } }
 				else if (type == 4) get_sample_var_in_ref(&vg, &idx, regions[i].first, regions[i].second, sample, verbose, outfile);

@@ -384,7 +384,8 @@ def test_cli_front_end_matches_reference_cli_lines(tmp_path):
     cases = [["-t", "6", "-r", "10:105"], ["-t", "6", "-r", "30:40,10:105,2000:3000,466:470"], ["-t", "4", "-s", "1", "-r", "14:105,660:700"],
              ["-t", "7", "-r", "10", "-b", "C", "-a", "T"], ["-t", "7", "-r", "58", "-b", "", "-a", "T"],
              ["-t", "2", "-s", "1", "-r", "10:105"], ["-t", "2", "-s", "1", "-r", "1:1002,660:700,55:62"],
-             ["-t", "3", "-s", "1", "-r", "1:1001,466:470,57:60"], ["-t", "5", "-s", "1", "-r", "1:1001,466:600"]]
+             ["-t", "3", "-s", "1", "-r", "1:1001,466:470,57:60"], ["-t", "5", "-s", "1", "-r", "1:1001,466:600"],
+             ["-t", "1", "-r", "20"], ["-t", "1", "-r", "500,20,990"]]
     for i, c in enumerate(cases):
         outs = []
         for exe, tag in ((cli, "gpu"), (ref, "cpu")):

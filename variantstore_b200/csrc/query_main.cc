@@ -1,6 +1,6 @@
 // vsgpu_query — front-end with the reference's `variantstore query` flags
 // (src/variantstore.cc:101-134, src/commands.cc:113-215):
-//   -p <ser prefix> -t <2|3|4|5|6|7> -r <beg[:end][,...]> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]
+//   -p <ser prefix> -t <1..7> -r <beg[:end][,...]> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]
 // -m is accepted and ignored (both modes give identical results; only the reference's paging differs).
 // Unlike query_main's per-region loop the whole region list goes to the GPU as one batch; the lines
 // printed per region are the reference's.
@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
 	int a0 = (argc > 1 && !strcmp(argv[1], "query")) ? 2 : 1;
 	argc -= a0 - 1; argv += a0 - 1;
 	const char* prefix = opt(argc, argv, "-p", nullptr); const char* tstr = opt(argc, argv, "-t", nullptr); const char* rstr = opt(argc, argv, "-r", nullptr);
-	if (!prefix || !tstr || !rstr) { fprintf(stderr, "usage: vsgpu_query [query] -p <prefix> -t <2|3|4|5|6|7> -r <regions> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]\n"); return 1; }
+	if (!prefix || !tstr || !rstr) { fprintf(stderr, "usage: vsgpu_query [query] -p <prefix> -t <1..7> -r <regions> -m <0|1> [-o file] [-s sample] [-a alts] [-b refs] [-v]\n"); return 1; }
 	const int type = atoi(tstr);
 	const std::string outfile = opt(argc, argv, "-o", ""), sample = opt(argc, argv, "-s", "");
 	const bool verbose = flag(argc, argv, "-v");
@@ -92,6 +92,15 @@ int main(int argc, char** argv) {
 				if (verbose) { char* text = nullptr; if (vsgpu_rows_t4(idx, hits + off[i], off[i + 1] - off[i], 1, &text) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
 			}
 			vsgpu_result_free(res);
+		}
+	} else if (type == 1) {
+		// closest_var prints nothing; with -v every call that finds a variant rewrites -o (query.h:472-479)
+		std::vector<uint32_t> lo(n), hi(n);
+		rc = vsgpu_query_t1(idx, n, x.data(), lo.data(), hi.data());
+		for (uint64_t i = 0; i < n && rc == 0 && verbose; i++) {
+			if (lo[i] == VSGPU_NONE) continue;                     // the operator returned false before printing
+			char* text = nullptr; uint64_t nrows = 0;
+			if (vsgpu_rows_t1(idx, lo[i], hi[i], 1, &text, &nrows) == 0) { write_rows(outfile, text, true); vsgpu_free(text); }
 		}
 	} else if (type == 5) {
 		uint32_t sid = 0;
