@@ -3,6 +3,7 @@ machine-checkable outputs the reference publishes for this path) and the committ
 import json
 import os
 
+import numpy as np
 import pytest
 
 import vs_testlib as T
@@ -82,6 +83,35 @@ def test_sample_sequence_equals_vcf_consensus():
         exec(src[src.index("def consensus"):src.index("out = {}")], ns)
         ref, cons = ns["consensus"](os.path.join(T.REF_DATA, "x.fa"), os.path.join(T.REF_DATA, "x.vcf.gz"))
         assert cons == seq and len(ref) == 1001
+    o.close()
+
+
+def test_sample_coordinate_operators_agree_with_the_consensus():
+    """Independent pins for t3 and t5 on data/x.*: a region of the sample's own coordinates is a slice of the
+    consensus sequence (FASTA + the sample's alt alleles, computed without the oracle), and a substitution row
+    of t5 carries the position at which its alt allele sits in that sequence.  Regions the reference hangs or
+    throws on are excluded (they have no answer to compare)."""
+    cons = EXPECTED["x"]["t2_consensus"]
+    o = Oracle.open(os.path.join(T.GOLDEN, "x_ser"))
+    rng = np.random.default_rng(0)
+    n = 4000
+    x = rng.integers(1, 1000, n).astype(np.uint64)
+    y = x + rng.integers(1, 200, n).astype(np.uint64)
+    ln, dg, st, ub, seqs = o.batch_t3(x, y, np.ones(n, np.uint32), want_text=True)
+    checked = 0
+    for i in range(n):
+        if st[i] == 0 and not ub[i]:
+            assert seqs[i] == cons[int(x[i]) - 1:int(y[i]) - 1], (int(x[i]), int(y[i]))
+            checked += 1
+    assert checked > n // 2
+    rows = o.t5_text(1, len(cons) + 1, "1").split("Pos\tRef\tAlt\tSamples\n", 1)[1].strip().split("\n")
+    subs = 0
+    for line in rows:
+        pos, ref, alt, _ = line.split("\t")
+        if ref and alt:
+            assert cons[int(pos) - 1:int(pos) - 1 + len(alt)] == alt, line
+            subs += 1
+    assert subs > 40 and len(rows) == 75          # every record of data/x.vcf.gz
     o.close()
 
 
