@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """bench.py — region queries/s (types 4/6) of the batched region path on B200.
 
-A step = one pass of the hot path over one batch of synthetic input: t6 (get_var_in_ref) over all
-regions, then t4 (get_sample_var_in_ref) over the same regions with one random sample each.
+A step = one pass of the hot path over one batch of synthetic input: t6 (get_var_in_ref) and t4
+(get_sample_var_in_ref, one random sample per region) over the same regions — by default from ONE
+fused launch (k_t4p<kFuse6>: the t6 slice falls out of the two index ranks t4 needs anyway;
+`--unfused` runs k_t6 then k_t4p as round 1 did, and `by_kernel` always reports both).
 Workload at N=1 = BASELINE.json configs[1]: a chr22-shaped synthetic index (~1.1 M records x 2,504
 samples) and 1 M random 1 kb regions (sorted, as the reference's read_regions does).  With N > 1
 every rank owns its own contig shard of that shape and its own regions (weak scaling, no collective
@@ -29,6 +31,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 POS_LO, REF_LEN = 16_050_000, 51_304_566          # scripts/bm_vs_query.sh:13, scripts/run_query.sh:6
+# the kernel instances a default run launches (variantstore_b200/csrc/kernels.cu: launch_t4x, 64-region tiles, 24 CTAs / SM)
+T4_INSTANCE = "k_t4p<64,24,8,k32=false,fuse6=false>"
+T4_FUSED_INSTANCE = "k_t4p<64,24,8,k32=false,fuse6=true>"
 
 
 def log(*a):
@@ -190,7 +195,8 @@ def workload_config(args, meta):
             "regions_per_gpu": args.regions, "region_width": args.width, "records": args.records, "samples": args.samples,
             "sharding": "one contig shard per GPU, regions routed by the host, no collective on the data path",
             "l2": "256 MiB buffer written between timed steps (L2 flush)",
-            "e2e_coordinates": "u64 (vsgpu_query_t6 / _t4)" if getattr(args, "e2e_u64", False) else "u32 (vsgpu_query_t6_u32 / _t4_u32)"}
+            "step": "k_t6 + k_t4p (two launches)" if getattr(args, "unfused", False) else "one fused launch of k_t4p<fuse6> answers t6 and t4",
+            "e2e_coordinates": "u64" if getattr(args, "e2e_u64", False) else "u32 (region bounds are parsed with std::stoi, commands.cc:76-80)"}
 
 
 def run_vsgpu(args):
@@ -227,6 +233,7 @@ def run_vsgpu(args):
     x, y, s = make_regions(args, meta, rank)
     n = len(x)
     b6, b4 = Batch(idx, 6, x, y), Batch(idx, 4, x, y, sample_ids=s)
+    b46 = None if args.unfused else Batch(idx, 46, x, y, sample_ids=s)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -235,32 +242,51 @@ def run_vsgpu(args):
         torch.cuda.synchronize()
 
     def step():
-        b6.run()
-        b4.run()
+        if b46 is not None:
+            b46.run()
+        else:
+            b6.run()
+            b4.run()
+
+    def timed(fn, batches, steps):
+        ms, per = [], [[] for _ in batches]
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+            for k, b in enumerate(batches):
+                per[k].append(b.timings_ms()[0])
+        return ms, [float(np.mean(p)) for p in per]
 
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step()
+        b6.run(); b4.run()
     torch.cuda.synchronize()
     algo6, launches6 = b6.stats()
     algo4, launches4 = b4.stats()
+    algo46, launches46 = b46.stats() if b46 is not None else (algo6 + algo4, launches6 + launches4)
+    # fused and unfused answers are the same arrays (checked here once, outside the timed region)
+    if b46 is not None and rank == 0:
+        lo_f, hi_f, cnt_f, off_f, hits_f = b46.fetch()
+        lo_u, hi_u, cnt_u = b6.fetch()
+        off_u, hits_u, _ = b4.fetch()
+        assert np.array_equal(lo_f, lo_u) and np.array_equal(hi_f, hi_u) and np.array_equal(cnt_f, cnt_u) and np.array_equal(off_f, off_u) and np.array_equal(hits_f, hits_u), "fused launch disagrees with k_t6 + k_t4p"
 
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    step_ms, k6_ms, k4_ms = [], [], []
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-        k6_ms.append(b6.timings_ms())
-        k4_ms.append(b4.timings_ms())
+    step_ms, kms = timed(step, [b46] if b46 is not None else [b6, b4], args.steps)
     barrier()
     sampler.stop_flag = True
+    # the unfused kernels on their own, for by_kernel (not part of `value` unless --unfused)
+    _, (t6_ms,) = timed(b6.run, [b6], max(3, args.steps // 2))
+    _, (t4_ms,) = timed(b4.run, [b4], max(3, args.steps // 2))
+    fused_ms = kms[0] if b46 is not None else None
     total_ms = float(np.sum(step_ms))
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -280,16 +306,20 @@ def run_vsgpu(args):
     px64, py64 = (px, py) if args.e2e_u64 else (torch.from_numpy(x.astype(np.int64)).pin_memory(), torch.from_numpy(y.astype(np.int64)).pin_memory())
     q6 = lib.vsgpu_query_t6 if args.e2e_u64 else lib.vsgpu_query_t6_u32
     q4 = lib.vsgpu_query_t4 if args.e2e_u64 else lib.vsgpu_query_t4_u32
+    q64 = lib.vsgpu_query_t6t4 if args.e2e_u64 else lib.vsgpu_query_t6t4_u32
     plo, phi, pcnt = (torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(3))      # page-locked result arrays
     vp = C.c_void_p
 
     def e2e_step():
-        rc = q6(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(plo.data_ptr()), vp(phi.data_ptr()), vp(pcnt.data_ptr()))
-        assert rc == 0, lib.vsgpu_last_error()
         r = vp()
-        rc = q4(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(ps.data_ptr()), C.byref(r))
+        if args.unfused:
+            rc = q6(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(plo.data_ptr()), vp(phi.data_ptr()), vp(pcnt.data_ptr()))
+            assert rc == 0, lib.vsgpu_last_error()
+            rc = q4(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(ps.data_ptr()), C.byref(r))
+        else:   # one fused call: x / y / samples up once; rec_lo, the two row counts and the hit codes back
+            rc = q64(h, n, vp(px.data_ptr()), vp(py.data_ptr()), vp(ps.data_ptr()), vp(plo.data_ptr()), None, vp(pcnt.data_ptr()), C.byref(r))
         assert rc == 0, lib.vsgpu_last_error()
-        total = int(lib.vsgpu_result_offsets(r)[n])
+        total = int(lib.vsgpu_result_total(r))
         lib.vsgpu_result_free(r)
         return total
 
@@ -308,8 +338,12 @@ def run_vsgpu(args):
         e2e_s = float(t.item())
     e2e_val = 2 * n * world / e2e_s
     cb = 8 if args.e2e_u64 else 4
-    h2d = n * 2 * cb + n * (2 * cb + 4)                  # t6 x, y; t4 x, y, sample ids
-    d2h = n * 12 + (n + 1) * 8 + hits_total * 4         # t6 lo, hi, counts; t4 offsets + hit codes
+    if args.unfused:
+        h2d = n * 2 * cb + n * (2 * cb + 4)              # t6 x, y; t4 x, y, sample ids
+        d2h = n * 12 + n * 4 + hits_total * 4            # t6 lo, hi, counts; t4 counts + hit codes
+    else:
+        h2d = n * (2 * cb + 4)                           # x, y, sample ids, once
+        d2h = n * 8 + n * 4 + hits_total * 4             # t6 lo + counts; t4 counts + hit codes
 
     if rank != 0:
         if dist is not None:
@@ -317,27 +351,38 @@ def run_vsgpu(args):
         return 0
 
     peak, peak_src = measured_peak()
-    walk_ms = float(np.mean([k[0] for k in k4_ms]))
-    t6_ms = float(np.mean([k[0] for k in k6_ms]))
-    achieved = algo4 / (walk_ms / 1000) / 1e9
-    traffic = None
+    dom_ms = fused_ms if fused_ms is not None else t4_ms
+    dom_algo = algo46 if fused_ms is not None else algo4
+    dom_name = T4_FUSED_INSTANCE if fused_ms is not None else T4_INSTANCE
+    achieved_conv = dom_algo / (dom_ms / 1000) / 1e9
+    # DRAM bytes of one launch of exactly this kernel instance on exactly this workload, from the committed ncu capture
+    # (profiles/traffic.json names the instance, the region count and the capture); null when they do not match this run
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_t4_dram_bytes_per_launch")
+            tj = json.load(open(tpath)).get(dom_name)
+            if tj and tj.get("regions") == n and tj.get("width") == args.width and tj.get("records") == args.records:
+                traffic, traffic_src = int(tj["dram_bytes_per_launch"]), tj.get("capture")
         except Exception:
             traffic = None
+    achieved = (traffic / (dom_ms / 1000) / 1e9) if traffic else None
     line = {
         "metric": "region queries/s (types 4/6)", "value": value, "unit": "regions/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic", "config": workload_config(args, meta),
-        "by_kernel": {"t6_regions_per_s": n / (t6_ms / 1000), "t4_regions_per_s": n / (walk_ms / 1000),
-                      "k_t6_ms": t6_ms, "k_t4_ms": walk_ms, "t6_algorithmic_GBps": algo6 / (t6_ms / 1000) / 1e9,
+        "by_kernel": {"fused_t6t4_ms": fused_ms, "k_t6_ms": t6_ms, "k_t4_ms": t4_ms, "t6_regions_per_s": n / (t6_ms / 1000), "t4_regions_per_s": n / (t4_ms / 1000),
+                      "fused_regions_per_s": (n / (fused_ms / 1000)) if fused_ms else None, "t6_algorithmic_GBps": algo6 / (t6_ms / 1000) / 1e9,
                       "t4_hits_per_region": hits_total / n, "index_open_s": open_s, "index_open_cached_s": open_cached_s, "device_bytes": int(idx.info.device_bytes)},
-        "roofline": {"bound": "hbm", "kernel": "k_t4", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo4},
-        "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": (launches6 + launches4) * args.steps,
+        # frac = DRAM bytes the kernel really moved (ncu dram__bytes_read + write of this instance on this workload) / its live
+        # CUDA-event duration / the measured HBM peak.  The SURVEY section 8(d) per-record convention is kept beside it: the
+        # hit map reads one bit where that convention charges 20 bytes, so it can exceed 1 and is not a roofline fraction.
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": dom_ms, "peak_source": peak_src,
+                     "algorithmic_convention": {"bytes_per_launch": dom_algo, "GBps": achieved_conv, "frac": achieved_conv / peak,
+                                                "note": "SURVEY 8(d): 288 (t6) + 292 + 20 v + 4 h (t4) per region; counts a 20-byte record read per scanned record, which the hit map replaces by one bit"}},
+        "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "call": "vsgpu_query_t6 + vsgpu_query_t4" if args.unfused else "vsgpu_query_t6t4"},
+        "gpu_launches": (launches46 if b46 is not None else launches6 + launches4) * args.steps,
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_other_ops:
@@ -389,6 +434,7 @@ def main():
     ap.add_argument("--cpu-sample-single", type=int, default=2_000, help="regions per type of the single-thread cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-ops", action="store_true", help="skip the t2 side measurement")
+    ap.add_argument("--unfused", action="store_true", help="a step = k_t6 then k_t4p (two launches, two host-buffer calls) instead of the fused launch / call")
     ap.add_argument("--e2e-u64", action="store_true", help="end-to-end arm through the 64-bit coordinate entry points instead of the 32-bit ones")
     ap.add_argument("--cache-dir", default=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"))
     args = ap.parse_args()

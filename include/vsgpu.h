@@ -98,8 +98,22 @@ int vsgpu_query_t4_u32(vsgpu_index* idx, uint64_t n, const uint32_t* x, const ui
                        const uint32_t* sample_ids, vsgpu_result** out);   /* 32-bit coordinates, see vsgpu_query_t6_u32 */
 uint64_t vsgpu_result_num_queries(const vsgpu_result* r);
 const uint64_t* vsgpu_result_offsets(const vsgpu_result* r);   /* n + 1 */
+const uint32_t* vsgpu_result_counts(const vsgpu_result* r);    /* n: rows per region = offsets[i + 1] - offsets[i].  A host-buffer call brings back
+                                                                  the counts (4 bytes a region over PCIe); whichever of offsets / counts did not travel is
+                                                                  built on the host the first time it is asked for */
+uint64_t vsgpu_result_total(const vsgpu_result* r);            /* rows over all regions = offsets[n] */
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r);
-void vsgpu_result_free(vsgpu_result* r);
+void vsgpu_result_free(vsgpu_result* r);                       /* before vsgpu_close of its index: the buffers go back to the index's page-locked pool */
+
+/* ---- t6 + t4 over the same regions in one pass — the loop body of query_main (src/commands.cc:150-193) run for
+ * `-t 6` and `-t 4` on one region list.  get_var_in_ref's slice comes from the two index ranks that
+ * get_sample_var_in_ref needs anyway (Index::find / is_empty, index.h:119-166), so one kernel (k_t4p<kFuse6>)
+ * answers both operators: x / y / sample_ids cross PCIe once, and per region rec_lo, counts6 (rec_hi optional: NULL)
+ * and the t4 row count come back with the hit codes.  Same answers as vsgpu_query_t6 + vsgpu_query_t4. */
+int vsgpu_query_t6t4(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids,
+                     uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts6, vsgpu_result** out);
+int vsgpu_query_t6t4_u32(vsgpu_index* idx, uint64_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample_ids,
+                         uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts6, vsgpu_result** out);
 
 /* ---- t1: closest_var(vg, idx, pos, vars) — include/query.h:441-483 (SURVEY.md §8f "next" row 1) -----
  * rec_lo[i] = rec_hi[i] = VSGPU_NONE where the operator returns false (no variant on the contig);
@@ -181,14 +195,16 @@ const float* vsgpu_text_stage_ms(const vsgpu_text* t);      /* t2: device time o
 
 /* ---- device-resident batches (bench harness; replaces the timing loop of src/bm_query.cc:74-135)
  * A batch keeps its regions and results in HBM so a run times the kernels alone.
- * type = 4, 6 or 7.  For type 7 pass refs/alts; for type 4 pass sample_ids. */
+ * type = 4, 6, 7 or 46 (t6 + t4 fused: one launch answers both, as vsgpu_query_t6t4).  For type 7 pass refs/alts;
+ * for types 4 and 46 pass sample_ids. */
 int vsgpu_batch_create(vsgpu_index* idx, int type, uint64_t n, const uint64_t* x, const uint64_t* y,
                        const uint32_t* sample_ids, const char* const* refs, const char* const* alts,
                        vsgpu_batch** out);
 /* Enqueue one pass of the hot path over the batch on the index's stream (no host sync). */
 int vsgpu_batch_run(vsgpu_batch* b);
 /* Synchronise, then copy results out.  Any pointer may be NULL.  t6: rec_lo/rec_hi/counts;
- * t4: counts (per query) and *out (CSR); t7: rec_lo receives the record ids. */
+ * t4: counts (per query) and *out (CSR); t7: rec_lo receives the record ids; 46: rec_lo/rec_hi/counts of t6
+ * and *out = the t4 CSR. */
 int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts, vsgpu_result** out);
 /* Algorithmic bytes of the last run (SURVEY.md §8d formulas) and the number of kernels it launched. */
 int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* kernel_launches);
@@ -196,6 +212,40 @@ int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* ker
  * (t6/t7: 1 kernel; t4: walk, scan, gather).  Synchronises. */
 int vsgpu_batch_timings(vsgpu_batch* b, float* ms, uint32_t cap, uint32_t* n);
 void vsgpu_batch_free(vsgpu_batch* b);                         /* before vsgpu_close of its index: a batch points into it */
+
+/* ---- several indexes on several GPUs behind one handle ---------------------------------------------
+ * The reference keeps one ser/ directory per contig and runs one process per contig (util.cc:93-96,
+ * eval_data_records/evaluation.txt:34); query_main (src/commands.cc:113-215) serves one.  A router opens
+ * nshards directories — whole contigs, or position ranges [range_lo[k], range_hi[k]) of a contig built
+ * from the records of that range (range_hi[k] = 0: to the contig's end; both arrays may be NULL: whole
+ * contigs) — on the GPUs of this node: devices[k] names the GPU of shard k, or devices = NULL spreads the
+ * shards over the first ndevices GPUs (0: all) by longest-processing-time on their size.  A query names a
+ * contig per region (vsgpu_router_contig_id; the contig of a shard is the one its sampleid_map.lst names)
+ * and is answered by the shard owning (contig, x): one host thread per GPU, the fused host-buffer call per
+ * shard, no traffic between GPUs.  Record ids and hit codes are local to shard_of[i]
+ * (vsgpu_router_shard_index gives that shard's index for vsgpu_rows_* / vsgpu_digest_*). */
+typedef struct vsgpu_router vsgpu_router;
+int vsgpu_router_open(uint32_t nshards, const char* const* ser_prefixes, const uint64_t* range_lo, const uint64_t* range_hi,
+                      const int* devices, int ndevices, vsgpu_router** out);
+void vsgpu_router_close(vsgpu_router* r);
+const char* vsgpu_router_last_error(void);
+uint32_t vsgpu_router_num_shards(const vsgpu_router* r);
+uint32_t vsgpu_router_num_contigs(const vsgpu_router* r);
+const char* vsgpu_router_contig_name(const vsgpu_router* r, uint32_t contig);
+int vsgpu_router_contig_id(const vsgpu_router* r, const char* name, uint32_t* contig);
+vsgpu_index* vsgpu_router_shard_index(const vsgpu_router* r, uint32_t shard);
+int vsgpu_router_shard_device(const vsgpu_router* r, uint32_t shard);
+/* t6 + t4 for n regions (contig[i], [x[i], y[i]), sample_ids[i]) in the caller's order: shard_of[i], rec_lo[i],
+ * counts6[i] (t6 slice = [rec_lo, rec_lo + counts6) except where the literal dedup rule lowered the count) and
+ * counts4[i]; the t4 hit codes as one CSR through vsgpu_router_offsets / _hits (valid until the next call). */
+int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig, const uint32_t* x, const uint32_t* y, const uint32_t* sample_ids,
+                            uint32_t* shard_of, uint32_t* rec_lo, uint32_t* counts6, uint32_t* counts4);
+const uint64_t* vsgpu_router_offsets(const vsgpu_router* r);   /* n + 1 */
+const uint32_t* vsgpu_router_hits(const vsgpu_router* r);
+/* Last call: wall-clock milliseconds each GPU's host thread spent on its shards and the regions it answered (up to cap
+ * entries; *ndev = GPUs in use), the routing time before and the scatter time after. */
+int vsgpu_router_stats(const vsgpu_router* r, uint32_t cap, int* devices, double* device_ms, uint64_t* device_regions, uint32_t* ndev,
+                       double* route_ms, double* scatter_ms);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@
 
 using namespace vsgpu;
 
-struct vsgpu_result { std::vector<uint64_t> offsets; std::vector<uint32_t> hits; std::vector<uint8_t> status; };
+struct vsgpu_result { std::vector<uint64_t> offsets; std::vector<uint32_t> hits; std::vector<uint8_t> status; std::vector<uint32_t> counts; };
 struct vsgpu_text { std::string bytes; std::vector<uint64_t> offsets; std::vector<uint8_t> status; };
 struct vsgpu_index : HostIndex {
 	DevIndex dev;
@@ -26,7 +26,7 @@ struct vsgpu_index : HostIndex {
 	std::vector<uint64_t> sidx_begin; std::vector<uint32_t> sidx, sid;
 	std::vector<uint32_t> bbs;
 	std::string seq_ascii;
-	std::vector<uint32_t> bucket;
+	std::vector<uint32_t> bucket, d4;
 	std::vector<uint2> t7;
 	std::vector<uint32_t> hitmap;
 };
@@ -53,7 +53,10 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 	d.D = f.D; d.M = f.M; d.R = f.R; d.num_cent = (uint32_t)f.cent.size(); d.words_per_set = f.words_per_set;
 	d.num_samples = f.num_samples; d.class_mode = f.class_mode; d.index_bits = f.index_bits; d.last_end = ix->last_end; d.t1_fallback_pos = ix->t1_fallback_pos;
 	build_buckets(f, ix->bucket, d.bucket_shift);
+	build_d4(f, ix->d4);
 	d.nbuckets = (uint32_t)ix->bucket.size() - 1; d.bucket = ix->bucket.data(); d.dstart = f.dstart.data();
+	d.d4 = (const uint4*)ix->d4.data();
+	{ const char* e = getenv("VSGPU_T4_ROW64"); d.walk2 = (!e || atoi(e) != 0) ? 1 : 0; }
 	ix->t7.resize(f.D);
 	for (uint32_t i = 0; i < f.D; i++) ix->t7[i] = make_uint2(f.t7_lo[i], f.t7_hi[i]);
 	d.dlev = (const uint4*)f.dlev.data(); d.dinfo = f.dinfo.data(); d.t7rng = ix->t7.data(); d.cent = (const uint4*)f.cent.data();
@@ -208,7 +211,11 @@ int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 	VecSink sink{&r->hits};
 	for (uint64_t i = 0; i < n; i++) {
 		if (x[i] < 1 || s[i] == 0 || s[i] >= ix->dev.num_samples) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
-		logic::walk_any(ix->dev, x[i], y[i], s[i], sink);
+		uint2 fused;                                       // the t6 slice a fused launch takes from the walk's two ranks
+		logic::walk_any(ix->dev, x[i], y[i], s[i], sink, &fused);
+		bool bad = false;
+		const uint2 b = logic::t6_bounds(ix->dev, x[i], y[i], &bad);
+		if (fused.x != b.x || fused.y != b.y) return set_err(VSGPU_EINVAL, "hostsim: fused t6 slice differs from t6_bounds");
 		r->offsets[i + 1] = r->hits.size();
 	}
 	*out = r.release();
@@ -222,6 +229,20 @@ int vsgpu_query_t4_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uin
 	std::vector<uint64_t> x64(x, x + n), y64(y, y + n);
 	return vsgpu_query_t4(ix, n, x64.data(), y64.data(), s, out);
 }
+int vsgpu_query_t6t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* s, uint32_t* lo, uint32_t* hi, uint32_t* c6, vsgpu_result** out) {
+	if (int rc = vsgpu_query_t6(ix, n, x, y, lo, hi, c6)) return rc;
+	return vsgpu_query_t4(ix, n, x, y, s, out);
+}
+int vsgpu_query_t6t4_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uint32_t* y, const uint32_t* s, uint32_t* lo, uint32_t* hi, uint32_t* c6, vsgpu_result** out) {
+	std::vector<uint64_t> x64(x, x + n), y64(y, y + n);
+	return vsgpu_query_t6t4(ix, n, x64.data(), y64.data(), s, lo, hi, c6, out);
+}
+const uint32_t* vsgpu_result_counts(const vsgpu_result* cr) {
+	vsgpu_result* r = const_cast<vsgpu_result*>(cr);
+	if (r->counts.size() + 1 != r->offsets.size()) { r->counts.resize(r->offsets.size() - 1); for (size_t i = 0; i + 1 < r->offsets.size(); i++) r->counts[i] = (uint32_t)(r->offsets[i + 1] - r->offsets[i]); }
+	return r->counts.data();
+}
+uint64_t vsgpu_result_total(const vsgpu_result* r) { return r->offsets.back(); }
 uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r->offsets.size() - 1; }
 const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r->offsets.data(); }
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r->hits.data(); }

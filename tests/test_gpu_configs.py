@@ -100,6 +100,51 @@ def test_multi_contig_sharded_cuda(tmp_path):
     sh.close()
 
 
+def test_router_contigs_and_position_shards_cuda(tmp_path):
+    """Config [2] in small through the C++ router (csrc/router.cc): three contigs, one of them cut into two
+    position-range shards (each built from the records of its range), regions of all of them interleaved
+    in one call, answers in the caller's order and equal to the oracle of the shard that owns the start."""
+    from variantstore_b200 import Router
+    specs = [("20", 400_000, 9000, 1, 400_000, 30), ("21", 500_000, 12000, 1, 500_000, 31),
+             ("22", 600_000, 8000, 1, 300_000, 32), ("22", 600_000, 8000, 280_000, 600_000 - 1000, 33)]   # (contig, ref_length, records, pos_lo, pos_hi, seed)
+    prefixes, oracles, ranges = [], [], [(0, 0), (0, 0), (0, 300_000), (300_000, 0)]
+    for k, (c, rl, nrec, plo, phi, seed) in enumerate(specs):
+        p = str(tmp_path / f"s{k}")
+        oracles.append(Oracle.synth(p, chr_name=c, ref_length=rl, pos_lo=max(2, plo), pos_hi=phi, n_records=nrec, n_samples=100, fmax=60, seed=seed, cqf_log2=18))
+        prefixes.append(p)
+    with Router(prefixes, ranges=ranges, ndevices=1) as r:
+        assert r.contigs == ["20", "21", "22"] and r.num_shards == 4
+        rng = np.random.default_rng(9)
+        n = 6000
+        contig = rng.integers(0, 3, n)
+        lens = np.array([400_000, 500_000, 600_000])[contig]
+        x = (rng.integers(1, 10**9, n) % (lens - 2000) + 1).astype(np.uint32)
+        y = x + rng.choice([10, 1000, 20_000], n).astype(np.uint32)
+        s = rng.integers(1, 101, n).astype(np.uint32)
+        so, lo, c6, c4, off, hits = r.query_t6t4(r.contig_ids([["20", "21", "22"][c] for c in contig]), x, y, s)
+        want_shard = np.where(contig < 2, contig, np.where(x < 300_000, 2, 3))
+        assert np.array_equal(so, want_shard) and np.array_equal(np.diff(off), c4) and off[-1] == len(hits)
+        for k in range(4):
+            idx = np.nonzero(so == k)[0]
+            assert len(idx) > 500
+            o6, d6 = oracles[k].batch_t6(x[idx], y[idx])
+            o4, d4, ub = oracles[k].batch_t4(x[idx], y[idx], s[idx])
+            sh = r.shard(k)
+            assert np.array_equal(o6, c6[idx]) and np.array_equal(d6, sh.digest_t6(lo[idx], lo[idx] + c6[idx]))
+            sub_off = np.concatenate([[0], np.cumsum(c4[idx])]).astype(np.uint64)
+            sub_hits = np.concatenate([hits[off[i]:off[i + 1]] for i in idx]) if len(idx) else np.zeros(0, np.uint32)
+            ok = (o4 == c4[idx]) & (d4 == sh.digest_t4(sub_off, sub_hits))
+            assert np.all(ok | (ub != 0))
+        st = r.stats()
+        assert st["devices"] == [0] and st["device_regions"] == [n] and st["device_ms"][0] > 0
+        # a start no shard owns (contig 22 has no shard for nothing; an unknown contig id) is an error, not a silent zero
+        from variantstore_b200 import VsgpuError
+        with pytest.raises(VsgpuError):
+            r.query_t6t4(np.array([7], np.uint32), x[:1], y[:1], s[:1])
+    for o in oracles:
+        o.close()
+
+
 def test_full_size_chr22_shape_cuda(tmp_path):
     """BASELINE.json config [1] at full size (1.1 M records x 2 504 samples, 1 M regions): the oracle
     checks a 3 000-region subsample bit for bit; the full batch is checked through size-independent

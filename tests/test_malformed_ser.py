@@ -96,3 +96,35 @@ def test_sample_coordinate_operators_need_the_vertex_blocks_again(ser_copy):
     with pytest.raises(VsgpuError):
         e.batch_sample_var_in_sample([1], [1001], [2])                     # sample id out of range (one sample)
     e.close()
+
+
+def test_short_but_well_formed_seq_buffer(ser_copy):
+    """seq_buffer.sdsl cut to a twentieth of its symbols with a coherent header (int_vector<0>: u64 size in bits, u8
+    width, words): every vertex slice past the new end must be refused at open — the materialiser and the
+    render / copy kernels read those slices unchecked."""
+    import struct
+    from variantstore_b200 import VsgpuError
+    p = os.path.join(ser_copy, "seq_buffer.sdsl")
+    data = open(p, "rb").read()
+    bits, width = struct.unpack_from("<QB", data)
+    keep = (bits // width) // 20
+    nwords = (keep * width + 63) // 64
+    open(p, "wb").write(struct.pack("<QB", keep * width, width) + data[9:9 + 8 * nwords])
+    with pytest.raises(VsgpuError) as ei:
+        open_hostsim(ser_copy)
+    assert ei.value.code == -2 and "beyond seq_buffer" in str(ei.value)
+
+
+@pytest.mark.parametrize("field,value", [(32, 1 << 40), (40, 1 << 40), (72, 0), (64, 0), (48, 13), (96, 1 << 50)])
+def test_cqf_header_fields_are_validated(ser_copy, field, value):
+    """nslots / xnslots / bits_per_slot / key_remainder_bits / key_bits / nblocks of the qfmetadata header (gqf_int.h:84-101)
+    drive every slot read of the scan; values that would index past the mapped blocks are refused."""
+    import struct
+    from variantstore_b200 import VsgpuError
+    p = os.path.join(ser_copy, "adj_list.cqf")
+    data = bytearray(open(p, "rb").read())
+    struct.pack_into("<Q", data, field, value)
+    open(p, "wb").write(bytes(data))
+    with pytest.raises(VsgpuError) as ei:
+        open_hostsim(ser_copy)
+    assert ei.value.code == -2

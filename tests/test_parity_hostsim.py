@@ -25,12 +25,14 @@ def t7_parity(o, e):
     return int(hit.sum())
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps"])
+@pytest.fixture(params=["hitmap", "hitmap-32bit-words", "class-bitmaps"])
 def walk_path(request, monkeypatch):
+    monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
+    monkeypatch.delenv("VSGPU_T4_ROW64", raising=False)
     if request.param == "class-bitmaps":
         monkeypatch.setenv("VSGPU_DISABLE_HITMAP", "1")
-    else:
-        monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
+    elif request.param == "hitmap-32bit-words":
+        monkeypatch.setenv("VSGPU_T4_ROW64", "0")          # walk_region_fast instead of walk_region_fast2
     return request.param
 
 

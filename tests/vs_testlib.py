@@ -395,4 +395,12 @@ def compare_all(oracle, eng, x, y, s, with_samples=True, skip_ub=True):
     if skip_ub:
         mism &= ub == 0
     bad4 = [int(i) for i in np.nonzero(mism)[0]]
+    # the fused pass (t6 slice from the two ranks of the t4 walk, one kernel) must give the very same arrays,
+    # through the 64-bit and the 32-bit coordinate entry points
+    for xs, ys in ((x, y), (np.minimum(x, 0xFFFFFFFF).astype(np.uint32), np.minimum(y, 0xFFFFFFFF).astype(np.uint32))):
+        if xs.dtype == np.uint32 and (np.any(x > 0xFFFFFFFF) or np.any(y > 0xFFFFFFFF)):
+            continue
+        flo, fhi, fcnt, foff, fhits, fc4 = eng.batch_var_and_sample_var_in_ref(xs, ys, s)
+        assert np.array_equal(flo, lo) and np.array_equal(fhi, hi) and np.array_equal(fcnt, cnt), "fused t6 differs from vsgpu_query_t6"
+        assert np.array_equal(foff, off) and np.array_equal(fhits, hits) and np.array_equal(fc4, np.diff(off).astype(np.uint32)), "fused t4 differs from vsgpu_query_t4"
     return bad6, bad4, int(ub.sum())

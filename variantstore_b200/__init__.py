@@ -4,6 +4,6 @@ Host-side mirror of the reference's query operator API (include/query.h) over th
 libvsgpu (include/vsgpu.h).  The library has no CPU path: importing works anywhere, but opening an
 index without a CUDA device raises.
 """
-from .api import Batch, VariantStoreIndex, VsgpuError, Variant, load_library, read_regions, read_sequences  # noqa: F401
+from .api import Batch, Router, VariantStoreIndex, VsgpuError, Variant, load_library, read_regions, read_sequences  # noqa: F401
 
-__all__ = ["Batch", "VariantStoreIndex", "VsgpuError", "Variant", "load_library", "read_regions", "read_sequences"]
+__all__ = ["Batch", "Router", "VariantStoreIndex", "VsgpuError", "Variant", "load_library", "read_regions", "read_sequences"]

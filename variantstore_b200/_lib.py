@@ -34,6 +34,10 @@ PROTOTYPES = {
     "vsgpu_query_t4_u32": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.POINTER(vp)]),
     "vsgpu_result_num_queries": (C.c_uint64, [vp]),
     "vsgpu_result_offsets": (u64p, [vp]),
+    "vsgpu_result_counts": (u32p, [vp]),
+    "vsgpu_result_total": (C.c_uint64, [vp]),
+    "vsgpu_query_t6t4": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    "vsgpu_query_t6t4_u32": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
     "vsgpu_result_hits": (u32p, [vp]),
     "vsgpu_result_free": (None, [vp]),
     "vsgpu_query_t1": (C.c_int, [vp, C.c_uint64, vp, vp, vp]),
@@ -68,9 +72,22 @@ PROTOTYPES = {
     "vsgpu_batch_stats": (C.c_int, [vp, u64p, u32p]),
     "vsgpu_batch_timings": (C.c_int, [vp, vp, C.c_uint32, u32p]),
     "vsgpu_batch_free": (None, [vp]),
+    "vsgpu_router_open": (C.c_int, [C.c_uint32, cpp, vp, vp, vp, C.c_int, C.POINTER(vp)]),
+    "vsgpu_router_close": (None, [vp]),
+    "vsgpu_router_last_error": (C.c_char_p, []),
+    "vsgpu_router_num_shards": (C.c_uint32, [vp]),
+    "vsgpu_router_num_contigs": (C.c_uint32, [vp]),
+    "vsgpu_router_contig_name": (C.c_char_p, [vp, C.c_uint32]),
+    "vsgpu_router_contig_id": (C.c_int, [vp, C.c_char_p, u32p]),
+    "vsgpu_router_shard_index": (vp, [vp, C.c_uint32]),
+    "vsgpu_router_shard_device": (C.c_int, [vp, C.c_uint32]),
+    "vsgpu_router_query_t6t4": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "vsgpu_router_offsets": (u64p, [vp]),
+    "vsgpu_router_hits": (u32p, [vp]),
+    "vsgpu_router_stats": (C.c_int, [vp, C.c_uint32, vp, vp, vp, u32p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 # subset a test-only host simulator has to provide
-QUERY_SUBSET = [s for s in PROTOTYPES if not s.startswith(("vsgpu_batch", "vsgpu_render")) and s != "vsgpu_set_stream"]
+QUERY_SUBSET = [s for s in PROTOTYPES if not s.startswith(("vsgpu_batch", "vsgpu_render", "vsgpu_router")) and s != "vsgpu_set_stream"]
 
 
 def load(path=None, subset=False):

@@ -90,12 +90,16 @@ class VariantStoreIndex:
     """`Index idx(prefix); VariantGraph vg(prefix, mode)` of query_main (commands.cc:116-132) in one
     object: loads ser/, flattens it and keeps it resident on one GPU."""
 
-    def __init__(self, prefix: str, device: int = 0, lib=None):
+    def __init__(self, prefix: str, device: int = 0, lib=None, _borrowed=None):
         self._lib = lib or _lib.load()
-        h = C.c_void_p()
-        rc = self._lib.vsgpu_open(prefix.encode(), device, C.byref(h))
-        if rc != 0:
-            raise VsgpuError(rc, self._lib.vsgpu_last_error().decode())
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = C.c_void_p()
+            rc = self._lib.vsgpu_open(prefix.encode(), device, C.byref(h))
+            if rc != 0:
+                raise VsgpuError(rc, self._lib.vsgpu_last_error().decode())
+        else:
+            h = C.c_void_p(_borrowed)          # a shard of a Router: the router closes it
         self._h = h
         self._batches = weakref.WeakSet()     # device-resident batches must be freed before the index they point into
         info = _lib.InfoT()
@@ -107,7 +111,8 @@ class VariantStoreIndex:
         if getattr(self, "_h", None):
             for b in list(getattr(self, "_batches", ())):
                 b.close()
-            self._lib.vsgpu_close(self._h)
+            if self._owned:
+                self._lib.vsgpu_close(self._h)
             self._h = None
 
     def __enter__(self):
@@ -170,6 +175,31 @@ class VariantStoreIndex:
         finally:
             self._lib.vsgpu_result_free(r)
         return off, hits
+
+    def batch_var_and_sample_var_in_ref(self, x, y, sample_ids, want_hi=True):
+        """t6 and t4 over the same regions from one fused pass (vsgpu_query_t6t4*): returns
+        (rec_lo, rec_hi or None, counts6, offsets[n+1], hit codes, counts4)."""
+        s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        n = len(x)
+        lo, cnt = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        hi = np.zeros(n, np.uint32) if want_hi else None
+        r = C.c_void_p()
+        if _is_u32(x) and _is_u32(y):
+            x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+            fn = self._lib.vsgpu_query_t6t4_u32
+        else:
+            x, y = _u64(x), _u64(y)
+            fn = self._lib.vsgpu_query_t6t4
+        self._check(fn(self._h, n, _ptr(x), _ptr(y), _ptr(s), _ptr(lo), _ptr(hi) if want_hi else None, _ptr(cnt), C.byref(r)))
+        try:
+            c4 = np.ctypeslib.as_array(self._lib.vsgpu_result_counts(r), shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+            off = np.ctypeslib.as_array(self._lib.vsgpu_result_offsets(r), shape=(n + 1,)).copy()
+            total = int(self._lib.vsgpu_result_total(r))
+            assert total == int(off[-1])
+            hits = np.ctypeslib.as_array(self._lib.vsgpu_result_hits(r), shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+        finally:
+            self._lib.vsgpu_result_free(r)
+        return lo, hi, cnt, off, hits, c4
 
     def render_var_in_ref(self, x, y, with_samples=True):
         """t6 over arrays with the rows rendered on the device: (offsets[n+1], text bytes, rows,
@@ -363,6 +393,85 @@ class VariantStoreIndex:
         return ids
 
 
+class Router:
+    """Several ser/ directories (whole contigs or position ranges of one) on the GPUs of this node behind one
+    handle (vsgpu_router_*): the multi-contig front-end the reference does not have — it runs one process per
+    contig (eval_data_records/evaluation.txt:34).  Routing, the per-GPU host threads and the scatter of the
+    answers are C++ (csrc/router.cc); this class only marshals arrays."""
+
+    def __init__(self, prefixes: Sequence[str], ranges: Optional[Sequence[Tuple[int, int]]] = None, devices: Optional[Sequence[int]] = None,
+                 ndevices: int = 0, lib=None):
+        self._lib = lib or _lib.load()
+        n = len(prefixes)
+        arr = (C.c_char_p * n)(*[p.encode() for p in prefixes])
+        lo = np.array([r[0] for r in ranges], np.uint64) if ranges is not None else None
+        hi = np.array([r[1] for r in ranges], np.uint64) if ranges is not None else None
+        dev = np.array(devices, np.int32) if devices is not None else None
+        h = C.c_void_p()
+        rc = self._lib.vsgpu_router_open(n, arr, _ptr(lo) if lo is not None else None, _ptr(hi) if hi is not None else None,
+                                         _ptr(dev) if dev is not None else None, int(ndevices), C.byref(h))
+        if rc != 0:
+            raise VsgpuError(rc, self._lib.vsgpu_router_last_error().decode())
+        self._h = h
+        self.num_shards = n
+        self.contigs = [self._lib.vsgpu_router_contig_name(h, i).decode() for i in range(self._lib.vsgpu_router_num_contigs(h))]
+        self.shard_device = [self._lib.vsgpu_router_shard_device(h, k) for k in range(n)]
+        self._shards = {}
+
+    def contig_ids(self, names) -> np.ndarray:
+        table = {c: i for i, c in enumerate(self.contigs)}
+        try:
+            return np.fromiter((table[str(c)] for c in names), np.uint32, count=len(names))
+        except KeyError as e:
+            raise VsgpuError(-1, f"no shard holds contig {e.args[0]}")
+
+    def shard(self, k: int) -> VariantStoreIndex:
+        """Shard k as an index object (rows / digests of its record ids and hit codes); owned by the router."""
+        if k not in self._shards:
+            self._shards[k] = VariantStoreIndex("", lib=self._lib, _borrowed=self._lib.vsgpu_router_shard_index(self._h, k))
+        return self._shards[k]
+
+    def query_t6t4(self, contig_ids, x, y, sample_ids):
+        """(shard_of, rec_lo, counts6, counts4, offsets[n+1], hit codes) in the caller's region order."""
+        c = np.ascontiguousarray(contig_ids, np.uint32); x = np.ascontiguousarray(x, np.uint32); y = np.ascontiguousarray(y, np.uint32)
+        s = np.ascontiguousarray(sample_ids, np.uint32)
+        n = len(x)
+        so, lo, c6, c4 = (np.zeros(n, np.uint32) for _ in range(4))
+        rc = self._lib.vsgpu_router_query_t6t4(self._h, n, _ptr(c), _ptr(x), _ptr(y), _ptr(s), _ptr(so), _ptr(lo), _ptr(c6), _ptr(c4))
+        if rc != 0:
+            raise VsgpuError(rc, self._lib.vsgpu_router_last_error().decode())
+        off = np.ctypeslib.as_array(self._lib.vsgpu_router_offsets(self._h), shape=(n + 1,)).copy()
+        total = int(off[-1])
+        hits = np.ctypeslib.as_array(self._lib.vsgpu_router_hits(self._h), shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+        return so, lo, c6, c4, off, hits
+
+    def stats(self):
+        dev = np.zeros(16, np.int32); ms = np.zeros(16, np.float64); reg = np.zeros(16, np.uint64)
+        nd = C.c_uint32(); r_ms, s_ms = C.c_double(), C.c_double()
+        self._lib.vsgpu_router_stats(self._h, 16, _ptr(dev), _ptr(ms), _ptr(reg), C.byref(nd), C.byref(r_ms), C.byref(s_ms))
+        k = nd.value
+        return {"devices": dev[:k].tolist(), "device_ms": ms[:k].tolist(), "device_regions": reg[:k].astype(int).tolist(), "route_ms": r_ms.value, "scatter_ms": s_ms.value}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for sh in self._shards.values():
+                sh.close()
+            self._lib.vsgpu_router_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Batch:
     """Device-resident batch of regions (vsgpu_batch_*): the bench harness that replaces the timing
     loop of src/bm_query.cc:74-135.  Inputs and results stay in HBM; run() only enqueues kernels."""
@@ -405,6 +514,17 @@ class Batch:
             rec = np.zeros(n, np.uint32)
             self._ix._check(self._lib.vsgpu_batch_fetch(self._h, _ptr(rec), None, None, None))
             return rec
+        if self.type == 46:               # fused: (rec_lo, rec_hi, counts6, offsets, hits)
+            lo, hi, cnt = (np.zeros(n, np.uint32) for _ in range(3))
+            r = C.c_void_p()
+            self._ix._check(self._lib.vsgpu_batch_fetch(self._h, _ptr(lo), _ptr(hi), _ptr(cnt), C.byref(r)))
+            try:
+                off = np.ctypeslib.as_array(self._lib.vsgpu_result_offsets(r), shape=(n + 1,)).copy()
+                total = int(off[-1])
+                hits = np.ctypeslib.as_array(self._lib.vsgpu_result_hits(r), shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+            finally:
+                self._lib.vsgpu_result_free(r)
+            return lo, hi, cnt, off, hits
         cnt = np.zeros(n, np.uint32)
         r = C.c_void_p()
         self._ix._check(self._lib.vsgpu_batch_fetch(self._h, None, None, _ptr(cnt), C.byref(r)))

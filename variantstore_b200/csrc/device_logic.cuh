@@ -331,10 +331,168 @@ VSGPU_HD void walk_region_fast(const DevIndex& ix, uint64_t x64, uint64_t y64, u
 	if (fast_setup(ix, x64, y64, s, sink, st)) fast_forward(ix, st, s, sink);
 }
 
+
+// ------------------------------------------------------------------ t4, second form of the hit-map walk (k_t4p's default)
+// Same rules and output as fast_setup / fast_forward above, restructured around what the ncu records of
+// those said (profiles/README.md): the walk is a chain of dependent loads, so the sample's hit-map row is
+// fetched as three 64-bit chunks at once, right after the ranks, and both the back-walk and the forward
+// scan work on those registers, a 64-entry chunk per step; the three per-start lookups read one packed
+// table (d4) instead of three.  The two ranks are handed back so that a fused launch can answer t6
+// (get_var_in_ref) for the same region without searching again.
+VSGPU_HD uint64_t ld64(const uint32_t* p) {          // two consecutive 32-bit words as one little-endian chunk; p is 8-byte aligned
+#if defined(__CUDA_ARCH__)
+	return __ldg((const unsigned long long*)p);
+#else
+	uint64_t v; __builtin_memcpy(&v, p, 8); return v;
+#endif
+}
+VSGPU_HD uint32_t ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__ffsll((long long)v) - 1;
+#else
+	return (uint32_t)__builtin_ctzll(v);
+#endif
+}
+VSGPU_HD uint32_t clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__clzll((long long)v);
+#else
+	return (uint32_t)__builtin_clzll(v);
+#endif
+}
+
+// three consecutive 64-bit chunks of the sample's hit-map row held in registers; other chunks come from global memory
+struct RowChunks {
+	const uint32_t* row; uint32_t q0; uint64_t v0, v1, v2;
+	VSGPU_HD uint64_t get(uint32_t q) const { const uint32_t j = q - q0; return j == 0 ? v0 : j == 1 ? v1 : j == 2 ? v2 : ld64(row + 2 * q); }
+};
+struct FwdState2 { RowChunks rc; uint32_t c, cur_k, limit, k_end, x, y; };
+
 template <class Sink>
-VSGPU_HD void walk_any(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink) {
+VSGPU_HD bool fwd_step2(const DevIndex& ix, FwdState2& st, uint32_t s, uint32_t ci, const uint4& e, Sink& sink) {
+	if (ci >= st.limit) return true;
+	if (e.x < st.cur_k) return false;                                          // hidden behind a taken detour / later sibling
+	if (e.x > st.cur_k && e.x >= st.k_end) return true;                        // the walk stopped before reaching P[e.x]
+	if (e.y & kEntMarker) return e.w >= st.y;
+	if (e.w >= st.y) return true;
+	if (e.w >= st.x) sink.emit(ci);
+	if (e.y & kEntAlt) {
+		const uint32_t tk = e.y & kEntTgtMask;
+		if (tk == kEntTgtMask || tk >= st.k_end) return true;
+		if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= st.x) sink.emit(ci | kHitRejoin);
+		st.cur_k = tk;
+	} else {
+		st.cur_k = e.y & kEntTgtMask;
+		if (st.cur_k >= st.k_end) { const uint32_t nl = ldg(ix.cent_begin_k + st.cur_k + 1); if (nl > st.limit) st.limit = nl; }
+	}
+	return false;
+}
+
+template <class Sink>
+VSGPU_HD bool fast2_setup(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink, FwdState2& st, uint32_t& rk, uint32_t& e_y) {
+	rk = 0; e_y = 0;
+	if (x64 > ix.index_bits) return false;
+	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
+	rank_le2(ix, x, y ? y - 1 : 0, rk, e_y);
+	if (!y) e_y = 0;
+	if (rk < 1 || rk >= ix.D) return false;
+	const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
+	// entries below `pos` are the back-walk's candidates: the chunk holding pos - 1, the one below it and the one
+	// above it are fetched now, together; everything up to the forward scan works on them
+	const uint32_t pos = ldg(&ix.d4[rk >= 2 ? rk - 2 : 0].z);
+	RowChunks& rc = st.rc;
+	rc.row = row;
+	const uint32_t qb = pos ? (pos - 1) >> 6 : 0, nq = ix.row_words >> 1;
+	rc.q0 = qb ? qb - 1 : 0;
+	rc.v0 = ld64(row + 2 * rc.q0);
+	rc.v1 = rc.q0 + 1 < nq ? ld64(row + 2 * rc.q0 + 2) : 0;
+	rc.v2 = rc.q0 + 2 < nq ? ld64(row + 2 * rc.q0 + 4) : 0;
+	const uint32_t next_start = ldg(ix.dstart + rk);
+	const uint32_t t = ldg(&ix.d4[rk - 1].w);
+	const uint4 dl = ldg(ix.d4 + e_y);
+	if ((uint64_t)next_start > (uint64_t)y + 1) return false;                   // is_empty gate
+	// ---- get_prev_vertex_with_sample (query.h:57-113): highest carried entry below pos whose source an ancestor state examines
+	const uint32_t cur = rk - 1;
+	uint32_t c_found = kNoneU32;
+	if (cur >= 2 && pos > 0) {
+		uint32_t q = (pos - 1) >> 6;
+		uint64_t m = rc.get(q) & (~(uint64_t)0 >> (63 - ((pos - 1) & 63)));
+		for (;;) {
+			while (m == 0 && q > 0) { q--; m = rc.get(q); }
+			if (m == 0) break;
+			const uint32_t b = 63 - clz64(m);
+			m &= ~((uint64_t)1 << b);
+			const uint32_t p = (q << 6) + b;
+			const uint2 a = ldg(ix.cent_anc + p);
+			if (a.x <= t && t <= a.y) { c_found = p; break; }
+		}
+	}
+	st.c = 0; st.cur_k = 0; st.limit = dl.y; st.k_end = dl.x; st.x = x; st.y = y;
+	if (c_found != kNoneU32) {
+		const uint4 e = ldg(ix.cent + c_found);
+		if (e.w >= y) return false;
+		if (e.w >= x) sink.emit(c_found | kHitStart);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask || tk >= st.k_end) return false;
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(c_found | kHitRejoin);
+			st.cur_k = tk;
+		} else {
+			st.cur_k = e.y & kEntTgtMask;
+			if (st.cur_k >= st.k_end) { const uint32_t nl = ldg(ix.cent_begin_k + st.cur_k + 1); if (nl > st.limit) st.limit = nl; }
+		}
+		st.c = c_found + 1;
+	} else {
+		if (1 >= y) return false;
+	}
+	return st.c < st.limit;
+}
+
+template <class Sink>
+VSGPU_HD void fast2_forward(const DevIndex& ix, FwdState2& st, uint32_t s, Sink& sink) {
+	uint32_t q = st.c >> 6;
+	uint64_t m = (st.rc.get(q) | ld64(ix.marker_bits + 2 * q)) & (~(uint64_t)0 << (st.c & 63));
+	for (;;) {
+		while (m == 0) {
+			q++;
+			if ((q << 6) >= st.limit) return;
+			m = st.rc.get(q) | ld64(ix.marker_bits + 2 * q);
+		}
+		const uint32_t ci = (q << 6) + ctz64(m);
+		m &= m - 1;
+		if (ci >= st.limit) return;
+		const uint4 e = ldg(ix.cent + ci);
+		if (fwd_step2(ix, st, s, ci, e, sink)) return;
+	}
+}
+
+// t6 slice bounds from the two ranks of a t4 setup (t6_bounds above, query.h:736-784)
+VSGPU_HD uint2 t6_from_ranks(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t rk, uint32_t e) {
+	uint2 r = make_uint2(kNoneU32, kNoneU32);
+	if (x64 > ix.index_bits) return r;
+	const uint32_t y = clamp_pos(y64);
+	if (rk >= 1 && rk < ix.D && (uint64_t)ldg(ix.dstart + rk) <= (uint64_t)y + 1) {
+		const uint32_t lo = ldg(&ix.dlev[rk - 1].y);
+		uint32_t hi;
+		if (e < ix.D) hi = ldg(&ix.dlev[e].z);
+		else hi = ((uint64_t)ix.last_end >= y) ? ldg(&ix.dlev[ix.D].z) : ix.R;
+		r = make_uint2(lo, hi > lo ? hi : lo);
+	}
+	return r;
+}
+
+// One region of t4 by whichever walk the index supports; *t6 (nullable) receives the region's t6 slice.
+template <class Sink>
+VSGPU_HD void walk_any(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink, uint2* t6 = nullptr) {
+	if (ix.hitmap && ix.walk2) {
+		FwdState2 st; uint32_t rk, e_y;
+		if (fast2_setup(ix, x64, y64, s, sink, st, rk, e_y)) fast2_forward(ix, st, s, sink);
+		if (t6) *t6 = t6_from_ranks(ix, x64, y64, rk, e_y);
+		return;
+	}
 	if (ix.hitmap) walk_region_fast(ix, x64, y64, s, sink);
 	else walk_region(ix, x64, y64, s, sink);
+	if (t6) { bool bad = false; *t6 = t6_bounds(ix, x64, y64, &bad); }
 }
 
 // ------------------------------------------------------------------ t2: query_sample_from_ref (query.h:120-189)

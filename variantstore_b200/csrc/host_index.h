@@ -30,6 +30,8 @@ void save_index_cache(const std::string& prefix, HostIndex& h);
 void build_host_index(const std::string& prefix, HostIndex& h, int* stage = nullptr);
 // direct-mapped rank buckets over positions: bucket[b] = number of distinct starts < (b << shift)
 void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& shift);
+// DevIndex::d4 (kernels.cuh), 4 words per distinct start: what the t4 walk looks up per start, in one row
+void build_d4(const FlatIndex& f, std::vector<uint32_t>& d4);
 
 void append_seq(const HostIndex* ix, uint32_t v, std::string& out);
 void append_carriers(const HostIndex* ix, uint32_t v, std::string& out);

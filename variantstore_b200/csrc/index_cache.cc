@@ -126,6 +126,13 @@ bool load_index_cache(const std::string& prefix, HostIndex& h) {
 		ok = x.M > 0 && x.bb_vertex.size() == x.M && x.vstart.size() == x.M && x.rec_begin.size() == (size_t)x.M + 1 && x.dstart.size() == x.D && x.dlev.size() == (size_t)x.D + 1
 		     && x.rec_pos.size() == x.R && x.cent_anc.size() == 2 * x.cent.size() && x.cent_seq.size() == 2 * x.cent.size() && x.nrp1.size() == x.M && x.first_reach.size() == (size_t)x.D + 1 && h.ser.sample_names.size() == h.ser.num_samples && h.ser.v_sinfo_begin.size() == (size_t)h.ser.num_vertices + 1;
 	}
+	if (ok) {   // slices of the sequence buffer and vertex ids the materialiser / render / copy kernels read unchecked
+		const FlatIndex& x = h.flat; const SerData& sd = h.ser;
+		ok = sd.v_offset.size() == sd.num_vertices && sd.v_length.size() == sd.num_vertices && x.rec_refv.size() == x.R && x.rec_altv.size() == x.R && x.rec_vertex.size() == x.R;
+		if (ok) { try { check_seq_ranges(sd); } catch (const std::exception&) { ok = false; } }
+		for (size_t c = 0; ok && c < x.cent.size(); c++) ok = (uint64_t)x.cent_seq[2 * c] + x.cent_seq[2 * c + 1] <= sd.seq.size();
+		for (uint32_t r = 0; ok && r < x.R; r++) ok = (x.rec_refv[r] == kNone || x.rec_refv[r] < sd.num_vertices) && (x.rec_altv[r] == kNone || x.rec_altv[r] < sd.num_vertices) && x.rec_vertex[r] < sd.num_vertices;
+	}
 	if (!ok) { h.ser = SerData(); h.flat = FlatIndex(); h.last_end = 0; h.t1_fallback_pos = 0; }
 	return ok;
 }

@@ -21,6 +21,13 @@ namespace vsgpu {
 namespace {
 using namespace logic;
 
+// CTA barrier that does not need the warp converged (PTX barrier.sync without .aligned; __syncthreads() is the
+// .aligned form).  The per-region walks leave their loops from many places; with the aligned barrier, compute-sanitizer
+// synccheck reported "divergent thread(s) in warp" at the barrier behind the walk for batches large enough that a CTA
+// takes several tiles, and the staged hits of one tile were then overwritten by the next (tools/debug_t4.py).
+__device__ __forceinline__ void cta_sync() { asm volatile("barrier.sync 0;" ::: "memory"); }
+// Every kernel below that walks regions and then meets at a CTA barrier uses it.
+
 
 // counts[i] = rows the reference returns when that is the slice length; regions whose slice needs the
 // literal dedup rule (a suspect duplicate inside, or a region running past the contig end over tail
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 	__shared__ uint64_t s_base;
 	__shared__ uint32_t s_tile;
 	if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);   // tiles start in ticket order
-	__syncthreads();
+	cta_sync();
 	const uint32_t tile = s_tile, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	volatile uint64_t* state = tile_state + 1;
 	const uint64_t i = (uint64_t)tile * kTile + threadIdx.x;
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
 	if (lane == 31) s_warp[warp] = incl;
-	__syncthreads();
+	cta_sync();
 	uint64_t wpre = 0, agg = 0;
 #pragma unroll
 	for (uint32_t w = 0; w < kTile / 32; w++) { if (w < warp) wpre += s_warp[w]; agg += s_warp[w]; }
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 		}
 		if (lane == 0) s_base = excl;
 	}
-	__syncthreads();
+	cta_sync();
 
 	// ---- phase 4: ordered write
 	if (i < n) {
@@ -257,11 +264,16 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 // ordered write of tile k are done after the walk of tile k+1, by which time the predecessors of
 // tile k have published their counts — the wait that cost k_t4 a third of its warp time is hidden
 // behind useful work.  Two staging buffers alternate.
-template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep>
-__global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
-                                               const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
-                                               uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                               uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr) {
+// k32: region bounds are read as 32-bit arrays (they are parsed with std::stoi, commands.cc:76-80).
+// kFuse6: the two ranks of the t4 setup also give the region's t6 slice (get_var_in_ref, query.h:736-784),
+// written in the same pass — one kernel answers both operators for a batch that asks for both.
+template <bool k32> __device__ __forceinline__ uint64_t ld_coord(const void* a, uint64_t i) { return k32 ? (uint64_t)((const uint32_t*)a)[i] : ((const uint64_t*)a)[i]; }
+
+template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep, bool k32, bool kFuse6>
+__global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint64_t n, const void* __restrict__ xs, const void* __restrict__ ys,
+                                                          const uint32_t* __restrict__ sample, uint64_t* __restrict__ offsets, uint32_t* __restrict__ counts,
+                                                          uint32_t* __restrict__ hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr,
+                                                          const T6Out t6) {
 	__shared__ uint32_t s_hits[2][kTile * kKeep];
 	__shared__ uint32_t s_warp[kTile / 32];
 	__shared__ uint64_t s_base;
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 	uint32_t buf = 0;
 	for (;;) {
 		if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);   // tiles start in ticket order
-		__syncthreads();
+		cta_sync();
 		const uint32_t tile = s_tile;
 		const bool has = tile < ntiles;
 		uint32_t cnt = 0, pre = 0; uint64_t agg = 0;
@@ -283,16 +295,26 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 			const uint64_t i = (uint64_t)tile * kTile + threadIdx.x;
 			SmemSink<kTile, kKeep> sink{s_hits[buf] + threadIdx.x, 0};
 			if (i < n) {
-				const uint64_t x = xs[i]; const uint32_t s = sample[i];
+				const uint64_t x = ld_coord<k32>(xs, i), y = ld_coord<k32>(ys, i); const uint32_t s = sample[i];
+				uint2 r = make_uint2(kNoneU32, kNoneU32);
 				if (x < 1 || s == 0 || s >= ix.num_samples) atomicOr(status, kStatusBadRegion);
-				else walk_any(ix, x, ys[i], s, sink);
+				else walk_any(ix, x, y, s, sink, kFuse6 ? &r : nullptr);
+				if (kFuse6) {
+					t6.lo[i] = r.x; if (t6.hi) t6.hi[i] = r.y;
+					const uint32_t c = r.x == kNoneU32 ? 0 : r.y - r.x;
+					if (t6.counts) t6.counts[i] = c;
+					if (t6.flagged && c) {
+						const bool literal = (ix.rec_dup_prefix && __ldg(ix.rec_dup_prefix + r.y) != __ldg(ix.rec_dup_prefix + r.x)) || (ix.tail_records && y > ix.last_end);
+						if (literal) t6.flagged[atomicAdd(status + 1, 1u)] = t6.flag_base + (uint32_t)i;
+					}
+				}
 			}
 			cnt = sink.n;
 			uint32_t incl = cnt;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
 			if (lane == 31) s_warp[warp] = incl;
-			__syncthreads();
+			cta_sync();
 			uint32_t wpre = 0;
 #pragma unroll
 			for (uint32_t w = 0; w < kTile / 32; w++) { if (w < warp) wpre += s_warp[w]; agg += s_warp[w]; }
@@ -318,21 +340,22 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 				}
 				if (lane == 0) s_base = excl;
 			}
-			__syncthreads();
+			cta_sync();
 			const uint64_t i = (uint64_t)p_tile * kTile + threadIdx.x;
 			if (i < n) {
 				const uint64_t off = s_base + p_pre;
 				offsets[i] = off;
 				if (i == n - 1) offsets[n] = off + p_cnt;
+				if (counts) counts[i] = p_cnt;
 				if (off + p_cnt > cap) atomicOr(status, kStatusOverflow);
 				else if (p_cnt <= kKeep) { const uint32_t* src = s_hits[buf ^ 1] + threadIdx.x; for (uint32_t j = 0; j < p_cnt; j++) hits[off + j] = src[j * kTile]; }
-				else { DirectSink direct{hits + off, 0}; walk_any(ix, xs[i], ys[i], sample[i], direct); }   // more hits than the staging holds: walk again, straight into place
+				else { DirectSink direct{hits + off, 0}; walk_any(ix, ld_coord<k32>(xs, i), ld_coord<k32>(ys, i), sample[i], direct); }   // more hits than the staging holds: walk again, straight into place
 			}
 		}
 		if (!has) break;
 		p_tile = tile; p_cnt = cnt; p_pre = pre; p_agg = agg;
 		buf ^= 1;
-		__syncthreads();        // s_tile / s_warp / s_base are reused by the next round
+		cta_sync();        // s_tile / s_warp / s_base are reused by the next round
 	}
 }
 
@@ -351,7 +374,7 @@ __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, c
 	__shared__ uint64_t s_base;
 	__shared__ uint32_t s_tile;
 	if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);
-	__syncthreads();
+	cta_sync();
 	const uint32_t tile = s_tile, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	volatile uint64_t* state = tile_state + 1;
 	const uint64_t i = (uint64_t)tile * kWarps + warp;
@@ -370,7 +393,7 @@ __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, c
 		}
 	}
 	if (lane == 0) s_cnt[warp] = cnt;
-	__syncthreads();
+	cta_sync();
 	uint64_t wpre = 0, agg = 0;
 #pragma unroll
 	for (uint32_t w = 0; w < kWarps; w++) { if (w < warp) wpre += s_cnt[w]; agg += s_cnt[w]; }
@@ -392,7 +415,7 @@ __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, c
 		}
 		if (lane == 0) s_base = excl;
 	}
-	__syncthreads();
+	cta_sync();
 	if (i < n) {
 		const uint64_t off = s_base + wpre;
 		if (lane == 0) { offsets[i] = off; if (i == n - 1) offsets[n] = off + cnt; }
@@ -431,11 +454,11 @@ __device__ __forceinline__ SegCount cta_scan_1024(SegCount mine, SegCount* s_war
 		if (lane >= (uint32_t)d) { inc.rows += r; inc.bytes += b; }
 	}
 	if (lane == 31) s_warp[warp] = inc;
-	__syncthreads();
+	cta_sync();
 	SegCount pre{0, 0}, tot{0, 0};
 #pragma unroll
 	for (uint32_t w = 0; w < 8; w++) { if (w < warp) { pre.rows += s_warp[w].rows; pre.bytes += s_warp[w].bytes; } tot.rows += s_warp[w].rows; tot.bytes += s_warp[w].bytes; }
-	__syncthreads();
+	cta_sync();
 	*total = tot;
 	return SegCount{pre.rows + inc.rows - mine.rows, pre.bytes + inc.bytes - mine.bytes};
 }
@@ -969,6 +992,32 @@ uint32_t t4_wide_entries() {              // scan ranges longer than this many w
 	return v ? v : 1;
 }
 uint64_t t4_state_words(uint64_t n) { return 2 + (n + 7) / 8; }
+
+bool t4x_supported(bool wide_regions) {
+	if (wide_regions) return false;
+	const char* pe = getenv("VSGPU_T4_PIPE");
+	return !pe || atoi(pe) != 0;
+}
+namespace {
+template <uint32_t kTile, uint32_t kMinCtas>
+cudaError_t launch_t4p_cfg(const DevIndex& ix, const T4Launch& a, cudaStream_t stream) {
+	const uint32_t tiles = (uint32_t)((a.n + kTile - 1) / kTile);
+	const uint32_t grid = min(tiles, grid_for((uint64_t)tiles * kTile, kTile, kMinCtas));
+	const T6Out t6 = a.fuse6 ? *a.fuse6 : T6Out{nullptr, nullptr, nullptr, nullptr, 0};
+#define VSGPU_T4P(K32, F6) k_t4p<kTile, kMinCtas, kScratchHits, K32, F6><<<grid, kTile, 0, stream>>>(ix, a.n, a.x, a.y, a.sample, a.offsets, a.counts, a.hits, a.cap, a.tile_state, a.status, a.base_ptr, t6)
+	if (a.coords32) { if (a.fuse6) VSGPU_T4P(true, true); else VSGPU_T4P(true, false); }
+	else { if (a.fuse6) VSGPU_T4P(false, true); else VSGPU_T4P(false, false); }
+#undef VSGPU_T4P
+	return cudaGetLastError();
+}
+}  // namespace
+cudaError_t launch_t4x(const DevIndex& ix, const T4Launch& a, cudaStream_t stream) {
+	if (a.n == 0) return cudaSuccess;
+	const uint32_t tile = t4_tile();
+	if (tile == 128) return launch_t4p_cfg<128, 12>(ix, a, stream);
+	if (tile == 256) return launch_t4p_cfg<256, 6>(ix, a, stream);
+	return launch_t4p_cfg<64, 24>(ix, a, stream);
+}
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
                       cudaStream_t stream, const uint64_t* base_ptr) {
@@ -982,15 +1031,8 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 	const int pipe = pe ? atoi(pe) : 1;
 	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each
 	else if (pipe) {
-		const uint32_t tiles = (uint32_t)((n + tile - 1) / tile);
-		if (tile == 128) k_t4p<128, 12, kScratchHits><<<min(tiles, grid_for((uint64_t)tiles * 128, 128, 12)), 128, 0, stream>>>(VSGPU_T4_ARGS);
-		else if (tile == 64) k_t4p<64, 24, kScratchHits><<<min(tiles, grid_for((uint64_t)tiles * 64, 64, 24)), 64, 0, stream>>>(VSGPU_T4_ARGS);
-		else {
-			const uint32_t pg = min(tiles, grid_for((uint64_t)tiles * 256, 256, min_ctas == 8 ? 8 : (min_ctas == 5 ? 5 : 6)));
-			if (min_ctas == 8) k_t4p<256, 8, kScratchHits><<<pg, 256, 0, stream>>>(VSGPU_T4_ARGS);
-			else if (min_ctas == 5) k_t4p<256, 5, kScratchHits><<<pg, 256, 0, stream>>>(VSGPU_T4_ARGS);
-			else k_t4p<256, 6, kScratchHits><<<pg, 256, 0, stream>>>(VSGPU_T4_ARGS);
-		}
+		const T4Launch a{n, x, y, false, sample, offsets, nullptr, hits, cap, tile_state, status, base_ptr, nullptr};
+		return launch_t4x(ix, a, stream);
 	}
 	else if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);
 	else if (tile == 128) k_t4<128, 10, kScratchHits><<<grid, 128, 0, stream>>>(VSGPU_T4_ARGS);

@@ -37,6 +37,8 @@ struct DevIndex {
 	const uint32_t* cent_begin_k;         // M + 1: first walk entry with src >= k
 	const uint32_t* dtin;                 // D + 1: pre-order time of back-walk state c in the back-walk forest
 	const uint2* cent_anc;                // per walk entry: pre-order interval of the state examining its source
+	const uint4* d4;                      // D + 1: {dlev.k, dlev.cent_begin, entries below the back-walk start of state d + 1, dtin[d]} (built at upload)
+	uint32_t walk2;                       // 1: the per-thread hit-map walk is walk_region_fast2 (64-entry row chunks fetched together); VSGPU_T4_ROW64=0 clears it
 };
 
 // Tables for rendering t6 rows as text on the device; uploaded on first use.
@@ -132,6 +134,20 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
                       cudaStream_t stream, const uint64_t* base_ptr = nullptr);
 uint32_t t4_wide_entries();
+
+// t6 outputs of a fused launch: as launch_t6's; hi / counts / flagged nullable
+struct T6Out { uint32_t* lo; uint32_t* hi; uint32_t* counts; uint32_t* flagged; uint32_t flag_base; };
+// launch_t4 with everything k_t4p can do: x / y as 64-bit or 32-bit arrays (coords32), per-region hit counts
+// beside the offsets (counts, nullable), and the t6 slice of every region from the same two ranks (fuse6, nullable).
+// Batches of few, wide regions (wide_regions) and the one-CTA-per-tile kernel take 64-bit coordinates only and
+// cannot fuse; t4x_supported() says whether a launch can take these options.
+struct T4Launch {
+	uint64_t n; const void* x; const void* y; bool coords32; const uint32_t* sample;
+	uint64_t* offsets; uint32_t* counts; uint32_t* hits; uint64_t cap; uint64_t* tile_state; uint32_t* status; const uint64_t* base_ptr;
+	const T6Out* fuse6;
+};
+bool t4x_supported(bool wide_regions);
+cudaError_t launch_t4x(const DevIndex& ix, const T4Launch& a, cudaStream_t stream);
 
 // status word bits
 constexpr uint32_t kStatusBadRegion = 1;   // some region had x < 1

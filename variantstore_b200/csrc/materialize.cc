@@ -2,6 +2,7 @@
 #include "host_index.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -12,8 +13,10 @@ namespace vsgpu {
 
 void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& shift) {
 	const uint64_t span = std::max<uint64_t>(f.dstart.empty() ? 1 : f.dstart.back(), 1);
+	uint64_t target = kBucketTarget;                       // tuning knob, read per open
+	if (const char* e = getenv("VSGPU_BUCKET_TARGET")) { const long v = atol(e); if (v >= 1 && v <= 4096) target = (uint64_t)v; }
 	shift = 0;
-	while (shift < 31 && (span >> (shift + 1)) * kBucketTarget >= f.D) shift++;    // ~kBucketTarget starts per bucket
+	while (shift < 31 && (span >> (shift + 1)) * target >= f.D) shift++;    // ~target starts per bucket
 	while ((span >> shift) + 2 > (1u << 28)) shift++;
 	const uint32_t nb = (uint32_t)(span >> shift) + 1;
 	bucket.assign(nb + 1, 0);
@@ -22,6 +25,15 @@ void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& 
 		const uint64_t lim = (uint64_t)b << shift;
 		while (j < f.dstart.size() && f.dstart[j] < lim) j++;
 		bucket[b] = (uint32_t)j;
+	}
+}
+
+void build_d4(const FlatIndex& f, std::vector<uint32_t>& d4) {
+	d4.assign(4 * ((size_t)f.D + 1), 0);
+	for (uint32_t d = 0; d <= f.D; d++) {
+		d4[4 * (size_t)d] = f.dlev[d].k; d4[4 * (size_t)d + 1] = f.dlev[d].cent_begin;
+		if (d < f.D) d4[4 * (size_t)d + 2] = (uint32_t)f.dinfo[d] + ((uint32_t)(f.dinfo[d] >> 32) & 0xFFFF);   // entries below it are back-walk candidates
+		d4[4 * (size_t)d + 3] = f.dtin[d];
 	}
 }
 

@@ -35,7 +35,9 @@ struct Mapped {
 	explicit Mapped(const std::string& path) {
 		fd = open(path.c_str(), O_RDONLY);
 		if (fd < 0) fail("cannot open " + path);
-		struct stat st; fstat(fd, &st); n = (size_t)st.st_size;
+		struct stat st;
+		if (fstat(fd, &st) != 0) { close(fd); fail("cannot stat " + path); }
+		n = (size_t)st.st_size;
 		if (n) { void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0); if (m == MAP_FAILED) { close(fd); fail("cannot map " + path); } p = (const uint8_t*)m; }
 	}
 	~Mapped() { if (p) munmap((void*)p, n); if (fd >= 0) close(fd); }
@@ -307,9 +309,14 @@ void read_cqf(const std::string& path, std::vector<CqfEntry>& out, uint64_t& ndi
 	               rbits = md(64), bps = md(72), nblocks = md(96);
 	ndistinct = md(112);
 	const uint64_t stride = 18 + 8 * bps;                  // packed qfblock: u16 offset, u64 occupieds, u64 runends, 64 slots
-	if (128 + total > m.n || nblocks * stride > total || bps != rbits + value_bits || bps > 57) fail("inconsistent CQF header in " + path);
+	if (128 + total > m.n || nblocks > total / stride || bps != rbits + value_bits || bps > 57) fail("inconsistent CQF header in " + path);
+	// every slot / occupied / runend bit the scan can touch lies inside the mapped blocks; key = quotient | remainder
+	if (bps == 0 || rbits == 0 || value_bits >= bps || nslots == 0 || (nslots & (nslots - 1)) || nslots > xnslots || xnslots > nblocks * 64 ||
+	    key_bits > 64 || key_bits != (uint64_t)__builtin_ctzll(nslots) + rbits)
+		fail("inconsistent CQF header in " + path);
 	const uint8_t* blocks = m.p + 128;
 	auto slot = [&](uint64_t i) -> uint64_t {
+		if (i >= xnslots) fail("CQF run reads past the last slot in " + path);
 		const uint8_t* b = blocks + (i >> 6) * stride + 18; uint64_t bit = (i & 63) * bps;
 		uint64_t lo = 0; size_t avail = (size_t)((blocks + total) - (b + bit / 8)); memcpy(&lo, b + bit / 8, std::min<size_t>(8, avail));
 		return (lo >> (bit & 7)) & ((1ULL << bps) - 1);
@@ -357,6 +364,14 @@ void read_cqf(const std::string& path, std::vector<CqfEntry>& out, uint64_t& ndi
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 PhaseClock::PhaseClock() : on(getenv("VSGPU_TRACE") != nullptr), t0(now_s()) {}
 void PhaseClock::lap(const char* what) { if (!on) return; const double t = now_s(); fprintf(stderr, "[vsgpu trace] open: %-28s %.3f s\n", what, t - t0); t0 = t; }
+
+// Every vertex names a slice of seq_buffer.sdsl; the row materialiser and the render / copy kernels
+// read those slices without further checks, so a slice past the end is refused here.
+void check_seq_ranges(const SerData& d) {
+	const uint64_t n = d.seq.size();
+	for (size_t v = 0; v < d.v_offset.size(); v++)
+		if ((uint64_t)d.v_offset[v] + d.v_length[v] > n) fail("vertex " + std::to_string(v) + " names sequence [" + std::to_string(d.v_offset[v]) + ", +" + std::to_string(d.v_length[v]) + ") beyond seq_buffer.sdsl (" + std::to_string(n) + " symbols)");
+}
 
 void load_ser(const std::string& prefix, SerData& d) {
 	PhaseClock pc;
@@ -454,6 +469,7 @@ void load_ser(const std::string& prefix, SerData& d) {
 		for (auto& t : th2) t.join();
 		if (order_bad) fail("vertex ids are not dense/in order in the vertex blocks");
 		d.v_sinfo_begin[nv] = ns;
+		check_seq_ranges(d);
 	}
 	pc.lap("vertex blocks: concatenate");
 	// ---- topology

@@ -50,6 +50,8 @@ struct SerData {
 
 // Throws std::runtime_error with a message naming the file that failed.
 void load_ser(const std::string& prefix, SerData& out);
+// Throws when a vertex names a slice of seq_buffer.sdsl that runs past its end (load_ser and the index cache call it).
+void check_seq_ranges(const SerData& d);
 
 // sample_info.index of every s_info in SerData order (second pass over vertex_list_<k>.proto); `expect`
 // = v_sinfo_begin.back()

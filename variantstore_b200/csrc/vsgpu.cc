@@ -63,6 +63,12 @@ struct vsgpu_result {
 	uint64_t* offsets = nullptr; size_t offsets_cap = 0;   // bytes
 	uint32_t* hits = nullptr; size_t hits_cap = 0;         // bytes
 	uint8_t* status = nullptr; size_t status_cap = 0;      // t5 only
+	// Host-buffer t4 calls bring back the per-region row counts (4 bytes a region over PCIe instead of 8); the
+	// other of offsets / counts is built on the host the first time it is asked for.
+	uint32_t* counts = nullptr; size_t counts_cap = 0;     // bytes
+	uint64_t total = 0;
+	bool have_offsets = false, have_counts = false;
+	std::mutex lazy_mu;
 	float kernel_ms = 0;                                   // t5 only
 };
 
@@ -186,7 +192,9 @@ void upload_index(vsgpu_index* ix) {
 	build_buckets(f, bucket, d.bucket_shift);
 	d.nbuckets = (uint32_t)bucket.size() - 1;
 	d.dstart = upload(ix, f.dstart);
+	{ std::vector<uint32_t> d4; build_d4(f, d4); d.d4 = (const uint4*)upload(ix, d4); }
 	d.bucket = upload(ix, bucket);
+	{ const char* e = getenv("VSGPU_T4_ROW64"); d.walk2 = (!e || atoi(e) != 0) ? 1 : 0; }
 	static_assert(sizeof(DLevel) == sizeof(uint4) && sizeof(CEntry) == sizeof(uint4), "AoS rows are 16 bytes");
 	d.dlev = (const uint4*)upload(ix, f.dlev);
 	d.dinfo = upload(ix, f.dinfo);
@@ -450,6 +458,11 @@ uint32_t finish_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64
 }  // namespace
 
 namespace {
+// The guessed hit capacity was too small: one exact pass over the resident 64-bit inputs on the index's stream.
+void hits_overflow_rerun(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, uint64_t& cap, bool wide, uint64_t known_total) {
+	const uint32_t st = finish_t4(ix, n, dx, dy, ds, ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, wide, known_total);
+	if (st & kStatusBadRegion) throw std::invalid_argument("region start < 1 or sample id out of range");
+}
 // Does this batch look like "few, wide regions" (the scan-bound end of the width sweep)?  Decided from
 // a sample of the region widths and the index's walk-entry density; such batches get a warp per region.
 extern "C++" template <class T>
@@ -480,6 +493,7 @@ vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const
 		if (tr) tr->mark("d2h offsets");
 	}
 	const uint64_t total = r->offsets[n];
+	r->have_offsets = true; r->total = total;
 	if (want_hits && total) {
 		r->hits = (uint32_t*)ix->pinned_acquire(total * 4, &r->hits_cap);
 		if (!r->hits) { ix->pinned_release(r->offsets, r->offsets_cap); throw std::runtime_error("CUDA: cannot allocate page-locked result memory"); }
@@ -492,37 +506,52 @@ vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const
 }  // namespace
 
 namespace {
+// t6 outputs of a fused host-buffer call (vsgpu_query_t6t4*): as vsgpu_query_t6's; rec_hi nullable
+struct T6Host { uint32_t* rec_lo; uint32_t* rec_hi; uint32_t* counts; };
+
+// t4 (optionally with t6 over the same regions, from the same kernel) with host buffers.  What crosses PCIe per
+// region: x, y (4 or 8 bytes each) and the sample id in; the row count (4 bytes), the hit codes and, when fused,
+// the t6 slice start and row count out.
 extern "C++" template <class T>
-int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uint32_t* sample_ids, vsgpu_result** out) {
+int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uint32_t* sample_ids, vsgpu_result** out, const T6Host* t6 = nullptr) {
 	constexpr bool k32 = sizeof(T) == 4;
-	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t4: null argument");
+	if (!ix || !out || (n && (!x || !y || !sample_ids)) || (t6 && n && (!t6->rec_lo || !t6->counts))) return set_err(VSGPU_EINVAL, "vsgpu_query_t4: null argument");
 	*out = nullptr;
 	if (int rc = check_device(ix)) return rc;
 	std::lock_guard<std::mutex> g(ix->mu);
-	Trace tr("t4");
+	Trace tr(t6 ? "t6t4" : "t4");
 	std::unique_ptr<vsgpu_result, void (*)(vsgpu_result*)> r(nullptr, vsgpu_result_free);
 	try {
 		if (n == 0) { *out = fetch_t4(ix, 0, ix->boffsets, ix->bhits, true); return VSGPU_OK; }
 		const bool wide = expect_wide_regions(ix, n, x, y);
+		const bool direct = t4x_supported(wide);               // k_t4p: reads the host's coordinate width, writes counts, fuses t6
+		const bool flag6 = t6 && t6_special(ix);
 		uint64_t per = 0;
 		const int chunks = wide ? (per = n, 1) : plan_chunks(n, &per);
 		const uint64_t state_words = t4_state_words(per);
-		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+		CU(ix->bs.ensure(n * 4));
 		if (k32) { CU(ix->bx32.ensure(n * 4)); CU(ix->by32.ensure(n * 4)); }
+		if (!k32 || !direct) { CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); }
 		CU(ix->boffsets.ensure((n + 1) * 8)); CU(ix->bstate.ensure(state_words * chunks * 8));
+		if (direct) CU(ix->bcnt.ensure(n * 4));
+		if (t6) CU(ix->bout.ensure(n * 12));
+		if (flag6) CU(ix->bflag.ensure(n * 4));
 		uint64_t cap = ix->bhits.cap / 4;
 		if (cap == 0) { cap = std::max<uint64_t>((wide ? 64 : 4) * n, 1024); CU(ix->bhits.ensure(cap * 4)); cap = ix->bhits.cap / 4; }
 		uint64_t* dx = ix->bx.as<uint64_t>(); uint64_t* dy = ix->by.as<uint64_t>(); uint32_t* ds = ix->bs.as<uint32_t>();
-		T* sx = k32 ? ix->bx32.as<T>() : (T*)dx; T* sy = k32 ? ix->by32.as<T>() : (T*)dy;
+		T* sx = k32 ? ix->bx32.as<T>() : (T*)dx; T* sy = k32 ? ix->by32.as<T>() : (T*)dy;      // where the host arrays land
 		uint64_t* d_off = ix->boffsets.as<uint64_t>();
+		uint32_t* d_cnt4 = direct ? ix->bcnt.as<uint32_t>() : nullptr;
+		uint32_t* d_lo = ix->bout.as<uint32_t>(); uint32_t* d_hi = d_lo + n; uint32_t* d_cnt6 = d_hi + n;
 		r.reset(new vsgpu_result);
 		r->owner = ix; r->n = n;
-		r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
+		if (direct) r->counts = (uint32_t*)ix->pinned_acquire(n * 4, &r->counts_cap);
+		else r->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &r->offsets_cap);
 		// page-locked room for the hit codes is a guess too (the device buffer may be far larger than this
 		// batch needs); a batch that outgrows it gets an exact buffer and one copy at the end
 		const uint64_t host_cap = std::min<uint64_t>(cap, std::max<uint64_t>(8 * n, 1u << 18));
 		r->hits = (uint32_t*)ix->pinned_acquire(host_cap * 4, &r->hits_cap);
-		if (!r->offsets || !r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		if ((!r->offsets && !r->counts) || !r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
 		// inputs on s_in, kernels on s_k (chunk c continues the offsets of chunk c-1), results on s_out as
 		// soon as their chunk is done
 		const int ks = in_streams();
@@ -537,9 +566,17 @@ int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uin
 		for (int c = 0; c < chunks; c++) {
 			const uint64_t a = c * per, m = std::min<uint64_t>(n, a + per) - a;
 			for (int k = 0; k < ks; k++) CU(cudaStreamWaitEvent(ix->s_k, ix->ev_in[c][k], 0));
-			if (k32) CU(launch_widen(m, (const uint32_t*)sx + a, (const uint32_t*)sy + a, dx + a, dy + a, ix->s_k));
-			CU(launch_t4(ix->dev, m, dx + a, dy + a, ds + a, d_off + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status, wide,
-			             ix->s_k, c ? d_off + a : nullptr));
+			if (direct) {
+				const T6Out f6{d_lo + a, t6 && t6->rec_hi ? d_hi + a : nullptr, d_cnt6 + a, flag6 ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a};
+				const T4Launch L{m, sx + a, sy + a, k32, ds + a, d_off + a, d_cnt4 + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status,
+				                 c ? d_off + a : nullptr, t6 ? &f6 : nullptr};
+				CU(launch_t4x(ix->dev, L, ix->s_k));
+			} else {
+				if (k32) CU(launch_widen(m, (const uint32_t*)sx + a, (const uint32_t*)sy + a, dx + a, dy + a, ix->s_k));
+				if (t6) CU(launch_t6(ix->dev, m, dx + a, dy + a, d_lo + a, d_hi + a, d_cnt6 + a, flag6 ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a, ix->d_status, ix->s_k));
+				CU(launch_t4(ix->dev, m, dx + a, dy + a, ds + a, d_off + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status, wide,
+				             ix->s_k, c ? d_off + a : nullptr));
+			}
 			CU(cudaEventRecord(ix->ev_k[c], ix->s_k));
 		}
 		tr.mark("enqueue");
@@ -549,7 +586,13 @@ int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uin
 			CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
 			CU(cudaMemcpyAsync(ix->pin_small + c, d_off + a + m, 8, cudaMemcpyDeviceToHost, ix->s_out));
 			CU(cudaEventRecord(ix->ev_out[c], ix->s_out));
-			CU(cudaMemcpyAsync(r->offsets + a, d_off + a, (m + (c == chunks - 1 ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, ix->s_out));
+			if (direct) CU(cudaMemcpyAsync(r->counts + a, d_cnt4 + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
+			else CU(cudaMemcpyAsync(r->offsets + a, d_off + a, (m + (c == chunks - 1 ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, ix->s_out));
+			if (t6) {
+				CU(cudaMemcpyAsync(t6->rec_lo + a, d_lo + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
+				if (t6->rec_hi) CU(cudaMemcpyAsync(t6->rec_hi + a, d_hi + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
+				CU(cudaMemcpyAsync(t6->counts + a, d_cnt6 + a, m * 4, cudaMemcpyDeviceToHost, ix->s_out));
+			}
 			CU(cudaEventSynchronize(ix->ev_out[c]));                   // the running total after chunk c: its hits are final
 			const uint64_t total = ix->pin_small[c];
 			if (total > cap) { overflow = true; continue; }
@@ -557,26 +600,43 @@ int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uin
 			if (!overflow && !host_small && total > done) CU(cudaMemcpyAsync(r->hits + done, ix->bhits.as<uint32_t>() + done, (total - done) * 4, cudaMemcpyDeviceToHost, ix->s_out));
 			done = total;
 		}
-		uint32_t st = read_status(ix, ix->d_status, nullptr, ix->s_out);
+		// status words, bad regions, and (fused) the t6 counts of the regions the kernel flagged for the literal rule
+		uint32_t st = 0;
+		if (t6) {
+			uint32_t nflag = 0;
+			st = read_status(ix, ix->d_status, &nflag, ix->s_out);
+			if ((st & kStatusBadRegion) == 0 && nflag) {
+				std::vector<uint32_t> flagged(nflag), tmp;
+				CU(cudaMemcpyAsync(flagged.data(), ix->bflag.p, (size_t)nflag * 4, cudaMemcpyDeviceToHost, ix->s_out));
+				CU(cudaStreamSynchronize(ix->s_out));
+				for (uint32_t i : flagged) { t6_literal(ix, x[i], y[i], tmp); t6->counts[i] = (uint32_t)tmp.size(); }
+			}
+		} else st = read_status(ix, ix->d_status, nullptr, ix->s_out);
 		tr.mark("pipeline");
+		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 		if (overflow) {
 			// the guess for the hit buffer was too small: size it from the total the kernels computed and
-			// run the batch again in one piece (inputs are resident; results are deterministic)
+			// run t4 again in one piece (inputs are resident; results are deterministic; the t6 answers stand)
 			uint64_t c2 = ix->bhits.cap / 4;
-			st |= finish_t4(ix, n, dx, dy, ds, ix->boffsets, ix->bstate, ix->bhits, c2, ix->d_status, wide, ix->pin_small[chunks - 1]);
-			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+			CU(cudaStreamSynchronize(ix->s_k)); CU(cudaStreamSynchronize(ix->s_out));
+			if (k32 && direct) {                                 // the exact pass runs on 64-bit coordinates
+				CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8));
+				dx = ix->bx.as<uint64_t>(); dy = ix->by.as<uint64_t>();
+				CU(launch_widen(n, (const uint32_t*)sx, (const uint32_t*)sy, dx, dy, ix->stream));
+			}
+			hits_overflow_rerun(ix, n, dx, dy, ds, c2, wide, ix->pin_small[chunks - 1]);
 			*out = fetch_t4(ix, n, ix->boffsets, ix->bhits, true, &tr);
 			return VSGPU_OK;
 		}
-		if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+		const uint64_t total = ix->pin_small[chunks - 1];
 		if (host_small) {
-			const uint64_t total = ix->pin_small[chunks - 1];
 			ix->pinned_release(r->hits, r->hits_cap);
 			r->hits = (uint32_t*)ix->pinned_acquire(total * 4, &r->hits_cap);
 			if (!r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
 			CU(cudaMemcpyAsync(r->hits, ix->bhits.p, total * 4, cudaMemcpyDeviceToHost, ix->s_out));
 			CU(cudaStreamSynchronize(ix->s_out));
 		}
+		r->total = total; r->have_counts = direct; r->have_offsets = !direct;
 		*out = r.release();
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
@@ -584,12 +644,46 @@ int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uin
 }  // namespace
 int vsgpu_query_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out) { return query_t4_impl(ix, n, x, y, sample_ids, out); }
 int vsgpu_query_t4_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample_ids, vsgpu_result** out) { return query_t4_impl(ix, n, x, y, sample_ids, out); }
+int vsgpu_query_t6t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts6, vsgpu_result** out) {
+	const T6Host t6{rec_lo, rec_hi, counts6};
+	return query_t4_impl(ix, n, x, y, sample_ids, out, &t6);
+}
+int vsgpu_query_t6t4_u32(vsgpu_index* ix, uint64_t n, const uint32_t* x, const uint32_t* y, const uint32_t* sample_ids, uint32_t* rec_lo, uint32_t* rec_hi, uint32_t* counts6, vsgpu_result** out) {
+	const T6Host t6{rec_lo, rec_hi, counts6};
+	return query_t4_impl(ix, n, x, y, sample_ids, out, &t6);
+}
 uint64_t vsgpu_result_num_queries(const vsgpu_result* r) { return r ? r->n : 0; }
-const uint64_t* vsgpu_result_offsets(const vsgpu_result* r) { return r ? r->offsets : nullptr; }
+const uint64_t* vsgpu_result_offsets(const vsgpu_result* cr) {
+	vsgpu_result* r = const_cast<vsgpu_result*>(cr);
+	if (!r) return nullptr;
+	std::lock_guard<std::mutex> g(r->lazy_mu);
+	if (!r->have_offsets && r->have_counts) {              // exclusive prefix sums of the counts
+		if (!r->offsets) r->offsets = (uint64_t*)r->owner->pinned_acquire((r->n + 1) * 8, &r->offsets_cap);
+		if (!r->offsets) return nullptr;
+		uint64_t acc = 0;
+		for (uint64_t i = 0; i < r->n; i++) { r->offsets[i] = acc; acc += r->counts[i]; }
+		r->offsets[r->n] = acc;
+		r->have_offsets = true;
+	}
+	return r->offsets;
+}
+const uint32_t* vsgpu_result_counts(const vsgpu_result* cr) {
+	vsgpu_result* r = const_cast<vsgpu_result*>(cr);
+	if (!r) return nullptr;
+	std::lock_guard<std::mutex> g(r->lazy_mu);
+	if (!r->have_counts && r->offsets) {
+		if (!r->counts) r->counts = (uint32_t*)r->owner->pinned_acquire(std::max<uint64_t>(r->n, 1) * 4, &r->counts_cap);
+		if (!r->counts) return nullptr;
+		for (uint64_t i = 0; i < r->n; i++) r->counts[i] = (uint32_t)(r->offsets[i + 1] - r->offsets[i]);
+		r->have_counts = true;
+	}
+	return r->counts;
+}
+uint64_t vsgpu_result_total(const vsgpu_result* r) { return r ? r->total : 0; }
 const uint32_t* vsgpu_result_hits(const vsgpu_result* r) { return r ? r->hits : nullptr; }
 void vsgpu_result_free(vsgpu_result* r) {
 	if (!r) return;
-	if (r->owner) { r->owner->pinned_release(r->offsets, r->offsets_cap); r->owner->pinned_release(r->hits, r->hits_cap); r->owner->pinned_release(r->status, r->status_cap); }
+	if (r->owner) { r->owner->pinned_release(r->offsets, r->offsets_cap); r->owner->pinned_release(r->hits, r->hits_cap); r->owner->pinned_release(r->status, r->status_cap); r->owner->pinned_release(r->counts, r->counts_cap); }
 	delete r;
 }
 
@@ -1045,7 +1139,9 @@ int vsgpu_query_t5(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 			float a = 0, b = 0;
 			CU(cudaEventElapsedTime(&a, ix->ev_t2[0], ix->ev_t2[1])); CU(cudaEventElapsedTime(&b, ix->ev_t2[2], ix->ev_t2[3]));
 			r->kernel_ms = a + b;
+			r->total = r->offsets[n];
 		}
+		r->have_offsets = true;
 		*out = r.release();
 	} catch (const std::invalid_argument& e) { return set_err(VSGPU_ESHAPE, e.what());
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
@@ -1079,8 +1175,8 @@ int vsgpu_query_t3(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids,
                        const char* const* refs, const char* const* alts, vsgpu_batch** out) {
 	if (!ix || !out || !x || n == 0) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: null argument");
-	if (type != 4 && type != 6 && type != 7) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: type must be 4, 6 or 7");
-	if ((type != 7 && !y) || (type == 4 && !sample_ids) || (type == 7 && (!refs || !alts))) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: missing input array");
+	if (type != 4 && type != 6 && type != 7 && type != 46) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: type must be 4, 6, 7 or 46");
+	if ((type != 7 && !y) || ((type == 4 || type == 46) && !sample_ids) || (type == 7 && (!refs || !alts))) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: missing input array");
 	if (int rc = check_device(ix)) return rc;
 	std::lock_guard<std::mutex> g(ix->mu);
 	try {
@@ -1092,7 +1188,11 @@ int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x,
 		CU(cudaMemcpyAsync(b->x.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
 		if (type != 7) { CU(b->y.ensure(n * 8)); CU(cudaMemcpyAsync(b->y.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream)); }
 		if (type == 6) { CU(b->out.ensure(n * 12)); if (t6_special(ix)) CU(b->flag.ensure(n * 4)); }
-		if (type == 4) { b->wide_regions = expect_wide_regions(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 8)); }
+		if (type == 4 || type == 46) { b->wide_regions = expect_wide_regions(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 12)); }
+		if (type == 46) {
+			if (!t4x_supported(b->wide_regions)) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: a fused t6 + t4 batch needs the pipelined t4 kernel and regions that are not a few, wide ones");
+			if (t6_special(ix)) CU(b->flag.ensure(n * 4));
+		}
 		if (type == 7) {
 			std::vector<uint64_t> qh(n);
 			for (uint64_t i = 0; i < n; i++) qh[i] = hash_query(refs[i], alts[i]);
@@ -1114,6 +1214,21 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
 		if (b->type == 6) { CU(cudaMemsetAsync(b->d_status, 0, 8, ix->stream)); CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + b->n, b->out.as<uint32_t>() + 2 * b->n, b->flag.as<uint32_t>(), 0, b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		else if (b->type == 46) {
+			// t6 + t4 from one launch of k_t4p<kFuse6>: the t6 slice comes from the two ranks of the t4 setup
+			const uint64_t n = b->n;
+			CU(b->offsets.ensure((n + 1) * 8)); CU(b->state.ensure(t4_state_words(n) * 8));
+			if (b->hits_cap == 0) { b->hits_cap = std::max<uint64_t>(4 * n, 1024); CU(b->hits.ensure(b->hits_cap * 4)); }
+			CU(cudaMemsetAsync(b->d_status, 0, 8, ix->stream));
+			CU(cudaMemsetAsync(b->state.p, 0, t4_state_words(n) * 8, ix->stream));
+			CU(cudaEventRecord(b->ev[0], ix->stream));
+			uint32_t* o = b->out.as<uint32_t>();
+			const T6Out f6{o, o + n, o + 2 * n, b->flag.as<uint32_t>(), 0};
+			const T4Launch L{n, b->x.p, b->y.p, false, b->s.as<uint32_t>(), b->offsets.as<uint64_t>(), nullptr, b->hits.as<uint32_t>(), b->hits_cap, b->state.as<uint64_t>(), b->d_status, nullptr, &f6};
+			CU(launch_t4x(ix->dev, L, ix->stream));
+			CU(cudaEventRecord(b->ev[1], ix->stream));
+			b->launches = 1;
+		}
 		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status, b->wide_regions);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
@@ -1135,6 +1250,31 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 			if (rec_lo) CU(cudaMemcpyAsync(rec_lo, b->rec.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
 			uint32_t st = read_status(ix, b->d_status);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "Can't find node corresponding to pos 0");
+		} else if (b->type == 46) {
+			// t6 part first (it owns the flagged list in the status words), then the CSR; counts = the t6 row counts
+			const uint32_t* o = b->out.as<uint32_t>();
+			if (rec_lo) CU(cudaMemcpyAsync(rec_lo, o, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			if (rec_hi) CU(cudaMemcpyAsync(rec_hi, o + n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			if (counts) CU(cudaMemcpyAsync(counts, o + 2 * n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+			uint64_t total = 0;
+			CU(cudaMemcpyAsync(&total, b->offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
+			uint32_t nflag = 0;
+			const uint32_t st = read_status(ix, b->d_status, &nflag, ix->stream);
+			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+			if (nflag && counts) {
+				std::vector<uint32_t> flagged(nflag), tmp;
+				CU(cudaMemcpyAsync(flagged.data(), b->flag.p, (size_t)nflag * 4, cudaMemcpyDeviceToHost, ix->stream));
+				CU(cudaStreamSynchronize(ix->stream));
+				for (uint32_t i : flagged) { t6_literal(ix, b->hx[i], b->hy[i], tmp); counts[i] = (uint32_t)tmp.size(); }
+			}
+			if (total > b->hits_cap) {                           // the hit buffer was a guess: exact size, t4 alone again
+				b->hits_cap = total + total / 16 + 1024;
+				CU(b->hits.ensure(b->hits_cap * 4));
+				run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, false);
+				read_status(ix, b->d_status);
+			}
+			vsgpu_result* r = fetch_t4(ix, n, b->offsets, b->hits, out != nullptr);
+			if (out) *out = r; else vsgpu_result_free(r);
 		} else {
 			uint32_t st = finish_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, b->d_status, b->wide_regions);
 			if (st & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
@@ -1159,6 +1299,15 @@ int vsgpu_batch_stats(vsgpu_batch* b, uint64_t* algorithmic_bytes, uint32_t* ker
 		try {
 			const uint64_t n = b->n; uint64_t bytes = 0;
 			if (b->type == 6) bytes = 288 * n;
+			else if (b->type == 46) {
+				// t6 (288) + t4 (292 + 20 v + 4 h) by the section 8(d) convention; v = the slice lengths the launch itself wrote
+				std::vector<uint32_t> o(n); uint64_t total = 0;
+				CU(cudaMemcpyAsync(o.data(), b->out.as<uint32_t>() + 2 * n, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+				CU(cudaMemcpyAsync(&total, b->offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->stream));
+				CU(cudaStreamSynchronize(ix->stream));
+				uint64_t v = 0; for (uint64_t i = 0; i < n; i++) v += o[i];
+				bytes = (288 + 292) * n + 20 * v + 4 * total;
+			}
 			else if (b->type == 7) {
 				const FlatIndex& f = ix->flat;
 				for (uint64_t i = 0; i < n; i++) {
