@@ -199,6 +199,169 @@ def workload_config(args, meta):
             "e2e_coordinates": "u64" if getattr(args, "e2e_u64", False) else "u32 (region bounds are parsed with std::stoi, commands.cc:76-80)"}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json config [2]: the whole-genome-shaped synthetic (24 contigs in GRCh37 lengths, ~85 M records x 2 504
+# samples, record counts per contig as in eval_data_records/logs/vs_v1.log), 10 M regions drawn in proportion to
+# contig length, position-range shards of at most --genome-shard-records records (the north star's "contig /
+# position shard"), placed on the GPUs by longest-processing-time and answered through the C++ router
+# (variantstore_b200/csrc/router.cc) in ONE process with host threads per GPU.  Runs for N >= 2 (or --genome).
+GENOME = {"1": (249_250_621, 6_468_094), "2": (243_199_373, 7_081_600), "3": (198_022_430, 5_832_276), "4": (191_154_276, 5_732_585),
+          "5": (180_915_260, 5_265_763), "6": (171_115_067, 5_024_119), "7": (159_138_663, 4_716_715), "8": (146_364_022, 4_597_105),
+          "9": (141_213_431, 3_560_687), "10": (135_534_747, 3_992_219), "11": (135_006_516, 4_045_628), "12": (133_851_895, 3_868_428),
+          "13": (115_169_878, 2_857_916), "14": (107_349_540, 2_655_067), "15": (102_531_392, 2_424_689), "16": (90_354_753, 2_697_949),
+          "17": (81_195_210, 2_329_288), "18": (78_077_248, 2_267_185), "19": (59_128_983, 1_832_506), "20": (63_025_520, 1_812_841),
+          "21": (48_129_895, 1_105_538), "22": (51_304_566, 1_103_547), "X": (155_270_560, 3_468_093), "Y": (59_373_566, 62_042)}
+
+
+def genome_plan(args):
+    """Position-range shards of every contig: [{contig, length, lo, hi, records, seed, prefix}]."""
+    out = []
+    sc = args.genome_scale
+    for ci, (c, (length, records)) in enumerate(GENOME.items()):
+        length = max(400_000, int(length * sc)) if sc < 1 else length
+        records = max(2_000, int(records * sc))
+        k = max(1, -(-records // args.genome_shard_records))
+        step = length // k
+        for j in range(k):
+            lo, hi = (1 if j == 0 else j * step), ((j + 1) * step if j + 1 < k else length + 1)
+            key = hashlib.sha1(f"g2|{c}|{length}|{records}|{k}|{j}|{args.samples}|{args.fmax}".encode()).hexdigest()[:10]
+            out.append({"contig": c, "length": length, "lo": lo, "hi": hi, "records": records // k, "seed": 7000 + 100 * ci + j,
+                        "prefix": os.path.join(args.cache_dir, f"genome_{key}", "ser")})
+    return out
+
+
+def build_shard(spec, samples, fmax):
+    """One shard's ser/ by the oracle's construct restatement (a child process of the bench runs this)."""
+    T = get_oracle()
+    prefix = spec["prefix"]
+    if os.path.exists(os.path.join(prefix, ".done")):
+        return
+    os.makedirs(os.path.dirname(prefix), exist_ok=True)
+    t0 = time.time()
+    # records of this shard only, in the coordinates of the whole contig; a margin keeps records off the range ends
+    pos_lo, pos_hi = max(2, spec["lo"] + 50), min(spec["hi"] - 1200, spec["length"] - 1200)
+    o = T.Oracle.synth(prefix, chr_name=spec["contig"], ref_length=spec["length"], pos_lo=pos_lo, pos_hi=pos_hi, n_records=spec["records"],
+                       n_samples=samples, fmax=fmax, seed=spec["seed"], cqf_log2=25 if spec["records"] > 200_000 else 20, fix_idx=False, gzip_level=1)
+    info = o.construct_info
+    o.close()
+    with open(os.path.join(prefix, ".done"), "w") as f:
+        json.dump({"oracle_info": info, "build_s": time.time() - t0}, f)
+
+
+def genome_build(args, plan, rank, world):
+    """Builds this rank's share of the missing shards with child processes (bounded by cores and free memory)."""
+    mine = [sp for i, sp in enumerate(plan) if i % world == rank and not os.path.exists(os.path.join(sp["prefix"], ".done"))]
+    if not mine:
+        return 0.0
+    cores = max(1, (os.cpu_count() or 1) // world)
+    try:
+        avail_gb = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) / 1e6
+    except Exception:
+        avail_gb = 64.0
+    per_gb = 0.6 + 4.2 * max(sp["records"] for sp in mine) / 1_100_000 + max(sp["length"] for sp in mine) * 3e-9   # measured: 4.1 GB for a chr22-sized build
+    workers = max(1, min(cores, int(avail_gb / world / per_gb), len(mine)))
+    t0 = time.time()
+    running, todo = [], list(mine)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    while todo or running:
+        while todo and len(running) < workers:
+            sp = todo.pop(0)
+            running.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--build-shard", json.dumps(sp), "--samples", str(args.samples), "--fmax", str(args.fmax)], env=env))
+        time.sleep(0.2)
+        for pr in list(running):
+            if pr.poll() is not None:
+                running.remove(pr)
+                if pr.returncode != 0:
+                    raise RuntimeError("building a genome shard failed")
+    log(f"[rank {rank}] built {len(mine)} genome shards with {workers} workers in {time.time() - t0:.0f}s")
+    return time.time() - t0
+
+
+def genome_regions(args, plan):
+    contigs = list(GENOME)
+    lengths = np.array([next(sp["length"] for sp in plan if sp["contig"] == c) for c in contigs], np.float64)
+    rng = np.random.default_rng(123)
+    n = max(1000, int(args.genome_regions * args.genome_scale))
+    ci = rng.choice(len(contigs), n, p=lengths / lengths.sum())
+    x = (rng.integers(0, 2**62, n) % (lengths[ci].astype(np.int64) - args.width - 1) + 1).astype(np.uint32)
+    y = (x + args.width).astype(np.uint32)
+    s = rng.integers(1, args.samples + 1, n).astype(np.uint32)
+    return contigs, ci, x, y, s
+
+
+def _oracle_check(job):
+    """Child process: the oracle's t6 / t4 counts and row digests for a handful of regions of one shard."""
+    prefix, x, y, s = job
+    T = get_oracle()
+    o = T.Oracle.open(prefix)
+    c6, d6 = o.batch_t6(np.array(x, np.uint64), np.array(y, np.uint64), False)
+    c4, d4, ub = o.batch_t4(np.array(x, np.uint64), np.array(y, np.uint64), np.array(s, np.uint32), False)
+    o.close()
+    return c6.tolist(), d6.tolist(), c4.tolist(), d4.tolist(), ub.tolist()
+
+
+def genome_block(args, world, steps=3):
+    """Rank 0, after every rank built its share: open all shards behind the router, time the routed fused call end to end
+    (host regions in, host answers out, routing inside), check a subsample of every contig against the oracle."""
+    from concurrent.futures import ProcessPoolExecutor
+    from variantstore_b200 import Router
+    plan = genome_plan(args)
+    os.environ.pop("VSGPU_INDEX_CACHE", None)              # 77 flattened-index caches would not fit the box's disk
+    t0 = time.time()
+    r = Router([sp["prefix"] for sp in plan], ranges=[(sp["lo"], sp["hi"] if sp["hi"] <= sp["length"] else 0) for sp in plan], ndevices=world)
+    open_s = time.time() - t0
+    contigs, ci, x, y, s = genome_regions(args, plan)
+    cid = r.contig_ids([contigs[i] for i in range(len(contigs))])[ci]
+    n = len(x)
+    times, stats = [], None
+    for it in range(steps + 1):
+        t0 = time.perf_counter()
+        so, lo, c6, c4, _, _ = r.query_t6t4(cid, x, y, s, csr=False)     # hit codes stay in the shards' page-locked results
+        dt = time.perf_counter() - t0
+        if it:
+            times.append(dt)
+        stats = r.stats()
+    t0 = time.perf_counter()
+    so, lo, c6, c4, off, hits = r.query_t6t4(cid, x, y, s)                # the same with the hit codes gathered into one CSR in region order
+    csr_s = time.perf_counter() - t0
+    # ---- parity: ~90 regions of one shard per contig (>= 2 000 regions over all contigs) against the oracle, row digests included
+    rng = np.random.default_rng(9)
+    jobs, picks = [], []
+    for c in range(len(contigs)):
+        ks = np.unique(so[ci == c])
+        k = int(ks[rng.integers(0, len(ks))])
+        idx = np.nonzero(so == k)[0]
+        idx = idx[rng.choice(len(idx), min(90, len(idx)), replace=False)]
+        picks.append((k, idx))
+        jobs.append((plan[k]["prefix"], x[idx].tolist(), y[idx].tolist(), s[idx].tolist()))
+    bad, checked = 0, 0
+    with ProcessPoolExecutor(max_workers=min(len(jobs), max(1, (os.cpu_count() or 2) // 2))) as ex:
+        for (k, idx), (oc6, od6, oc4, od4, ub) in zip(picks, ex.map(_oracle_check, jobs)):
+            sh = r.shard(k)
+            e6 = sh.digest_t6(lo[idx], lo[idx] + c6[idx], False)
+            sub_off = np.concatenate([[0], np.cumsum(c4[idx])]).astype(np.uint64)
+            sub_hits = np.concatenate([hits[off[i]:off[i + 1]] for i in idx]) if len(idx) else np.zeros(0, np.uint32)
+            e4 = sh.digest_t4(sub_off, sub_hits, False)
+            ok = (np.array(oc6) == c6[idx]) & (np.array(od6, np.uint64) == e6) & ((np.array(ub) != 0) | ((np.array(oc4) == c4[idx]) & (np.array(od4, np.uint64) == e4)))
+            bad += int((~ok).sum()); checked += len(idx)
+    dev_bytes = {}
+    for k in range(r.num_shards):
+        dev_bytes[r.shard_device[k]] = dev_bytes.get(r.shard_device[k], 0) + int(r.shard(k).info.device_bytes)
+    t = float(np.median(times))
+    out = {"workload": f"{len(GENOME)} contigs in GRCh37 lengths x {args.genome_scale:g}, {sum(sp['records'] for sp in plan)} records x {args.samples} samples in {len(plan)} position-range shards "
+                       f"(<= {args.genome_shard_records} records each), {n} random {args.width} bp regions drawn in proportion to contig length, unsorted, one sample each; t6 + t4 per region",
+           "n_gpus": world, "shards": len(plan), "records": int(sum(sp["records"] for sp in plan)), "regions": n,
+           "e2e_regions_per_s": 2 * n / t, "e2e_ms": 1000 * t, "e2e_ms_with_csr_gather": 1000 * csr_s, "route_ms": stats["route_ms"], "scatter_ms": stats["scatter_ms"],
+           "per_gpu_ms": stats["device_ms"], "per_gpu_regions": stats["device_regions"],
+           "imbalance_regions_max_over_mean": float(max(stats["device_regions"]) / (np.mean(stats["device_regions"]) or 1)),
+           "device_bytes_per_gpu": [dev_bytes.get(d, 0) for d in sorted(dev_bytes)], "t4_rows": int(off[-1]), "open_all_shards_s": open_s,
+           "router": "C++ (csrc/router.cc): routing + host threads per GPU + scatter inside the timed region; one process drives all GPUs",
+           "parity": {"regions": checked, "contigs": len(contigs), "mismatches": bad, "status": "ok" if bad == 0 and checked >= 2000 * min(1.0, args.genome_scale * 10) else "FAILED",
+                      "against": "oracle (t6 / t4 row counts and row digests of ~90 regions of one shard per contig)"}}
+    r.close()
+    return out
+
+
 def run_vsgpu(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -345,6 +508,26 @@ def run_vsgpu(args):
         h2d = n * (2 * cb + 4)                           # x, y, sample ids, once
         d2h = n * 8 + n * 4 + hits_total * 4             # t6 lo + counts; t4 counts + hit codes
 
+    genome = None
+    if (world >= 2 or args.genome) and not args.no_genome:
+        # every rank builds its share of the genome shards on the host, then rank 0 alone drives all GPUs through the
+        # router while the others wait on a CPU (gloo) barrier — the engine's multi-GPU front-end is one process
+        for b in (b6, b4, b46):
+            if b is not None:
+                b.close()
+        cpu_group = dist.new_group(backend="gloo") if dist is not None else None
+        try:
+            build_s = genome_build(args, genome_plan(args), rank, world)
+            if cpu_group is not None:
+                dist.barrier(group=cpu_group)
+            if rank == 0:
+                genome = genome_block(args, world)
+                genome["build_shards_s_rank0"] = build_s
+        except Exception as ex:
+            genome = {"failed": repr(ex)[:400]}
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -385,6 +568,27 @@ def run_vsgpu(args):
         "gpu_launches": (launches46 if b46 is not None else launches6 + launches4) * args.steps,
         "clocks": sampler.summary(),
     }
+    if genome is not None:
+        line["genome"] = genome
+    if world == 1 and not args.no_other_ops:
+        # The same step with the answers as the text `-v` writes (print_var rows with every carrier's name and genotype, as the
+        # reference's operators build them): t6 rows and t4 rows rendered on the device, host regions in -> host text out.  A
+        # bounded slice of the regions: one region's t6 rows are ~46 KB of text, so this leg is the PCIe rate of the text.
+        try:
+            m = min(n, args.rows_regions)
+            sl = slice(0, n, max(1, n // m))
+            rx, ry, rs = (np.ascontiguousarray(a[sl][:m]) for a in (x, y, s))
+            vt = []
+            for rep in range(3):
+                t0 = time.perf_counter()
+                o6, text6, rows6, ms6 = idx.render_var_in_ref(rx, ry, True)
+                o4, text4, rows4, ms4 = idx.render_sample_var_in_ref(rx, ry, rs, True)
+                vt.append(time.perf_counter() - t0)
+            line["e2e_rows"] = {"value": 2 * len(rx) / float(np.median(vt)), "unit": "regions/s", "regions": int(len(rx)), "t6_rows": rows6, "t4_rows": rows4,
+                                "text_bytes": int(len(text6) + len(text4)), "render_kernels_ms": ms6 + ms4,
+                                "call": "vsgpu_render_t6 + vsgpu_render_t4 (rows as print_var text with carrier lists, query.h:43-50)"}
+        except Exception as ex:
+            line["e2e_rows"] = {"failed": repr(ex)[:300]}
     if world == 1 and not args.no_other_ops:
         # Reported beside the headline, never part of it: the widened operator t2 (a sample's sequence over the same
         # regions) through its C-ABI call — device time of its kernels and end to end.
@@ -433,11 +637,21 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="regions per type per step of the reference arm")
     ap.add_argument("--cpu-sample-single", type=int, default=2_000, help="regions per type of the single-thread cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other-ops", action="store_true", help="skip the t2 side measurement")
+    ap.add_argument("--no-other-ops", action="store_true", help="skip the side measurements (t2, rows as text)")
+    ap.add_argument("--rows-regions", type=int, default=20_000, help="regions of the e2e_rows leg (answers as -v text)")
     ap.add_argument("--unfused", action="store_true", help="a step = k_t6 then k_t4p (two launches, two host-buffer calls) instead of the fused launch / call")
     ap.add_argument("--e2e-u64", action="store_true", help="end-to-end arm through the 64-bit coordinate entry points instead of the 32-bit ones")
     ap.add_argument("--cache-dir", default=os.environ.get("VSGPU_BENCH_CACHE", "/tmp/vsgpu_bench"))
+    ap.add_argument("--genome", action="store_true", help="run the whole-genome block (config [2]) also at N = 1")
+    ap.add_argument("--no-genome", action="store_true", help="skip the whole-genome block at N >= 2")
+    ap.add_argument("--genome-scale", type=float, default=1.0, help="fraction of the 84.8 M records / 10 M regions / contig lengths")
+    ap.add_argument("--genome-regions", type=int, default=10_000_000)
+    ap.add_argument("--genome-shard-records", type=int, default=1_200_000)
+    ap.add_argument("--build-shard", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.build_shard:
+        build_shard(json.loads(args.build_shard), args.samples, args.fmax)
+        return
     import __graft_entry__
     if not os.path.exists(os.path.join(ROOT, "variantstore_b200", "libvsgpu.so")) or not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
         __graft_entry__.build()

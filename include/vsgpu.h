@@ -155,6 +155,11 @@ int vsgpu_digest_t7(const vsgpu_index* idx, uint64_t n, const uint32_t* rec, uin
  * the batch exceeds VSGPU_RENDER_MAX_BYTES (default 2 GiB): split the batch. */
 typedef struct vsgpu_text vsgpu_text;
 int vsgpu_render_t6(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, int with_samples, vsgpu_text** out);
+/* The same for t4: get_sample_var_in_ref(vg, idx, x, y, sample, print = true, outfile) — include/query.h:618-729 with print_var
+ * (:43-50): t4 runs on the device and the rows of its hit codes (position / ref / alt by the emission rules of :677-710,
+ * carriers of the row's vertex) are rendered there too.  Region i owns bytes [offsets[i], offsets[i+1]); byte-identical to
+ * vsgpu_rows_t4 on the codes vsgpu_query_t4 returns for it. */
+int vsgpu_render_t4(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, int with_samples, vsgpu_text** out);
 const char* vsgpu_text_bytes(const vsgpu_text* t);          /* NUL-terminated after the last region */
 const uint64_t* vsgpu_text_offsets(const vsgpu_text* t);    /* n + 1 byte offsets */
 uint64_t vsgpu_text_num_rows(const vsgpu_text* t);          /* rows rendered over all regions */
@@ -237,11 +242,14 @@ vsgpu_index* vsgpu_router_shard_index(const vsgpu_router* r, uint32_t shard);
 int vsgpu_router_shard_device(const vsgpu_router* r, uint32_t shard);
 /* t6 + t4 for n regions (contig[i], [x[i], y[i]), sample_ids[i]) in the caller's order: shard_of[i], rec_lo[i],
  * counts6[i] (t6 slice = [rec_lo, rec_lo + counts6) except where the literal dedup rule lowered the count) and
- * counts4[i]; the t4 hit codes as one CSR through vsgpu_router_offsets / _hits (valid until the next call). */
+ * counts4[i]; the t4 hit codes per region through vsgpu_router_region_hits, or as one CSR in the caller's order through
+ * vsgpu_router_offsets / _hits (all valid until the next call). */
 int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig, const uint32_t* x, const uint32_t* y, const uint32_t* sample_ids,
                             uint32_t* shard_of, uint32_t* rec_lo, uint32_t* counts6, uint32_t* counts4);
-const uint64_t* vsgpu_router_offsets(const vsgpu_router* r);   /* n + 1 */
+const uint64_t* vsgpu_router_offsets(const vsgpu_router* r);   /* n + 1; the first call after a query gathers the CSR (host threads) */
 const uint32_t* vsgpu_router_hits(const vsgpu_router* r);
+/* The hit codes of region i of the last call where the device->host copy put them (page-locked memory of its shard's result): no gather. */
+int vsgpu_router_region_hits(const vsgpu_router* r, uint64_t i, const uint32_t** hits, uint32_t* count);
 /* Last call: wall-clock milliseconds each GPU's host thread spent on its shards and the regions it answered (up to cap
  * entries; *ndev = GPUs in use), the routing time before and the scatter time after. */
 int vsgpu_router_stats(const vsgpu_router* r, uint32_t cap, int* devices, double* device_ms, uint64_t* device_regions, uint32_t* ndev,

@@ -26,7 +26,7 @@ struct vsgpu_index : HostIndex {
 	std::vector<uint64_t> sidx_begin; std::vector<uint32_t> sidx, sid;
 	std::vector<uint32_t> bbs;
 	std::string seq_ascii;
-	std::vector<uint32_t> bucket, d4;
+	std::vector<uint32_t> bucket, d4, car, marker_list, can_entry, can_pmax; std::vector<uint64_t> car_begin, can_begin;
 	std::vector<uint2> t7;
 	std::vector<uint32_t> hitmap;
 };
@@ -63,7 +63,12 @@ int vsgpu_open(const char* prefix, int, vsgpu_index** out) {
 	d.bb_set = f.bb_set.data(); d.vstart = f.vstart.data(); d.bitmap = f.bitmap.data(); d.list_begin = f.list_begin.data();
 	d.list_ids = f.list_ids.data(); d.rec_pos = f.rec_pos.data(); d.rec_hash = f.rec_hash.data(); d.rec_flags = f.rec_flags.data();
 	d.marker_bits = f.marker_bits.data(); d.cent_begin_k = f.cent_begin.data(); d.dtin = f.dtin.data(); d.cent_anc = (const uint2*)f.cent_anc.data(); d.row_words = f.row_words; d.hitmap = nullptr;
-	if (!getenv("VSGPU_DISABLE_HITMAP")) {   // host copy of k_build_hitmap
+	if (want_sparse_walk(f)) {
+		build_sparse_walk(f, ix->car_begin, ix->car, ix->marker_list);
+		d.car_begin = ix->car_begin.data(); d.car = ix->car.data(); d.marker_list = ix->marker_list.data(); d.num_markers = (uint32_t)ix->marker_list.size(); d.marker_span = marker_span(f, ix->marker_list);
+		build_canonical_walks(f, ix->car_begin, ix->car, ix->marker_list, ix->can_begin, ix->can_entry, ix->can_pmax);
+		d.can_begin = ix->can_begin.data(); d.can_entry = ix->can_entry.data(); d.can_pmax = ix->can_pmax.data();
+	} else if (!getenv("VSGPU_DISABLE_HITMAP")) {   // host copy of k_build_hitmap
 		ix->hitmap.assign((size_t)f.num_samples * f.row_words, 0);
 		for (size_t c = 0; c < f.cent.size(); c++) {
 			const CEntry& e = f.cent[c];

@@ -135,6 +135,8 @@ def test_router_contigs_and_position_shards_cuda(tmp_path):
             sub_hits = np.concatenate([hits[off[i]:off[i + 1]] for i in idx]) if len(idx) else np.zeros(0, np.uint32)
             ok = (o4 == c4[idx]) & (d4 == sh.digest_t4(sub_off, sub_hits))
             assert np.all(ok | (ub != 0))
+        for i in (0, 17, 999, n - 1):                      # one region's hit codes where the copy from its GPU put them
+            assert np.array_equal(r.hits_of(i), hits[off[i]:off[i + 1]])
         st = r.stats()
         assert st["devices"] == [0] and st["device_regions"] == [n] and st["device_ms"][0] > 0
         # a start no shard owns (contig 22 has no shard for nothing; an unknown contig id) is an error, not a silent zero

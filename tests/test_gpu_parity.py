@@ -29,7 +29,7 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "tile-256", "chunked-calls"])
+@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "tile-256", "chunked-calls", "carried-entry-lists", "hitmap-32bit-words"])
 def walk_path(request, monkeypatch):
     """The t4 kernel paths: the sample-major hit map with one thread per region (default), the
     per-entry class-bitmap test used when the map does not fit the memory budget, and the
@@ -43,6 +43,14 @@ def walk_path(request, monkeypatch):
     monkeypatch.delenv("VSGPU_WIDE_ENTRIES", raising=False)
     monkeypatch.delenv("VSGPU_T4_PIPE", raising=False)
     monkeypatch.delenv("VSGPU_T4_TILE", raising=False)
+    monkeypatch.delenv("VSGPU_T4_ROW64", raising=False)
+    monkeypatch.delenv("VSGPU_SPARSE_WALK", raising=False)   # default: per-sample carried-entry lists for explicit-id cohorts, the hit map otherwise
+    if request.param == "carried-entry-lists":
+        monkeypatch.setenv("VSGPU_SPARSE_WALK", "1")          # the lists for every cohort
+    elif request.param != "hitmap":
+        monkeypatch.setenv("VSGPU_SPARSE_WALK", "0")          # never: the explicit-id cases take the named path too
+    if request.param == "hitmap-32bit-words":
+        monkeypatch.setenv("VSGPU_T4_ROW64", "0")             # walk_region_fast (32 entries per step) instead of the 64-entry chunks
     if request.param == "cta-per-tile":
         monkeypatch.setenv("VSGPU_T4_PIPE", "0")        # k_t4 instead of the persistent pipelined k_t4p
     if request.param == "tile-256":
@@ -259,6 +267,37 @@ def test_rows_rendered_on_device_cuda(tmp_path, sparse):
         y = np.concatenate([y, [4001, 9000, 4001, 4001, 5000]]).astype(np.uint64)
         _check_render(o, e, x, y)
         off, text, rows, ms = e.render_var_in_ref(np.zeros(0, np.uint64), np.zeros(0, np.uint64))
+        assert len(off) == 1 and text == b"" and rows == 0
+
+
+@pytest.mark.parametrize("sparse,overlap", [(False, True), (True, True), (False, False)])
+def test_t4_rows_rendered_on_device_cuda(tmp_path, sparse, overlap):
+    """get_sample_var_in_ref with print (query.h:719-726): the rows of every region's t4 answer written by a kernel
+    (vsgpu_render_t4) — byte for byte the oracle's `-o` rows, and the host materialiser's (vsgpu_rows_t4) on the same hit
+    codes, START / REJOIN rows included, with and without the carrier lists."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 6, overlap=overlap, sparse=sparse, n_samples=40 if sparse else 12, n_records=320)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"), force_enc=0 if sparse else -1)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        starts = np.arange(1, 4001, 7, dtype=np.uint64)
+        x = np.tile(starts, len(names))
+        y = x + np.tile(np.where(np.arange(len(starts)) % 3 == 0, 40, 700).astype(np.uint64), len(names))
+        s = np.repeat(np.arange(1, len(names) + 1, dtype=np.uint32), len(starts))
+        off4, hits = e.batch_sample_var_in_ref(x, y, s)
+        assert int(((hits & 0x80000000) != 0).sum()) > 0                      # rows the walk started on (ref column empty)
+        for ws in (True, False):
+            off, text, rows, ms = e.render_sample_var_in_ref(x, y, s, with_samples=ws)
+            assert rows == len(hits) and off[-1] == len(text) and ms > 0
+            want = b"".join(e.rows_t4_text(hits[off4[i]:off4[i + 1]], ws).encode() for i in range(0, len(x), 37))
+            got = b"".join(text[off[i]:off[i + 1]] for i in range(0, len(x), 37))
+            assert got == want
+        off, text, rows, ms = e.render_sample_var_in_ref(x, y, s, with_samples=True)
+        rng = np.random.default_rng(3)
+        for i in rng.choice(len(x), 150, replace=False):
+            otext, ub = o.t4_text(int(x[i]), int(y[i]), names[int(s[i]) - 1])
+            if ub:
+                continue
+            assert text[off[i]:off[i + 1]].decode() == "\n".join(otext.split("\n")[2:]), (int(x[i]), int(y[i]), int(s[i]))
+        off, text, rows, ms = e.render_sample_var_in_ref(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
         assert len(off) == 1 and text == b"" and rows == 0
 
 

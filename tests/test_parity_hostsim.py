@@ -25,10 +25,15 @@ def t7_parity(o, e):
     return int(hit.sum())
 
 
-@pytest.fixture(params=["hitmap", "hitmap-32bit-words", "class-bitmaps"])
+@pytest.fixture(params=["hitmap", "hitmap-32bit-words", "class-bitmaps", "carried-entry-lists"])
 def walk_path(request, monkeypatch):
     monkeypatch.delenv("VSGPU_DISABLE_HITMAP", raising=False)
     monkeypatch.delenv("VSGPU_T4_ROW64", raising=False)
+    monkeypatch.delenv("VSGPU_SPARSE_WALK", raising=False)      # default: lists for explicit-id cohorts, hit map otherwise
+    if request.param == "carried-entry-lists":
+        monkeypatch.setenv("VSGPU_SPARSE_WALK", "1")              # ... here for every cohort
+    elif request.param != "hitmap":
+        monkeypatch.setenv("VSGPU_SPARSE_WALK", "0")              # ... here never (the explicit-id cases take the named path)
     if request.param == "class-bitmaps":
         monkeypatch.setenv("VSGPU_DISABLE_HITMAP", "1")
     elif request.param == "hitmap-32bit-words":

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--tcga-records", type=int, default=3_000_000)
     ap.add_argument("--tcga-samples", type=int, default=10_000)
     ap.add_argument("--lookups", type=int, default=10_000_000)
+    ap.add_argument("--t4-regions", type=int, default=1_000_000)
     args = ap.parse_args()
     import torch
     import vs_testlib as T
@@ -71,6 +72,35 @@ def main():
                           "algorithmic_GBps": algo / (ms / 1000) / 1e9, "class_mode": int(idx.info.class_mode),
                           "device_bytes": int(idx.info.device_bytes), "parity_sample_ok": ok, "build_s": build_s}), flush=True)
         idx.close()
+        # ---- t4 on the same cohort: 1 M sorted 1 kb regions, a random sample each — the reference's own worst case
+        # (eval_data_records/logs/query_luad.out:120: 3 319 s for 1 000 regions); per-sample carried-entry lists
+        # (default for explicit-id cohorts) against the hit map (VSGPU_SPARSE_WALK=0)
+        n4 = args.t4_regions
+        x = np.sort(rng.integers(10_000, 243_199_373 - 1000, n4)).astype(np.uint64)
+        y = x + np.uint64(1000)
+        s = rng.integers(1, args.tcga_samples + 1, n4).astype(np.uint32)
+        sub = rng.choice(n4, 1500, replace=False)
+        oc4, od4, ub = o.batch_t4(x[sub], y[sub], s[sub], False)
+        for mode in ("1", "0"):
+            os.environ["VSGPU_SPARSE_WALK"] = mode
+            t0 = time.time()
+            idx = VariantStoreIndex(prefix, device=0)
+            open_s = time.time() - t0
+            idx.set_stream(torch.cuda.current_stream().cuda_stream)
+            b4 = Batch(idx, 4, x, y, sample_ids=s)
+            ms4 = timed(b4, steps=5, warmup=2)
+            off, hits, cnt = b4.fetch()
+            ed4 = idx.digest_t4(off, hits, False)
+            ok = bool(np.all(((oc4 == np.diff(off)[sub]) & (od4 == ed4[sub])) | (ub != 0)))
+            t0 = time.perf_counter()
+            for _ in range(3):
+                idx.batch_sample_var_in_ref(x.astype(np.uint32), y.astype(np.uint32), s)
+            e2e_s = (time.perf_counter() - t0) / 3
+            print(json.dumps({"config": "tcga-like sparse t4", "membership": "per-sample carried-entry lists" if mode == "1" else "hit map", "records": args.tcga_records,
+                              "samples": args.tcga_samples, "regions": n4, "k_t4_ms": ms4, "t4_regions_per_s": n4 / (ms4 / 1000), "t4_rows_per_region": float(cnt.mean()),
+                              "e2e_regions_per_s": n4 / e2e_s, "device_bytes": int(idx.info.device_bytes), "open_s": open_s, "parity_sample_ok": ok}), flush=True)
+            b4.close(); idx.close()
+        os.environ.pop("VSGPU_SPARSE_WALK", None)
         o.close()
     if "width" in args.what:
         import bench

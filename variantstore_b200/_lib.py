@@ -52,6 +52,7 @@ PROTOTYPES = {
     "vsgpu_digest_t4": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, vp]),
     "vsgpu_digest_t7": (C.c_int, [vp, C.c_uint64, vp, vp, vp]),
     "vsgpu_render_t6": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp)]),
+    "vsgpu_render_t4": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.c_int, C.POINTER(vp)]),
     "vsgpu_text_bytes": (vp, [vp]),
     "vsgpu_text_offsets": (u64p, [vp]),
     "vsgpu_text_num_rows": (C.c_uint64, [vp]),
@@ -84,6 +85,7 @@ PROTOTYPES = {
     "vsgpu_router_query_t6t4": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "vsgpu_router_offsets": (u64p, [vp]),
     "vsgpu_router_hits": (u32p, [vp]),
+    "vsgpu_router_region_hits": (C.c_int, [vp, C.c_uint64, C.POINTER(u32p), u32p]),
     "vsgpu_router_stats": (C.c_int, [vp, C.c_uint32, vp, vp, vp, u32p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 # subset a test-only host simulator has to provide

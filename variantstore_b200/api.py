@@ -217,6 +217,22 @@ class VariantStoreIndex:
             self._lib.vsgpu_text_free(t)
         return off, text, rows, ms
 
+    def render_sample_var_in_ref(self, x, y, sample_ids, with_samples=True):
+        """t4 over arrays with the rows rendered on the device (vsgpu_render_t4): (offsets[n+1], text bytes, rows, kernel ms)."""
+        x, y = _u64(x), _u64(y)
+        s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        n = len(x)
+        t = C.c_void_p()
+        self._check(self._lib.vsgpu_render_t4(self._h, n, _ptr(x), _ptr(y), _ptr(s), int(with_samples), C.byref(t)))
+        try:
+            off = np.ctypeslib.as_array(self._lib.vsgpu_text_offsets(t), shape=(n + 1,)).copy()
+            text = C.string_at(self._lib.vsgpu_text_bytes(t), int(off[-1]))
+            rows = int(self._lib.vsgpu_text_num_rows(t))
+            ms = float(self._lib.vsgpu_text_kernel_ms(t))
+        finally:
+            self._lib.vsgpu_text_free(t)
+        return off, text, rows, ms
+
     def batch_sample_var_in_sample(self, x, y, sample_ids):
         """t5 over arrays (get_sample_var_in_sample, query.h:490-612): (offsets[n+1], hit codes, status, kernel ms);
         status 2 = the reference never returns."""
@@ -431,19 +447,29 @@ class Router:
             self._shards[k] = VariantStoreIndex("", lib=self._lib, _borrowed=self._lib.vsgpu_router_shard_index(self._h, k))
         return self._shards[k]
 
-    def query_t6t4(self, contig_ids, x, y, sample_ids):
-        """(shard_of, rec_lo, counts6, counts4, offsets[n+1], hit codes) in the caller's region order."""
+    def query_t6t4(self, contig_ids, x, y, sample_ids, csr=True):
+        """(shard_of, rec_lo, counts6, counts4, offsets[n+1], hit codes) in the caller's region order; csr=False leaves the
+        hit codes in the shards' results (offsets / hits come back None; hits_of(i) reads one region's)."""
         c = np.ascontiguousarray(contig_ids, np.uint32); x = np.ascontiguousarray(x, np.uint32); y = np.ascontiguousarray(y, np.uint32)
         s = np.ascontiguousarray(sample_ids, np.uint32)
         n = len(x)
-        so, lo, c6, c4 = (np.zeros(n, np.uint32) for _ in range(4))
+        so, lo, c6, c4 = (np.empty(n, np.uint32) for _ in range(4))
         rc = self._lib.vsgpu_router_query_t6t4(self._h, n, _ptr(c), _ptr(x), _ptr(y), _ptr(s), _ptr(so), _ptr(lo), _ptr(c6), _ptr(c4))
         if rc != 0:
             raise VsgpuError(rc, self._lib.vsgpu_router_last_error().decode())
+        if not csr:
+            return so, lo, c6, c4, None, None
         off = np.ctypeslib.as_array(self._lib.vsgpu_router_offsets(self._h), shape=(n + 1,)).copy()
         total = int(off[-1])
         hits = np.ctypeslib.as_array(self._lib.vsgpu_router_hits(self._h), shape=(total,)).copy() if total else np.zeros(0, np.uint32)
         return so, lo, c6, c4, off, hits
+
+    def hits_of(self, i: int) -> np.ndarray:
+        p, c = _lib.u32p(), C.c_uint32()
+        rc = self._lib.vsgpu_router_region_hits(self._h, int(i), C.byref(p), C.byref(c))
+        if rc != 0:
+            raise VsgpuError(rc, self._lib.vsgpu_router_last_error().decode())
+        return np.ctypeslib.as_array(p, shape=(c.value,)).copy() if c.value else np.zeros(0, np.uint32)
 
     def stats(self):
         dev = np.zeros(16, np.int32); ms = np.zeros(16, np.float64); reg = np.zeros(16, np.uint64)

@@ -481,9 +481,103 @@ VSGPU_HD uint2 t6_from_ranks(const DevIndex& ix, uint64_t x64, uint64_t y64, uin
 	return r;
 }
 
+// ------------------------------------------------------------------ t4 on a sparse cohort: per-sample carried-entry lists
+// car[car_begin[s] .. car_begin[s+1]) = the walk entries whose target sample s carries, ascending.  The hit map of such a
+// cohort is gigabytes of zeros and a back-walk over it scans words until it meets a set bit — tens of thousands of
+// dependent loads for a sample with a few hundred variants on the contig.  Here the back-walk is a predecessor search
+// and the forward walk a merge of the sample's list with the (global, short) list of marker entries.  Same rules, same
+// order, same output as the other walks.
+VSGPU_HD uint64_t lower_bound_u32(const uint32_t* a, uint64_t lo, uint64_t hi, uint32_t v) {      // first index in [lo, hi) with a[i] >= v
+	while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (ldg(a + m) < v) lo = m + 1; else hi = m; }
+	return lo;
+}
+template <class Sink>
+VSGPU_HD void walk_region_sparse(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink, uint32_t& rk, uint32_t& e_y) {
+	rk = 0; e_y = 0;
+	if (x64 > ix.index_bits) return;
+	const uint32_t x = clamp_pos(x64), y = clamp_pos(y64);
+	rank_le2(ix, x, y ? y - 1 : 0, rk, e_y);
+	if (!y) e_y = 0;
+	if (rk < 1 || rk >= ix.D) return;
+	const uint32_t pos = ldg(&ix.d4[rk >= 2 ? rk - 2 : 0].z);
+	const uint32_t next_start = ldg(ix.dstart + rk);
+	const uint32_t t = ldg(&ix.d4[rk - 1].w);
+	const uint4 dl = ldg(ix.d4 + e_y);
+	const uint64_t cb = ldg(ix.car_begin + s), ce = ldg(ix.car_begin + s + 1);
+	if ((uint64_t)next_start > (uint64_t)y + 1) return;                         // is_empty gate
+	// ---- get_prev_vertex_with_sample: the sample's carried entries below pos, highest first, until one whose source an ancestor state examines
+	uint64_t i_next = cb;                                                       // where the forward scan starts in the sample's list
+	uint32_t c_found = kNoneU32;
+	if (rk - 1 >= 2 && pos > 0) {
+		for (uint64_t i = lower_bound_u32(ix.car, cb, ce, pos); i > cb;) {
+			i--;
+			const uint32_t p = ldg(ix.car + i);
+			const uint2 a = ldg(ix.cent_anc + p);
+			if (a.x <= t && t <= a.y) { c_found = p; i_next = i + 1; break; }
+		}
+	}
+	FwdState st;
+	st.row = nullptr; st.c = 0; st.cur_k = 0; st.limit = dl.y; st.k_end = dl.x; st.x = x; st.y = y;
+	if (c_found != kNoneU32) {
+		const uint4 e = ldg(ix.cent + c_found);
+		if (e.w >= y) return;
+		if (e.w >= x) sink.emit(c_found | kHitStart);
+		if (e.y & kEntAlt) {
+			const uint32_t tk = e.y & kEntTgtMask;
+			if (tk == kEntTgtMask || tk >= st.k_end) return;
+			if ((e.y & kEntTgtCarriers) && member(ix, s, ldg(ix.bb_set + tk)) && ldg(ix.vstart + tk) >= x) sink.emit(c_found | kHitRejoin);
+			st.cur_k = tk;
+		} else {
+			st.cur_k = e.y & kEntTgtMask;
+			if (st.cur_k >= st.k_end) { const uint32_t nl = ldg(ix.cent_begin_k + st.cur_k + 1); if (nl > st.limit) st.limit = nl; }
+		}
+		st.c = c_found + 1;
+	} else {
+		if (1 >= y) return;
+		// The walk starts at the head of the contig.  Which entries it takes up to x is the sample's business alone
+		// (can_entry), and none of them can be reported while the running maximum of their arrivals stays below x: join
+		// the walk at the last such entry — it is stepped through fwd_step like any other, which also leaves the walk
+		// position it implies — instead of stepping through every entry the sample carries before x.
+		uint64_t lo = ldg(ix.can_begin + s), hi = ldg(ix.can_begin + s + 1);
+		const uint64_t lo0 = lo;
+		while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (ldg(ix.can_pmax + m) < x) lo = m + 1; else hi = m; }
+		if (lo > lo0) {
+			const uint32_t c0 = ldg(ix.can_entry + lo - 1);
+			if (c0 < st.limit) {
+				const uint4 e0 = ldg(ix.cent + c0);
+				st.cur_k = e0.x;
+				if (fwd_step(ix, st, s, c0, e0, sink)) return;
+				st.c = c0 + 1;
+				i_next = lower_bound_u32(ix.car, cb, ce, st.c);
+			}
+		}
+	}
+	if (st.c >= st.limit) return;
+	// ---- forward: merge of the sample's entries and the markers from st.c on, in entry order, until the scan bound
+	// A marker only matters when its arrival is >= y (it then ends the walk), and such a marker lies at most marker_span
+	// entries below the scan bound — the markers of the long gap between two entries a sparse sample carries are skipped.
+	const uint32_t m_lo = st.limit > ix.marker_span ? st.limit - ix.marker_span : 0;
+	uint64_t im = lower_bound_u32(ix.marker_list, 0, ix.num_markers, st.c > m_lo ? st.c : m_lo);
+	uint64_t ic = i_next;
+	for (;;) {
+		const uint32_t a = ic < ce ? ldg(ix.car + ic) : kNoneU32, b = im < ix.num_markers ? ldg(ix.marker_list + im) : kNoneU32;
+		const uint32_t ci = a < b ? a : b;
+		if (ci >= st.limit) return;                                               // (kNoneU32 >= any limit)
+		if (a < b) ic++; else im++;
+		const uint4 e = ldg(ix.cent + ci);
+		if (fwd_step(ix, st, s, ci, e, sink)) return;
+	}
+}
+
 // One region of t4 by whichever walk the index supports; *t6 (nullable) receives the region's t6 slice.
 template <class Sink>
 VSGPU_HD void walk_any(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t s, Sink& sink, uint2* t6 = nullptr) {
+	if (ix.car_begin) {
+		uint32_t rk, e_y;
+		walk_region_sparse(ix, x64, y64, s, sink, rk, e_y);
+		if (t6) *t6 = t6_from_ranks(ix, x64, y64, rk, e_y);
+		return;
+	}
 	if (ix.hitmap && ix.walk2) {
 		FwdState2 st; uint32_t rk, e_y;
 		if (fast2_setup(ix, x64, y64, s, sink, st, rk, e_y)) fast2_forward(ix, st, s, sink);
@@ -506,6 +600,20 @@ VSGPU_HD void walk_any(const DevIndex& ix, uint64_t x64, uint64_t y64, uint32_t 
 // get_prev_vertex_with_sample (query.h:57-113) for back-walk state `cur`: the walk entry it stops on,
 // or kNoneU32 when it reaches the start of the contig.
 VSGPU_HD uint32_t back_walk(const DevIndex& ix, uint32_t s, uint64_t cur) {
+	if (ix.car_begin) {
+		if (cur < 2 || cur > ix.D) return kNoneU32;
+		const uint64_t info = ldg(ix.dinfo + (cur - 1));
+		const uint32_t t = ldg(ix.dtin + cur);
+		const uint32_t pos = (uint32_t)info + ((uint32_t)(info >> 32) & 0xFFFF);
+		const uint64_t cb = ldg(ix.car_begin + s), ce = ldg(ix.car_begin + s + 1);
+		for (uint64_t i = lower_bound_u32(ix.car, cb, ce, pos); i > cb;) {
+			i--;
+			const uint32_t p = ldg(ix.car + i);
+			const uint2 a = ldg(ix.cent_anc + p);
+			if (a.x <= t && t <= a.y) return p;
+		}
+		return kNoneU32;
+	}
 	if (ix.hitmap) {
 		if (cur < 2 || cur > ix.D) return kNoneU32;
 		const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
@@ -541,6 +649,13 @@ VSGPU_HD uint32_t back_walk(const DevIndex& ix, uint32_t s, uint64_t cur) {
 // first walk entry in [c, limit) whose target the sample carries (markers are not edges), or kNoneU32
 VSGPU_HD uint32_t next_carried(const DevIndex& ix, uint32_t s, uint32_t c, uint32_t limit) {
 	if (c >= limit) return kNoneU32;
+	if (ix.car_begin) {
+		const uint64_t cb = ldg(ix.car_begin + s), ce = ldg(ix.car_begin + s + 1);
+		const uint64_t i = lower_bound_u32(ix.car, cb, ce, c);
+		if (i >= ce) return kNoneU32;
+		const uint32_t ci = ldg(ix.car + i);
+		return ci < limit ? ci : kNoneU32;
+	}
 	if (ix.hitmap) {
 		const uint32_t* row = ix.hitmap + (uint64_t)s * ix.row_words;
 		uint32_t w = c >> 5;

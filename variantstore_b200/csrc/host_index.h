@@ -33,10 +33,20 @@ void build_buckets(const FlatIndex& f, std::vector<uint32_t>& bucket, uint32_t& 
 // DevIndex::d4 (kernels.cuh), 4 words per distinct start: what the t4 walk looks up per start, in one row
 void build_d4(const FlatIndex& f, std::vector<uint32_t>& d4);
 
+// per-sample carried walk entries + marker entries (DevIndex::car_begin / car / marker_list) and when to use them
+void build_sparse_walk(const FlatIndex& f, std::vector<uint64_t>& car_begin, std::vector<uint32_t>& car, std::vector<uint32_t>& marker_list);
+bool want_sparse_walk(const FlatIndex& f);
+uint32_t marker_span(const FlatIndex& f, const std::vector<uint32_t>& marker_list);
+// per sample: the entries its walk from the head of the contig takes, with the running maximum of their arrivals (DevIndex::can_*)
+void build_canonical_walks(const FlatIndex& f, const std::vector<uint64_t>& car_begin, const std::vector<uint32_t>& car, const std::vector<uint32_t>& marker_list,
+                           std::vector<uint64_t>& can_begin, std::vector<uint32_t>& can_entry, std::vector<uint32_t>& can_pmax);
+
 void append_seq(const HostIndex* ix, uint32_t v, std::string& out);
 void append_carriers(const HostIndex* ix, uint32_t v, std::string& out);
 void t6_row(const HostIndex* ix, uint32_t r, bool with_samples, std::string& out);
 void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& out);
+// the parts of that row as vertex ids (what the device-side renderer's tables are built from); sample == kNone (0xFFFFFFFF): t4
+void hit_row_parts(const HostIndex* ix, uint32_t code, uint32_t sample, uint64_t& pos, uint32_t& refv, uint32_t& altv, uint32_t& u);
 // t5 row (get_sample_var_in_sample, query.h:553-590): the t4 row of the same hit code with var_pos in the sample's coordinates
 void t5_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool with_samples, std::string& out);
 void digests_t5(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* samples, bool with_samples, uint64_t* digests);

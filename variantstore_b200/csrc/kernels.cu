@@ -554,13 +554,83 @@ __device__ __forceinline__ void warp_excl2(uint32_t lane, uint32_t a, uint32_t b
 	ta = __shfl_sync(0xFFFFFFFFu, ia, 31); tb = __shfl_sync(0xFFFFFFFFu, ib, 31);
 }
 
+// One row of print_var text (query.h:43-50) written by a warp at its final position: "pos\tref\talt\t", then the carriers of
+// the row's vertex expanded from its class bitmap / id list (get_samples, query.h:268-285).  sq = {ref_off, ref_len, alt_off,
+// alt_len} into rt.seq, cr = {carrier set id, s_info count | row flags << 28, s_info begin lo, hi}.  Rows of t6 records
+// (k_render) and rows of t4 hit codes (k_render_hits) are the same text.
+__device__ __forceinline__ void render_row(const DevIndex& ix, const RenderTables& rt, uint32_t pos_value, const uint4 sq, const uint4 cr, char* out, uint32_t row_bytes,
+                                           int ws, uint8_t* stage, uint32_t lane) {
+	const uint64_t kBase = 0x0505054E47544341ULL;                      // "ACTGN" + 5,5,5 by 3-bit code: map_int, src/util.cc:32-41
+	// ---- "pos\t"
+	uint32_t at = 0;
+	{
+		uint32_t p = pos_value, nd = 1;
+		for (uint32_t q = p; q >= 10; q /= 10) nd++;
+		if (lane == 0) { uint32_t q = p; for (uint32_t i = nd; i-- > 0;) { out[i] = (char)('0' + q % 10); q /= 10; } out[nd] = '\t'; }
+		at = nd + 1;
+	}
+	// ---- ref \t alt \t
+	for (uint32_t i = lane; i < sq.y; i += 32) out[at + i] = (char)(kBase >> (8 * (__ldg(rt.seq + sq.x + i) & 7)));
+	at += sq.y;
+	if (lane == 0) out[at] = '\t';
+	at += 1;
+	for (uint32_t i = lane; i < sq.w; i += 32) out[at + i] = (char)(kBase >> (8 * (__ldg(rt.seq + sq.z + i) & 7)));
+	at += sq.w;
+	if (lane == 0) { out[at] = '\t'; out[row_bytes - 1] = '\n'; }
+	at += 1;
+	if (!ws || ((cr.y >> 28) & 4)) return;                        // no carrier list asked for / the row has none
+	// ---- carriers
+	const uint64_t sbegin = (uint64_t)cr.z | ((uint64_t)cr.w << 32);
+	uint32_t slot0 = 0;                                              // s_info entries consumed so far
+	const uint32_t rounds = ix.class_mode ? (ix.words_per_set + 31) / 32 : ((cr.y & 0x0FFFFFFFu) + 31) / 32;
+	for (uint32_t rd = 0; rd < rounds; rd++) {
+		// this lane's items of the round: class mode = the members of one bitmap word (the ref bit owns an
+		// s_info entry but is not printed); explicit-id mode = one s_info entry
+		uint64_t all = 0; uint32_t base_id = 0, nslots = 0, bytes = 0;
+		if (ix.class_mode) {
+			const uint32_t w = rd * 32 + lane;
+			all = w < ix.words_per_set ? __ldg(ix.bitmap + (uint64_t)cr.x * ix.words_per_set + w) : 0;
+			base_id = w * 64; nslots = (uint32_t)__popcll(all);
+			for (uint64_t m = (w == 0 ? all & ~1ULL : all); m; m &= m - 1) bytes += name_len(rt, base_id + (uint32_t)__ffsll((long long)m) - 1) + 6;
+		} else {
+			const uint32_t j = rd * 32 + lane;
+			if (j < (cr.y & 0x0FFFFFFFu)) { base_id = __ldg(rt.s_sample_id + sbegin + j); all = 1; nslots = 1; if (base_id) bytes = name_len(rt, base_id) + 6; }
+		}
+		uint32_t eslot, ebytes, tslot, tbytes;
+		warp_excl2(lane, nslots, bytes, eslot, ebytes, tslot, tbytes);
+		for (uint32_t win0 = 0; win0 < tbytes; win0 += kRenderWin) {
+			const uint32_t wlen = min(kRenderWin, tbytes - win0);
+			char* dst = out + at + win0;
+			const uint32_t sh = (uint32_t)((uintptr_t)dst & 3);
+			if (bytes && ebytes < win0 + wlen && ebytes + bytes > win0) {
+				uint32_t slot = slot0 + eslot, o = ebytes;
+				for (uint64_t m = all; m; m &= m - 1) {
+					const uint32_t id = ix.class_mode ? base_id + (uint32_t)__ffsll((long long)m) - 1 : base_id;
+					if (id != 0) {
+						const uint32_t len = name_len(rt, id) + 6;
+						if (o + len > win0 && o < win0 + wlen) {
+							const uint32_t b0 = o < win0 ? win0 - o : 0, b1 = min(len, win0 + wlen - o);
+							put_carrier(rt, stage + sh + (o + b0 - win0), id, __ldg(rt.s_flags + sbegin + slot), b0, b1);
+						}
+						o += len;
+					}
+					slot++;
+				}
+			}
+			__syncwarp();
+			flush_window(stage, sh, wlen, dst, lane);
+			__syncwarp();
+		}
+		slot0 += tslot; at += tbytes;
+	}
+}
+
 __global__ void __launch_bounds__(256) k_render(const DevIndex ix, const RenderTables rt, const uint64_t* __restrict__ tp, uint64_t nseg, const uint32_t* __restrict__ seg_lo, int ws,
                                                 const uint64_t* __restrict__ row_off, const uint64_t* __restrict__ byte_off, uint64_t row_begin, uint64_t row_end, char* __restrict__ text) {
 	__shared__ __align__(16) uint8_t s_stage[8][kRenderWin + 16];
 	const uint32_t lane = threadIdx.x & 31;
 	uint8_t* stage = s_stage[threadIdx.x >> 5];
 	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-	const uint64_t kBase = 0x0505054E47544341ULL;                      // "ACTGN" + 5,5,5 by 3-bit code: map_int, src/util.cc:32-41
 	for (uint64_t row = row_begin + warp0; row < row_end; row += nwarps) {
 		// segment of this row: last s with row_off[s] <= row (empty segments share an offset with their successor)
 		uint64_t a = 0, b = nseg;
@@ -571,68 +641,59 @@ __global__ void __launch_bounds__(256) k_render(const DevIndex ix, const RenderT
 		char* out = text + __ldg(byte_off + a) + (t0 - __ldg(tp + lo));
 		const uint32_t row_bytes = (uint32_t)(__ldg(tp + r + 1) - t0);
 		const uint4 sq = __ldg(rt.rec_seq + r), cr = __ldg(rt.rec_car + r);
-		// ---- "pos\t"
-		uint32_t at = 0;
-		{
-			uint32_t p = __ldg(ix.rec_pos + r), nd = 1;
-			for (uint32_t q = p; q >= 10; q /= 10) nd++;
-			if (lane == 0) { uint32_t q = p; for (uint32_t i = nd; i-- > 0;) { out[i] = (char)('0' + q % 10); q /= 10; } out[nd] = '\t'; }
-			at = nd + 1;
-		}
-		// ---- ref \t alt \t
-		for (uint32_t i = lane; i < sq.y; i += 32) out[at + i] = (char)(kBase >> (8 * (__ldg(rt.seq + sq.x + i) & 7)));
-		at += sq.y;
-		if (lane == 0) out[at] = '\t';
-		at += 1;
-		for (uint32_t i = lane; i < sq.w; i += 32) out[at + i] = (char)(kBase >> (8 * (__ldg(rt.seq + sq.z + i) & 7)));
-		at += sq.w;
-		if (lane == 0) { out[at] = '\t'; out[row_bytes - 1] = '\n'; }
-		at += 1;
-		if (!ws || ((cr.y >> 28) & 4)) continue;                        // no carrier list asked for / the row has none
-		// ---- carriers
-		const uint64_t sbegin = (uint64_t)cr.z | ((uint64_t)cr.w << 32);
-		uint32_t slot0 = 0;                                              // s_info entries consumed so far
-		const uint32_t rounds = ix.class_mode ? (ix.words_per_set + 31) / 32 : ((cr.y & 0x0FFFFFFFu) + 31) / 32;
-		for (uint32_t rd = 0; rd < rounds; rd++) {
-			// this lane's items of the round: class mode = the members of one bitmap word (the ref bit owns an
-			// s_info entry but is not printed); explicit-id mode = one s_info entry
-			uint64_t all = 0; uint32_t base_id = 0, nslots = 0, bytes = 0;
-			if (ix.class_mode) {
-				const uint32_t w = rd * 32 + lane;
-				all = w < ix.words_per_set ? __ldg(ix.bitmap + (uint64_t)cr.x * ix.words_per_set + w) : 0;
-				base_id = w * 64; nslots = (uint32_t)__popcll(all);
-				for (uint64_t m = (w == 0 ? all & ~1ULL : all); m; m &= m - 1) bytes += name_len(rt, base_id + (uint32_t)__ffsll((long long)m) - 1) + 6;
-			} else {
-				const uint32_t j = rd * 32 + lane;
-				if (j < (cr.y & 0x0FFFFFFFu)) { base_id = __ldg(rt.s_sample_id + sbegin + j); all = 1; nslots = 1; if (base_id) bytes = name_len(rt, base_id) + 6; }
-			}
-			uint32_t eslot, ebytes, tslot, tbytes;
-			warp_excl2(lane, nslots, bytes, eslot, ebytes, tslot, tbytes);
-			for (uint32_t win0 = 0; win0 < tbytes; win0 += kRenderWin) {
-				const uint32_t wlen = min(kRenderWin, tbytes - win0);
-				char* dst = out + at + win0;
-				const uint32_t sh = (uint32_t)((uintptr_t)dst & 3);
-				if (bytes && ebytes < win0 + wlen && ebytes + bytes > win0) {
-					uint32_t slot = slot0 + eslot, o = ebytes;
-					for (uint64_t m = all; m; m &= m - 1) {
-						const uint32_t id = ix.class_mode ? base_id + (uint32_t)__ffsll((long long)m) - 1 : base_id;
-						if (id != 0) {
-							const uint32_t len = name_len(rt, id) + 6;
-							if (o + len > win0 && o < win0 + wlen) {
-								const uint32_t b0 = o < win0 ? win0 - o : 0, b1 = min(len, win0 + wlen - o);
-								put_carrier(rt, stage + sh + (o + b0 - win0), id, __ldg(rt.s_flags + sbegin + slot), b0, b1);
-							}
-							o += len;
-						}
-						slot++;
-					}
-				}
-				__syncwarp();
-				flush_window(stage, sh, wlen, dst, lane);
-				__syncwarp();
-			}
-			slot0 += tslot; at += tbytes;
-		}
+		render_row(ix, rt, __ldg(ix.rec_pos + r), sq, cr, out, row_bytes, ws, stage, lane);
+	}
+}
+
+// ------------------------------------------------------------------ t4 rows as text, on the device
+// A t4 row depends on the walk-entry code alone (entry, and whether the walk started on it / the row is the vertex the
+// alt edge rejoins): HitTables hold, per entry and variant, what t4_row of materialize.cc computes — position, ref / alt
+// slices, the vertex whose carriers are printed, and the row's text length.  k_hits_sums / k_hits_offsets scan the row
+// lengths of the batch's hit codes, k_render_hits writes the rows (a warp each), k_region_text_offsets reads the text
+// offset of every region off its first row.
+__device__ __forceinline__ uint32_t hit_variant(uint32_t code) { return (code & kHitRejoin) ? 2u : (code & kHitStart) ? 1u : 0u; }
+__device__ __forceinline__ uint32_t hit_len(const HitTables& ht, const uint32_t* __restrict__ hits, uint64_t h, uint64_t nh, int ws) {
+	if (h >= nh) return 0;
+	const uint32_t code = hits[h];
+	return __ldg(ht.len[ws][hit_variant(code)] + (code & 0x3FFFFFFFu));
+}
+__global__ void __launch_bounds__(256) k_hits_sums(const HitTables ht, const uint32_t* __restrict__ hits, uint64_t nh, int ws, uint64_t* __restrict__ cta_sums) {
+	__shared__ SegCount s_warp[8];
+	SegCount mine{0, 0};
+	const uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+	for (int j = 0; j < 4; j++) mine.bytes += hit_len(ht, hits, base + j, nh, ws);
+	SegCount tot;
+	cta_scan_1024(mine, s_warp, &tot);
+	if (threadIdx.x == 0) { cta_sums[2 * (uint64_t)blockIdx.x] = 0; cta_sums[2 * (uint64_t)blockIdx.x + 1] = tot.bytes; }
+}
+__global__ void __launch_bounds__(256) k_hits_offsets(const HitTables ht, const uint32_t* __restrict__ hits, uint64_t nh, int ws, const uint64_t* __restrict__ cta_sums, uint64_t nctas,
+                                                      uint64_t* __restrict__ byte_off) {
+	__shared__ SegCount s_warp[8];
+	uint32_t c[4]; SegCount mine{0, 0};
+	const uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+	for (int j = 0; j < 4; j++) { c[j] = hit_len(ht, hits, base + j, nh, ws); mine.bytes += c[j]; }
+	SegCount tot;
+	SegCount ex = cta_scan_1024(mine, s_warp, &tot);
+	ex.bytes += cta_sums[2 * (uint64_t)blockIdx.x + 1];
+#pragma unroll
+	for (int j = 0; j < 4; j++) { if (base + j < nh) byte_off[base + j] = ex.bytes; ex.bytes += c[j]; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) byte_off[nh] = cta_sums[2 * nctas + 1];
+}
+__global__ void __launch_bounds__(256) k_region_text_offsets(uint64_t n, const uint64_t* __restrict__ offsets, const uint64_t* __restrict__ byte_off, uint64_t* __restrict__ out) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = byte_off[offsets[i]];
+}
+__global__ void __launch_bounds__(256) k_render_hits(const DevIndex ix, const RenderTables rt, const HitTables ht, const uint32_t* __restrict__ hits, int ws,
+                                                     const uint64_t* __restrict__ byte_off, uint64_t row_begin, uint64_t row_end, char* __restrict__ text) {
+	__shared__ __align__(16) uint8_t s_stage[8][kRenderWin + 16];
+	const uint32_t lane = threadIdx.x & 31;
+	uint8_t* stage = s_stage[threadIdx.x >> 5];
+	const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t row = row_begin + warp0; row < row_end; row += nwarps) {
+		const uint32_t code = hits[row], v = hit_variant(code), c = code & 0x3FFFFFFFu;
+		const uint64_t b0 = __ldg(byte_off + row);
+		render_row(ix, rt, __ldg(ht.pos[v] + c), __ldg(ht.seq[v] + c), __ldg(ht.car[v] + c), text + b0, (uint32_t)(__ldg(byte_off + row + 1) - b0), ws, stage, lane);
 	}
 }
 
@@ -915,6 +976,24 @@ cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t n
                           const uint64_t* row_off, const uint64_t* byte_off, uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream) {
 	if (row_end <= row_begin) return cudaSuccess;
 	k_render<<<grid_for((row_end - row_begin) * 32, 256, 8), 256, 0, stream>>>(ix, rt, rt.text_prefix[with_samples ? 1 : 0], nseg, seg_lo, with_samples ? 1 : 0, row_off, byte_off, row_begin, row_end, text);
+	return cudaGetLastError();
+}
+cudaError_t launch_hit_offsets(const HitTables& ht, const uint32_t* hits, uint64_t nh, int with_samples, uint64_t n, const uint64_t* offsets, uint64_t* byte_off, uint64_t* region_off,
+                               uint64_t* scratch, cudaStream_t stream) {
+	const int ws = with_samples ? 1 : 0;
+	const uint64_t nctas = (nh + 1023) / 1024;
+	if (nh) {
+		k_hits_sums<<<(uint32_t)nctas, 256, 0, stream>>>(ht, hits, nh, ws, scratch);
+		k_seg_bases<<<1, 256, 0, stream>>>(nctas, scratch);
+		k_hits_offsets<<<(uint32_t)nctas, 256, 0, stream>>>(ht, hits, nh, ws, scratch, nctas, byte_off);
+	} else cudaMemsetAsync(byte_off, 0, 8, stream);
+	k_region_text_offsets<<<grid_for(n + 1, 256, 8), 256, 0, stream>>>(n, offsets, byte_off, region_off);
+	return cudaGetLastError();
+}
+cudaError_t launch_render_hits(const DevIndex& ix, const RenderTables& rt, const HitTables& ht, const uint32_t* hits, int with_samples, const uint64_t* byte_off,
+                               uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream) {
+	if (row_end <= row_begin) return cudaSuccess;
+	k_render_hits<<<grid_for((row_end - row_begin) * 32, 256, 8), 256, 0, stream>>>(ix, rt, ht, hits, with_samples ? 1 : 0, byte_off, row_begin, row_end, text);
 	return cudaGetLastError();
 }
 cudaError_t launch_widen(uint64_t n, const uint32_t* x32, const uint32_t* y32, uint64_t* x, uint64_t* y, cudaStream_t stream) {

@@ -38,6 +38,19 @@ struct DevIndex {
 	const uint32_t* dtin;                 // D + 1: pre-order time of back-walk state c in the back-walk forest
 	const uint2* cent_anc;                // per walk entry: pre-order interval of the state examining its source
 	const uint4* d4;                      // D + 1: {dlev.k, dlev.cent_begin, entries below the back-walk start of state d + 1, dtin[d]} (built at upload)
+	// Sparse cohorts (explicit-id encoding, or few carriers per sample): instead of the hit map, per sample the sorted list of
+	// the walk entries it carries — 4 bytes per genotype entry, a predecessor search for the back-walk, a range scan forward.
+	const uint64_t* car_begin;            // num_samples + 1 (nullptr: not built; then the hit map or the class bitmaps answer)
+	const uint32_t* car;                  // walk-entry ids, ascending per sample (markers excluded)
+	const uint32_t* marker_list;          // the marker entries, ascending; num_markers of them
+	uint32_t num_markers;
+	uint32_t marker_span;                 // a marker can only end walks whose scan bound lies at most this many entries behind it (max over markers)
+	// The walk of a sample from the start of the contig (what a region gets when nothing the sample carries lies on the
+	// back-walk's chain) does not depend on the region: can_entry lists the entries that walk takes, can_pmax the running
+	// maximum of their arrival positions, so a region joins the walk at the last entry arriving before x instead of at entry 0.
+	const uint64_t* can_begin;            // num_samples + 1
+	const uint32_t* can_entry;
+	const uint32_t* can_pmax;
 	uint32_t walk2;                       // 1: the per-thread hit-map walk is walk_region_fast2 (64-entry row chunks fetched together); VSGPU_T4_ROW64=0 clears it
 };
 
@@ -55,6 +68,21 @@ struct RenderTables {
 	const char* name_chars;
 	const uint4* item16;         // num_samples: "name(0|0) " + its length in byte 15 when that fits 15 bytes, else zeros
 };
+
+// Tables for rendering t4 rows (get_sample_var_in_ref with print, query.h:677-726) on the device: per walk entry and variant
+// (0: plain, 1: the walk started on it — a substitution prints ref "", 2: the row is the backbone vertex the alt edge rejoins)
+// what the row prints.  Built on the host with the rules of materialize.cc (hit_row); uploaded on first use.
+struct HitTables {
+	const uint32_t* pos[3];      // num_cent each: var_pos
+	const uint4* seq[3];         // {ref_off, ref_len, alt_off, alt_len} into RenderTables::seq
+	const uint4* car[3];         // {carrier set id, s_info count | row flags << 28, s_info begin lo, hi} of the vertex whose carriers are printed
+	const uint32_t* len[2][3];   // bytes of the row without / with the carrier list
+};
+// byte_off[nh + 1] = exclusive text offsets of the rows of hits[0 .. nh); region_off[i] = byte_off[offsets[i]] for i <= n; scratch as launch_render_offsets
+cudaError_t launch_hit_offsets(const HitTables& ht, const uint32_t* hits, uint64_t nh, int with_samples, uint64_t n, const uint64_t* offsets, uint64_t* byte_off, uint64_t* region_off,
+                               uint64_t* scratch, cudaStream_t stream);
+cudaError_t launch_render_hits(const DevIndex& ix, const RenderTables& rt, const HitTables& ht, const uint32_t* hits, int with_samples, const uint64_t* byte_off,
+                               uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream);
 
 // Tables of t2 = query_sample_from_ref (include/query.h:120-189); uploaded on first use.
 struct T2Tables {

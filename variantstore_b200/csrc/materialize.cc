@@ -37,6 +37,81 @@ void build_d4(const FlatIndex& f, std::vector<uint32_t>& d4) {
 	}
 }
 
+// Sparse cohorts: per sample the ascending list of the walk entries whose target it carries, and the marker entries.
+void build_sparse_walk(const FlatIndex& f, std::vector<uint64_t>& car_begin, std::vector<uint32_t>& car, std::vector<uint32_t>& marker_list) {
+	const size_t E = f.cent.size();
+	car_begin.assign((size_t)f.num_samples + 1, 0);
+	marker_list.clear();
+	auto for_carriers = [&](uint32_t set_id, auto&& fn) {
+		if (f.class_mode) {
+			for (uint32_t w = 0; w < f.words_per_set; w++)
+				for (uint64_t m = f.bitmap[(uint64_t)set_id * f.words_per_set + w]; m; m &= m - 1) { const uint32_t s = w * 64 + (uint32_t)__builtin_ctzll(m); if (s && s < f.num_samples) fn(s); }
+		} else for (uint64_t i = f.list_begin[set_id]; i < f.list_begin[set_id + 1]; i++) { const uint32_t s = f.list_ids[i]; if (s && s < f.num_samples) fn(s); }
+	};
+	for (size_t c = 0; c < E; c++) {
+		if (f.cent[c].tgt & kEntMarker) { marker_list.push_back((uint32_t)c); continue; }
+		for_carriers(f.cent[c].set_id, [&](uint32_t s) { car_begin[s + 1]++; });
+	}
+	for (uint32_t s = 0; s < f.num_samples; s++) car_begin[s + 1] += car_begin[s];
+	car.assign(car_begin[f.num_samples], 0);
+	std::vector<uint64_t> at(car_begin.begin(), car_begin.end() - 1);
+	for (size_t c = 0; c < E; c++) {
+		if (f.cent[c].tgt & kEntMarker) continue;
+		for_carriers(f.cent[c].set_id, [&](uint32_t s) { car[at[s]++] = (uint32_t)c; });
+	}
+}
+// The walk of every sample from the head of the contig under the rules of get_sample_var_in_ref (query.h:649-716) as the
+// kernels apply them (device_logic.cuh: fwd_step), with no region bounds: first carrying entry of the current vertex wins,
+// a taken entry hides everything before the vertex it rejoins, an alt vertex without an out-edge ends the path.
+void build_canonical_walks(const FlatIndex& f, const std::vector<uint64_t>& car_begin, const std::vector<uint32_t>& car, const std::vector<uint32_t>& marker_list,
+                           std::vector<uint64_t>& can_begin, std::vector<uint32_t>& can_entry, std::vector<uint32_t>& can_pmax) {
+	(void)marker_list;                                      // markers are not edges: with no region end they never stop the walk
+	const uint32_t S = f.num_samples;
+	std::vector<std::vector<uint32_t>> taken(S);
+	parallel_for(S, [&](uint64_t a, uint64_t b) {
+		for (uint64_t s = a; s < b; s++) {
+			uint32_t cur_k = 0;
+			for (uint64_t i = car_begin[s]; i < car_begin[s + 1]; i++) {
+				const CEntry& e = f.cent[car[i]];
+				if (e.src < cur_k) continue;                        // hidden behind a taken detour / an earlier sibling
+				taken[s].push_back(car[i]);
+				const uint32_t tk = e.tgt & kEntTgtMask;
+				if ((e.tgt & kEntAlt) && tk == kEntTgtNone) break;  // the path ends on this vertex
+				cur_k = tk;
+			}
+		}
+	});
+	can_begin.assign((size_t)S + 1, 0);
+	for (uint32_t s = 0; s < S; s++) can_begin[s + 1] = can_begin[s] + taken[s].size();
+	can_entry.resize(can_begin[S]); can_pmax.resize(can_begin[S]);
+	parallel_for(S, [&](uint64_t a, uint64_t b) {
+		for (uint64_t s = a; s < b; s++) {
+			uint32_t pm = 0; uint64_t at = can_begin[s];
+			for (uint32_t c : taken[s]) { pm = std::max(pm, f.cent[c].arrival); can_entry[at] = c; can_pmax[at] = pm; at++; }
+		}
+	});
+}
+// marker_span (DevIndex): a marker ends a walk only if its arrival is >= the region's y; the region's scan bound is then at
+// most the first entry of the backbone vertex starting at or after that arrival.  The largest distance, in entries, from a
+// marker to that bound says how far below a scan bound a marker can still matter.
+uint32_t marker_span(const FlatIndex& f, const std::vector<uint32_t>& marker_list) {
+	uint32_t span = 0;
+	for (uint32_t c : marker_list) {
+		const uint32_t a = f.cent[c].arrival;
+		const uint32_t k = (uint32_t)(std::lower_bound(f.vstart.begin(), f.vstart.end(), a) - f.vstart.begin());
+		const uint32_t reach = f.cent_begin[std::min<uint32_t>(k, f.M)];
+		if (reach > c) span = std::max(span, reach - c);
+	}
+	return span + 1;
+}
+// Which membership structure the t4 walk gets: the per-sample lists when the cohort is sparse (explicit-id encoding, or on
+// average fewer than one carried entry per 1024), else the hit map.  VSGPU_SPARSE_WALK=0/1 overrides.
+bool want_sparse_walk(const FlatIndex& f) {
+	if (const char* e = getenv("VSGPU_SPARSE_WALK")) return atoi(e) != 0;
+	if (!f.class_mode) return true;
+	return false;
+}
+
 void build_host_index(const std::string& prefix, HostIndex& h, int* stage) {
 	h.prefix = prefix;
 	if (stage) *stage = 0;
@@ -187,12 +262,14 @@ uint32_t host_sample_index(const HostIndex* ix, uint32_t vertex, uint32_t sample
 // Row of a t4 / t5 hit code: emission rules of get_sample_var_in_ref (query.h:677-710) and, with
 // sample != kNone, of get_sample_var_in_sample (:553-590) — the same three cases with var_pos = ref_pos
 // for an insertion and the sample's own position in the vertex otherwise.
-static void hit_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool with_samples, std::string& out) {
+// What the row of a hit code prints, as vertex ids: var_pos, the vertex whose sequence is the ref column (kNone: ""), the one
+// of the alt column, and the vertex u whose carriers are listed.  sample == kNone: t4; else t5 (positions in the sample's coordinates).
+void hit_row_parts(const HostIndex* ix, uint32_t code, uint32_t sample, uint64_t& pos, uint32_t& refv, uint32_t& altv, uint32_t& u) {
 	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
 	const bool t5 = sample != kNone;
 	const uint32_t c = code & VSGPU_HIT_ENTRY_MASK;
 	const CEntry& e = f.cent[c];
-	uint32_t u, ref_pos, cur_ref_v; bool cur_ref_empty = false, u_is_bb; uint32_t u_k = kNone;
+	uint32_t ref_pos, cur_ref_v; bool cur_ref_empty = false, u_is_bb; uint32_t u_k = kNone;
 	if (code & VSGPU_HIT_REJOIN) {
 		u_k = e.tgt & kEntTgtMask; u = f.bb_vertex[u_k]; u_is_bb = true;
 		ref_pos = f.vstart[u_k]; cur_ref_v = u;                         // state left by the alt vertex: ref_pos = index(N), cur_ref = seq(N)
@@ -209,15 +286,26 @@ static void hit_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool wi
 		uint32_t tk = e.tgt & kEntTgtMask;
 		next_ref_pos = tk == kEntTgtNone ? (uint64_t)ref_pos + s.v_length[u] : f.vstart[tk];
 	}
-	std::string ref, alt; uint64_t pos;
-	if (ref_pos == next_ref_pos) { pos = t5 ? (uint64_t)ref_pos : (uint64_t)ref_pos - 1; append_seq(ix, u, alt); }   // insertion
+	refv = kNone; altv = kNone;
+	if (ref_pos == next_ref_pos) { pos = t5 ? (uint64_t)ref_pos : (uint64_t)ref_pos - 1; altv = u; }   // insertion
 	else if (u_is_bb) {                                                                                   // deletion: cur_ref = seq(find(ref_pos - 1))
 		uint64_t p = ref_pos > 1 ? ref_pos - 1 : 1;
 		uint32_t rk = p >= f.index_bits ? f.D : host_rank(f, p);
 		if (rk < 1) rk = 1;
 		uint32_t wk = f.dlev[rk - 1].k;
-		append_seq(ix, f.bb_vertex[wk], ref); pos = t5 ? host_sample_index(ix, u, sample) : f.vstart[wk];
-	} else { pos = t5 ? host_sample_index(ix, u, sample) : ref_pos; if (!cur_ref_empty) append_seq(ix, cur_ref_v, ref); append_seq(ix, u, alt); } // substitution
+		refv = f.bb_vertex[wk]; pos = t5 ? host_sample_index(ix, u, sample) : f.vstart[wk];
+	} else { pos = t5 ? host_sample_index(ix, u, sample) : ref_pos; if (!cur_ref_empty) refv = cur_ref_v; altv = u; } // substitution
+}
+
+// Row of a t4 / t5 hit code: emission rules of get_sample_var_in_ref (query.h:677-710) and, with
+// sample != kNone, of get_sample_var_in_sample (:553-590) — the same three cases with var_pos = ref_pos
+// for an insertion and the sample's own position in the vertex otherwise.
+static void hit_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool with_samples, std::string& out) {
+	uint64_t pos; uint32_t refv, altv, u;
+	hit_row_parts(ix, code, sample, pos, refv, altv, u);
+	std::string ref, alt;
+	if (refv != kNone) append_seq(ix, refv, ref);
+	if (altv != kNone) append_seq(ix, altv, alt);
 	out += std::to_string(pos); out += '\t'; out += ref; out += '\t'; out += alt; out += '\t';
 	if (with_samples) append_carriers(ix, u, out);
 	out += '\n';

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -61,11 +62,15 @@ struct vsgpu_router {
 	std::vector<std::string> contigs;
 	std::map<std::string, uint32_t> contig_id;
 	std::vector<std::vector<uint32_t>> by_contig;     // shard ids of a contig, ascending lo
+	// the same as flat arrays for the routing loop: contig c owns rt_lo / rt_hi / rt_shard [rt_begin[c], rt_begin[c+1])
+	std::vector<uint32_t> rt_begin, rt_shard; std::vector<uint64_t> rt_lo, rt_hi;
 	std::vector<int> devices;                         // distinct devices in use
 	std::vector<double> device_ms; std::vector<uint64_t> device_regions;
 	double route_ms = 0, scatter_ms = 0;
 	std::mutex mu;
-	// result of the last call, in the caller's region order
+	// last call: where region i sits (shard_of_last[i], slot[i]); the hit codes stay in the shards' page-locked results and
+	// are gathered into one CSR in the caller's order only when vsgpu_router_offsets / _hits ask for it
+	std::vector<uint32_t> slot; std::vector<uint32_t> shard_of_last; uint64_t last_n = 0; bool csr_valid = false;
 	std::vector<uint32_t> hits; std::vector<uint64_t> offsets;
 	~vsgpu_router() { for (auto& s : shards) { if (s.res) vsgpu_result_free(s.res); if (s.ix) vsgpu_close(s.ix); } }
 };
@@ -145,6 +150,11 @@ int vsgpu_router_open(uint32_t nshards, const char* const* ser_prefixes, const u
 		std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return r->shards[a].lo < r->shards[b].lo; });
 		for (size_t i = 1; i < v.size(); i++) if (r->shards[v[i]].lo < r->shards[v[i - 1]].hi) return rerr(VSGPU_EINVAL, "vsgpu_router_open: position ranges of contig " + r->contigs[r->shards[v[i]].contig] + " overlap");
 	}
+	r->rt_begin.assign(1, 0);
+	for (auto& v : r->by_contig) {
+		for (uint32_t k : v) { r->rt_shard.push_back(k); r->rt_lo.push_back(r->shards[k].lo); r->rt_hi.push_back(r->shards[k].hi); }
+		r->rt_begin.push_back((uint32_t)r->rt_shard.size());
+	}
 	r->device_ms.assign(devs.size(), 0); r->device_regions.assign(devs.size(), 0);
 	*out = r.release();
 	return VSGPU_OK;
@@ -170,24 +180,24 @@ int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig,
 	const uint32_t S = (uint32_t)r->shards.size();
 	const double t0 = now_ms();
 	// ---- route: shard of every region (contig, then the position range holding its start); counting sort keeps the order
-	const unsigned NT = 16;
+	const unsigned NT = 32;
 	std::vector<std::vector<uint64_t>> cnt(NT, std::vector<uint64_t>(S, 0));
 	std::atomic<int64_t> bad{-1};
+	const uint32_t nc = (uint32_t)r->by_contig.size();
+	const uint32_t* rtb = r->rt_begin.data(); const uint32_t* rts = r->rt_shard.data(); const uint64_t* rtl = r->rt_lo.data(); const uint64_t* rth = r->rt_hi.data();
 	par_for(n, NT, [&](unsigned t, uint64_t a, uint64_t b) {
+		uint64_t* mycnt = cnt[t].data();
 		for (uint64_t i = a; i < b; i++) {
 			const uint32_t c = contig[i];
 			uint32_t k = VSGPU_NONE;
-			if (c < r->by_contig.size()) {
-				const auto& v = r->by_contig[c];
-				if (v.size() == 1) { const Shard& s = r->shards[v[0]]; if (x[i] >= s.lo && x[i] < s.hi) k = v[0]; }
-				else {
-					size_t lo = 0, hi = v.size();
-					while (lo < hi) { const size_t m = (lo + hi) / 2; if (r->shards[v[m]].lo <= x[i]) lo = m + 1; else hi = m; }
-					if (lo > 0 && x[i] < r->shards[v[lo - 1]].hi) k = v[lo - 1];
-				}
+			if (c < nc) {
+				uint32_t lo = rtb[c], hi = rtb[c + 1];
+				const uint64_t xi = x[i];
+				while (hi - lo > 1) { const uint32_t m = (lo + hi) >> 1; if (rtl[m] <= xi) lo = m; else hi = m; }     // last range starting at or before x
+				if (lo < rtb[c + 1] && xi >= rtl[lo] && xi < rth[lo]) k = rts[lo];
 			}
 			if (k == VSGPU_NONE) { int64_t e = -1; bad.compare_exchange_strong(e, (int64_t)i); k = 0; }
-			shard_of[i] = k; cnt[t][k]++;
+			shard_of[i] = k; mycnt[k]++;
 		}
 	});
 	if (bad.load() >= 0) return rerr(VSGPU_EINVAL, "region " + std::to_string(bad.load()) + ": no shard owns this contig / start position");
@@ -202,62 +212,104 @@ int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig,
 		cudaSetDevice(s.device);
 		if (!s.px.ensure(s.n * 4) || !s.py.ensure(s.n * 4) || !s.ps.ensure(s.n * 4) || !s.plo.ensure(s.n * 4) || !s.pc6.ensure(s.n * 4)) return rerr(VSGPU_ENOMEM, "cannot allocate page-locked routing buffers");
 	}
-	std::vector<uint64_t> slot(n);               // position of region i inside its shard's batch
+	if (r->slot.size() < n) r->slot.resize(n);     // position of region i inside its shard's batch
+	uint32_t* slot = r->slot.data();
+	std::vector<uint32_t*> bx(S), by(S), bs(S);
+	for (uint32_t k = 0; k < S; k++) { bx[k] = (uint32_t*)r->shards[k].px.p; by[k] = (uint32_t*)r->shards[k].py.p; bs[k] = (uint32_t*)r->shards[k].ps.p; }
 	par_for(n, NT, [&](unsigned t, uint64_t a, uint64_t b) {
+		uint64_t* mycnt = cnt[t].data();
 		for (uint64_t i = a; i < b; i++) {
-			Shard& s = r->shards[shard_of[i]];
-			const uint64_t j = cnt[t][shard_of[i]]++;
-			slot[i] = j;
-			((uint32_t*)s.px.p)[j] = x[i]; ((uint32_t*)s.py.p)[j] = y[i]; ((uint32_t*)s.ps.p)[j] = sample_ids[i];
+			const uint32_t k = shard_of[i];
+			const uint64_t j = mycnt[k]++;
+			slot[i] = (uint32_t)j;
+			bx[k][j] = x[i]; by[k][j] = y[i]; bs[k][j] = sample_ids[i];
 		}
 	});
 	const double t1 = now_ms();
 	r->route_ms = t1 - t0;
-	// ---- one host thread per GPU: its shards' fused calls, one after the other
+	// ---- host threads per GPU (VSGPU_ROUTER_THREADS, default 4) take that GPU's shards from a queue: every shard is its
+	// own index with its own streams, so the copies of one shard's call overlap the kernels of another's
+	unsigned per_gpu = 4;
+	if (const char* e = getenv("VSGPU_ROUTER_THREADS")) per_gpu = (unsigned)std::max(1, atoi(e));
 	std::vector<std::thread> th;
-	for (size_t di = 0; di < r->devices.size(); di++) th.emplace_back([&, di]() {
-		const int d = r->devices[di];
-		const double a = now_ms();
-		uint64_t regions = 0;
-		for (auto& s : r->shards) {
-			if (s.device != d || !s.n) continue;
-			const double b = now_ms();
-			s.rc = vsgpu_query_t6t4_u32(s.ix, s.n, (const uint32_t*)s.px.p, (const uint32_t*)s.py.p, (const uint32_t*)s.ps.p, (uint32_t*)s.plo.p, nullptr, (uint32_t*)s.pc6.p, &s.res);
-			if (s.rc) s.err = vsgpu_last_error();
-			s.ms = now_ms() - b;
-			regions += s.n;
-		}
-		r->device_ms[di] = now_ms() - a; r->device_regions[di] = regions;
-	});
+	std::vector<std::atomic<uint32_t>> next(r->devices.size());
+	std::vector<std::atomic<uint64_t>> dregions(r->devices.size());
+	std::vector<double> dstart(r->devices.size(), 0), dend(r->devices.size(), 0);
+	std::vector<std::vector<uint32_t>> queue(r->devices.size());
+	for (size_t di = 0; di < r->devices.size(); di++) {
+		next[di] = 0; dregions[di] = 0;
+		for (uint32_t k = 0; k < S; k++) if (r->shards[k].device == r->devices[di] && r->shards[k].n) queue[di].push_back(k);
+		std::stable_sort(queue[di].begin(), queue[di].end(), [&](uint32_t a, uint32_t b) { return r->shards[a].n > r->shards[b].n; });   // largest batch first
+	}
+	std::mutex end_mu;
+	for (size_t di = 0; di < r->devices.size(); di++) {
+		dstart[di] = now_ms();
+		for (unsigned w = 0; w < std::min<size_t>(per_gpu, std::max<size_t>(queue[di].size(), 1)); w++) th.emplace_back([&, di]() {
+			for (uint32_t qi; (qi = next[di]++) < queue[di].size();) {
+				Shard& s = r->shards[queue[di][qi]];
+				const double b = now_ms();
+				s.rc = vsgpu_query_t6t4_u32(s.ix, s.n, (const uint32_t*)s.px.p, (const uint32_t*)s.py.p, (const uint32_t*)s.ps.p, (uint32_t*)s.plo.p, nullptr, (uint32_t*)s.pc6.p, &s.res);
+				if (s.rc) s.err = vsgpu_last_error();
+				s.ms = now_ms() - b;
+				dregions[di] += s.n;
+			}
+			const double e = now_ms();
+			std::lock_guard<std::mutex> g2(end_mu);
+			dend[di] = std::max(dend[di], e);
+		});
+	}
 	for (auto& t : th) t.join();
+	for (size_t di = 0; di < r->devices.size(); di++) { r->device_ms[di] = queue[di].empty() ? 0 : dend[di] - dstart[di]; r->device_regions[di] = dregions[di]; }
 	for (uint32_t k = 0; k < S; k++) if (r->shards[k].rc) return rerr(r->shards[k].rc, "shard " + std::to_string(k) + ": " + r->shards[k].err);
 	const double t2 = now_ms();
-	// ---- scatter back into the caller's order; the hit codes as one CSR (offsets by a prefix sum over counts4)
-	std::vector<const uint32_t*> c4(S, nullptr), hs(S, nullptr); std::vector<const uint64_t*> so(S, nullptr);
-	for (uint32_t k = 0; k < S; k++) if (r->shards[k].n) { c4[k] = vsgpu_result_counts(r->shards[k].res); so[k] = vsgpu_result_offsets(r->shards[k].res); hs[k] = vsgpu_result_hits(r->shards[k].res); }
-	par_for(n, NT, [&](unsigned, uint64_t a, uint64_t b) {
+	// ---- scatter the per-region words back into the caller's order (the hit codes stay where the GPUs' copies put them)
+	std::vector<const uint32_t*> c4(S, nullptr);
+	for (uint32_t k = 0; k < S; k++) if (r->shards[k].n) c4[k] = vsgpu_result_counts(r->shards[k].res);
+	std::vector<const uint32_t*> plo(S), pc6(S);
+	for (uint32_t k = 0; k < S; k++) { plo[k] = (const uint32_t*)r->shards[k].plo.p; pc6[k] = (const uint32_t*)r->shards[k].pc6.p; }
+	par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) {
 		for (uint64_t i = a; i < b; i++) {
-			const uint32_t k = shard_of[i]; const uint64_t j = slot[i]; const Shard& s = r->shards[k];
-			rec_lo[i] = ((const uint32_t*)s.plo.p)[j]; counts6[i] = ((const uint32_t*)s.pc6.p)[j]; counts4[i] = c4[k][j];
+			const uint32_t k = shard_of[i]; const uint32_t j = slot[i];
+			rec_lo[i] = plo[k][j]; counts6[i] = pc6[k][j]; counts4[i] = c4[k][j];
 		}
 	});
-	r->offsets.resize(n + 1);
-	uint64_t acc = 0;
-	for (uint64_t i = 0; i < n; i++) { r->offsets[i] = acc; acc += counts4[i]; }
-	r->offsets[n] = acc;
-	r->hits.resize(acc);
-	par_for(n, NT, [&](unsigned, uint64_t a, uint64_t b) {
-		for (uint64_t i = a; i < b; i++) {
-			const uint32_t k = shard_of[i]; const uint64_t j = slot[i];
-			if (counts4[i]) memcpy(r->hits.data() + r->offsets[i], hs[k] + so[k][j], (size_t)counts4[i] * 4);
-		}
-	});
+	if (r->shard_of_last.size() < n) r->shard_of_last.resize(n);
+	par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) { memcpy(r->shard_of_last.data() + a, shard_of + a, (b - a) * 4); });
+	r->csr_valid = false; r->last_n = n;
 	r->scatter_ms = now_ms() - t2;
 	return VSGPU_OK;
 }
 
-const uint64_t* vsgpu_router_offsets(const vsgpu_router* r) { return r ? r->offsets.data() : nullptr; }
-const uint32_t* vsgpu_router_hits(const vsgpu_router* r) { return r ? r->hits.data() : nullptr; }
+namespace {
+void gather_csr(vsgpu_router* r) {
+	if (r->csr_valid) return;
+	const uint64_t n = r->last_n; const uint32_t S = (uint32_t)r->shards.size();
+	std::vector<const uint32_t*> c4(S, nullptr), hs(S, nullptr); std::vector<const uint64_t*> so(S, nullptr);
+	for (uint32_t k = 0; k < S; k++) if (r->shards[k].n && r->shards[k].res) { c4[k] = vsgpu_result_counts(r->shards[k].res); so[k] = vsgpu_result_offsets(r->shards[k].res); hs[k] = vsgpu_result_hits(r->shards[k].res); }
+	r->offsets.resize(n + 1);
+	uint64_t acc = 0;
+	for (uint64_t i = 0; i < n; i++) { r->offsets[i] = acc; acc += c4[r->shard_of_last[i]][r->slot[i]]; }
+	r->offsets[n] = acc;
+	r->hits.resize(acc);
+	par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) {
+		for (uint64_t i = a; i < b; i++) {
+			const uint32_t k = r->shard_of_last[i]; const uint32_t j = r->slot[i]; const uint32_t c = c4[k][j];
+			if (c) memcpy(r->hits.data() + r->offsets[i], hs[k] + so[k][j], (size_t)c * 4);
+		}
+	});
+	r->csr_valid = true;
+}
+}  // namespace
+const uint64_t* vsgpu_router_offsets(const vsgpu_router* cr) { vsgpu_router* r = const_cast<vsgpu_router*>(cr); if (!r) return nullptr; std::lock_guard<std::mutex> g(r->mu); gather_csr(r); return r->offsets.data(); }
+const uint32_t* vsgpu_router_hits(const vsgpu_router* cr) { vsgpu_router* r = const_cast<vsgpu_router*>(cr); if (!r) return nullptr; std::lock_guard<std::mutex> g(r->mu); gather_csr(r); return r->hits.data(); }
+int vsgpu_router_region_hits(const vsgpu_router* r, uint64_t i, const uint32_t** hits, uint32_t* count) {
+	if (!r || !hits || !count || i >= r->last_n) return rerr(VSGPU_EINVAL, "vsgpu_router_region_hits: bad argument");
+	const Shard& s = r->shards[r->shard_of_last[i]];
+	const uint64_t j = r->slot[i];
+	*count = vsgpu_result_counts(s.res)[j];
+	*hits = vsgpu_result_hits(s.res) + vsgpu_result_offsets(s.res)[j];
+	return VSGPU_OK;
+}
 
 int vsgpu_router_stats(const vsgpu_router* r, uint32_t cap, int* devices, double* device_ms, uint64_t* device_regions, uint32_t* ndev, double* route_ms, double* scatter_ms) {
 	if (!r) return rerr(VSGPU_EINVAL, "vsgpu_router_stats: null router");

@@ -90,6 +90,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 	bool own_stream = false;
 	std::vector<void*> allocs;
 	uint64_t device_bytes = 0;
+	bool sparse_walk = false;         // per-sample carried-entry lists instead of the hit map (sparse cohorts)
 	double hits_per_base = 0;         // walk-entry carriers per base for an average sample
 	double entries_per_base = 0;      // walk entries per covered base
 	uint32_t* d_status = nullptr;     // two words: status bits, length of the t6 flagged list
@@ -109,6 +110,9 @@ struct vsgpu_index : vsgpu::HostIndex {
 	bool render_ready = false;
 	RenderTables render{};
 	DevBuf bseg, brow_off, bbyte_off, bscratch, btext;
+	bool hit_tables_ready = false;
+	HitTables hit_tables{};
+	std::vector<uint64_t> set_text_bytes; std::vector<uint32_t> set_pop;     // per carrier set: bytes of its printed carrier list, members (class mode)
 	// t2 (query_sample_from_ref): tables uploaded on first use
 	bool t2_ready = false;
 	T2Tables t2{};
@@ -236,6 +240,16 @@ void upload_index(vsgpu_index* ix) {
 	// Sample-major hit map: num_samples rows of row_words words.  Built on the device; skipped (the
 	// kernels then test class bitmaps per entry) when it would not fit the budget:
 	// VSGPU_HITMAP_MAX_GB (default 64) and at most half of the free device memory.
+	if (want_sparse_walk(f)) {
+		std::vector<uint64_t> car_begin; std::vector<uint32_t> car, marker_list;
+		build_sparse_walk(f, car_begin, car, marker_list);
+		d.car_begin = upload(ix, car_begin); d.car = upload(ix, car); d.marker_list = upload(ix, marker_list); d.num_markers = (uint32_t)marker_list.size(); d.marker_span = marker_span(f, marker_list);
+		std::vector<uint64_t> can_begin; std::vector<uint32_t> can_entry, can_pmax;
+		build_canonical_walks(f, car_begin, car, marker_list, can_begin, can_entry, can_pmax);
+		d.can_begin = upload(ix, can_begin); d.can_entry = upload(ix, can_entry); d.can_pmax = upload(ix, can_pmax);
+		ix->sparse_walk = true;
+		return;                                              // no hit map: the lists answer every membership question of the walks
+	}
 	const uint64_t hm_bytes = (uint64_t)f.num_samples * f.row_words * 4;
 	double max_gb = 64.0;
 	if (const char* e = getenv("VSGPU_HITMAP_MAX_GB")) max_gb = atof(e);
@@ -467,7 +481,7 @@ void hits_overflow_rerun(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const 
 // a sample of the region widths and the index's walk-entry density; such batches get a warp per region.
 extern "C++" template <class T>
 bool expect_wide_regions(const vsgpu_index* ix, uint64_t n, const T* x, const T* y) {
-	if (n == 0) return false;
+	if (n == 0 || ix->sparse_walk) return false;        // (the warp-per-region kernel scans hit-map rows)
 	const uint64_t step = std::max<uint64_t>(1, n / 1024);
 	// the widest sampled region, in walk entries: beyond the kernel's threshold the batch is launched
 	// with the warp-cooperative path compiled in
@@ -844,6 +858,7 @@ void ensure_render_tables(vsgpu_index* ix) {
 		}
 		tp0[r + 1] = tp0[r] + hdr; tp1[r + 1] = tp1[r] + hdr + car;
 	}
+	ix->set_text_bytes = set_bytes; ix->set_pop = set_pop;
 	rt.rec_seq = upload(ix, rec_seq); rt.rec_car = upload(ix, rec_car);
 	rt.text_prefix[0] = upload(ix, tp0); rt.text_prefix[1] = upload(ix, tp1);
 	rt.seq = upload(ix, s.seq); rt.s_flags = upload(ix, s.s_flags); rt.s_sample_id = upload(ix, s.s_sample_id);
@@ -863,6 +878,122 @@ void ensure_render_tables(vsgpu_index* ix) {
 	ix->render_ready = true;
 }
 }  // namespace
+
+namespace {
+// Per walk entry and variant, the row t4_row would print, as numbers k_render_hits can use (kernels.cuh: HitTables).
+void ensure_hit_tables(vsgpu_index* ix) {
+	ensure_render_tables(ix);
+	if (ix->hit_tables_ready) return;
+	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
+	const size_t E = f.cent.size();
+	std::vector<uint32_t> name_len(s.num_samples);
+	for (uint32_t i = 0; i < s.num_samples; i++) name_len[i] = (uint32_t)s.sample_names[i].size();
+	for (int v = 0; v < 3; v++) {
+		std::vector<uint32_t> pos(E, 0), len0(E, 0), len1(E, 0);
+		std::vector<uint4> seq(E, make_uint4(0, 0, 0, 0)), car(E, make_uint4(0, 4u << 28, 0, 0));
+		parallel_for(E, [&](uint64_t a, uint64_t b) {
+			for (uint64_t c = a; c < b; c++) {
+				const CEntry& e = f.cent[c];
+				if (e.tgt & kEntMarker) continue;
+				if (v == 2 && !((e.tgt & kEntAlt) && (e.tgt & kEntTgtCarriers) && (e.tgt & kEntTgtMask) != kEntTgtNone)) continue;   // only such entries produce REJOIN codes
+				const uint32_t code = (uint32_t)c | (v == 1 ? VSGPU_HIT_START : v == 2 ? VSGPU_HIT_REJOIN : 0);
+				uint64_t p; uint32_t refv, altv, u;
+				hit_row_parts(ix, code, kNone, p, refv, altv, u);
+				pos[c] = (uint32_t)p;
+				seq[c] = make_uint4(refv == kNone ? 0 : s.v_offset[refv], refv == kNone ? 0 : s.v_length[refv], altv == kNone ? 0 : s.v_offset[altv], altv == kNone ? 0 : s.v_length[altv]);
+				const uint64_t sb = s.v_sinfo_begin[u], sc = s.v_sinfo_begin[u + 1] - sb;
+				const uint32_t set = f.class_mode ? s.v_class[u] : 0;
+				uint64_t carb = 0;
+				if (f.class_mode) { if (ix->set_pop[set] != sc) throw std::runtime_error("vertex " + std::to_string(u) + ": s_info entries differ from the members of its sample class"); carb = ix->set_text_bytes[set]; }
+				else for (uint64_t i = sb; i < sb + sc; i++) { const uint32_t id = s.s_sample_id[i]; if (id >= s.num_samples) throw std::runtime_error("vertex names a sample beyond sampleid_map.lst"); if (id) carb += name_len[id] + 6; }
+				car[c] = make_uint4(set, (uint32_t)sc, (uint32_t)sb, (uint32_t)(sb >> 32));
+				uint32_t digits = 1; for (uint64_t q = p; q >= 10; q /= 10) digits++;
+				const uint64_t hdr = digits + 1 + seq[c].y + 1 + seq[c].w + 1 + 1;
+				if (hdr + carb > 0xFFFFFFFFull) throw std::runtime_error("a t4 row is longer than 4 GiB");
+				len0[c] = (uint32_t)hdr; len1[c] = (uint32_t)(hdr + carb);
+			}
+		});
+		ix->hit_tables.pos[v] = upload(ix, pos); ix->hit_tables.seq[v] = upload(ix, seq); ix->hit_tables.car[v] = upload(ix, car);
+		ix->hit_tables.len[0][v] = upload(ix, len0); ix->hit_tables.len[1][v] = upload(ix, len1);
+	}
+	ix->hit_tables_ready = true;
+}
+}  // namespace
+
+// get_sample_var_in_ref(vg, idx, x, y, sample, print = true, outfile) for a batch: t4 on the device, then its rows as text
+int vsgpu_render_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, int with_samples, vsgpu_text** out) {
+	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_render_t4: null argument");
+	*out = nullptr;
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	std::unique_ptr<vsgpu_text, void (*)(vsgpu_text*)> t(new vsgpu_text, vsgpu_text_free);
+	t->owner = ix; t->n = n;
+	try {
+		ensure_hit_tables(ix);
+		cudaStream_t st = ix->stream;                       // run_t4 / finish_t4 work on the index's stream
+		t->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &t->offsets_cap);
+		if (!t->offsets) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		t->offsets[0] = 0;
+		if (n == 0) { t->bytes = (char*)ix->pinned_acquire(1, &t->bytes_cap); if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory"); t->bytes[0] = 0; *out = t.release(); return VSGPU_OK; }
+		CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+		CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
+		const bool wide = expect_wide_regions(ix, n, x, y);
+		uint64_t cap = ix->bhits.cap / 4;
+		if (cap == 0) { cap = std::max<uint64_t>((wide ? 64 : 4) * n, 1024); CU(ix->bhits.ensure(cap * 4)); cap = ix->bhits.cap / 4; }
+		run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, ix->d_status, wide);
+		const uint32_t status = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, wide);
+		if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
+		uint64_t nh = 0;
+		CU(cudaMemcpyAsync(&nh, ix->boffsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		// row lengths -> text offsets of every row and of every region
+		CU(ix->brow_off.ensure((nh + 1) * 8)); CU(ix->bbyte_off.ensure((n + 1) * 8)); CU(ix->bscratch.ensure(((nh + 1023) / 1024 + 2) * 16));
+		CU(cudaEventRecord(ix->ev_render[0], st));
+		CU(launch_hit_offsets(ix->hit_tables, ix->bhits.as<uint32_t>(), nh, with_samples, n, ix->boffsets.as<uint64_t>(), ix->brow_off.as<uint64_t>(), ix->bbyte_off.as<uint64_t>(),
+		                      ix->bscratch.as<uint64_t>(), st));
+		CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		const uint64_t total = t->offsets[n];
+		uint64_t max_bytes = 2ull << 30;
+		if (const char* e = getenv("VSGPU_RENDER_MAX_BYTES")) max_bytes = strtoull(e, nullptr, 10);
+		if (total > max_bytes) return set_err(VSGPU_ESHAPE, "vsgpu_render_t4: the rows of this batch take " + std::to_string(total) + " bytes (limit VSGPU_RENDER_MAX_BYTES = " + std::to_string(max_bytes) + "); split the batch");
+		t->nrows = nh; t->nbytes = total;
+		t->bytes = (char*)ix->pinned_acquire(total + 1, &t->bytes_cap);
+		if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		if (total) {
+			CU(ix->btext.ensure(total));
+			// rows in chunks of about 32 MB of text: the copy of one chunk overlaps the rendering of the next
+			uint64_t chunk_bytes = 32ull << 20;
+			if (const char* e = getenv("VSGPU_RENDER_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+			const int chunks = (int)std::min<uint64_t>(vsgpu_index::kMaxChunks, (total + chunk_bytes - 1) / chunk_bytes);
+			// region boundaries as chunk boundaries (their row / byte offsets are on the host already)
+			std::vector<uint64_t> roff(n + 1);
+			CU(cudaMemcpyAsync(roff.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+			CU(cudaStreamSynchronize(st));
+			uint64_t r0 = 0;
+			for (int c = 0; c < chunks && r0 < n; c++) {
+				uint64_t r1 = n;
+				if (c + 1 < chunks) { const uint64_t target = total / chunks * (c + 1); r1 = std::lower_bound(t->offsets + r0 + 1, t->offsets + n, target) - t->offsets; }
+				if (r1 <= r0) continue;
+				CU(launch_render_hits(ix->dev, ix->render, ix->hit_tables, ix->bhits.as<uint32_t>(), with_samples, ix->brow_off.as<uint64_t>(), roff[r0], roff[r1], ix->btext.as<char>(), st));
+				CU(cudaEventRecord(ix->ev_k[c], st));
+				CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
+				if (t->offsets[r1] > t->offsets[r0]) CU(cudaMemcpyAsync(t->bytes + t->offsets[r0], ix->btext.as<char>() + t->offsets[r0], t->offsets[r1] - t->offsets[r0], cudaMemcpyDeviceToHost, ix->s_out));
+				r0 = r1;
+			}
+			CU(cudaEventRecord(ix->ev_render[1], st));
+			CU(cudaStreamSynchronize(ix->s_out));
+			CU(cudaStreamSynchronize(st));
+		} else { CU(cudaEventRecord(ix->ev_render[1], st)); CU(cudaStreamSynchronize(st)); }
+		t->bytes[total] = 0;
+		CU(cudaEventElapsedTime(&t->kernel_ms, ix->ev_render[0], ix->ev_render[1]));
+		*out = t.release();
+	} catch (const std::invalid_argument& e) { return set_err(VSGPU_ESHAPE, e.what());
+	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
 
 int vsgpu_render_t6(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, int with_samples, vsgpu_text** out) {
 	if (!ix || !out || (n && (!x || !y))) return set_err(VSGPU_EINVAL, "vsgpu_render_t6: null argument");
