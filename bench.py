@@ -507,6 +507,31 @@ def run_vsgpu(args):
     else:
         h2d = n * (2 * cb + 4)                           # x, y, sample ids, once
         d2h = n * 8 + n * 4 + hits_total * 4             # t6 lo + counts; t4 counts + hit codes
+    # The roof over e2e on this box: every rank moves exactly these bytes (page-locked, H2D and D2H at the same time on two
+    # streams, no kernels), all ranks together — what the step would cost if the GPU work and every call overhead were free.
+    hb, db = torch.empty(h2d, dtype=torch.uint8).pin_memory(), torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    gh, gd = torch.empty(h2d, dtype=torch.uint8, device="cuda"), torch.empty(d2h, dtype=torch.uint8, device="cuda")
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    def copies():
+        with torch.cuda.stream(sa):
+            gh.copy_(hb, non_blocking=True)
+        with torch.cuda.stream(sb):
+            db.copy_(gd, non_blocking=True)
+    for _ in range(3):
+        copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        copies()
+    torch.cuda.synchronize()
+    ceil_s = (time.perf_counter() - t0) / 10
+    if dist is not None:
+        t = torch.tensor([ceil_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ceil_s = float(t.item())
+    pcie_ceiling = {"regions_per_s": 2 * n * world / ceil_s, "ms_per_step": 1000 * ceil_s, "aggregate_GBps": (h2d + d2h) * world / ceil_s / 1e9,
+                    "what": "the step's H2D + D2H bytes copied concurrently by all ranks from / to page-locked memory, nothing else"}
+    del hb, db, gh, gd
 
     genome = None
     if (world >= 2 or args.genome) and not args.no_genome:
@@ -564,7 +589,7 @@ def run_vsgpu(args):
                      "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": dom_ms, "peak_source": peak_src,
                      "algorithmic_convention": {"bytes_per_launch": dom_algo, "GBps": achieved_conv, "frac": achieved_conv / peak,
                                                 "note": "SURVEY 8(d): 288 (t6) + 292 + 20 v + 4 h (t4) per region; counts a 20-byte record read per scanned record, which the hit map replaces by one bit"}},
-        "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "call": "vsgpu_query_t6 + vsgpu_query_t4" if args.unfused else "vsgpu_query_t6t4"},
+        "e2e": {"value": e2e_val, "unit": "regions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "pcie_ceiling": pcie_ceiling, "frac_of_pcie_ceiling": e2e_val / pcie_ceiling["regions_per_s"], "call": "vsgpu_query_t6 + vsgpu_query_t4" if args.unfused else "vsgpu_query_t6t4"},
         "gpu_launches": (launches46 if b46 is not None else launches6 + launches4) * args.steps,
         "clocks": sampler.summary(),
     }

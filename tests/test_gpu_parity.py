@@ -434,3 +434,54 @@ def test_cli_front_end_matches_reference_cli_lines(tmp_path):
             lines = [l for l in p.stdout.split("\n") if l.startswith(("Number of variants", "Chromosome"))]
             outs.append((lines, open(of).read() if os.path.exists(of) else None))
         assert outs[0] == outs[1], c
+
+
+def test_cli_regions_file_at_batch_scale(tmp_path):
+    """A 100 000-line --regions-file (a batch no command line could carry) through vsgpu_query: the reference's count line for
+    every region, in read_regions' sorted order (commands.cc:64-93), equal to the oracle's counts for t6 and t4; and the same
+    regions split over two ser/ directories behind --prefixes (the router front-end)."""
+    import subprocess
+    prefix = os.path.join(T.GOLDEN, "x_ser")
+    cli = os.path.join(T.ROOT, "variantstore_b200", "vsgpu_query")
+    subprocess.run(["make", "-s", "../vsgpu_query"], cwd=T.CSRC_DIR, check=True)
+    o = Oracle.open(prefix)
+    rng = np.random.default_rng(41)
+    n = 100_000
+    x = rng.integers(1, 1001, n)
+    y = x + rng.choice([1, 5, 40, 300], n)
+    f = tmp_path / "regions.txt"
+    f.write_text("# beg:end\n" + "\n".join(f"{a}:{b}" for a, b in zip(x, y)) + "\n")
+    order = np.lexsort((y, x))                                             # std::sort of (beg, end) tuples
+    xs, ys = x[order].astype(np.uint64), y[order].astype(np.uint64)
+    c6, _ = o.batch_t6(xs, ys, False)
+    c4, _, ub = o.batch_t4(xs, ys, np.ones(n, np.uint32), False)
+    for t, want in (("6", c6), ("4", c4)):
+        p = subprocess.run([cli, "query", "-p", prefix, "-m", "0", "-t", t, "-s", "1", "--regions-file", str(f)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        got = np.array([int(l.rsplit(": ", 1)[1]) for l in p.stdout.split("\n") if l.startswith("Number of variants")])
+        assert len(got) == n and np.all((got == want) | ((ub != 0) if t == "4" else False))
+    # router front-end: the same contig twice under two names would clash, so a second contig: the small fixture
+    p2 = os.path.join(T.GOLDEN, "xsmall_ser")
+    o2 = Oracle.open(p2)
+    chr1, chr2 = T.open_engine(prefix, "cuda"), T.open_engine(p2, "cuda")
+    names = [chr1.chr, chr2.chr]
+    chr1.close(); chr2.close()
+    if names[0] != names[1]:
+        m = 5000
+        which = rng.integers(0, 2, m)
+        xx = np.where(which == 0, rng.integers(1, 1001, m), rng.integers(1, 80, m))
+        yy = xx + rng.choice([1, 10, 60], m)
+        f2 = tmp_path / "regions2.txt"
+        f2.write_text("\n".join(f"{names[w]}\t{a}:{b}" for w, a, b in zip(which, xx, yy)) + "\n")
+        p = subprocess.run([cli, "query", "--prefixes", f"{prefix},{p2}", "-m", "0", "-t", "6", "--regions-file", str(f2), "--devices", "1"], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        got = {}
+        for l in p.stdout.split("\n"):
+            if "Number of variants" in l:
+                got.setdefault(l.split("\t")[0], []).append(int(l.rsplit(": ", 1)[1]))
+        for w, oo in ((0, o), (1, o2)):
+            sel = which == w
+            od = np.lexsort((yy[sel], xx[sel]))
+            want, _ = oo.batch_t6(xx[sel][od].astype(np.uint64), yy[sel][od].astype(np.uint64), False)
+            assert np.array_equal(np.array(got[names[w]]), want)
+    o.close(); o2.close()

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Append one row per kernel of an .ncu-rep capture to profiles/r1_ncu_summary.csv.
+"""Append one row per kernel of an .ncu-rep capture to profiles/r<round>_ncu_summary.csv (NCU_SUMMARY=<file> picks it; default the
+round-2 file, created with the round-1 header when missing).
 
 usage: python tools/ncu_summary.py gpurun_out/r19_t4p.ncu-rep r19_t4p "what this capture shows"
 Reads the report with `ncu -i ... --page raw --csv` (works without a GPU)."""
@@ -8,7 +9,10 @@ import io
 import subprocess
 import sys
 
-OUT = "profiles/r1_ncu_summary.csv"
+import os
+OUT = os.environ.get("NCU_SUMMARY", "profiles/r2_ncu_summary.csv")
+if not os.path.exists(OUT):
+    open(OUT, "w").write(open("profiles/r1_ncu_summary.csv").readline())
 
 
 def main():
