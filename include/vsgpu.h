@@ -91,7 +91,10 @@ int vsgpu_query_t6_u32(vsgpu_index* idx, uint64_t n, const uint32_t* x, const ui
 
 /* ---- t4: get_sample_var_in_ref(vg, idx, pos_x, pos_y, sample) — include/query.h:618-729 ---------
  * Result = CSR: offsets[n+1] into hits[]; each hit is a walk-entry code (VSGPU_HIT_*), in the
- * order the reference pushes the rows.  sample_ids are sampleid_map ids (1..num_samples-1). */
+ * order the reference pushes the rows.  sample_ids are sampleid_map ids (1..num_samples-1).  Id 0 ("ref") is refused
+ * with VSGPU_EINVAL, like a region start < 1: the reference accepts the name but then reports every backbone vertex of the
+ * region as a "deletion" row (the ref path carries "ref" everywhere, query.h:677-700) — an answer no caller can want; a
+ * batch with such an entry fails as a whole, as the reference's process would on its first abort(). */
 int vsgpu_query_t4(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y,
                    const uint32_t* sample_ids, vsgpu_result** out);
 int vsgpu_query_t4_u32(vsgpu_index* idx, uint64_t n, const uint32_t* x, const uint32_t* y,

@@ -407,6 +407,21 @@ def test_error_paths_cuda(tmp_path):
         assert list(cnt) == [0, 0]
         off, hits = e.batch_sample_var_in_ref(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
         assert len(off) == 1 and len(hits) == 0
+        # sample id 0 ("ref") and ids past the sample map are refused, in the plain and in the fused call
+        for sid in (0, 99):
+            with pytest.raises(VsgpuError):
+                e.batch_sample_var_in_ref([10], [105], [sid])
+            with pytest.raises(VsgpuError):
+                e.batch_var_and_sample_var_in_ref([10], [105], [sid])
+        # hit codes / offsets handed back for digests are checked, not trusted (stale or garbled arrays must not index past the tables)
+        off, hits = e.batch_sample_var_in_ref([10], [105], [1])
+        with pytest.raises(VsgpuError):
+            e.digest_t4(off, hits | np.uint32(0x3FFFFFF0))
+        with pytest.raises(VsgpuError):
+            e.digest_t4(off[::-1].copy(), hits)
+        assert len(e.digest_t4(off, hits)) == 1
+        # a region whose t6 rows are decided by the literal dedup rule comes back through the render path (api.get_var_in_ref)
+        assert [v.var_pos for v in e.get_var_in_ref(10, 105)] == [10, 14, 34, 39, 52, 58, 100, 103]
     with pytest.raises(VsgpuError):
         T.open_engine(str(tmp_path / "missing"), "cuda")
 

@@ -387,7 +387,12 @@ class VariantStoreIndex:
         lo, hi, cnt = self.batch_var_in_ref([pos_x], [pos_y])
         if cnt[0] == hi[0] - lo[0]:
             return _parse_rows(self.rows_t6_text(lo[0], hi[0]))
-        return _parse_rows(self.rows_t6_text(lo[0], hi[0]))[: int(cnt[0])]
+        # the literal dedup rule decided this region's rows (a repeated record in the slice, or a region past the contig end
+        # over tail records: DESIGN.md section 9): they are not a prefix of the slice — the render path builds them exactly
+        off, text, rows, _ = self.render_var_in_ref([pos_x], [pos_y])
+        out = _parse_rows(text.decode())
+        assert len(out) == int(cnt[0])
+        return out
 
     def get_sample_var_in_ref(self, pos_x: int, pos_y: int, sample_id: str) -> List[Variant]:
         off, hits = self.batch_sample_var_in_ref([pos_x], [pos_y], [self.sample_id(sample_id)])

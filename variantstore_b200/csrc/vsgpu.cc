@@ -793,8 +793,20 @@ int vsgpu_digest_t6(const vsgpu_index* ix, uint64_t n, const uint32_t* lo, const
 	return bad ? set_err(VSGPU_EINVAL, "vsgpu_digest_t6: bad record slice") : VSGPU_OK;
 }
 
+namespace {
+// hit codes and offsets handed back by a caller: every code names a walk entry, offsets do not decrease
+bool csr_ok(const vsgpu_index* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits) {
+	const uint64_t E = ix->flat.cent.size();
+	for (uint64_t i = 0; i < n; i++) if (offsets[i + 1] < offsets[i]) return false;
+	if (n && offsets[n] > offsets[0] && !hits) return false;
+	std::atomic<bool> ok{true};
+	parallel_for(n ? offsets[n] - offsets[0] : 0, [&](uint64_t a, uint64_t b) { for (uint64_t j = offsets[0] + a; j < offsets[0] + b; j++) if ((hits[j] & VSGPU_HIT_ENTRY_MASK) >= E) { ok = false; return; } });
+	return ok;
+}
+}  // namespace
 int vsgpu_digest_t4(const vsgpu_index* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, int with_samples, uint64_t* digests) {
 	if (!ix || (n && (!offsets || !digests))) return set_err(VSGPU_EINVAL, "vsgpu_digest_t4: null argument");
+	if (!csr_ok(ix, n, offsets, hits)) return set_err(VSGPU_EINVAL, "vsgpu_digest_t4: offsets decrease or a hit code names no walk entry");
 	digests_t4(ix, n, offsets, hits, with_samples != 0, digests);
 	return VSGPU_OK;
 }
@@ -1295,6 +1307,8 @@ int vsgpu_rows_t5(const vsgpu_index* ix, const uint32_t* hits, uint64_t nhits, u
 int vsgpu_digest_t5(const vsgpu_index* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* sample_ids, int with_samples, uint64_t* digests) {
 	if (!ix || (n && (!offsets || !digests || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_digest_t5: null argument");
 	if (ix->sindex.empty() && n && offsets[n]) return set_err(VSGPU_EINVAL, "vsgpu_digest_t5: no t5 query has run on this index");
+	if (!csr_ok(ix, n, offsets, hits)) return set_err(VSGPU_EINVAL, "vsgpu_digest_t5: offsets decrease or a hit code names no walk entry");
+	for (uint64_t i = 0; i < n; i++) if (sample_ids[i] == 0 || sample_ids[i] >= ix->ser.num_samples) return set_err(VSGPU_EINVAL, "vsgpu_digest_t5: sample id out of range");
 	digests_t5(ix, n, offsets, hits, sample_ids, with_samples != 0, digests);
 	return VSGPU_OK;
 }
