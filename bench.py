@@ -635,6 +635,74 @@ def run_vsgpu(args):
                                                               "copy_algorithmic_bytes": 2 * nbytes}}
         except Exception as ex:
             line["other_ops"] = {"failed": str(ex)}
+    if world == 1 and not args.no_other_ops and not args.no_sparse:
+        # BASELINE config [3] beside the headline: a TCGA-like sparse cohort (explicit sample ids, 1-3 carriers per allele) — batched
+        # t7 lookups (device time, and end to end incl. hashing the query strings on the host) and t4 over 1 M regions, the
+        # reference's own worst case (eval_data_records/logs/query_luad.out:120: 3 319 s for 1 000 regions).
+        try:
+            T = get_oracle()
+            sp = os.path.join(args.cache_dir, f"tcga_{args.sparse_records}_{args.sparse_samples}", "ser")
+            if not os.path.exists(os.path.join(sp, ".done")):
+                os.makedirs(os.path.dirname(sp), exist_ok=True)
+                so = T.Oracle.synth(sp, chr_name="2", ref_length=243_199_373, pos_lo=10_000, n_records=args.sparse_records, n_samples=args.sparse_samples,
+                                    mode=1, seed=77, cqf_log2=25, gzip_level=1)
+                so.close()
+                open(os.path.join(sp, ".done"), "w").write("ok")
+            so = T.Oracle.open(sp)
+            av = so.all_variants()
+            with VariantStoreIndex(sp, device=local) as sidx:
+                sidx.set_stream(torch.cuda.current_stream().cuda_stream)
+                rng = np.random.default_rng(5)
+                m7 = args.sparse_lookups
+                pick = rng.integers(0, len(av), m7)
+                pos7 = np.array([av[i][0] for i in pick], np.uint64)
+                pos7[m7 // 2:] += 1                           # half of the lookups miss by construction
+                refs7, alts7 = [av[i][1] for i in pick], [av[i][2] for i in pick]
+                b7 = Batch(sidx, 7, pos7, refs=refs7, alts=alts7)
+                b7.run()
+                _, (t7_ms,) = timed(b7.run, [b7], 5)
+                # end to end through the C ABI: C strings in host memory -> host hashing -> H2D -> k_t7 -> D2H of the record ids
+                ra7 = (C.c_char_p * m7)(*[r.encode() for r in refs7])
+                aa7 = (C.c_char_p * m7)(*[a.encode() for a in alts7])
+                rec7 = np.zeros(m7, np.uint32)
+                t7_e2e = 1e9
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    rc = sidx._lib.vsgpu_query_t7(sidx._h, m7, C.c_void_p(pos7.ctypes.data), ra7, aa7, C.c_void_p(rec7.ctypes.data))
+                    t7_e2e = min(t7_e2e, time.perf_counter() - t0)
+                    assert rc == 0, sidx._lib.vsgpu_last_error()
+                sub = rng.choice(m7, 2000, replace=False)
+                f7, _, _ = so.batch_t7(pos7[sub], [refs7[i] for i in sub], [alts7[i] for i in sub])
+                ok7 = bool(np.array_equal(rec7[sub] != 0xFFFFFFFF, f7 == 1))
+                x4 = np.sort(rng.integers(10_000, 243_199_373 - 1000, n)).astype(np.uint64)
+                y4 = x4 + np.uint64(args.width)
+                s4 = rng.integers(1, args.sparse_samples + 1, n).astype(np.uint32)
+                b4s = Batch(sidx, 4, x4, y4, sample_ids=s4)
+                b4s.run()
+                _, (t4s_ms,) = timed(b4s.run, [b4s], 5)
+                off4, hits4, _ = b4s.fetch()
+                sub = rng.choice(n, 1000, replace=False)
+                oc4, od4, ub4 = so.batch_t4(x4[sub], y4[sub], s4[sub], False)
+                ok4 = bool(np.all(((oc4 == np.diff(off4)[sub]) & (od4 == sidx.digest_t4(off4, hits4, False)[sub])) | (ub4 != 0)))
+                px4, py4, ps4 = (torch.from_numpy(a.astype(np.int32)).pin_memory() for a in (x4, y4, s4))
+                t4s_e2e = 1e9
+                for _ in range(4):
+                    r4 = C.c_void_p()
+                    t0 = time.perf_counter()
+                    rc = sidx._lib.vsgpu_query_t4_u32(sidx._h, n, C.c_void_p(px4.data_ptr()), C.c_void_p(py4.data_ptr()), C.c_void_p(ps4.data_ptr()), C.byref(r4))
+                    t4s_e2e = min(t4s_e2e, time.perf_counter() - t0)
+                    assert rc == 0, sidx._lib.vsgpu_last_error()
+                    sidx._lib.vsgpu_result_free(r4)
+                line.setdefault("other_ops", {})["sparse_cohort"] = {
+                    "workload": f"TCGA-like: {args.sparse_records} records x {args.sparse_samples} samples, explicit sample ids; membership = per-sample carried-entry lists",
+                    "t7_lookups": m7, "k_t7_ms": t7_ms, "t7_lookups_per_s_kernel": m7 / (t7_ms / 1e3), "t7_lookups_per_s_e2e_c_abi_incl_host_hashing": m7 / t7_e2e,
+                    "t7_found_fraction": float((rec7 != 0xFFFFFFFF).mean()), "t7_parity_sample_ok": ok7,
+                    "t4_regions": n, "k_t4_ms": t4s_ms, "t4_regions_per_s_kernel": n / (t4s_ms / 1e3), "t4_regions_per_s_e2e": n / t4s_e2e, "t4_parity_sample_ok": ok4,
+                    "device_bytes": int(sidx.info.device_bytes)}
+                b7.close(); b4s.close()
+            so.close()
+        except Exception as ex:
+            line.setdefault("other_ops", {})["sparse_cohort"] = {"failed": repr(ex)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         try:
             nq, times, load_s = cpu_sample(args, prefix, meta, 1, args.cpu_sample_single)
@@ -663,6 +731,10 @@ def main():
     ap.add_argument("--cpu-sample-single", type=int, default=2_000, help="regions per type of the single-thread cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-ops", action="store_true", help="skip the side measurements (t2, rows as text)")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the sparse-cohort side measurement (config [3])")
+    ap.add_argument("--sparse-records", type=int, default=3_000_000)
+    ap.add_argument("--sparse-samples", type=int, default=10_000)
+    ap.add_argument("--sparse-lookups", type=int, default=2_000_000)
     ap.add_argument("--rows-regions", type=int, default=20_000, help="regions of the e2e_rows leg (answers as -v text)")
     ap.add_argument("--unfused", action="store_true", help="a step = k_t6 then k_t4p (two launches, two host-buffer calls) instead of the fused launch / call")
     ap.add_argument("--e2e-u64", action="store_true", help="end-to-end arm through the 64-bit coordinate entry points instead of the 32-bit ones")
