@@ -734,7 +734,7 @@ def main():
     ap.add_argument("--no-sparse", action="store_true", help="skip the sparse-cohort side measurement (config [3])")
     ap.add_argument("--sparse-records", type=int, default=3_000_000)
     ap.add_argument("--sparse-samples", type=int, default=10_000)
-    ap.add_argument("--sparse-lookups", type=int, default=2_000_000)
+    ap.add_argument("--sparse-lookups", type=int, default=10_000_000)
     ap.add_argument("--rows-regions", type=int, default=20_000, help="regions of the e2e_rows leg (answers as -v text)")
     ap.add_argument("--unfused", action="store_true", help="a step = k_t6 then k_t4p (two launches, two host-buffer calls) instead of the fused launch / call")
     ap.add_argument("--e2e-u64", action="store_true", help="end-to-end arm through the 64-bit coordinate entry points instead of the 32-bit ones")

@@ -198,7 +198,12 @@ const uint8_t* vsgpu_result_status(const vsgpu_result* r);      /* n bytes (t5 r
 float vsgpu_result_kernel_ms(const vsgpu_result* r);            /* t5: device time of the count and write launches (CUDA events) */
 int vsgpu_rows_t5(const vsgpu_index* idx, const uint32_t* hits, uint64_t nhits, uint32_t sample_id, int with_samples, char** text);
 int vsgpu_digest_t5(const vsgpu_index* idx, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* sample_ids, int with_samples, uint64_t* digests);
-const uint8_t* vsgpu_text_status(const vsgpu_text* t);      /* n bytes (t2 results; NULL for rendered t6 rows) */
+/* t5 with print (get_sample_var_in_sample(..., print = true, outfile), query.h:596-606) for a batch, rows written on the device: region i's
+ * rows are vsgpu_text_bytes()[offsets[i] .. offsets[i+1]) — byte for byte vsgpu_rows_t5 on the codes vsgpu_query_t5 returns for it;
+ * vsgpu_text_status()[i] = 2 where the reference never returns (no rows).  vsgpu_text_stage_ms: count, write, rows.  The first call
+ * uploads sample_info.index of every genotype entry (4 bytes each) beside the t3 tables. */
+int vsgpu_render_t5(vsgpu_index* idx, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, int with_samples, vsgpu_text** out);
+const uint8_t* vsgpu_text_status(const vsgpu_text* t);      /* n bytes (t2 / t3 results and rendered t5 rows; NULL for rendered t6 / t4 rows) */
 const float* vsgpu_text_stage_ms(const vsgpu_text* t);      /* t2: device time of the count, plan and copy launches (CUDA events); their sum = vsgpu_text_kernel_ms */
 
 /* ---- device-resident batches (bench harness; replaces the timing loop of src/bm_query.cc:74-135)

@@ -301,6 +301,43 @@ def test_t4_rows_rendered_on_device_cuda(tmp_path, sparse, overlap):
         assert len(off) == 1 and text == b"" and rows == 0
 
 
+@pytest.mark.parametrize("sparse,overlap", [(False, True), (True, True), (False, False)])
+def test_t5_rows_rendered_on_device_cuda(tmp_path, sparse, overlap):
+    """get_sample_var_in_sample with print (query.h:596-606): the rows of every region's t5 answer written by a kernel
+    (vsgpu_render_t5) — byte for byte the host materialiser's (vsgpu_rows_t5) on the codes vsgpu_query_t5 returns and the
+    oracle's rows; the position column is the sample's own coordinate, so it differs from sample to sample for one code."""
+    fa, vcf, names = T.write_fuzz_inputs(str(tmp_path), 8, overlap=overlap, sparse=sparse, n_samples=40 if sparse else 12, n_records=320)
+    o = Oracle.construct(fa, vcf, str(tmp_path / "ser"), force_enc=0 if sparse else -1)
+    with T.open_engine(str(tmp_path / "ser"), "cuda") as e:
+        starts = np.arange(1, 4001, 11, dtype=np.uint64)
+        x = np.tile(starts, len(names))
+        y = x + np.tile(np.where(np.arange(len(starts)) % 3 == 0, 40, 700).astype(np.uint64), len(names))
+        s = np.repeat(np.arange(1, len(names) + 1, dtype=np.uint32), len(starts))
+        off5, hits, status, _ = e.batch_sample_var_in_sample(x, y, s)
+        assert len(hits) > 1000
+        for ws in (True, False):
+            off, text, rows, st, ms = e.render_sample_var_in_sample(x, y, s, with_samples=ws)
+            assert rows == len(hits) and off[-1] == len(text) and np.array_equal(st, status) and ms[2] > 0
+            pick = range(0, len(x), 23)
+            want = b"".join(e.rows_t5_text(hits[off5[i]:off5[i + 1]], int(s[i]), ws).encode() for i in pick)
+            got = b"".join(text[off[i]:off[i + 1]] for i in pick)
+            assert got == want
+        off, text, rows, st, ms = e.render_sample_var_in_sample(x, y, s, with_samples=True)
+        _, _, ost, ub = o.batch_t5(x, y, s, True)
+        rng = np.random.default_rng(3)
+        checked = 0
+        for i in rng.choice(len(x), 200, replace=False):
+            if ost[i] != 0 or ub[i]:
+                assert ost[i] == 0 or off[i] == off[i + 1]
+                continue
+            want = o.t5_text(int(x[i]), int(y[i]), names[int(s[i]) - 1]).split("Pos\tRef\tAlt\tSamples\n", 1)[1]
+            assert text[off[i]:off[i + 1]].decode() == want, (int(x[i]), int(y[i]), int(s[i]))
+            checked += 1
+        assert checked > 50
+        off, text, rows, st, ms = e.render_sample_var_in_sample(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint32))
+        assert len(off) == 1 and text == b"" and rows == 0
+
+
 def test_rows_rendered_with_long_and_mixed_names_cuda(tmp_path):
     """items of up to 15 bytes come from per-sample templates; longer names (and a mix) take the generic path"""
     for k, fmt in enumerate(["a_rather_long_sample_name_{:04d}", "n{:d}", "x{:09d}"]):          # 30-char, 2..3-char, 10-char names (items of 36, 8-9, 16 bytes)

@@ -116,10 +116,13 @@ def main():
             s = rng.integers(1, 2505, n).astype(np.uint32)
             b6, b4 = Batch(idx, 6, x, y), Batch(idx, 4, x, y, sample_ids=s)
             ms6, ms4 = timed(b6), timed(b4)
+            b46 = Batch(idx, 46, x, y, sample_ids=s)
+            ms46 = timed(b46)
+            b46.close()
             off, hits, cnt = b4.fetch()
             lo, hi, c6 = b6.fetch()
             algo4, _ = b4.stats()
-            print(json.dumps({"config": "width sweep", "width": width, "regions": n, "k_t6_ms": ms6, "k_t4_ms": ms4,
+            print(json.dumps({"config": "width sweep", "width": width, "regions": n, "k_t6_ms": ms6, "k_t4_ms": ms4, "k_fused_t6t4_ms": ms46, "fused_region_queries_per_s": 2 * n / (ms46 / 1000),
                               "t6_regions_per_s": n / (ms6 / 1000), "t4_regions_per_s": n / (ms4 / 1000),
                               "t6_rows_per_region": float(c6.mean()), "t4_rows_per_region": float(cnt.mean()),
                               "t4_rows_per_s": float(cnt.sum()) / (ms4 / 1000), "t4_algorithmic_GBps": algo4 / (ms4 / 1000) / 1e9}), flush=True)

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "vsgpu_digest_t7": (C.c_int, [vp, C.c_uint64, vp, vp, vp]),
     "vsgpu_render_t6": (C.c_int, [vp, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp)]),
     "vsgpu_render_t4": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.c_int, C.POINTER(vp)]),
+    "vsgpu_render_t5": (C.c_int, [vp, C.c_uint64, vp, vp, vp, C.c_int, C.POINTER(vp)]),
     "vsgpu_text_bytes": (vp, [vp]),
     "vsgpu_text_offsets": (u64p, [vp]),
     "vsgpu_text_num_rows": (C.c_uint64, [vp]),

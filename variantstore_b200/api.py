@@ -233,6 +233,24 @@ class VariantStoreIndex:
             self._lib.vsgpu_text_free(t)
         return off, text, rows, ms
 
+    def render_sample_var_in_sample(self, x, y, sample_ids, with_samples=True):
+        """t5 over arrays with the rows rendered on the device (vsgpu_render_t5): (offsets[n+1], text bytes, rows, status[n],
+        (count, write, rows) kernel ms); status 2 = the reference never returns (no rows)."""
+        x, y = _u64(x), _u64(y)
+        s = np.ascontiguousarray(sample_ids, dtype=np.uint32)
+        n = len(x)
+        t = C.c_void_p()
+        self._check(self._lib.vsgpu_render_t5(self._h, n, _ptr(x), _ptr(y), _ptr(s), int(with_samples), C.byref(t)))
+        try:
+            off = np.ctypeslib.as_array(self._lib.vsgpu_text_offsets(t), shape=(n + 1,)).copy()
+            text = C.string_at(self._lib.vsgpu_text_bytes(t), int(off[-1]))
+            rows = int(self._lib.vsgpu_text_num_rows(t))
+            status = np.frombuffer(C.string_at(self._lib.vsgpu_text_status(t), n), np.uint8).copy() if n else np.zeros(0, np.uint8)
+            ms = tuple(float(v) for v in np.ctypeslib.as_array(self._lib.vsgpu_text_stage_ms(t), shape=(3,)))
+        finally:
+            self._lib.vsgpu_text_free(t)
+        return off, text, rows, status, ms
+
     def batch_sample_var_in_sample(self, x, y, sample_ids):
         """t5 over arrays (get_sample_var_in_sample, query.h:490-612): (offsets[n+1], hit codes, status, kernel ms);
         status 2 = the reference never returns."""
@@ -375,6 +393,12 @@ class VariantStoreIndex:
         hits = np.ascontiguousarray(hits, np.uint32)
         p = C.c_void_p()
         self._check(self._lib.vsgpu_rows_t4(self._h, _ptr(hits), len(hits), int(with_samples), C.byref(p)))
+        return self._take_text(p)
+
+    def rows_t5_text(self, hits, sample_id: int, with_samples=True):
+        hits = np.ascontiguousarray(hits, np.uint32)
+        p = C.c_void_p()
+        self._check(self._lib.vsgpu_rows_t5(self._h, _ptr(hits), len(hits), int(sample_id), int(with_samples), C.byref(p)))
         return self._take_text(p)
 
     def rows_t7_text(self, rec):

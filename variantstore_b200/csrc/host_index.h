@@ -46,7 +46,7 @@ void append_carriers(const HostIndex* ix, uint32_t v, std::string& out);
 void t6_row(const HostIndex* ix, uint32_t r, bool with_samples, std::string& out);
 void t4_row(const HostIndex* ix, uint32_t code, bool with_samples, std::string& out);
 // the parts of that row as vertex ids (what the device-side renderer's tables are built from); sample == kNone (0xFFFFFFFF): t4
-void hit_row_parts(const HostIndex* ix, uint32_t code, uint32_t sample, uint64_t& pos, uint32_t& refv, uint32_t& altv, uint32_t& u);
+void hit_row_parts(const HostIndex* ix, uint32_t code, uint32_t sample, uint64_t& pos, uint32_t& refv, uint32_t& altv, uint32_t& u, bool* insertion = nullptr);
 // t5 row (get_sample_var_in_sample, query.h:553-590): the t4 row of the same hit code with var_pos in the sample's coordinates
 void t5_row(const HostIndex* ix, uint32_t code, uint32_t sample, bool with_samples, std::string& out);
 void digests_t5(const HostIndex* ix, uint64_t n, const uint64_t* offsets, const uint32_t* hits, const uint32_t* samples, bool with_samples, uint64_t* digests);

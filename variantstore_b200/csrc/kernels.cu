@@ -652,28 +652,63 @@ __global__ void __launch_bounds__(256) k_render(const DevIndex ix, const RenderT
 // lengths of the batch's hit codes, k_render_hits writes the rows (a warp each), k_region_text_offsets reads the text
 // offset of every region off its first row.
 __device__ __forceinline__ uint32_t hit_variant(uint32_t code) { return (code & kHitRejoin) ? 2u : (code & kHitStart) ? 1u : 0u; }
-__device__ __forceinline__ uint32_t hit_len(const HitTables& ht, const uint32_t* __restrict__ hits, uint64_t h, uint64_t nh, int ws) {
+__device__ __forceinline__ uint32_t ndigits(uint32_t p) { uint32_t nd = 1; for (; p >= 10; p /= 10) nd++; return nd; }
+// pos5 (nullable): the rows are t5's — same text with the position column replaced, so the length moves by the digit counts
+__device__ __forceinline__ uint32_t hit_len(const HitTables& ht, const uint32_t* __restrict__ hits, uint64_t h, uint64_t nh, int ws, const uint32_t* __restrict__ pos5) {
 	if (h >= nh) return 0;
-	const uint32_t code = hits[h];
-	return __ldg(ht.len[ws][hit_variant(code)] + (code & 0x3FFFFFFFu));
+	const uint32_t code = hits[h], v = hit_variant(code), c = code & 0x3FFFFFFFu;
+	uint32_t len = __ldg(ht.len[ws][v] + c);
+	if (pos5) len = len - ndigits(__ldg(ht.pos[v] + c)) + ndigits(pos5[h]);
+	return len;
 }
-__global__ void __launch_bounds__(256) k_hits_sums(const HitTables ht, const uint32_t* __restrict__ hits, uint64_t nh, int ws, uint64_t* __restrict__ cta_sums) {
+// t5 rows (get_sample_var_in_sample, query.h:553-590): var_pos of every hit code of a t5 answer — ref_pos for an insertion
+// (one more than t4 prints), else the sample's own `index` in the vertex whose carriers the row lists (0 when the sample is
+// not among them, as the reference's default-constructed sample_info).  One thread per row; its region (and so its sample)
+// by a search over the CSR offsets.  gsidx = sample_info.index of every s_info entry, in s_info order.
+__global__ void __launch_bounds__(256) k_t5_row_pos(const DevIndex ix, const RenderTables rt, const HitTables ht, const uint32_t* __restrict__ gsidx, uint64_t n,
+                                                    const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ samples, const uint32_t* __restrict__ hits, uint64_t nh,
+                                                    uint32_t* __restrict__ pos5) {
+	for (uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t a = 0, b = n;                                     // last region with offsets[a] <= h (empty regions share an offset with their successor)
+		while (b - a > 1) { const uint64_t m = (a + b) >> 1; if (__ldg(offsets + m) <= h) a = m; else b = m; }
+		const uint32_t s = __ldg(samples + a);
+		const uint32_t code = hits[h], v = hit_variant(code), c = code & 0x3FFFFFFFu;
+		const uint4 cr = __ldg(ht.car[v] + c);
+		uint32_t p = 0;
+		if (cr.y >> 31) p = __ldg(ht.pos[v] + c) + 1;
+		else {
+			const uint64_t sb = (uint64_t)cr.z | ((uint64_t)cr.w << 32);
+			const uint32_t cnt = cr.y & 0x0FFFFFFFu;
+			if (ix.class_mode) {
+				const uint64_t* row = ix.bitmap + (uint64_t)cr.x * ix.words_per_set;
+				uint32_t r = 0;
+				for (uint32_t w = 0; w < (s >> 6); w++) r += (uint32_t)__popcll(__ldg(row + w));
+				r += (uint32_t)__popcll(__ldg(row + (s >> 6)) & (((uint64_t)1 << (s & 63)) - 1));
+				if (r < cnt) p = __ldg(gsidx + sb + r);
+			} else {
+				for (uint32_t i = 0; i < cnt; i++) if (__ldg(rt.s_sample_id + sb + i) == s) { p = __ldg(gsidx + sb + i); break; }
+			}
+		}
+		pos5[h] = p;
+	}
+}
+__global__ void __launch_bounds__(256) k_hits_sums(const HitTables ht, const uint32_t* __restrict__ hits, uint64_t nh, int ws, const uint32_t* __restrict__ pos5, uint64_t* __restrict__ cta_sums) {
 	__shared__ SegCount s_warp[8];
 	SegCount mine{0, 0};
 	const uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
 #pragma unroll
-	for (int j = 0; j < 4; j++) mine.bytes += hit_len(ht, hits, base + j, nh, ws);
+	for (int j = 0; j < 4; j++) mine.bytes += hit_len(ht, hits, base + j, nh, ws, pos5);
 	SegCount tot;
 	cta_scan_1024(mine, s_warp, &tot);
 	if (threadIdx.x == 0) { cta_sums[2 * (uint64_t)blockIdx.x] = 0; cta_sums[2 * (uint64_t)blockIdx.x + 1] = tot.bytes; }
 }
-__global__ void __launch_bounds__(256) k_hits_offsets(const HitTables ht, const uint32_t* __restrict__ hits, uint64_t nh, int ws, const uint64_t* __restrict__ cta_sums, uint64_t nctas,
+__global__ void __launch_bounds__(256) k_hits_offsets(const HitTables ht, const uint32_t* __restrict__ hits, uint64_t nh, int ws, const uint32_t* __restrict__ pos5, const uint64_t* __restrict__ cta_sums, uint64_t nctas,
                                                       uint64_t* __restrict__ byte_off) {
 	__shared__ SegCount s_warp[8];
 	uint32_t c[4]; SegCount mine{0, 0};
 	const uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
 #pragma unroll
-	for (int j = 0; j < 4; j++) { c[j] = hit_len(ht, hits, base + j, nh, ws); mine.bytes += c[j]; }
+	for (int j = 0; j < 4; j++) { c[j] = hit_len(ht, hits, base + j, nh, ws, pos5); mine.bytes += c[j]; }
 	SegCount tot;
 	SegCount ex = cta_scan_1024(mine, s_warp, &tot);
 	ex.bytes += cta_sums[2 * (uint64_t)blockIdx.x + 1];
@@ -684,7 +719,7 @@ __global__ void __launch_bounds__(256) k_hits_offsets(const HitTables ht, const 
 __global__ void __launch_bounds__(256) k_region_text_offsets(uint64_t n, const uint64_t* __restrict__ offsets, const uint64_t* __restrict__ byte_off, uint64_t* __restrict__ out) {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = byte_off[offsets[i]];
 }
-__global__ void __launch_bounds__(256) k_render_hits(const DevIndex ix, const RenderTables rt, const HitTables ht, const uint32_t* __restrict__ hits, int ws,
+__global__ void __launch_bounds__(256) k_render_hits(const DevIndex ix, const RenderTables rt, const HitTables ht, const uint32_t* __restrict__ hits, int ws, const uint32_t* __restrict__ pos5,
                                                      const uint64_t* __restrict__ byte_off, uint64_t row_begin, uint64_t row_end, char* __restrict__ text) {
 	__shared__ __align__(16) uint8_t s_stage[8][kRenderWin + 16];
 	const uint32_t lane = threadIdx.x & 31;
@@ -693,7 +728,7 @@ __global__ void __launch_bounds__(256) k_render_hits(const DevIndex ix, const Re
 	for (uint64_t row = row_begin + warp0; row < row_end; row += nwarps) {
 		const uint32_t code = hits[row], v = hit_variant(code), c = code & 0x3FFFFFFFu;
 		const uint64_t b0 = __ldg(byte_off + row);
-		render_row(ix, rt, __ldg(ht.pos[v] + c), __ldg(ht.seq[v] + c), __ldg(ht.car[v] + c), text + b0, (uint32_t)(__ldg(byte_off + row + 1) - b0), ws, stage, lane);
+		render_row(ix, rt, pos5 ? pos5[row] : __ldg(ht.pos[v] + c), __ldg(ht.seq[v] + c), __ldg(ht.car[v] + c), text + b0, (uint32_t)(__ldg(byte_off + row + 1) - b0), ws, stage, lane);
 	}
 }
 
@@ -978,22 +1013,28 @@ cudaError_t launch_render(const DevIndex& ix, const RenderTables& rt, uint64_t n
 	k_render<<<grid_for((row_end - row_begin) * 32, 256, 8), 256, 0, stream>>>(ix, rt, rt.text_prefix[with_samples ? 1 : 0], nseg, seg_lo, with_samples ? 1 : 0, row_off, byte_off, row_begin, row_end, text);
 	return cudaGetLastError();
 }
+cudaError_t launch_t5_row_pos(const DevIndex& ix, const RenderTables& rt, const HitTables& ht, const uint32_t* gsidx, uint64_t n, const uint64_t* offsets, const uint32_t* samples,
+                              const uint32_t* hits, uint64_t nh, uint32_t* pos5, cudaStream_t stream) {
+	if (nh == 0 || n == 0) return cudaSuccess;
+	k_t5_row_pos<<<grid_for(nh, 256, 8), 256, 0, stream>>>(ix, rt, ht, gsidx, n, offsets, samples, hits, nh, pos5);
+	return cudaGetLastError();
+}
 cudaError_t launch_hit_offsets(const HitTables& ht, const uint32_t* hits, uint64_t nh, int with_samples, uint64_t n, const uint64_t* offsets, uint64_t* byte_off, uint64_t* region_off,
-                               uint64_t* scratch, cudaStream_t stream) {
+                               uint64_t* scratch, cudaStream_t stream, const uint32_t* pos5) {
 	const int ws = with_samples ? 1 : 0;
 	const uint64_t nctas = (nh + 1023) / 1024;
 	if (nh) {
-		k_hits_sums<<<(uint32_t)nctas, 256, 0, stream>>>(ht, hits, nh, ws, scratch);
+		k_hits_sums<<<(uint32_t)nctas, 256, 0, stream>>>(ht, hits, nh, ws, pos5, scratch);
 		k_seg_bases<<<1, 256, 0, stream>>>(nctas, scratch);
-		k_hits_offsets<<<(uint32_t)nctas, 256, 0, stream>>>(ht, hits, nh, ws, scratch, nctas, byte_off);
+		k_hits_offsets<<<(uint32_t)nctas, 256, 0, stream>>>(ht, hits, nh, ws, pos5, scratch, nctas, byte_off);
 	} else cudaMemsetAsync(byte_off, 0, 8, stream);
 	k_region_text_offsets<<<grid_for(n + 1, 256, 8), 256, 0, stream>>>(n, offsets, byte_off, region_off);
 	return cudaGetLastError();
 }
 cudaError_t launch_render_hits(const DevIndex& ix, const RenderTables& rt, const HitTables& ht, const uint32_t* hits, int with_samples, const uint64_t* byte_off,
-                               uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream) {
+                               uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream, const uint32_t* pos5) {
 	if (row_end <= row_begin) return cudaSuccess;
-	k_render_hits<<<grid_for((row_end - row_begin) * 32, 256, 8), 256, 0, stream>>>(ix, rt, ht, hits, with_samples ? 1 : 0, byte_off, row_begin, row_end, text);
+	k_render_hits<<<grid_for((row_end - row_begin) * 32, 256, 8), 256, 0, stream>>>(ix, rt, ht, hits, with_samples ? 1 : 0, pos5, byte_off, row_begin, row_end, text);
 	return cudaGetLastError();
 }
 cudaError_t launch_widen(uint64_t n, const uint32_t* x32, const uint32_t* y32, uint64_t* x, uint64_t* y, cudaStream_t stream) {

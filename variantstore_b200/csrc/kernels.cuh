@@ -80,9 +80,13 @@ struct HitTables {
 };
 // byte_off[nh + 1] = exclusive text offsets of the rows of hits[0 .. nh); region_off[i] = byte_off[offsets[i]] for i <= n; scratch as launch_render_offsets
 cudaError_t launch_hit_offsets(const HitTables& ht, const uint32_t* hits, uint64_t nh, int with_samples, uint64_t n, const uint64_t* offsets, uint64_t* byte_off, uint64_t* region_off,
-                               uint64_t* scratch, cudaStream_t stream);
+                               uint64_t* scratch, cudaStream_t stream, const uint32_t* pos5 = nullptr);
 cudaError_t launch_render_hits(const DevIndex& ix, const RenderTables& rt, const HitTables& ht, const uint32_t* hits, int with_samples, const uint64_t* byte_off,
-                               uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream);
+                               uint64_t row_begin, uint64_t row_end, char* text, cudaStream_t stream, const uint32_t* pos5 = nullptr);
+// t5 rows: pos5[h] = var_pos of hit h of a t5 answer (offsets / samples: the batch's CSR and sample ids; gsidx: sample_info.index per s_info entry);
+// passed to the two launchers above, the rows come out as get_sample_var_in_sample prints them (query.h:553-590)
+cudaError_t launch_t5_row_pos(const DevIndex& ix, const RenderTables& rt, const HitTables& ht, const uint32_t* gsidx, uint64_t n, const uint64_t* offsets, const uint32_t* samples,
+                              const uint32_t* hits, uint64_t nh, uint32_t* pos5, cudaStream_t stream);
 
 // Tables of t2 = query_sample_from_ref (include/query.h:120-189); uploaded on first use.
 struct T2Tables {

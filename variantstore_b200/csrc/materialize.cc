@@ -264,7 +264,7 @@ uint32_t host_sample_index(const HostIndex* ix, uint32_t vertex, uint32_t sample
 // for an insertion and the sample's own position in the vertex otherwise.
 // What the row of a hit code prints, as vertex ids: var_pos, the vertex whose sequence is the ref column (kNone: ""), the one
 // of the alt column, and the vertex u whose carriers are listed.  sample == kNone: t4; else t5 (positions in the sample's coordinates).
-void hit_row_parts(const HostIndex* ix, uint32_t code, uint32_t sample, uint64_t& pos, uint32_t& refv, uint32_t& altv, uint32_t& u) {
+void hit_row_parts(const HostIndex* ix, uint32_t code, uint32_t sample, uint64_t& pos, uint32_t& refv, uint32_t& altv, uint32_t& u, bool* insertion) {
 	const FlatIndex& f = ix->flat; const SerData& s = ix->ser;
 	const bool t5 = sample != kNone;
 	const uint32_t c = code & VSGPU_HIT_ENTRY_MASK;
@@ -287,6 +287,7 @@ void hit_row_parts(const HostIndex* ix, uint32_t code, uint32_t sample, uint64_t
 		next_ref_pos = tk == kEntTgtNone ? (uint64_t)ref_pos + s.v_length[u] : f.vstart[tk];
 	}
 	refv = kNone; altv = kNone;
+	if (insertion) *insertion = ref_pos == next_ref_pos;
 	if (ref_pos == next_ref_pos) { pos = t5 ? (uint64_t)ref_pos : (uint64_t)ref_pos - 1; altv = u; }   // insertion
 	else if (u_is_bb) {                                                                                   // deletion: cur_ref = seq(find(ref_pos - 1))
 		uint64_t p = ref_pos > 1 ? ref_pos - 1 : 1;

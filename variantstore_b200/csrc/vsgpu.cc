@@ -116,7 +116,8 @@ struct vsgpu_index : vsgpu::HostIndex {
 	// t2 (query_sample_from_ref): tables uploaded on first use
 	bool t2_ready = false;
 	T2Tables t2{};
-	DevBuf bcnt, bst8, brecs, btile, bkeep;
+	DevBuf bcnt, bst8, brecs, btile, bkeep, bpos5;
+	const uint32_t* d_gsidx = nullptr;   // sample_info.index per s_info entry, s_info order (t5 rows rendered on the device); uploaded on first use
 	bool t3_ready = false;
 	T3Tables t3{};
 	cudaEvent_t ev_t2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -144,7 +145,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 		cudaSetDevice(device);
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bx32, &by32, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs, &btile, &bkeep}) b->release();
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bx32, &by32, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs, &btile, &bkeep, &bpos5}) b->release();
 		for (cudaEvent_t e : ev_render) if (e) cudaEventDestroy(e);
 		for (cudaEvent_t e : ev_t2) if (e) cudaEventDestroy(e);
 		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i][0], ev_in[i][1], ev_in[i][2], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
@@ -909,8 +910,8 @@ void ensure_hit_tables(vsgpu_index* ix) {
 				if (e.tgt & kEntMarker) continue;
 				if (v == 2 && !((e.tgt & kEntAlt) && (e.tgt & kEntTgtCarriers) && (e.tgt & kEntTgtMask) != kEntTgtNone)) continue;   // only such entries produce REJOIN codes
 				const uint32_t code = (uint32_t)c | (v == 1 ? VSGPU_HIT_START : v == 2 ? VSGPU_HIT_REJOIN : 0);
-				uint64_t p; uint32_t refv, altv, u;
-				hit_row_parts(ix, code, kNone, p, refv, altv, u);
+				uint64_t p; uint32_t refv, altv, u; bool ins = false;
+				hit_row_parts(ix, code, kNone, p, refv, altv, u, &ins);
 				pos[c] = (uint32_t)p;
 				seq[c] = make_uint4(refv == kNone ? 0 : s.v_offset[refv], refv == kNone ? 0 : s.v_length[refv], altv == kNone ? 0 : s.v_offset[altv], altv == kNone ? 0 : s.v_length[altv]);
 				const uint64_t sb = s.v_sinfo_begin[u], sc = s.v_sinfo_begin[u + 1] - sb;
@@ -918,7 +919,8 @@ void ensure_hit_tables(vsgpu_index* ix) {
 				uint64_t carb = 0;
 				if (f.class_mode) { if (ix->set_pop[set] != sc) throw std::runtime_error("vertex " + std::to_string(u) + ": s_info entries differ from the members of its sample class"); carb = ix->set_text_bytes[set]; }
 				else for (uint64_t i = sb; i < sb + sc; i++) { const uint32_t id = s.s_sample_id[i]; if (id >= s.num_samples) throw std::runtime_error("vertex names a sample beyond sampleid_map.lst"); if (id) carb += name_len[id] + 6; }
-				car[c] = make_uint4(set, (uint32_t)sc, (uint32_t)sb, (uint32_t)(sb >> 32));
+				if (sc >= (1u << 28)) throw std::runtime_error("vertex " + std::to_string(u) + " has too many s_info entries to render");
+				car[c] = make_uint4(set, (uint32_t)sc | (ins ? 1u << 31 : 0), (uint32_t)sb, (uint32_t)(sb >> 32));     // bit 31: an insertion row (t5 prints ref_pos)
 				uint32_t digits = 1; for (uint64_t q = p; q >= 10; q /= 10) digits++;
 				const uint64_t hdr = digits + 1 + seq[c].y + 1 + seq[c].w + 1 + 1;
 				if (hdr + carb > 0xFFFFFFFFull) throw std::runtime_error("a t4 row is longer than 4 GiB");
@@ -929,6 +931,64 @@ void ensure_hit_tables(vsgpu_index* ix) {
 		ix->hit_tables.len[0][v] = upload(ix, len0); ix->hit_tables.len[1][v] = upload(ix, len1);
 	}
 	ix->hit_tables_ready = true;
+}
+}  // namespace
+
+namespace {
+// Rows of a finished t4 / t5 answer (CSR in boffsets / bhits, on the index's stream) as text into t: row lengths -> text offsets of
+// every row and region, then the rows in chunks whose copies overlap the rendering of the next.  t5_samples: device sample ids (t5 rows).
+void render_hit_rows(vsgpu_index* ix, vsgpu_text* t, uint64_t n, int with_samples, const uint32_t* t5_samples) {
+	cudaStream_t st = ix->stream;
+	uint64_t nh = 0;
+	CU(cudaMemcpyAsync(&nh, ix->boffsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	// row lengths -> text offsets of every row and of every region
+	CU(ix->brow_off.ensure((nh + 1) * 8)); CU(ix->bbyte_off.ensure((n + 1) * 8)); CU(ix->bscratch.ensure(((nh + 1023) / 1024 + 2) * 16));
+	CU(cudaEventRecord(ix->ev_render[0], st));
+	const uint32_t* pos5 = nullptr;
+	if (t5_samples) {                                  // t5: the position column of every row, from the row's sample
+		CU(ix->bpos5.ensure(std::max<uint64_t>(nh, 1) * 4));
+		CU(launch_t5_row_pos(ix->dev, ix->render, ix->hit_tables, ix->d_gsidx, n, ix->boffsets.as<uint64_t>(), t5_samples, ix->bhits.as<uint32_t>(), nh, ix->bpos5.as<uint32_t>(), st));
+		pos5 = ix->bpos5.as<uint32_t>();
+	}
+	CU(launch_hit_offsets(ix->hit_tables, ix->bhits.as<uint32_t>(), nh, with_samples, n, ix->boffsets.as<uint64_t>(), ix->brow_off.as<uint64_t>(), ix->bbyte_off.as<uint64_t>(),
+	                      ix->bscratch.as<uint64_t>(), st, pos5));
+	CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const uint64_t total = t->offsets[n];
+	uint64_t max_bytes = 2ull << 30;
+	if (const char* e = getenv("VSGPU_RENDER_MAX_BYTES")) max_bytes = strtoull(e, nullptr, 10);
+	if (total > max_bytes) throw std::invalid_argument("the rows of this batch take " + std::to_string(total) + " bytes (limit VSGPU_RENDER_MAX_BYTES = " + std::to_string(max_bytes) + "); split the batch");
+	t->nrows = nh; t->nbytes = total;
+	t->bytes = (char*)ix->pinned_acquire(total + 1, &t->bytes_cap);
+	if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+	if (total) {
+		CU(ix->btext.ensure(total));
+		// rows in chunks of about 32 MB of text: the copy of one chunk overlaps the rendering of the next
+		uint64_t chunk_bytes = 32ull << 20;
+		if (const char* e = getenv("VSGPU_RENDER_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+		const int chunks = (int)std::min<uint64_t>(vsgpu_index::kMaxChunks, (total + chunk_bytes - 1) / chunk_bytes);
+		// region boundaries as chunk boundaries (their row / byte offsets are on the host already)
+		std::vector<uint64_t> roff(n + 1);
+		CU(cudaMemcpyAsync(roff.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		uint64_t r0 = 0;
+		for (int c = 0; c < chunks && r0 < n; c++) {
+			uint64_t r1 = n;
+			if (c + 1 < chunks) { const uint64_t target = total / chunks * (c + 1); r1 = std::lower_bound(t->offsets + r0 + 1, t->offsets + n, target) - t->offsets; }
+			if (r1 <= r0) continue;
+			CU(launch_render_hits(ix->dev, ix->render, ix->hit_tables, ix->bhits.as<uint32_t>(), with_samples, ix->brow_off.as<uint64_t>(), roff[r0], roff[r1], ix->btext.as<char>(), st, pos5));
+			CU(cudaEventRecord(ix->ev_k[c], st));
+			CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
+			if (t->offsets[r1] > t->offsets[r0]) CU(cudaMemcpyAsync(t->bytes + t->offsets[r0], ix->btext.as<char>() + t->offsets[r0], t->offsets[r1] - t->offsets[r0], cudaMemcpyDeviceToHost, ix->s_out));
+			r0 = r1;
+		}
+		CU(cudaEventRecord(ix->ev_render[1], st));
+		CU(cudaStreamSynchronize(ix->s_out));
+		CU(cudaStreamSynchronize(st));
+	} else { CU(cudaEventRecord(ix->ev_render[1], st)); CU(cudaStreamSynchronize(st)); }
+	t->bytes[total] = 0;
+	CU(cudaEventElapsedTime(&t->kernel_ms, ix->ev_render[0], ix->ev_render[1]));
 }
 }  // namespace
 
@@ -957,50 +1017,7 @@ int vsgpu_render_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64
 		run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, ix->d_status, wide);
 		const uint32_t status = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, wide);
 		if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
-		uint64_t nh = 0;
-		CU(cudaMemcpyAsync(&nh, ix->boffsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-		// row lengths -> text offsets of every row and of every region
-		CU(ix->brow_off.ensure((nh + 1) * 8)); CU(ix->bbyte_off.ensure((n + 1) * 8)); CU(ix->bscratch.ensure(((nh + 1023) / 1024 + 2) * 16));
-		CU(cudaEventRecord(ix->ev_render[0], st));
-		CU(launch_hit_offsets(ix->hit_tables, ix->bhits.as<uint32_t>(), nh, with_samples, n, ix->boffsets.as<uint64_t>(), ix->brow_off.as<uint64_t>(), ix->bbyte_off.as<uint64_t>(),
-		                      ix->bscratch.as<uint64_t>(), st));
-		CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-		const uint64_t total = t->offsets[n];
-		uint64_t max_bytes = 2ull << 30;
-		if (const char* e = getenv("VSGPU_RENDER_MAX_BYTES")) max_bytes = strtoull(e, nullptr, 10);
-		if (total > max_bytes) return set_err(VSGPU_ESHAPE, "vsgpu_render_t4: the rows of this batch take " + std::to_string(total) + " bytes (limit VSGPU_RENDER_MAX_BYTES = " + std::to_string(max_bytes) + "); split the batch");
-		t->nrows = nh; t->nbytes = total;
-		t->bytes = (char*)ix->pinned_acquire(total + 1, &t->bytes_cap);
-		if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
-		if (total) {
-			CU(ix->btext.ensure(total));
-			// rows in chunks of about 32 MB of text: the copy of one chunk overlaps the rendering of the next
-			uint64_t chunk_bytes = 32ull << 20;
-			if (const char* e = getenv("VSGPU_RENDER_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
-			const int chunks = (int)std::min<uint64_t>(vsgpu_index::kMaxChunks, (total + chunk_bytes - 1) / chunk_bytes);
-			// region boundaries as chunk boundaries (their row / byte offsets are on the host already)
-			std::vector<uint64_t> roff(n + 1);
-			CU(cudaMemcpyAsync(roff.data(), ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-			CU(cudaStreamSynchronize(st));
-			uint64_t r0 = 0;
-			for (int c = 0; c < chunks && r0 < n; c++) {
-				uint64_t r1 = n;
-				if (c + 1 < chunks) { const uint64_t target = total / chunks * (c + 1); r1 = std::lower_bound(t->offsets + r0 + 1, t->offsets + n, target) - t->offsets; }
-				if (r1 <= r0) continue;
-				CU(launch_render_hits(ix->dev, ix->render, ix->hit_tables, ix->bhits.as<uint32_t>(), with_samples, ix->brow_off.as<uint64_t>(), roff[r0], roff[r1], ix->btext.as<char>(), st));
-				CU(cudaEventRecord(ix->ev_k[c], st));
-				CU(cudaStreamWaitEvent(ix->s_out, ix->ev_k[c], 0));
-				if (t->offsets[r1] > t->offsets[r0]) CU(cudaMemcpyAsync(t->bytes + t->offsets[r0], ix->btext.as<char>() + t->offsets[r0], t->offsets[r1] - t->offsets[r0], cudaMemcpyDeviceToHost, ix->s_out));
-				r0 = r1;
-			}
-			CU(cudaEventRecord(ix->ev_render[1], st));
-			CU(cudaStreamSynchronize(ix->s_out));
-			CU(cudaStreamSynchronize(st));
-		} else { CU(cudaEventRecord(ix->ev_render[1], st)); CU(cudaStreamSynchronize(st)); }
-		t->bytes[total] = 0;
-		CU(cudaEventElapsedTime(&t->kernel_ms, ix->ev_render[0], ix->ev_render[1]));
+		render_hit_rows(ix, t.get(), n, with_samples, nullptr);
 		*out = t.release();
 	} catch (const std::invalid_argument& e) { return set_err(VSGPU_ESHAPE, e.what());
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
@@ -1239,6 +1256,33 @@ int query_seq_impl(vsgpu_index* ix, bool t3, uint64_t n, const uint64_t* x, cons
 }
 }  // namespace
 // ------------------------------------------------------------------ t5: get_sample_var_in_sample
+namespace {
+// t5 of a batch on stream st: inputs up, count, scan, write.  Leaves the CSR in boffsets / bhits, the per-region status in
+// bst8, the sample ids in bs; returns the number of hit codes; *bad = a sample id was out of range.
+uint64_t t5_on_device(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, cudaStream_t st, bool* bad) {
+	const uint64_t nctas = (n + 255) / 256;
+	*bad = false;
+	CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
+	CU(ix->bcnt.ensure(n * 4)); CU(ix->bst8.ensure(n)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->boffsets.ensure((n + 1) * 8));
+	CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(ix->ev_t2[0], st));
+	CU(launch_t5_count(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bst8.as<uint8_t>(),
+	                   ix->bscratch.as<uint64_t>(), ix->d_status, st));
+	CU(cudaEventRecord(ix->ev_t2[1], st));
+	CU(cudaMemcpyAsync(ix->pin_small, ix->bscratch.as<uint64_t>() + 2 * nctas, 8, cudaMemcpyDeviceToHost, st));
+	const uint32_t status = read_status(ix, ix->d_status, nullptr, st);
+	if (status & kStatusBadRegion) { *bad = true; return 0; }
+	const uint64_t total = ix->pin_small[0];
+	CU(ix->bhits.ensure(std::max<uint64_t>(total, 1) * 4));
+	CU(cudaEventRecord(ix->ev_t2[2], st));
+	CU(launch_t5_write(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bscratch.as<uint64_t>(),
+	                   ix->boffsets.as<uint64_t>(), ix->bhits.as<uint32_t>(), st));
+	CU(cudaEventRecord(ix->ev_t2[3], st));
+	return total;
+}
+}  // namespace
 int vsgpu_query_t5(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, vsgpu_result** out) {
 	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_query_t5: null argument");
 	*out = nullptr;
@@ -1254,27 +1298,11 @@ int vsgpu_query_t5(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		if (!r->offsets || !r->status) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
 		r->offsets[0] = 0;
 		if (n) {
-			const uint64_t nctas = (n + 255) / 256;
-			CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
-			CU(ix->bcnt.ensure(n * 4)); CU(ix->bst8.ensure(n)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->boffsets.ensure((n + 1) * 8));
-			CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
-			CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
-			CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
-			CU(cudaEventRecord(ix->ev_t2[0], st));
-			CU(launch_t5_count(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bst8.as<uint8_t>(),
-			                   ix->bscratch.as<uint64_t>(), ix->d_status, st));
-			CU(cudaEventRecord(ix->ev_t2[1], st));
-			CU(cudaMemcpyAsync(ix->pin_small, ix->bscratch.as<uint64_t>() + 2 * nctas, 8, cudaMemcpyDeviceToHost, st));
-			const uint32_t status = read_status(ix, ix->d_status, nullptr, st);
-			if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "vsgpu_query_t5: sample id out of range");
-			const uint64_t total = ix->pin_small[0];
-			CU(ix->bhits.ensure(std::max<uint64_t>(total, 1) * 4));
+			bool bad = false;
+			const uint64_t total = t5_on_device(ix, n, x, y, sample_ids, st, &bad);
+			if (bad) return set_err(VSGPU_EINVAL, "vsgpu_query_t5: sample id out of range");
 			r->hits = (uint32_t*)ix->pinned_acquire(std::max<uint64_t>(total, 1) * 4, &r->hits_cap);
 			if (!r->hits) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
-			CU(cudaEventRecord(ix->ev_t2[2], st));
-			CU(launch_t5_write(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bscratch.as<uint64_t>(),
-			                   ix->boffsets.as<uint64_t>(), ix->bhits.as<uint32_t>(), st));
-			CU(cudaEventRecord(ix->ev_t2[3], st));
 			CU(cudaMemcpyAsync(r->offsets, ix->boffsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
 			CU(cudaMemcpyAsync(r->status, ix->bst8.p, n, cudaMemcpyDeviceToHost, st));
 			if (total) CU(cudaMemcpyAsync(r->hits, ix->bhits.p, total * 4, cudaMemcpyDeviceToHost, st));
@@ -1286,6 +1314,38 @@ int vsgpu_query_t5(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_
 		}
 		r->have_offsets = true;
 		*out = r.release();
+	} catch (const std::invalid_argument& e) { return set_err(VSGPU_ESHAPE, e.what());
+	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
+	return VSGPU_OK;
+}
+// get_sample_var_in_sample(vg, idx, x, y, sample, print = true, outfile) for a batch: t5 on the device, then its rows as text
+// (vsgpu_rows_t5's, written by the kernels of vsgpu_render_t4 with the position column taken from the sample's own coordinate)
+int vsgpu_render_t5(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample_ids, int with_samples, vsgpu_text** out) {
+	if (!ix || !out || (n && (!x || !y || !sample_ids))) return set_err(VSGPU_EINVAL, "vsgpu_render_t5: null argument");
+	*out = nullptr;
+	if (int rc = check_device(ix)) return rc;
+	std::lock_guard<std::mutex> g(ix->mu);
+	std::unique_ptr<vsgpu_text, void (*)(vsgpu_text*)> t(new vsgpu_text, vsgpu_text_free);
+	t->owner = ix; t->n = n;
+	try {
+		ensure_t3_tables(ix);
+		ensure_hit_tables(ix);
+		if (!ix->d_gsidx) ix->d_gsidx = upload(ix, ix->sindex);
+		cudaStream_t st = ix->stream;
+		t->offsets = (uint64_t*)ix->pinned_acquire((n + 1) * 8, &t->offsets_cap);
+		t->status = (uint8_t*)ix->pinned_acquire(n + 1, &t->status_cap);
+		if (!t->offsets || !t->status) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+		t->offsets[0] = 0;
+		if (n == 0) { t->bytes = (char*)ix->pinned_acquire(1, &t->bytes_cap); if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory"); t->bytes[0] = 0; *out = t.release(); return VSGPU_OK; }
+		bool bad = false;
+		t5_on_device(ix, n, x, y, sample_ids, st, &bad);
+		if (bad) return set_err(VSGPU_EINVAL, "vsgpu_render_t5: sample id out of range");
+		CU(cudaMemcpyAsync(t->status, ix->bst8.p, n, cudaMemcpyDeviceToHost, st));
+		render_hit_rows(ix, t.get(), n, with_samples, ix->bs.as<uint32_t>());
+		float a = 0, b = 0;
+		CU(cudaEventElapsedTime(&a, ix->ev_t2[0], ix->ev_t2[1])); CU(cudaEventElapsedTime(&b, ix->ev_t2[2], ix->ev_t2[3]));
+		t->stage_ms[0] = a; t->stage_ms[1] = b; t->stage_ms[2] = t->kernel_ms;          // count, write, rows
+		*out = t.release();
 	} catch (const std::invalid_argument& e) { return set_err(VSGPU_ESHAPE, e.what());
 	} catch (const std::exception& e) { cudaDeviceSynchronize(); return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
