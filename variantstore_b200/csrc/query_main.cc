@@ -179,12 +179,14 @@ int main(int argc, char** argv) {
 		vsgpu_result* res = nullptr;
 		rc = vsgpu_query_t4(idx, n, x.data(), y.data(), s.data(), &res);
 		if (rc == 0) {
-			const uint64_t* off = vsgpu_result_offsets(res); const uint32_t* hits = vsgpu_result_hits(res);
-			for (uint64_t i = 0; i < n; i++) {
-				printf("Number of variants get_sample_var_in_ref: %lu\n", (unsigned long)(off[i + 1] - off[i]));
-				if (verbose) { char* text = nullptr; if (vsgpu_rows_t4(idx, hits + off[i], off[i + 1] - off[i], 1, &text) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
-			}
+			const uint64_t* off = vsgpu_result_offsets(res);
+			for (uint64_t i = 0; i < n; i++) printf("Number of variants get_sample_var_in_ref: %lu\n", (unsigned long)(off[i + 1] - off[i]));
 			vsgpu_result_free(res);
+			if (verbose && n) {                                    // as for type 6: -o ends up holding the last region's rows (query.h:719-726)
+				vsgpu_text* text = nullptr;
+				rc = vsgpu_render_t4(idx, 1, &x[n - 1], &y[n - 1], &sid, 1, &text);
+				if (rc == 0) { write_rows(outfile, vsgpu_text_bytes(text), true); vsgpu_text_free(text); }
+			}
 		}
 	} else if (type == 1) {
 		// closest_var prints nothing; with -v every call that finds a variant rewrites -o (query.h:472-479)
@@ -202,13 +204,17 @@ int main(int argc, char** argv) {
 		vsgpu_result* res = nullptr;
 		rc = vsgpu_query_t5(idx, n, x.data(), y.data(), s.data(), &res);
 		if (rc == 0) {
-			const uint64_t* off = vsgpu_result_offsets(res); const uint32_t* hits = vsgpu_result_hits(res); const uint8_t* st = vsgpu_result_status(res);
+			const uint64_t* off = vsgpu_result_offsets(res); const uint8_t* st = vsgpu_result_status(res);
 			for (uint64_t i = 0; i < n; i++) {
 				if (st[i] == 2) { fprintf(stderr, "region %lu:%lu: the reference never returns from get_sample_var_in_sample (query.h:505-510)\n", (unsigned long)x[i], (unsigned long)y[i]); vsgpu_result_free(res); vsgpu_close(idx); return 3; }
 				printf("Number of variants get_sample_var_in_sample: %lu\n", (unsigned long)(off[i + 1] - off[i]));
-				if (verbose) { char* text = nullptr; if (vsgpu_rows_t5(idx, hits + off[i], off[i + 1] - off[i], sid, 1, &text) == 0) { write_rows(outfile, text, true); vsgpu_free(text); } }
 			}
 			vsgpu_result_free(res);
+			if (verbose && n) {                                    // -o ends up holding the last region's rows (query.h:596-606)
+				vsgpu_text* text = nullptr;
+				rc = vsgpu_render_t5(idx, 1, &x[n - 1], &y[n - 1], &sid, 1, &text);
+				if (rc == 0) { write_rows(outfile, vsgpu_text_bytes(text), true); vsgpu_text_free(text); }
+			}
 		}
 	} else if (type == 2 || type == 3) {
 		// query_sample_from_ref / query_sample_from_sample print nothing; with -v every call rewrites -o with "<sequence>\n"
