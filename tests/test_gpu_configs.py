@@ -57,6 +57,15 @@ def test_width_sweep_cuda(tmp_path, monkeypatch, wide_entries):
             s = rng.integers(1, 301, n).astype(np.uint32)
             bad6, bad4, _ = T.compare_all(o, e, x, y, s)
             assert not bad6 and not bad4, width
+            # the device-resident fused batch gives the separate calls' answers at every width (few, wide regions: two launches)
+            from variantstore_b200 import Batch
+            lo, hi, cnt = e.batch_var_in_ref(x, y)
+            off, hits = e.batch_sample_var_in_ref(x, y, s)
+            b = Batch(e, 46, x, y, sample_ids=s)
+            b.run()
+            flo, fhi, fcnt, foff, fhits = b.fetch()
+            b.close()
+            assert np.array_equal(flo, lo) and np.array_equal(fhi, hi) and np.array_equal(fcnt, cnt) and np.array_equal(foff, off) and np.array_equal(fhits, hits), width
         # whole contig and beyond
         x = np.array([1, 1, 2_999_000], np.uint64)
         y = np.array([3_000_001, 10_000_000, 3_100_000], np.uint64)

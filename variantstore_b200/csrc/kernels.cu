@@ -814,20 +814,21 @@ __global__ void __launch_bounds__(256) k_t2_plan(const DevIndex ix, const T2Tabl
 	if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = cta_sums[2 * nctas + 1];
 }
 // ------------------------------------------------------------------ t5: get_sample_var_in_sample (query.h:490-612)
-// count: one thread per region walks (logic::t5_walk) and counts its rows; write: offsets from the scan
-// of the counts, then the same walk writes the hit codes at their final place (region order = the
-// reference's push order).
-struct T5CountSink { uint32_t n; __device__ __forceinline__ void emit(uint32_t) { n++; } };
+// count: one thread per region walks (logic::t5_walk), counts its rows and keeps the first kT5Keep hit codes; write: offsets
+// from the scan of the counts, then the kept codes are copied to their final place (region order = the reference's push
+// order) — only a region with more rows than were kept walks a second time.
+constexpr uint32_t kT5Keep = 8;
+struct T5CountSink { uint32_t n; uint32_t* keep; __device__ __forceinline__ void emit(uint32_t code) { if (n < kT5Keep) keep[n] = code; n++; } };
 __global__ void __launch_bounds__(256) k_t5_count(const DevIndex ix, const T2Tables t2, const T3Tables t3, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
                                                   const uint32_t* __restrict__ sample, uint32_t* __restrict__ cnt, uint8_t* __restrict__ status,
-                                                  uint64_t* __restrict__ cta_sums, uint32_t* gstatus) {
+                                                  uint64_t* __restrict__ cta_sums, uint32_t* gstatus, uint32_t* __restrict__ keep) {
 	__shared__ SegCount s_warp[8];
 	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	SegCount mine{0, 0};
 	if (i < n) {
 		const uint32_t s = sample[i];
 		uint32_t st = 0;
-		T5CountSink sink{0};
+		T5CountSink sink{0, keep + i * kT5Keep};
 		if (s == 0 || s >= ix.num_samples) atomicOr(gstatus, kStatusBadRegion);
 		else st = t5_walk(ix, t2, t3, xs[i], ys[i], s, sink);
 		if (st) sink.n = 0;
@@ -840,7 +841,7 @@ __global__ void __launch_bounds__(256) k_t5_count(const DevIndex ix, const T2Tab
 }
 __global__ void __launch_bounds__(256) k_t5_write(const DevIndex ix, const T2Tables t2, const T3Tables t3, uint64_t n, const uint64_t* __restrict__ xs, const uint64_t* __restrict__ ys,
                                                   const uint32_t* __restrict__ sample, const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ cta_sums,
-                                                  uint64_t nctas, uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits) {
+                                                  uint64_t nctas, uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, const uint32_t* __restrict__ keep) {
 	__shared__ SegCount s_warp[8];
 	const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	SegCount mine{0, 0};
@@ -850,7 +851,8 @@ __global__ void __launch_bounds__(256) k_t5_write(const DevIndex ix, const T2Tab
 	ex.rows += cta_sums[2 * (uint64_t)blockIdx.x];
 	if (i < n) {
 		offsets[i] = ex.rows;
-		if (mine.rows) { DirectSink sink{hits + ex.rows, 0}; t5_walk(ix, t2, t3, xs[i], ys[i], sample[i], sink); }
+		if (mine.rows > kT5Keep) { DirectSink sink{hits + ex.rows, 0}; t5_walk(ix, t2, t3, xs[i], ys[i], sample[i], sink); }
+		else for (uint32_t j = 0; j < (uint32_t)mine.rows; j++) hits[ex.rows + j] = keep[i * kT5Keep + j];
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = cta_sums[2 * nctas];
 }
@@ -1058,19 +1060,20 @@ cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const
 	k_t7<<<grid_for(n, 256, 8), 256, 0, stream>>>(ix, n, pos, qhash, rec, status);
 	return cudaGetLastError();
 }
+uint64_t t5_keep_words(uint64_t n) { return n * kT5Keep; }
 cudaError_t launch_t5_count(const DevIndex& ix, const T2Tables& t2, const T3Tables& t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                            uint32_t* cnt, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream) {
+                            uint32_t* cnt, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, uint32_t* keep, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	const uint64_t nctas = (n + 255) / 256;
-	k_t5_count<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, t3, n, x, y, sample, cnt, status, cta_sums, gstatus);
+	k_t5_count<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, t3, n, x, y, sample, cnt, status, cta_sums, gstatus, keep);
 	k_seg_bases<<<1, 256, 0, stream>>>(nctas, cta_sums);
 	return cudaGetLastError();
 }
 cudaError_t launch_t5_write(const DevIndex& ix, const T2Tables& t2, const T3Tables& t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                            const uint32_t* cnt, const uint64_t* cta_sums, uint64_t* offsets, uint32_t* hits, cudaStream_t stream) {
+                            const uint32_t* cnt, const uint64_t* cta_sums, uint64_t* offsets, uint32_t* hits, const uint32_t* keep, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	const uint64_t nctas = (n + 255) / 256;
-	k_t5_write<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, t3, n, x, y, sample, cnt, cta_sums, nctas, offsets, hits);
+	k_t5_write<<<(uint32_t)nctas, 256, 0, stream>>>(ix, t2, t3, n, x, y, sample, cnt, cta_sums, nctas, offsets, hits, keep);
 	return cudaGetLastError();
 }
 uint64_t t2_ctas(uint64_t n) { return (n + 255) / 256; }

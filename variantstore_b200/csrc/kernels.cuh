@@ -128,10 +128,12 @@ cudaError_t launch_t2_copy(const T2Tables& t2, const uint4* recs, const uint32_t
 
 // t5 = get_sample_var_in_sample (query.h:490-612): count (+ scan of the CTA sums, as t2), then write.  cnt[n], status[n];
 // offsets[n+1]; hits sized from the total in cta_sums[2 * ceil(n / 256)].
+// keep: 8 hit codes of room per region (t5_keep_words(n) 32-bit words), filled by the count launch and read by the write launch
+uint64_t t5_keep_words(uint64_t n);
 cudaError_t launch_t5_count(const DevIndex& ix, const T2Tables& t2, const T3Tables& t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                            uint32_t* cnt, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, cudaStream_t stream);
+                            uint32_t* cnt, uint8_t* status, uint64_t* cta_sums, uint32_t* gstatus, uint32_t* keep, cudaStream_t stream);
 cudaError_t launch_t5_write(const DevIndex& ix, const T2Tables& t2, const T3Tables& t3, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
-                            const uint32_t* cnt, const uint64_t* cta_sums, uint64_t* offsets, uint32_t* hits, cudaStream_t stream);
+                            const uint32_t* cnt, const uint64_t* cta_sums, uint64_t* offsets, uint32_t* hits, const uint32_t* keep, cudaStream_t stream);
 
 // Segment s of a render call = records [seg_lo[s], seg_hi[s]) ((NONE, NONE) = empty).  Three small
 // launches turn the per-segment row and byte counts into exclusive offsets: row_off / byte_off get

@@ -1263,13 +1263,13 @@ uint64_t t5_on_device(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint
 	const uint64_t nctas = (n + 255) / 256;
 	*bad = false;
 	CU(ix->bx.ensure(n * 8)); CU(ix->by.ensure(n * 8)); CU(ix->bs.ensure(n * 4));
-	CU(ix->bcnt.ensure(n * 4)); CU(ix->bst8.ensure(n)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->boffsets.ensure((n + 1) * 8));
+	CU(ix->bcnt.ensure(n * 4)); CU(ix->bst8.ensure(n)); CU(ix->bscratch.ensure((nctas + 1) * 16)); CU(ix->boffsets.ensure((n + 1) * 8)); CU(ix->bkeep.ensure(t5_keep_words(n) * 4));
 	CU(cudaMemcpyAsync(ix->bx.p, x, n * 8, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(ix->by.p, y, n * 8, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(ix->bs.p, sample_ids, n * 4, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(ix->ev_t2[0], st));
 	CU(launch_t5_count(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bst8.as<uint8_t>(),
-	                   ix->bscratch.as<uint64_t>(), ix->d_status, st));
+	                   ix->bscratch.as<uint64_t>(), ix->d_status, ix->bkeep.as<uint32_t>(), st));
 	CU(cudaEventRecord(ix->ev_t2[1], st));
 	CU(cudaMemcpyAsync(ix->pin_small, ix->bscratch.as<uint64_t>() + 2 * nctas, 8, cudaMemcpyDeviceToHost, st));
 	const uint32_t status = read_status(ix, ix->d_status, nullptr, st);
@@ -1278,7 +1278,7 @@ uint64_t t5_on_device(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint
 	CU(ix->bhits.ensure(std::max<uint64_t>(total, 1) * 4));
 	CU(cudaEventRecord(ix->ev_t2[2], st));
 	CU(launch_t5_write(ix->dev, ix->t2, ix->t3, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->bcnt.as<uint32_t>(), ix->bscratch.as<uint64_t>(),
-	                   ix->boffsets.as<uint64_t>(), ix->bhits.as<uint32_t>(), st));
+	                   ix->boffsets.as<uint64_t>(), ix->bhits.as<uint32_t>(), ix->bkeep.as<uint32_t>(), st));
 	CU(cudaEventRecord(ix->ev_t2[3], st));
 	return total;
 }
@@ -1395,8 +1395,7 @@ int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x,
 		if (type == 6) { CU(b->out.ensure(n * 12)); if (t6_special(ix)) CU(b->flag.ensure(n * 4)); }
 		if (type == 4 || type == 46) { b->wide_regions = expect_wide_regions(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 12)); }
 		if (type == 46) {
-			if (!t4x_supported(b->wide_regions)) return set_err(VSGPU_EINVAL, "vsgpu_batch_create: a fused t6 + t4 batch needs the pipelined t4 kernel and regions that are not a few, wide ones");
-			if (t6_special(ix)) CU(b->flag.ensure(n * 4));
+			if (t6_special(ix)) CU(b->flag.ensure(n * 4));           // (a batch of few, wide regions runs k_t6 and the warp-per-region t4 kernel: two launches)
 		}
 		if (type == 7) {
 			std::vector<uint64_t> qh(n);
@@ -1419,6 +1418,16 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 		for (auto& e : b->ev) if (!e) CU(cudaEventCreate(&e));
 		if (b->type == 6) { CU(cudaMemsetAsync(b->d_status, 0, 8, ix->stream)); CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t6(ix->dev, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->out.as<uint32_t>(), b->out.as<uint32_t>() + b->n, b->out.as<uint32_t>() + 2 * b->n, b->flag.as<uint32_t>(), 0, b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
 		else if (b->type == 7) { CU(cudaEventRecord(b->ev[0], ix->stream)); CU(launch_t7(ix->dev, b->n, b->x.as<uint64_t>(), b->hash.as<uint64_t>(), b->rec.as<uint32_t>(), b->d_status, ix->stream)); CU(cudaEventRecord(b->ev[1], ix->stream)); b->launches = 1; }
+		else if (b->type == 46 && !t4x_supported(b->wide_regions)) {
+			const uint64_t n = b->n;
+			uint32_t* o = b->out.as<uint32_t>();
+			CU(cudaMemsetAsync(b->d_status, 0, 8, ix->stream));
+			CU(cudaEventRecord(b->ev[0], ix->stream));
+			CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), o, o + n, o + 2 * n, b->flag.as<uint32_t>(), 0, b->d_status, ix->stream));
+			run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, b->wide_regions);
+			CU(cudaEventRecord(b->ev[1], ix->stream));
+			b->launches = 2;
+		}
 		else if (b->type == 46) {
 			// t6 + t4 from one launch of k_t4p<kFuse6>: the t6 slice comes from the two ranks of the t4 setup
 			const uint64_t n = b->n;
@@ -1475,7 +1484,7 @@ int vsgpu_batch_fetch(vsgpu_batch* b, uint32_t* rec_lo, uint32_t* rec_hi, uint32
 			if (total > b->hits_cap) {                           // the hit buffer was a guess: exact size, t4 alone again
 				b->hits_cap = total + total / 16 + 1024;
 				CU(b->hits.ensure(b->hits_cap * 4));
-				run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, false);
+				run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, b->wide_regions);
 				read_status(ix, b->d_status);
 			}
 			vsgpu_result* r = fetch_t4(ix, n, b->offsets, b->hits, out != nullptr);
