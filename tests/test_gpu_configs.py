@@ -63,6 +63,7 @@ def test_width_sweep_cuda(tmp_path, monkeypatch, wide_entries):
             off, hits = e.batch_sample_var_in_ref(x, y, s)
             b = Batch(e, 46, x, y, sample_ids=s)
             b.run()
+            assert all(t > 0 for t in b.timings_ms())
             flo, fhi, fcnt, foff, fhits = b.fetch()
             b.close()
             assert np.array_equal(flo, lo) and np.array_equal(fhi, hi) and np.array_equal(fcnt, cnt) and np.array_equal(foff, off) and np.array_equal(fhits, hits), width

@@ -1424,8 +1424,9 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 			CU(cudaMemsetAsync(b->d_status, 0, 8, ix->stream));
 			CU(cudaEventRecord(b->ev[0], ix->stream));
 			CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), o, o + n, o + 2 * n, b->flag.as<uint32_t>(), 0, b->d_status, ix->stream));
-			run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, b->wide_regions);
 			CU(cudaEventRecord(b->ev[1], ix->stream));
+			run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, b->wide_regions);
+			CU(cudaEventRecord(b->ev[2], ix->stream));
 			b->launches = 2;
 		}
 		else if (b->type == 46) {
