@@ -32,6 +32,7 @@ def timed(batch, steps=10, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="tcga,width")
+    ap.add_argument("--widths", default="", help="comma list: only these widths of the sweep (and no t7 line)")
     ap.add_argument("--tcga-records", type=int, default=3_000_000)
     ap.add_argument("--tcga-samples", type=int, default=10_000)
     ap.add_argument("--lookups", type=int, default=10_000_000)
@@ -110,7 +111,10 @@ def main():
         idx = VariantStoreIndex(prefix, device=0)
         idx.set_stream(torch.cuda.current_stream().cuda_stream)
         rng = np.random.default_rng(6)
+        only = [int(w) for w in args.widths.split(",") if w]
         for width, n in [(100, 1_000_000), (1000, 1_000_000), (10_000, 1_000_000), (100_000, 200_000), (1_000_000, 50_000), (10_000_000, 10_000)]:
+            if only and width not in only:
+                continue
             x = np.sort(rng.integers(meta["pos_lo"], meta["ref_length"] - min(width, 30_000_000), n)).astype(np.uint64)
             y = x + np.uint64(width)
             s = rng.integers(1, 2505, n).astype(np.uint32)
@@ -129,6 +133,9 @@ def main():
                               "t6_rows_per_region": float(c6.mean()), "t4_rows_per_region": float(cnt.mean()),
                               "t4_rows_per_s": float(cnt.sum()) / (ms4 / 1000), "t4_algorithmic_GBps": algo4 / (ms4 / 1000) / 1e9}), flush=True)
             b6.close(); b4.close()
+        if only:
+            idx.close()
+            return
         # t7 on the same index (the sweep's third operator has no width): 1 M lookups, half of them misses
         o = T.Oracle.open(prefix)
         av = o.all_variants()

@@ -1122,12 +1122,12 @@ bool t4x_supported(bool wide_regions) {
 	return !pe || atoi(pe) != 0;
 }
 namespace {
-template <uint32_t kTile, uint32_t kMinCtas>
+template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep = kScratchHits>
 cudaError_t launch_t4p_cfg(const DevIndex& ix, const T4Launch& a, cudaStream_t stream) {
 	const uint32_t tiles = (uint32_t)((a.n + kTile - 1) / kTile);
 	const uint32_t grid = min(tiles, grid_for((uint64_t)tiles * kTile, kTile, kMinCtas));
 	const T6Out t6 = a.fuse6 ? *a.fuse6 : T6Out{nullptr, nullptr, nullptr, nullptr, 0};
-#define VSGPU_T4P(K32, F6) k_t4p<kTile, kMinCtas, kScratchHits, K32, F6><<<grid, kTile, 0, stream>>>(ix, a.n, a.x, a.y, a.sample, a.offsets, a.counts, a.hits, a.cap, a.tile_state, a.status, a.base_ptr, t6)
+#define VSGPU_T4P(K32, F6) k_t4p<kTile, kMinCtas, kKeep, K32, F6><<<grid, kTile, 0, stream>>>(ix, a.n, a.x, a.y, a.sample, a.offsets, a.counts, a.hits, a.cap, a.tile_state, a.status, a.base_ptr, t6)
 	if (a.coords32) { if (a.fuse6) VSGPU_T4P(true, true); else VSGPU_T4P(true, false); }
 	else { if (a.fuse6) VSGPU_T4P(false, true); else VSGPU_T4P(false, false); }
 #undef VSGPU_T4P
