@@ -114,7 +114,7 @@ class ClockSampler(threading.Thread):
                     for name, bit in self.REASONS.items():
                         if r & bit:
                             self.reasons.add(name)
-                    time.sleep(0.002)
+                    time.sleep(0.0005)
                 else:
                     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
                     out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
@@ -445,7 +445,7 @@ def run_vsgpu(args):
     barrier()
     step_ms, kms = timed(step, [b46] if b46 is not None else [b6, b4], args.steps)
     barrier()
-    sampler.stop_flag = True
+    # (the clock sampler keeps running through the by-kernel and end-to-end loops below: they are measured regions too)
     # the unfused kernels on their own, for by_kernel (not part of `value` unless --unfused)
     _, (t6_ms,) = timed(b6.run, [b6], max(3, args.steps // 2))
     _, (t4_ms,) = timed(b4.run, [b4], max(3, args.steps // 2))
@@ -495,6 +495,7 @@ def run_vsgpu(args):
         hits_total = e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.stop_flag = True
     if dist is not None:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
