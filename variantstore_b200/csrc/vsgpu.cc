@@ -131,7 +131,8 @@ struct vsgpu_index : vsgpu::HostIndex {
 		size_t best = SIZE_MAX;
 		for (size_t i = 0; i < pinned_free.size(); i++) if (pinned_free[i].second >= bytes && (best == SIZE_MAX || pinned_free[i].second < pinned_free[best].second)) best = i;
 		if (best != SIZE_MAX) { auto b = pinned_free[best]; pinned_free.erase(pinned_free.begin() + best); *cap = b.second; return b.first; }
-		size_t want = 4096; while (want < bytes) want <<= 1;
+		size_t want = 4096; while (want < bytes && want < (64u << 20)) want <<= 1;      // powers of two up to 64 MB, then 64 MB steps
+		if (want < bytes) want = (bytes + (64u << 20) - 1) / (64u << 20) * (64u << 20);
 		void* p = nullptr;
 		if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
 		*cap = want; return p;
