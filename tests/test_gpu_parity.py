@@ -29,13 +29,14 @@ def _t7_check(o, e, limit=None):
     return int(hit.sum()), len(pos)
 
 
-@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "tile-256", "chunked-calls", "carried-entry-lists", "hitmap-32bit-words"])
+@pytest.fixture(params=["hitmap", "class-bitmaps", "warp-cooperative", "cta-per-tile", "tile-256", "chunked-calls", "carried-entry-lists", "hitmap-32bit-words", "spill", "spill-scratch-full"])
 def walk_path(request, monkeypatch):
     """The t4 kernel paths: the sample-major hit map with one thread per region (default), the
     per-entry class-bitmap test used when the map does not fit the memory budget, and the
     warp-cooperative scan for wide regions (forced onto every region longer than 8 walk entries);
     plus the non-persistent variant of the per-thread kernel, and host-buffer calls cut into chunks
-    of 256 regions (copies of one chunk overlapping the kernels of the next; offsets chained)."""
+    of 256 regions (copies of one chunk overlapping the kernels of the next; offsets chained); and the
+    spilling instance of k_t4p (rows beyond the staged 8 go to a scratch), with ample and with too little scratch."""
     monkeypatch.delenv("VSGPU_CHUNK_REGIONS", raising=False)
     if request.param == "chunked-calls":
         monkeypatch.setenv("VSGPU_CHUNK_REGIONS", "128")
@@ -44,10 +45,16 @@ def walk_path(request, monkeypatch):
     monkeypatch.delenv("VSGPU_T4_PIPE", raising=False)
     monkeypatch.delenv("VSGPU_T4_TILE", raising=False)
     monkeypatch.delenv("VSGPU_T4_ROW64", raising=False)
+    monkeypatch.delenv("VSGPU_T4_SPILL", raising=False)
+    monkeypatch.delenv("VSGPU_T4_SPILL_WORDS", raising=False)
+    if request.param.startswith("spill"):
+        monkeypatch.setenv("VSGPU_T4_SPILL", "1")             # k_t4p's spilling instance for every batch (default: only where many rows per region are expected)
+        if request.param == "spill-scratch-full":
+            monkeypatch.setenv("VSGPU_T4_SPILL_WORDS", "64")  # 8 chunks per CTA and tile: most threads run out of scratch and take the second walk
     monkeypatch.delenv("VSGPU_SPARSE_WALK", raising=False)   # default: per-sample carried-entry lists for explicit-id cohorts, the hit map otherwise
     if request.param == "carried-entry-lists":
         monkeypatch.setenv("VSGPU_SPARSE_WALK", "1")          # the lists for every cohort
-    elif request.param != "hitmap":
+    elif request.param not in ("hitmap", "spill", "spill-scratch-full"):
         monkeypatch.setenv("VSGPU_SPARSE_WALK", "0")          # never: the explicit-id cases take the named path too
     if request.param == "hitmap-32bit-words":
         monkeypatch.setenv("VSGPU_T4_ROW64", "0")             # walk_region_fast (32 entries per step) instead of the 64-entry chunks

@@ -14,6 +14,7 @@
 //       per vsgpu_open.
 // Integer-only; nothing here is a contraction, so no tensor-core path exists.
 #include <cstdlib>
+#include <type_traits>
 
 #include "device_logic.cuh"
 
@@ -78,6 +79,31 @@ template <uint32_t kTile, uint32_t kKeep>
 struct SmemSink {            // first kKeep codes of this thread, strided so lanes hit distinct banks
 	uint32_t* slot; uint32_t n;
 	__device__ __forceinline__ void emit(uint32_t code) { if (n < kKeep) slot[n * kTile] = code; n++; }
+};
+
+// The same, for batches whose regions have more rows than the staging holds: codes beyond the first kKeep go to this CTA's
+// scratch in global memory, in chunks of 7 codes + the offset of the next chunk (32 bytes, one sector), handed out by a
+// shared-memory cursor.  After the look-back the thread copies its chain into place instead of walking the region again.
+// A thread that finds the scratch full stops spilling and takes the second walk.  (Chunks that double in size, so that the
+// copy follows fewer links, were slower: they fill the scratch sooner — profiles/r2_spill.txt.)
+constexpr uint32_t kSpillChunk = 8;
+template <uint32_t kTile, uint32_t kKeep>
+struct SpillSink {
+	uint32_t* slot; uint32_t n;
+	uint32_t* spill; uint32_t* cursor; uint32_t cap;
+	uint32_t first, cur, r; bool ok;
+	__device__ __forceinline__ void emit(uint32_t code) {
+		if (n < kKeep) slot[n * kTile] = code;
+		else if (ok) {
+			if (r == kSpillChunk - 1 || n == kKeep) {
+				const uint32_t c = atomicAdd(cursor, kSpillChunk);
+				if (c + kSpillChunk > cap) ok = false;
+				else { if (n == kKeep) first = c; else spill[cur + kSpillChunk - 1] = c; cur = c; r = 0; }
+			}
+			if (ok) spill[cur + r++] = code;
+		}
+		n++;
+	}
 };
 
 // A batch may be launched as several chunks of regions (so that transfers overlap the kernels); the
@@ -269,12 +295,16 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4(const DevIndex ix, uint6
 // written in the same pass — one kernel answers both operators for a batch that asks for both.
 template <bool k32> __device__ __forceinline__ uint64_t ld_coord(const void* a, uint64_t i) { return k32 ? (uint64_t)((const uint32_t*)a)[i] : ((const uint64_t*)a)[i]; }
 
-template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep, bool k32, bool kFuse6>
+// kSpill: codes beyond the staging go to a per-CTA scratch (SpillSink) — for batches of regions with many rows.
+template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep, bool k32, bool kFuse6, bool kSpill>
 __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint64_t n, const void* __restrict__ xs, const void* __restrict__ ys,
                                                           const uint32_t* __restrict__ sample, uint64_t* __restrict__ offsets, uint32_t* __restrict__ counts,
                                                           uint32_t* __restrict__ hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr,
-                                                          const T6Out t6) {
+                                                          const T6Out t6, uint32_t* spill, uint32_t spill_words) {
 	__shared__ uint32_t s_hits[2][kTile * kKeep];
+	__shared__ uint32_t s_cursor[2];
+	uint32_t* const my_spill = kSpill ? spill + (uint64_t)blockIdx.x * 2 * spill_words : nullptr;     // two halves of spill_words each
+	uint32_t p_first = 0; bool p_ok = false;
 	__shared__ uint32_t s_warp[kTile / 32];
 	__shared__ uint64_t s_base;
 	__shared__ uint32_t s_tile;
@@ -285,15 +315,18 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 	uint32_t p_tile = 0xFFFFFFFFu, p_cnt = 0, p_pre = 0; uint64_t p_agg = 0;
 	uint32_t buf = 0;
 	for (;;) {
-		if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);   // tiles start in ticket order
+		if (threadIdx.x == 0) { s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull); if (kSpill) s_cursor[buf] = 0; }   // tiles start in ticket order
 		cta_sync();
 		const uint32_t tile = s_tile;
 		const bool has = tile < ntiles;
 		uint32_t cnt = 0, pre = 0; uint64_t agg = 0;
+		uint32_t c_first = 0; bool c_ok = false;
 		if (has) {
 			// ---- walk this thread's region of the new tile
 			const uint64_t i = (uint64_t)tile * kTile + threadIdx.x;
-			SmemSink<kTile, kKeep> sink{s_hits[buf] + threadIdx.x, 0};
+			typename std::conditional<kSpill, SpillSink<kTile, kKeep>, SmemSink<kTile, kKeep>>::type sink;
+			sink.slot = s_hits[buf] + threadIdx.x; sink.n = 0;
+			if constexpr (kSpill) { sink.spill = my_spill + buf * spill_words; sink.cursor = &s_cursor[buf]; sink.cap = spill_words; sink.first = 0; sink.cur = 0; sink.r = 0; sink.ok = true; }
 			if (i < n) {
 				const uint64_t x = ld_coord<k32>(xs, i), y = ld_coord<k32>(ys, i); const uint32_t s = sample[i];
 				uint2 r = make_uint2(kNoneU32, kNoneU32);
@@ -310,6 +343,7 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 				}
 			}
 			cnt = sink.n;
+			if constexpr (kSpill) { c_first = sink.first; c_ok = sink.ok; }
 			uint32_t incl = cnt;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
@@ -349,11 +383,19 @@ __global__ void __launch_bounds__(kTile, kMinCtas) k_t4p(const DevIndex ix, uint
 				if (counts) counts[i] = p_cnt;
 				if (off + p_cnt > cap) atomicOr(status, kStatusOverflow);
 				else if (p_cnt <= kKeep) { const uint32_t* src = s_hits[buf ^ 1] + threadIdx.x; for (uint32_t j = 0; j < p_cnt; j++) hits[off + j] = src[j * kTile]; }
+				else if (kSpill && p_ok) {                         // the staged codes, then the chain of spilled chunks
+					const uint32_t* src = s_hits[buf ^ 1] + threadIdx.x;
+					for (uint32_t j = 0; j < kKeep; j++) hits[off + j] = src[j * kTile];
+					const uint32_t* sp = my_spill + (buf ^ 1) * spill_words;
+					uint32_t c = p_first;
+					for (uint32_t j = kKeep; j < p_cnt; c = sp[c + kSpillChunk - 1])
+						for (uint32_t q = 0; q < kSpillChunk - 1 && j < p_cnt; q++, j++) hits[off + j] = sp[c + q];
+				}
 				else { DirectSink direct{hits + off, 0}; walk_any(ix, ld_coord<k32>(xs, i), ld_coord<k32>(ys, i), sample[i], direct); }   // more hits than the staging holds: walk again, straight into place
 			}
 		}
 		if (!has) break;
-		p_tile = tile; p_cnt = cnt; p_pre = pre; p_agg = agg;
+		p_tile = tile; p_cnt = cnt; p_pre = pre; p_agg = agg; p_first = c_first; p_ok = c_ok;
 		buf ^= 1;
 		cta_sync();        // s_tile / s_warp / s_base are reused by the next round
 	}
@@ -1116,20 +1158,31 @@ uint32_t t4_wide_entries() {              // scan ranges longer than this many w
 }
 uint64_t t4_state_words(uint64_t n) { return 2 + (n + 7) / 8; }
 
+// scratch of the spilling instance: two halves of kSpillWords 32-bit words per CTA of the largest grid launch_t4x uses
+constexpr uint32_t kSpillWords = 16384;
+static uint32_t spill_words() {               // VSGPU_T4_SPILL_WORDS: a small value makes threads run out of scratch (tests of the second-walk fallback)
+	const char* e = getenv("VSGPU_T4_SPILL_WORDS");
+	return e ? (uint32_t)std::min<uint64_t>(kSpillWords, std::max<uint64_t>(kSpillChunk, strtoull(e, nullptr, 10) / kSpillChunk * kSpillChunk)) : kSpillWords;
+}
+uint64_t t4x_spill_bytes() { return (uint64_t)grid_for(~0ull >> 8, 64, 24) * 2 * kSpillWords * 4; }
 bool t4x_supported(bool wide_regions) {
 	if (wide_regions) return false;
 	const char* pe = getenv("VSGPU_T4_PIPE");
 	return !pe || atoi(pe) != 0;
 }
 namespace {
-template <uint32_t kTile, uint32_t kMinCtas, uint32_t kKeep = kScratchHits>
+template <uint32_t kTile, uint32_t kMinCtas, bool kAllowSpill = false, uint32_t kKeep = kScratchHits>
 cudaError_t launch_t4p_cfg(const DevIndex& ix, const T4Launch& a, cudaStream_t stream) {
 	const uint32_t tiles = (uint32_t)((a.n + kTile - 1) / kTile);
 	const uint32_t grid = min(tiles, grid_for((uint64_t)tiles * kTile, kTile, kMinCtas));
 	const T6Out t6 = a.fuse6 ? *a.fuse6 : T6Out{nullptr, nullptr, nullptr, nullptr, 0};
-#define VSGPU_T4P(K32, F6) k_t4p<kTile, kMinCtas, kKeep, K32, F6><<<grid, kTile, 0, stream>>>(ix, a.n, a.x, a.y, a.sample, a.offsets, a.counts, a.hits, a.cap, a.tile_state, a.status, a.base_ptr, t6)
-	if (a.coords32) { if (a.fuse6) VSGPU_T4P(true, true); else VSGPU_T4P(true, false); }
-	else { if (a.fuse6) VSGPU_T4P(false, true); else VSGPU_T4P(false, false); }
+#define VSGPU_T4P(K32, F6, SP) k_t4p<kTile, kMinCtas, kKeep, K32, F6, SP><<<grid, kTile, 0, stream>>>(ix, a.n, a.x, a.y, a.sample, a.offsets, a.counts, a.hits, a.cap, a.tile_state, a.status, a.base_ptr, t6, a.spill, spill_words())
+	if (kAllowSpill && a.spill) {
+		if (a.coords32) { if (a.fuse6) VSGPU_T4P(true, true, kAllowSpill); else VSGPU_T4P(true, false, kAllowSpill); }
+		else { if (a.fuse6) VSGPU_T4P(false, true, kAllowSpill); else VSGPU_T4P(false, false, kAllowSpill); }
+	}
+	else if (a.coords32) { if (a.fuse6) VSGPU_T4P(true, true, false); else VSGPU_T4P(true, false, false); }
+	else { if (a.fuse6) VSGPU_T4P(false, true, false); else VSGPU_T4P(false, false, false); }
 #undef VSGPU_T4P
 	return cudaGetLastError();
 }
@@ -1139,11 +1192,11 @@ cudaError_t launch_t4x(const DevIndex& ix, const T4Launch& a, cudaStream_t strea
 	const uint32_t tile = t4_tile();
 	if (tile == 128) return launch_t4p_cfg<128, 12>(ix, a, stream);
 	if (tile == 256) return launch_t4p_cfg<256, 6>(ix, a, stream);
-	return launch_t4p_cfg<64, 24>(ix, a, stream);
+	return launch_t4p_cfg<64, 24, true>(ix, a, stream);
 }
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
-                      cudaStream_t stream, const uint64_t* base_ptr) {
+                      cudaStream_t stream, const uint64_t* base_ptr, uint32_t* spill) {
 	if (n == 0) return cudaSuccess;
 	const uint32_t tile = t4_tile();
 	const uint32_t grid = (uint32_t)((n + tile - 1) / tile);
@@ -1154,7 +1207,7 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 	const int pipe = pe ? atoi(pe) : 1;
 	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each
 	else if (pipe) {
-		const T4Launch a{n, x, y, false, sample, offsets, nullptr, hits, cap, tile_state, status, base_ptr, nullptr};
+		const T4Launch a{n, x, y, false, sample, offsets, nullptr, hits, cap, tile_state, status, base_ptr, nullptr, spill};
 		return launch_t4x(ix, a, stream);
 	}
 	else if (tile == 64) k_t4<64, 16, kScratchHits><<<grid, 64, 0, stream>>>(VSGPU_T4_ARGS);

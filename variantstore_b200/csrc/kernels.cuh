@@ -166,7 +166,7 @@ cudaError_t launch_t7(const DevIndex& ix, uint64_t n, const uint64_t* pos, const
 uint64_t t4_state_words(uint64_t n);
 cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const uint64_t* y, const uint32_t* sample,
                       uint64_t* offsets, uint32_t* hits, uint64_t cap, uint64_t* tile_state, uint32_t* status, bool wide_regions,
-                      cudaStream_t stream, const uint64_t* base_ptr = nullptr);
+                      cudaStream_t stream, const uint64_t* base_ptr = nullptr, uint32_t* spill = nullptr);
 uint32_t t4_wide_entries();
 
 // t6 outputs of a fused launch: as launch_t6's; hi / counts / flagged nullable
@@ -179,7 +179,9 @@ struct T4Launch {
 	uint64_t n; const void* x; const void* y; bool coords32; const uint32_t* sample;
 	uint64_t* offsets; uint32_t* counts; uint32_t* hits; uint64_t cap; uint64_t* tile_state; uint32_t* status; const uint64_t* base_ptr;
 	const T6Out* fuse6;
+	uint32_t* spill = nullptr;     // t4x_spill_bytes() of scratch: regions with more rows than the staging holds spill there instead of walking twice (64-region tiles only)
 };
+uint64_t t4x_spill_bytes();
 bool t4x_supported(bool wide_regions);
 cudaError_t launch_t4x(const DevIndex& ix, const T4Launch& a, cudaStream_t stream);
 

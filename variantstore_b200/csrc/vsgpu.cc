@@ -116,7 +116,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 	// t2 (query_sample_from_ref): tables uploaded on first use
 	bool t2_ready = false;
 	T2Tables t2{};
-	DevBuf bcnt, bst8, brecs, btile, bkeep, bpos5;
+	DevBuf bcnt, bst8, brecs, btile, bkeep, bpos5, bspill;
 	const uint32_t* d_gsidx = nullptr;   // sample_info.index per s_info entry, s_info order (t5 rows rendered on the device); uploaded on first use
 	bool t3_ready = false;
 	T3Tables t3{};
@@ -146,7 +146,7 @@ struct vsgpu_index : vsgpu::HostIndex {
 		cudaSetDevice(device);
 		for (auto& b : pinned_free) cudaFreeHost(b.first);
 		for (void* p : stage) if (p) cudaFreeHost(p);
-		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bx32, &by32, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs, &btile, &bkeep, &bpos5}) b->release();
+		for (DevBuf* b : {&bx, &by, &bs, &bout, &boffsets, &bhits, &bstate, &bhash, &brec, &bflag, &bx32, &by32, &bseg, &brow_off, &bbyte_off, &bscratch, &btext, &bcnt, &bst8, &brecs, &btile, &bkeep, &bpos5, &bspill}) b->release();
 		for (cudaEvent_t e : ev_render) if (e) cudaEventDestroy(e);
 		for (cudaEvent_t e : ev_t2) if (e) cudaEventDestroy(e);
 		for (int i = 0; i < kMaxChunks; i++) for (cudaEvent_t e : {ev_in[i][0], ev_in[i][1], ev_in[i][2], ev_k[i], ev_out[i]}) if (e) cudaEventDestroy(e);
@@ -162,15 +162,16 @@ struct vsgpu_batch {
 	vsgpu_index* idx = nullptr;
 	int device = 0;                  // copied from the index: freeing a batch must not touch an index that may be gone
 	int type = 0; uint64_t n = 0;
-	DevBuf x, y, s, hash, out, offsets, hits, state, rec, flag;
+	DevBuf x, y, s, hash, out, offsets, hits, state, rec, flag, spill;
 	uint64_t hits_cap = 0;
+	bool many_rows = false;          // regions expected to have more rows than k_t4p stages: run its spilling instance
 	uint32_t launches = 0;
 	uint64_t algo_bytes = 0; bool algo_valid = false;
 	std::vector<uint64_t> hx, hy;   // host copies kept for the byte accounting
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint32_t* d_status = nullptr;    // per batch: several batches may be in flight on one index
 	bool wide_regions = false;
-	~vsgpu_batch() { if (idx) cudaSetDevice(device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec, &flag}) b->release(); }
+	~vsgpu_batch() { if (idx) cudaSetDevice(device); if (d_status) cudaFree(d_status); for (auto e : ev) if (e) cudaEventDestroy(e); for (DevBuf* b : {&x, &y, &s, &hash, &out, &offsets, &hits, &state, &rec, &flag, &spill}) b->release(); }
 };
 
 namespace {
@@ -444,13 +445,13 @@ namespace {
 // region) and, if the kernel reports an overflow, re-sized from the total it computed and the pass
 // repeated — results are deterministic, so a batch pays that at most once.
 void run_t4(vsgpu_index* ix, uint64_t n, const uint64_t* dx, const uint64_t* dy, const uint32_t* ds, DevBuf& offsets, DevBuf& state,
-            DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr, uint32_t* d_status = nullptr, bool wide_regions = false) {
+            DevBuf& hits, uint64_t& hits_cap, uint32_t* launches, cudaEvent_t* ev = nullptr, uint32_t* d_status = nullptr, bool wide_regions = false, uint32_t* spill = nullptr) {
 	if (!d_status) d_status = ix->d_status;
 	CU(offsets.ensure((n + 1) * 8)); CU(state.ensure(t4_state_words(n) * 8));
 	if (hits_cap == 0) { hits_cap = std::max<uint64_t>((wide_regions ? 64 : 4) * n, 1024); CU(hits.ensure(hits_cap * 4)); }
 	CU(cudaMemsetAsync(state.p, 0, t4_state_words(n) * 8, ix->stream));
 	if (ev) CU(cudaEventRecord(ev[0], ix->stream));
-	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, wide_regions, ix->stream));
+	CU(launch_t4(ix->dev, n, dx, dy, ds, offsets.as<uint64_t>(), hits.as<uint32_t>(), hits_cap, state.as<uint64_t>(), d_status, wide_regions, ix->stream, nullptr, spill));
 	if (ev) CU(cudaEventRecord(ev[1], ix->stream));
 	if (launches) *launches = 1;
 }
@@ -495,6 +496,22 @@ bool expect_wide_regions(const vsgpu_index* ix, uint64_t n, const T* x, const T*
 	if (const char* e = getenv("VSGPU_WIDE_MAX_REGIONS")) max_regions = strtoull(e, nullptr, 10);
 	return n <= max_regions && (double)wmax * ix->entries_per_base > (double)t4_wide_entries();
 }
+
+// Will the regions of this batch typically have more rows than k_t4p stages per region (kScratchHits)?  From a sample of the
+// widths and the index's carried walk entries per base of an average sample.  Such batches run the kernel's spilling
+// instance (codes beyond the staging go to a scratch and are copied into place, instead of a second walk).
+extern "C++" template <class T>
+bool expect_many_rows(const vsgpu_index* ix, uint64_t n, const T* x, const T* y) {
+	if (n == 0) return false;
+	if (const char* e = getenv("VSGPU_T4_SPILL")) return atoi(e) != 0;
+	const uint64_t step = std::max<uint64_t>(1, n / 1024);
+	double sum = 0; uint64_t k = 0;
+	for (uint64_t i = 0; i < n; i += step, k++) if (y[i] > x[i]) sum += (double)std::min<uint64_t>(y[i] - x[i], ix->flat.ref_length);
+	const double rows = k ? sum / (double)k * ix->hits_per_base : 0;          // measured (profiles/r2_spill.txt): wins from ~5 to a few dozen rows per region
+	return rows > 0.6 * kScratchHits && rows < 64;
+}
+// the scratch of the spilling instance, allocated on first use
+uint32_t* spill_of(DevBuf& b) { CU(b.ensure(t4x_spill_bytes())); return b.as<uint32_t>(); }
 
 // copy a finished t4 answer (device offsets[n+1] + hits) into a pooled page-locked result
 vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const DevBuf& hits, bool want_hits, Trace* tr = nullptr) {
@@ -542,6 +559,7 @@ int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uin
 		const bool wide = expect_wide_regions(ix, n, x, y);
 		const bool direct = t4x_supported(wide);               // k_t4p: reads the host's coordinate width, writes counts, fuses t6
 		const bool flag6 = t6 && t6_special(ix);
+		uint32_t* const spill = !wide && expect_many_rows(ix, n, x, y) ? spill_of(ix->bspill) : nullptr;
 		uint64_t per = 0;
 		const int chunks = wide ? (per = n, 1) : plan_chunks(n, &per);
 		const uint64_t state_words = t4_state_words(per);
@@ -585,13 +603,13 @@ int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uin
 			if (direct) {
 				const T6Out f6{d_lo + a, t6 && t6->rec_hi ? d_hi + a : nullptr, d_cnt6 + a, flag6 ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a};
 				const T4Launch L{m, sx + a, sy + a, k32, ds + a, d_off + a, d_cnt4 + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status,
-				                 c ? d_off + a : nullptr, t6 ? &f6 : nullptr};
+				                 c ? d_off + a : nullptr, t6 ? &f6 : nullptr, spill};
 				CU(launch_t4x(ix->dev, L, ix->s_k));
 			} else {
 				if (k32) CU(launch_widen(m, (const uint32_t*)sx + a, (const uint32_t*)sy + a, dx + a, dy + a, ix->s_k));
 				if (t6) CU(launch_t6(ix->dev, m, dx + a, dy + a, d_lo + a, d_hi + a, d_cnt6 + a, flag6 ? ix->bflag.as<uint32_t>() : nullptr, (uint32_t)a, ix->d_status, ix->s_k));
 				CU(launch_t4(ix->dev, m, dx + a, dy + a, ds + a, d_off + a, ix->bhits.as<uint32_t>(), cap, ix->bstate.as<uint64_t>() + c * state_words, ix->d_status, wide,
-				             ix->s_k, c ? d_off + a : nullptr));
+				             ix->s_k, c ? d_off + a : nullptr, spill));
 			}
 			CU(cudaEventRecord(ix->ev_k[c], ix->s_k));
 		}
@@ -1015,7 +1033,8 @@ int vsgpu_render_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64
 		const bool wide = expect_wide_regions(ix, n, x, y);
 		uint64_t cap = ix->bhits.cap / 4;
 		if (cap == 0) { cap = std::max<uint64_t>((wide ? 64 : 4) * n, 1024); CU(ix->bhits.ensure(cap * 4)); cap = ix->bhits.cap / 4; }
-		run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, ix->d_status, wide);
+		run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, ix->d_status, wide,
+		       !wide && expect_many_rows(ix, n, x, y) ? spill_of(ix->bspill) : nullptr);
 		const uint32_t status = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, wide);
 		if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 		render_hit_rows(ix, t.get(), n, with_samples, nullptr);
@@ -1394,7 +1413,7 @@ int vsgpu_batch_create(vsgpu_index* ix, int type, uint64_t n, const uint64_t* x,
 		CU(cudaMemcpyAsync(b->x.p, x, n * 8, cudaMemcpyHostToDevice, ix->stream));
 		if (type != 7) { CU(b->y.ensure(n * 8)); CU(cudaMemcpyAsync(b->y.p, y, n * 8, cudaMemcpyHostToDevice, ix->stream)); }
 		if (type == 6) { CU(b->out.ensure(n * 12)); if (t6_special(ix)) CU(b->flag.ensure(n * 4)); }
-		if (type == 4 || type == 46) { b->wide_regions = expect_wide_regions(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 12)); }
+		if (type == 4 || type == 46) { b->wide_regions = expect_wide_regions(ix, n, x, y); b->many_rows = !b->wide_regions && expect_many_rows(ix, n, x, y); CU(b->s.ensure(n * 4)); CU(cudaMemcpyAsync(b->s.p, sample_ids, n * 4, cudaMemcpyHostToDevice, ix->stream)); CU(b->out.ensure(n * 12)); }
 		if (type == 46) {
 			if (t6_special(ix)) CU(b->flag.ensure(n * 4));           // (a batch of few, wide regions runs k_t6 and the warp-per-region t4 kernel: two launches)
 		}
@@ -1440,12 +1459,14 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 			CU(cudaEventRecord(b->ev[0], ix->stream));
 			uint32_t* o = b->out.as<uint32_t>();
 			const T6Out f6{o, o + n, o + 2 * n, b->flag.as<uint32_t>(), 0};
-			const T4Launch L{n, b->x.p, b->y.p, false, b->s.as<uint32_t>(), b->offsets.as<uint64_t>(), nullptr, b->hits.as<uint32_t>(), b->hits_cap, b->state.as<uint64_t>(), b->d_status, nullptr, &f6};
+			const T4Launch L{n, b->x.p, b->y.p, false, b->s.as<uint32_t>(), b->offsets.as<uint64_t>(), nullptr, b->hits.as<uint32_t>(), b->hits_cap, b->state.as<uint64_t>(), b->d_status, nullptr, &f6,
+			                 b->many_rows ? spill_of(b->spill) : nullptr};
 			CU(launch_t4x(ix->dev, L, ix->stream));
 			CU(cudaEventRecord(b->ev[1], ix->stream));
 			b->launches = 1;
 		}
-		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status, b->wide_regions);
+		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status, b->wide_regions,
+		            b->many_rows ? spill_of(b->spill) : nullptr);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
