@@ -42,8 +42,16 @@ def test_tcga_like_sparse_t7_cuda(tmp_path):
         assert not bad6 and not bad4
 
 
-@pytest.mark.parametrize("wide_entries", [None, "64"])
-def test_width_sweep_cuda(tmp_path, monkeypatch, wide_entries):
+@pytest.mark.parametrize("wide_entries,pool", [(None, None), ("64", None), (None, "3"), (None, "off")])
+def test_width_sweep_cuda(tmp_path, monkeypatch, wide_entries, pool):
+    """pool: the warp-per-region kernel keeps the rows beyond its 1 024 staged ones in chunks from a pool (default); with 3
+    chunks most warps find it empty and walk their region a second time; "off": no pool at all."""
+    monkeypatch.delenv("VSGPU_T4W_POOL_CHUNKS", raising=False)
+    monkeypatch.delenv("VSGPU_T4W_POOL", raising=False)
+    if pool == "off":
+        monkeypatch.setenv("VSGPU_T4W_POOL", "0")
+    elif pool:
+        monkeypatch.setenv("VSGPU_T4W_POOL_CHUNKS", pool)
     if wide_entries:
         monkeypatch.setenv("VSGPU_WIDE_ENTRIES", wide_entries)     # push more regions onto the warp-cooperative path
     else:

@@ -124,10 +124,31 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 // for self-consistency (a hidden entry must not have contributed), falling back to a lane-by-lane
 // pass for the batch when that check or a rare entry kind (rejoin carrier, walk past the bound) says so.
 // Output order is kept with ballot/popc ranks.  Same answers as fast_forward.
+// Codes beyond the `keep` staged in shared memory go to chunks of kPoolChunk codes taken from a pool in global memory (one
+// atomicAdd per chunk by lane 0; the warp's chunk ids sit in shared memory), so that a region with more rows than the staging
+// holds is copied into place — coalesced, by its warp — instead of walked twice.  reserve() is called by all lanes before
+// positions up to `upto` are written; a warp that finds the pool (or its chunk list) exhausted clears *ok and re-walks.
+constexpr uint32_t kPoolChunk = 1024, kMaxWarpChunks = 128;
 struct CoopSink {            // all lanes call emit with identical arguments; lane 0 writes
 	uint32_t* slot; uint32_t stride, keep; uint32_t* direct; uint32_t n; bool writer;
-	__device__ __forceinline__ void put(uint32_t pos, uint32_t code) { if (direct) direct[pos] = code; else if (pos < keep) slot[pos * stride] = code; }
-	__device__ __forceinline__ void emit(uint32_t code) { if (writer) put(n, code); n++; }
+	uint32_t* pool; unsigned long long* cursor; uint32_t pool_chunks; volatile uint32_t* chunk_ids; volatile uint32_t* nchunks; volatile uint32_t* ok;
+	__device__ __forceinline__ void reserve(uint32_t upto) {
+		if (direct || !pool || upto <= keep) return;
+		while (*ok && upto > keep + *nchunks * kPoolChunk) {
+			uint32_t c = 0xFFFFFFFFu;
+			if (*nchunks < kMaxWarpChunks && (threadIdx.x & 31) == 0) c = (uint32_t)atomicAdd(cursor, 1ull);
+			c = __shfl_sync(0xFFFFFFFFu, c, 0);
+			__syncwarp();
+			if ((threadIdx.x & 31) == 0) { if (c >= pool_chunks) *ok = 0; else { chunk_ids[*nchunks] = c; *nchunks = *nchunks + 1; } }
+			__syncwarp();
+		}
+	}
+	__device__ __forceinline__ void put(uint32_t pos, uint32_t code) {
+		if (direct) direct[pos] = code;
+		else if (pos < keep) slot[pos * stride] = code;
+		else if (pool && *ok) { const uint32_t k = pos - keep; pool[(uint64_t)chunk_ids[k / kPoolChunk] * kPoolChunk + (k % kPoolChunk)] = code; }
+	}
+	__device__ __forceinline__ void emit(uint32_t code) { reserve(n + 1); if (writer) put(n, code); n++; }
 };
 
 __device__ __forceinline__ uint32_t warp_excl_max(uint32_t v, uint32_t lane) {   // exclusive prefix max, identity 0
@@ -200,6 +221,7 @@ __device__ __noinline__ uint32_t coop_forward(const DevIndex& ix, FwdState st, u
 			// ---- emit in order
 			const bool emit = live && e.w >= st.x && lane <= first_stop && !(lane == first_stop && stop_before);
 			const uint32_t emit_mask = __ballot_sync(0xFFFFFFFFu, emit);
+			sink.reserve(sink.n + __popc(emit_mask));
 			if (emit) sink.put(sink.n + __popc(emit_mask & lt), ci);
 			sink.n += __popc(emit_mask);
 			if (first_stop < 32) return sink.n;
@@ -409,10 +431,13 @@ template <uint32_t kKeepW>
 __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, const uint64_t* __restrict__ xs,
                                                 const uint64_t* __restrict__ ys, const uint32_t* __restrict__ sample,
                                                 uint64_t* __restrict__ offsets, uint32_t* __restrict__ hits, uint64_t cap,
-                                                uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr) {
+                                                uint64_t* tile_state, uint32_t* status, const uint64_t* base_ptr, uint32_t* pool, uint32_t pool_chunks) {
 	constexpr uint32_t kWarps = 8;
 	__shared__ uint32_t s_hits[kWarps * kKeepW];
 	__shared__ uint32_t s_cnt[kWarps];
+	__shared__ uint32_t s_chunk[kWarps][kMaxWarpChunks];
+	__shared__ uint32_t s_nchunk[kWarps], s_pool_ok[kWarps];
+	if ((threadIdx.x & 31) == 0) { s_nchunk[threadIdx.x >> 5] = 0; s_pool_ok[threadIdx.x >> 5] = pool ? 1 : 0; }
 	__shared__ uint64_t s_base;
 	__shared__ uint32_t s_tile;
 	if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd((unsigned long long*)&tile_state[0], 1ull);
@@ -427,7 +452,7 @@ __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, c
 		if (x < 1 || s == 0 || s >= ix.num_samples) { if (lane == 0) atomicOr(status, kStatusBadRegion); }
 		else {
 			valid = true;
-			CoopSink sink{s_hits + warp * kKeepW, 1, kKeepW, nullptr, 0, lane == 0};
+			CoopSink sink{s_hits + warp * kKeepW, 1, kKeepW, nullptr, 0, lane == 0, pool ? pool + 2 : nullptr, (unsigned long long*)pool, pool_chunks, s_chunk[warp], &s_nchunk[warp], &s_pool_ok[warp]};   // (the pool's first 8 bytes are its cursor)
 			FwdState st;
 			if (!ix.hitmap) walk_region(ix, x, y, s, sink);
 			else if (fast_setup(ix, x, y, s, sink, st)) sink.n = coop_forward(ix, st, s, sink);
@@ -463,6 +488,11 @@ __global__ void __launch_bounds__(256, 4) k_t4w(const DevIndex ix, uint64_t n, c
 		if (lane == 0) { offsets[i] = off; if (i == n - 1) offsets[n] = off + cnt; }
 		if (off + cnt > cap) { if (lane == 0) atomicOr(status, kStatusOverflow); }
 		else if (cnt <= kKeepW) { for (uint32_t j = lane; j < cnt; j += 32) hits[off + j] = s_hits[warp * kKeepW + j]; }
+		else if (valid && pool && s_pool_ok[warp]) {             // the staged codes, then the warp's pool chunks, 128 bytes per step
+			for (uint32_t j = lane; j < kKeepW; j += 32) hits[off + j] = s_hits[warp * kKeepW + j];
+			const uint32_t* codes = pool + 2;
+			for (uint32_t k = lane; k < cnt - kKeepW; k += 32) hits[off + kKeepW + k] = codes[(uint64_t)s_chunk[warp][k / kPoolChunk] * kPoolChunk + (k % kPoolChunk)];
+		}
 		else if (valid) {
 			CoopSink direct{nullptr, 0, 0, hits + off, 0, lane == 0};
 			FwdState st;
@@ -1164,6 +1194,9 @@ static uint32_t spill_words() {               // VSGPU_T4_SPILL_WORDS: a small v
 	const char* e = getenv("VSGPU_T4_SPILL_WORDS");
 	return e ? (uint32_t)std::min<uint64_t>(kSpillWords, std::max<uint64_t>(kSpillChunk, strtoull(e, nullptr, 10) / kSpillChunk * kSpillChunk)) : kSpillWords;
 }
+// the chunk pool of the warp-per-region kernel: an 8-byte cursor, then kPoolChunks chunks of kPoolChunk codes
+constexpr uint32_t kPoolChunks = 262144;
+uint64_t t4w_pool_bytes() { return 8 + (uint64_t)kPoolChunks * kPoolChunk * 4; }
 uint64_t t4x_spill_bytes() { return (uint64_t)grid_for(~0ull >> 8, 64, 24) * 2 * kSpillWords * 4; }
 bool t4x_supported(bool wide_regions) {
 	if (wide_regions) return false;
@@ -1205,7 +1238,12 @@ cudaError_t launch_t4(const DevIndex& ix, uint64_t n, const uint64_t* x, const u
 #define VSGPU_T4_ARGS ix, n, x, y, sample, offsets, hits, cap, tile_state, status, base_ptr
 	const char* pe = getenv("VSGPU_T4_PIPE");      // 1: persistent pipelined kernel (default), 0: one CTA per tile
 	const int pipe = pe ? atoi(pe) : 1;
-	if (wide_regions) k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS);   // few, wide regions: a warp each
+	if (wide_regions) {                                                                           // few, wide regions: a warp each
+		if (spill) cudaMemsetAsync(spill, 0, 8, stream);                                           // here `spill` is the chunk pool (t4w_pool_bytes()): its cursor
+		uint32_t chunks = kPoolChunks;                                                              // VSGPU_T4W_POOL_CHUNKS: a small pool (tests of the second-walk fallback)
+		if (const char* e = getenv("VSGPU_T4W_POOL_CHUNKS")) chunks = (uint32_t)std::min<uint64_t>(kPoolChunks, strtoull(e, nullptr, 10));
+		k_t4w<1024><<<(uint32_t)((n + 7) / 8), 256, 0, stream>>>(VSGPU_T4_ARGS, spill, spill ? chunks : 0);
+	}
 	else if (pipe) {
 		const T4Launch a{n, x, y, false, sample, offsets, nullptr, hits, cap, tile_state, status, base_ptr, nullptr, spill};
 		return launch_t4x(ix, a, stream);

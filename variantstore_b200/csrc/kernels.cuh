@@ -182,6 +182,7 @@ struct T4Launch {
 	uint32_t* spill = nullptr;     // t4x_spill_bytes() of scratch: regions with more rows than the staging holds spill there instead of walking twice (64-region tiles only)
 };
 uint64_t t4x_spill_bytes();
+uint64_t t4w_pool_bytes();       // launch_t4 with wide_regions: `spill` = this many bytes (a pool of hit-code chunks), or nullptr
 bool t4x_supported(bool wide_regions);
 cudaError_t launch_t4x(const DevIndex& ix, const T4Launch& a, cudaStream_t stream);
 

@@ -510,8 +510,12 @@ bool expect_many_rows(const vsgpu_index* ix, uint64_t n, const T* x, const T* y)
 	const double rows = k ? sum / (double)k * ix->hits_per_base : 0;          // measured (profiles/r2_spill.txt): wins from ~5 to a few dozen rows per region
 	return rows > 0.6 * kScratchHits && rows < 64;
 }
-// the scratch of the spilling instance, allocated on first use
+// the scratch of the spilling instance of k_t4p / the chunk pool of the warp-per-region kernel, allocated on first use
 uint32_t* spill_of(DevBuf& b) { CU(b.ensure(t4x_spill_bytes())); return b.as<uint32_t>(); }
+uint32_t* pool_of(DevBuf& b) {
+	if (const char* e = getenv("VSGPU_T4W_POOL")) if (atoi(e) == 0) return nullptr;
+	CU(b.ensure(t4w_pool_bytes())); return b.as<uint32_t>();
+}
 
 // copy a finished t4 answer (device offsets[n+1] + hits) into a pooled page-locked result
 vsgpu_result* fetch_t4(vsgpu_index* ix, uint64_t n, const DevBuf& offsets, const DevBuf& hits, bool want_hits, Trace* tr = nullptr) {
@@ -559,7 +563,7 @@ int query_t4_impl(vsgpu_index* ix, uint64_t n, const T* x, const T* y, const uin
 		const bool wide = expect_wide_regions(ix, n, x, y);
 		const bool direct = t4x_supported(wide);               // k_t4p: reads the host's coordinate width, writes counts, fuses t6
 		const bool flag6 = t6 && t6_special(ix);
-		uint32_t* const spill = !wide && expect_many_rows(ix, n, x, y) ? spill_of(ix->bspill) : nullptr;
+		uint32_t* const spill = wide ? pool_of(ix->bspill) : expect_many_rows(ix, n, x, y) ? spill_of(ix->bspill) : nullptr;
 		uint64_t per = 0;
 		const int chunks = wide ? (per = n, 1) : plan_chunks(n, &per);
 		const uint64_t state_words = t4_state_words(per);
@@ -1034,7 +1038,7 @@ int vsgpu_render_t4(vsgpu_index* ix, uint64_t n, const uint64_t* x, const uint64
 		uint64_t cap = ix->bhits.cap / 4;
 		if (cap == 0) { cap = std::max<uint64_t>((wide ? 64 : 4) * n, 1024); CU(ix->bhits.ensure(cap * 4)); cap = ix->bhits.cap / 4; }
 		run_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, nullptr, nullptr, ix->d_status, wide,
-		       !wide && expect_many_rows(ix, n, x, y) ? spill_of(ix->bspill) : nullptr);
+		       wide ? pool_of(ix->bspill) : expect_many_rows(ix, n, x, y) ? spill_of(ix->bspill) : nullptr);
 		const uint32_t status = finish_t4(ix, n, ix->bx.as<uint64_t>(), ix->by.as<uint64_t>(), ix->bs.as<uint32_t>(), ix->boffsets, ix->bstate, ix->bhits, cap, ix->d_status, wide);
 		if (status & kStatusBadRegion) return set_err(VSGPU_EINVAL, "region start < 1 or sample id out of range");
 		render_hit_rows(ix, t.get(), n, with_samples, nullptr);
@@ -1445,7 +1449,8 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 			CU(cudaEventRecord(b->ev[0], ix->stream));
 			CU(launch_t6(ix->dev, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), o, o + n, o + 2 * n, b->flag.as<uint32_t>(), 0, b->d_status, ix->stream));
 			CU(cudaEventRecord(b->ev[1], ix->stream));
-			run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, b->wide_regions);
+			run_t4(ix, n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, nullptr, nullptr, b->d_status, b->wide_regions,
+			       b->wide_regions ? pool_of(b->spill) : nullptr);
 			CU(cudaEventRecord(b->ev[2], ix->stream));
 			b->launches = 2;
 		}
@@ -1466,7 +1471,7 @@ int vsgpu_batch_run(vsgpu_batch* b) {
 			b->launches = 1;
 		}
 		else run_t4(ix, b->n, b->x.as<uint64_t>(), b->y.as<uint64_t>(), b->s.as<uint32_t>(), b->offsets, b->state, b->hits, b->hits_cap, &b->launches, b->ev, b->d_status, b->wide_regions,
-		            b->many_rows ? spill_of(b->spill) : nullptr);
+		            b->wide_regions ? pool_of(b->spill) : b->many_rows ? spill_of(b->spill) : nullptr);
 	} catch (const std::exception& e) { return set_err(VSGPU_ENODEVICE, e.what()); }
 	return VSGPU_OK;
 }
