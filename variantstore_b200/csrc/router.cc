@@ -8,6 +8,7 @@
 // owns its (contig, start), one host thread per GPU runs that GPU's shards through the fused host-
 // buffer call, and the answers are scattered back into the caller's region order.  Nothing here talks
 // to another GPU; the only shared resource is the host's PCIe / memory path.
+#include "thread_pool.h"
 #include "../../include/vsgpu.h"
 
 #include <algorithm>
@@ -72,21 +73,14 @@ struct vsgpu_router {
 	// are gathered into one CSR in the caller's order only when vsgpu_router_offsets / _hits ask for it
 	std::vector<uint32_t> slot; std::vector<uint32_t> shard_of_last; uint64_t last_n = 0; bool csr_valid = false;
 	std::vector<uint32_t> hits; std::vector<uint64_t> offsets;
+	// workers of the routing / scatter / gather loops (thread_pool.h): kept for the router's lifetime
+	vsgpu::ThreadPool pool{std::min(63u, std::max(1u, std::thread::hardware_concurrency()) - 1)};
 	~vsgpu_router() { for (auto& s : shards) { if (s.res) vsgpu_result_free(s.res); if (s.ix) vsgpu_close(s.ix); } }
 };
 
 namespace {
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-template <class F>
-void par_for(uint64_t n, unsigned max_threads, F&& fn) {
-	unsigned nt = std::max(1u, std::min<unsigned>(std::min(max_threads, std::thread::hardware_concurrency()), (unsigned)((n + 65535) / 65536)));
-	if (nt <= 1) { fn(0, (uint64_t)0, n); return; }
-	std::vector<std::thread> th;
-	const uint64_t chunk = (n + nt - 1) / nt;
-	for (unsigned t = 0; t < nt; t++) { const uint64_t a = t * chunk, b = std::min<uint64_t>(n, a + chunk); if (a < b) th.emplace_back([=, &fn]() { fn(t, a, b); }); }
-	for (auto& t : th) t.join();
-}
 }  // namespace
 
 extern "C" {
@@ -185,7 +179,7 @@ int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig,
 	std::atomic<int64_t> bad{-1};
 	const uint32_t nc = (uint32_t)r->by_contig.size();
 	const uint32_t* rtb = r->rt_begin.data(); const uint32_t* rts = r->rt_shard.data(); const uint64_t* rtl = r->rt_lo.data(); const uint64_t* rth = r->rt_hi.data();
-	par_for(n, NT, [&](unsigned t, uint64_t a, uint64_t b) {
+	r->pool.par_for(n, NT, [&](unsigned t, uint64_t a, uint64_t b) {
 		uint64_t* mycnt = cnt[t].data();
 		for (uint64_t i = a; i < b; i++) {
 			const uint32_t c = contig[i];
@@ -216,7 +210,7 @@ int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig,
 	uint32_t* slot = r->slot.data();
 	std::vector<uint32_t*> bx(S), by(S), bs(S);
 	for (uint32_t k = 0; k < S; k++) { bx[k] = (uint32_t*)r->shards[k].px.p; by[k] = (uint32_t*)r->shards[k].py.p; bs[k] = (uint32_t*)r->shards[k].ps.p; }
-	par_for(n, NT, [&](unsigned t, uint64_t a, uint64_t b) {
+	r->pool.par_for(n, NT, [&](unsigned t, uint64_t a, uint64_t b) {
 		uint64_t* mycnt = cnt[t].data();
 		for (uint64_t i = a; i < b; i++) {
 			const uint32_t k = shard_of[i];
@@ -231,7 +225,6 @@ int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig,
 	// own index with its own streams, so the copies of one shard's call overlap the kernels of another's
 	unsigned per_gpu = 4;
 	if (const char* e = getenv("VSGPU_ROUTER_THREADS")) per_gpu = (unsigned)std::max(1, atoi(e));
-	std::vector<std::thread> th;
 	std::vector<std::atomic<uint32_t>> next(r->devices.size());
 	std::vector<std::atomic<uint64_t>> dregions(r->devices.size());
 	std::vector<double> dstart(r->devices.size(), 0), dend(r->devices.size(), 0);
@@ -242,23 +235,28 @@ int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig,
 		std::stable_sort(queue[di].begin(), queue[di].end(), [&](uint32_t a, uint32_t b) { return r->shards[a].n > r->shards[b].n; });   // largest batch first
 	}
 	std::mutex end_mu;
+	// (device, worker) pairs as pool tasks: each drains its device's queue; the calls block on CUDA, the pool's threads wait with them
+	std::vector<std::pair<size_t, unsigned>> tasks;
 	for (size_t di = 0; di < r->devices.size(); di++) {
 		dstart[di] = now_ms();
-		for (unsigned w = 0; w < std::min<size_t>(per_gpu, std::max<size_t>(queue[di].size(), 1)); w++) th.emplace_back([&, di]() {
-			for (uint32_t qi; (qi = next[di]++) < queue[di].size();) {
-				Shard& s = r->shards[queue[di][qi]];
-				const double b = now_ms();
-				s.rc = vsgpu_query_t6t4_u32(s.ix, s.n, (const uint32_t*)s.px.p, (const uint32_t*)s.py.p, (const uint32_t*)s.ps.p, (uint32_t*)s.plo.p, nullptr, (uint32_t*)s.pc6.p, &s.res);
-				if (s.rc) s.err = vsgpu_last_error();
-				s.ms = now_ms() - b;
-				dregions[di] += s.n;
-			}
-			const double e = now_ms();
-			std::lock_guard<std::mutex> g2(end_mu);
-			dend[di] = std::max(dend[di], e);
-		});
+		for (unsigned w = 0; w < std::min<size_t>(per_gpu, std::max<size_t>(queue[di].size(), 1)); w++) tasks.emplace_back(di, w);
 	}
-	for (auto& t : th) t.join();
+	// interleave the devices so that a pool smaller than the task list still starts every GPU at once
+	std::stable_sort(tasks.begin(), tasks.end(), [](const std::pair<size_t, unsigned>& a, const std::pair<size_t, unsigned>& b) { return a.second < b.second; });
+	r->pool.run((unsigned)tasks.size(), [&](unsigned t) {
+		const size_t di = tasks[t].first;
+		for (uint32_t qi; (qi = next[di]++) < queue[di].size();) {
+			Shard& s = r->shards[queue[di][qi]];
+			const double b = now_ms();
+			s.rc = vsgpu_query_t6t4_u32(s.ix, s.n, (const uint32_t*)s.px.p, (const uint32_t*)s.py.p, (const uint32_t*)s.ps.p, (uint32_t*)s.plo.p, nullptr, (uint32_t*)s.pc6.p, &s.res);
+			if (s.rc) s.err = vsgpu_last_error();
+			s.ms = now_ms() - b;
+			dregions[di] += s.n;
+		}
+		const double e = now_ms();
+		std::lock_guard<std::mutex> g2(end_mu);
+		dend[di] = std::max(dend[di], e);
+	});
 	for (size_t di = 0; di < r->devices.size(); di++) { r->device_ms[di] = queue[di].empty() ? 0 : dend[di] - dstart[di]; r->device_regions[di] = dregions[di]; }
 	for (uint32_t k = 0; k < S; k++) if (r->shards[k].rc) return rerr(r->shards[k].rc, "shard " + std::to_string(k) + ": " + r->shards[k].err);
 	const double t2 = now_ms();
@@ -267,14 +265,14 @@ int vsgpu_router_query_t6t4(vsgpu_router* r, uint64_t n, const uint32_t* contig,
 	for (uint32_t k = 0; k < S; k++) if (r->shards[k].n) c4[k] = vsgpu_result_counts(r->shards[k].res);
 	std::vector<const uint32_t*> plo(S), pc6(S);
 	for (uint32_t k = 0; k < S; k++) { plo[k] = (const uint32_t*)r->shards[k].plo.p; pc6[k] = (const uint32_t*)r->shards[k].pc6.p; }
-	par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) {
+	r->pool.par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) {
 		for (uint64_t i = a; i < b; i++) {
 			const uint32_t k = shard_of[i]; const uint32_t j = slot[i];
 			rec_lo[i] = plo[k][j]; counts6[i] = pc6[k][j]; counts4[i] = c4[k][j];
 		}
 	});
 	if (r->shard_of_last.size() < n) r->shard_of_last.resize(n);
-	par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) { memcpy(r->shard_of_last.data() + a, shard_of + a, (b - a) * 4); });
+	r->pool.par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) { memcpy(r->shard_of_last.data() + a, shard_of + a, (b - a) * 4); });
 	r->csr_valid = false; r->last_n = n;
 	r->scatter_ms = now_ms() - t2;
 	return VSGPU_OK;
@@ -291,7 +289,7 @@ void gather_csr(vsgpu_router* r) {
 	for (uint64_t i = 0; i < n; i++) { r->offsets[i] = acc; acc += c4[r->shard_of_last[i]][r->slot[i]]; }
 	r->offsets[n] = acc;
 	r->hits.resize(acc);
-	par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) {
+	r->pool.par_for(n, 64, [&](unsigned, uint64_t a, uint64_t b) {
 		for (uint64_t i = a; i < b; i++) {
 			const uint32_t k = r->shard_of_last[i]; const uint32_t j = r->slot[i]; const uint32_t c = c4[k][j];
 			if (c) memcpy(r->hits.data() + r->offsets[i], hs[k] + so[k][j], (size_t)c * 4);
