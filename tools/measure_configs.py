@@ -103,6 +103,45 @@ def main():
             b4.close(); idx.close()
         os.environ.pop("VSGPU_SPARSE_WALK", None)
         o.close()
+    if "published" in args.what:
+        # The shape of the reference's own evaluation logs: 1000 random regions of 43 185 bp on chr22, one
+        # sample, types 6 and 4 (eval_data_records/logs/query_chr22_on_disk_vs_v1.log: 1946.6 s and 1237.98 s per 1000 regions, one
+        # thread, on-disk vertex blocks, unknown CPU).  Here: the chr22-shaped synthetic, the same shape through the C ABI with host
+        # buffers (counts + hit codes, and with the rows as -v text), beside the oracle port on one host thread.
+        import bench
+        class A: pass
+        a = A(); a.records, a.samples, a.fmax, a.cache_dir, a.regions, a.width = 1_103_547, 2504, 1100, "/tmp/vsgpu_bench", 1_000_000, 1000
+        prefix, meta = bench.ensure_index(a, 0)
+        idx = VariantStoreIndex(prefix, device=0)
+        rng = np.random.default_rng(43185)
+        n, width = 1000, 43_185
+        x = np.sort(rng.integers(meta["pos_lo"], meta["ref_length"] - width, n)).astype(np.uint64)
+        y = x + np.uint64(width)
+        s = np.full(n, 1234, np.uint32)
+        def best(fn, reps=5):
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter(); r = fn(); ts.append(time.perf_counter() - t0)
+            return min(ts), r
+        idx.batch_var_and_sample_var_in_ref(x, y, s)
+        t_counts, r = best(lambda: idx.batch_var_and_sample_var_in_ref(x, y, s))
+        lo, hi, c6, off4, hits4, _ = r
+        idx.render_var_in_ref(x, y, True); idx.render_sample_var_in_ref(x, y, s, True)
+        t_rows6, r6 = best(lambda: idx.render_var_in_ref(x, y, True), 3)
+        t_rows4, r4 = best(lambda: idx.render_sample_var_in_ref(x, y, s, True), 3)
+        o = T.Oracle.open(prefix)
+        t0 = time.perf_counter(); oc6, od6 = o.batch_t6(x, y, True)[:2]; t_o6 = time.perf_counter() - t0
+        t0 = time.perf_counter(); oc4, od4, ub4 = o.batch_t4(x, y, s, True); t_o4 = time.perf_counter() - t0
+        ok6 = bool(np.array_equal(oc6, c6) and np.array_equal(od6, idx.digest_t6(lo, hi, True)))
+        ok4 = bool(np.all(((oc4 == np.diff(off4)) & (od4 == idx.digest_t4(off4, hits4, True))) | (ub4 != 0)))
+        print(json.dumps({"config": "published shape: 1000 regions x 43185 bp, one sample, chr22-shaped synthetic",
+                          "t6_rows_per_region": float(c6.mean()), "t4_rows_per_region": float(np.diff(off4).mean()),
+                          "vsgpu_t6_and_t4_counts_and_codes_s": t_counts, "vsgpu_t6_rows_as_text_s": t_rows6, "vsgpu_t4_rows_as_text_s": t_rows4,
+                          "t6_text_bytes": int(len(r6[1])), "t4_text_bytes": int(len(r4[1])),
+                          "oracle_1_thread_t6_s": t_o6, "oracle_1_thread_t4_s": t_o4, "parity_t6": ok6, "parity_t4": ok4,
+                          "reference_published_t6_s": 1946.6, "reference_published_t4_s": 1237.98,
+                          "note": "oracle rows are digested, not printed; vsgpu text legs include the copy of the text into a Python bytes object"}), flush=True)
+        o.close(); idx.close()
     if "width" in args.what:
         import bench
         class A: pass
