@@ -32,6 +32,7 @@ def timed(batch, steps=10, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="tcga,width")
+    ap.add_argument("--skip-oracle", action="store_true")
     ap.add_argument("--widths", default="", help="comma list: only these widths of the sweep (and no t7 line)")
     ap.add_argument("--tcga-records", type=int, default=3_000_000)
     ap.add_argument("--tcga-samples", type=int, default=10_000)
@@ -129,6 +130,18 @@ def main():
         idx.render_var_in_ref(x, y, True); idx.render_sample_var_in_ref(x, y, s, True)
         t_rows6, r6 = best(lambda: idx.render_var_in_ref(x, y, True), 3)
         t_rows4, r4 = best(lambda: idx.render_sample_var_in_ref(x, y, s, True), 3)
+        # the same two calls through the C ABI alone (text left in the library's page-locked buffer)
+        import ctypes as C
+        lib, h = idx._lib, idx._h
+        def c_call(fn, *a):
+            t = C.c_void_p()
+            t0 = time.perf_counter(); rc = fn(h, n, *a, 1, C.byref(t)); dt = time.perf_counter() - t0
+            assert rc == 0
+            lib.vsgpu_text_free(t)
+            return dt
+        vp = C.c_void_p
+        t_c6 = min(c_call(lib.vsgpu_render_t6, vp(x.ctypes.data), vp(y.ctypes.data)) for _ in range(3))
+        t_c4 = min(c_call(lib.vsgpu_render_t4, vp(x.ctypes.data), vp(y.ctypes.data), vp(s.ctypes.data)) for _ in range(3))
         o = T.Oracle.open(prefix)
         t0 = time.perf_counter(); oc6, od6 = o.batch_t6(x, y, True)[:2]; t_o6 = time.perf_counter() - t0
         t0 = time.perf_counter(); oc4, od4, ub4 = o.batch_t4(x, y, s, True); t_o4 = time.perf_counter() - t0
@@ -137,11 +150,14 @@ def main():
         print(json.dumps({"config": "published shape: 1000 regions x 43185 bp, one sample, chr22-shaped synthetic",
                           "t6_rows_per_region": float(c6.mean()), "t4_rows_per_region": float(np.diff(off4).mean()),
                           "vsgpu_t6_and_t4_counts_and_codes_s": t_counts, "vsgpu_t6_rows_as_text_s": t_rows6, "vsgpu_t4_rows_as_text_s": t_rows4,
-                          "t6_text_bytes": int(len(r6[1])), "t4_text_bytes": int(len(r4[1])),
+                          "t6_text_bytes": int(len(r6[1])), "t4_text_bytes": int(len(r4[1])), "vsgpu_t6_rows_c_abi_s": t_c6, "vsgpu_t4_rows_c_abi_s": t_c4,
+                          "t6_render_kernels_ms": r6[3], "t4_render_kernels_ms": r4[3],
                           "oracle_1_thread_t6_s": t_o6, "oracle_1_thread_t4_s": t_o4, "parity_t6": ok6, "parity_t4": ok4,
                           "reference_published_t6_s": 1946.6, "reference_published_t4_s": 1237.98,
                           "note": "oracle rows are digested, not printed; vsgpu text legs include the copy of the text into a Python bytes object"}), flush=True)
         o.close(); idx.close()
+        if args.skip_oracle:
+            pass
     if "width" in args.what:
         import bench
         class A: pass

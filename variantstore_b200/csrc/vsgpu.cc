@@ -962,6 +962,7 @@ namespace {
 // every row and region, then the rows in chunks whose copies overlap the rendering of the next.  t5_samples: device sample ids (t5 rows).
 void render_hit_rows(vsgpu_index* ix, vsgpu_text* t, uint64_t n, int with_samples, const uint32_t* t5_samples) {
 	cudaStream_t st = ix->stream;
+	Trace tr("hit rows");
 	uint64_t nh = 0;
 	CU(cudaMemcpyAsync(&nh, ix->boffsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -979,14 +980,17 @@ void render_hit_rows(vsgpu_index* ix, vsgpu_text* t, uint64_t n, int with_sample
 	CU(cudaMemcpyAsync(t->offsets, ix->bbyte_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	const uint64_t total = t->offsets[n];
+	tr.mark("row offsets");
 	uint64_t max_bytes = 2ull << 30;
 	if (const char* e = getenv("VSGPU_RENDER_MAX_BYTES")) max_bytes = strtoull(e, nullptr, 10);
 	if (total > max_bytes) throw std::invalid_argument("the rows of this batch take " + std::to_string(total) + " bytes (limit VSGPU_RENDER_MAX_BYTES = " + std::to_string(max_bytes) + "); split the batch");
 	t->nrows = nh; t->nbytes = total;
 	t->bytes = (char*)ix->pinned_acquire(total + 1, &t->bytes_cap);
 	if (!t->bytes) throw std::runtime_error("CUDA: cannot allocate page-locked result memory");
+	tr.mark("page-locked text buffer");
 	if (total) {
 		CU(ix->btext.ensure(total));
+		tr.mark("device text buffer");
 		// rows in chunks of about 32 MB of text: the copy of one chunk overlaps the rendering of the next
 		uint64_t chunk_bytes = 32ull << 20;
 		if (const char* e = getenv("VSGPU_RENDER_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
@@ -1011,6 +1015,7 @@ void render_hit_rows(vsgpu_index* ix, vsgpu_text* t, uint64_t n, int with_sample
 		CU(cudaStreamSynchronize(st));
 	} else { CU(cudaEventRecord(ix->ev_render[1], st)); CU(cudaStreamSynchronize(st)); }
 	t->bytes[total] = 0;
+	tr.mark("render + copy");
 	CU(cudaEventElapsedTime(&t->kernel_ms, ix->ev_render[0], ix->ev_render[1]));
 }
 }  // namespace
