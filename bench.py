@@ -32,8 +32,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 POS_LO, REF_LEN = 16_050_000, 51_304_566          # scripts/bm_vs_query.sh:13, scripts/run_query.sh:6
 # the kernel instances a default run launches (variantstore_b200/csrc/kernels.cu: launch_t4x, 64-region tiles, 24 CTAs / SM)
-T4_INSTANCE = "k_t4p<64,24,8,k32=false,fuse6=false>"
-T4_FUSED_INSTANCE = "k_t4p<64,24,8,k32=false,fuse6=true>"
+T4_INSTANCE = "k_t4p<64,24,8,k32=false,fuse6=false,spill=false>"
+T4_FUSED_INSTANCE = "k_t4p<64,24,8,k32=false,fuse6=true,spill=false>"
 
 
 def log(*a):
